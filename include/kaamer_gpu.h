@@ -1,0 +1,195 @@
+/*
+ * kaamer_gpu.h — C ABI of libkaamer_gpu.so, the B200 (sm_100a) implementation of the
+ * zorino/kaamer search hot path.  Plain C types only: this is what a cgo shim in
+ * pkg/search binds.  All `file:line` citations are relative to the
+ * reference repository root.
+ *
+ * Conventions
+ *  - every function returns KAAMER_OK (0) or a negative error code and never aborts the
+ *    process; kaamer_gpu_last_error() returns a thread-local message for the last failure;
+ *  - input pointers are caller-owned and only read during the call (cgo pointer rule);
+ *  - outputs are library-owned (pinned host memory) and released by the matching *_free;
+ *  - a handle may be used from several threads; calls on one handle are serialised;
+ *  - hits are ordered (Kmatch desc, subject id asc): the reference's tie order is random
+ *    (pkg/search/search.go:132-152), this is the canonical representative;
+ *  - there is NO CPU fallback: without a CUDA device every entry point fails.
+ */
+#ifndef KAAMER_GPU_H
+#define KAAMER_GPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KAAMER_OK 0
+#define KAAMER_ERR_CUDA (-1)
+#define KAAMER_ERR_ARG (-2)
+#define KAAMER_ERR_IO (-3)
+#define KAAMER_ERR_FORMAT (-4)
+#define KAAMER_ERR_NOMEM (-5)
+#define KAAMER_ERR_LIMIT (-6)
+
+#define KAAMER_KMER_SIZE 7 /* pkg/search/search.go:45 */
+
+typedef struct kaamer_gpu kaamer_gpu_t;
+
+/* Flat index (".kidx"): what pkg/makedb exports once from the badger
+ * stores by walking kmer_store -> kcomb_store exactly as KmerSearch does
+ * (pkg/search/search.go:421-429).  keys ascending (== badger's big-endian byte order,
+ * pkg/kvstore/k_store.go:69-70); postings per key = unique protein ids, descending
+ * (pkg/kvstore/kv_store.go:284-305). */
+typedef struct kaamer_index_view {
+  uint64_t n_keys;
+  uint64_t n_postings;
+  const uint32_t *keys;      /* [n_keys] */
+  const uint64_t *offsets;   /* [n_keys+1] */
+  const uint32_t *postings;  /* [n_postings] */
+  uint64_t n_proteins;       /* KStats.NumberOfProteins (pkg/kvstore/kstats.proto) */
+  uint64_t n_aa;             /* KStats.NumberOfAA */
+  uint64_t n_kmers;          /* KStats.NumberOfKmers */
+  uint32_t max_protein_id;
+  uint32_t _pad;
+  /* optional protein table indexed by protein id (needed by kaamer_gpu_align):
+   * residues of id i = prot_residues[prot_seq_off[i] .. prot_seq_off[i+1]) */
+  const uint64_t *prot_seq_off; /* [max_protein_id+2] or NULL */
+  const uint8_t *prot_residues; /* or NULL */
+  /* optional key-range shard (mode S): only k-mer keys whose dense code is in
+   * [shard_lo, shard_hi) are resident; 0,0 = whole key space */
+  uint64_t shard_lo, shard_hi;
+} kaamer_index_view;
+
+/* Replaces kvstore.KVStoresNew(dbPath, ..., readOnly=true) at server start
+ * (api/server.go:65, pkg/kvstore/kv_stores.go:46-104) for the search path. */
+int kaamer_gpu_open(const char *kidx_path, int device, kaamer_gpu_t **out);
+int kaamer_gpu_open_view(const kaamer_index_view *view, int device, kaamer_gpu_t **out);
+/* Replaces pkg/makedb (processProteinInputFASTA, inputFASTA.go:195-250) + pkg/indexdb
+ * (IndexStore, indexdb.go:68-150) for the device index: records -> sorted unique
+ * (k-mer, protein id) -> CSR, built on the GPU.  ids[i] is the protein id of record i. */
+int kaamer_gpu_build(const uint8_t *residues, const uint64_t *seq_off, const uint32_t *ids,
+                     uint64_t n_records, int keep_proteins, int device, kaamer_gpu_t **out);
+void kaamer_gpu_close(kaamer_gpu_t *h);
+
+/* KStats (api/server.go:125-132 /api/dbinfo; feeds the e-value, pkg/align/align.go:141) */
+int kaamer_gpu_dbstats(kaamer_gpu_t *h, uint64_t *n_proteins, uint64_t *n_aa, uint64_t *n_kmers);
+/* export of the resident index (sizes, then copy into caller buffers; also `.kidx` writer) */
+int kaamer_gpu_index_sizes(kaamer_gpu_t *h, uint64_t *n_keys, uint64_t *n_postings);
+int kaamer_gpu_index_copy(kaamer_gpu_t *h, uint32_t *keys, uint64_t *offsets, uint32_t *postings);
+int kaamer_gpu_save(kaamer_gpu_t *h, const char *kidx_path);
+
+/* SearchOptions subset that reaches the hot path (pkg/search/search.go:56-71;
+ * defaults api/server.go:194-207: 10 / 0.05 / 10). */
+typedef struct kaamer_opts {
+  int64_t min_kmatch;     /* MinKMatch */
+  double min_kratio;      /* MinKRatio */
+  int32_t max_results;    /* MaxResults */
+  uint8_t want_positions; /* ExtractPositions (always on for nucleotide, search.go:416) */
+  uint8_t _pad[3];
+} kaamer_opts;
+
+/* CSR result of a batch. For protein search rows == queries (row i = query i). */
+typedef struct kaamer_hits {
+  uint32_t n_rows;
+  uint32_t _pad;
+  uint64_t n_hits;
+  uint64_t *hit_off;     /* [n_rows+1] */
+  uint32_t *subject_id;  /* [n_hits]  Hit.Key   (search.go:112) */
+  uint32_t *kmatch;      /* [n_hits]  Hit.Kmatch (search.go:113) */
+  int32_t *size_in_kmer; /* [n_rows]  Query.SizeInKmer (search.go:290-293) */
+  /* want_positions: PositionHits[hit] as one byte per query k-mer position (search.go:442-452) */
+  uint64_t *pos_off; /* [n_hits+1] or NULL */
+  uint8_t *pos;      /* or NULL */
+  /* nucleotide search only (rows == surviving ORFs, search_nucleotide.go:78-123) */
+  uint32_t *row_contig;  /* [n_rows] index of the contig in the batch */
+  int64_t *row_start;    /* Location.StartPosition after SetBestStartCodon (dna.go:252-257) */
+  int64_t *row_end;      /* Location.EndPosition */
+  uint8_t *row_plus;     /* Location.PlusStrand */
+  uint64_t *row_seq_off; /* [n_rows+1] */
+  uint8_t *row_seq;      /* Query.Sequence (amino acids, after start-codon trimming) */
+  /* work counters of the batch */
+  uint64_t n_lookups;    /* query k-mers looked up */
+  uint64_t n_increments; /* (query, subject) counter increments */
+  void *_owner;
+} kaamer_hits;
+
+/* Replaces, per batch of protein queries, the key producer loop (search_protein.go:94-98),
+ * KmerSearch (search.go:414-440), sortMapByValue (:132-152) and FilterResults (:189-220).
+ * residues: query sequences as read by GetQueriesFasta (already upper-cased by the host
+ * reader, search.go:295); seq_off[nq+1].  Queries with SizeInKmer < 7 yield no hits
+ * (search_protein.go:74-76 kills the worker instead; documented deviation). */
+int kaamer_gpu_search_proteins(kaamer_gpu_t *h, const uint8_t *residues, const uint64_t *seq_off,
+                               uint32_t nq, const kaamer_opts *opts, kaamer_hits **out);
+
+/* Replaces GetORFs (dna.go:65-181) + the per-ORF loop of NucleotideSearch / FastqSearch
+ * (search_nucleotide.go:76-130, search_fastq.go:78-140) incl. SetBestStartCodon (dna.go:198-272). */
+int kaamer_gpu_search_nucleotide(kaamer_gpu_t *h, const uint8_t *nt, const uint64_t *contig_off,
+                                 uint32_t n_contigs, const kaamer_opts *opts, kaamer_hits **out);
+void kaamer_gpu_free_hits(kaamer_hits *);
+
+/* GetORFs alone (dna.go:65-181), for parity tests of the translation kernels. */
+typedef struct kaamer_orfs {
+  uint64_t n_orfs;
+  uint32_t *contig;
+  int64_t *start, *end;
+  uint8_t *plus;
+  uint64_t *seq_off; /* [n_orfs+1] */
+  uint8_t *seq;
+  uint64_t *alts_off; /* [n_orfs+1] */
+  int32_t *alts;      /* StartsAlternative */
+  void *_owner;
+} kaamer_orfs;
+int kaamer_gpu_get_orfs(kaamer_gpu_t *h, const uint8_t *nt, const uint64_t *contig_off,
+                        uint32_t n_contigs, kaamer_orfs **out);
+void kaamer_gpu_free_orfs(kaamer_orfs *);
+
+/* align.Align (pkg/align/align.go:46-161) for a batch of (query, subject) pairs.
+ * Subjects are protein ids resolved in the resident protein table. */
+typedef struct kaamer_aln_opts {
+  double lambda, K;        /* MatrixScores.Lambda/K (matrixScores.go:59: 0.267 / 0.041) */
+  int32_t gap_open;        /* MatrixScores.GapOpen: only used by the `score == -GapOpen` test (align.go:127) */
+  int32_t gap_extend;      /* MatrixScores.GapExtend (align.go:130) */
+  uint64_t number_of_aa;   /* KStats.NumberOfAA (align.go:141); 0 = use the index' value */
+} kaamer_aln_opts;
+typedef struct kaamer_aln {
+  float identity, similarity;                 /* float32 (align.go:72-101) */
+  int32_t length, mismatches, gap_openings, raw;
+  double bitscore, evalue;                    /* float64 (align.go:136,141) */
+  int32_t query_start, query_end, subject_start, subject_end;
+  int32_t dp_score;                           /* optimum of the DP (sum of segment scores) */
+  int32_t status;                             /* 0 ok, 1 illegal letter (biogo error ignored, align.go:67) */
+} kaamer_aln;
+int kaamer_gpu_align(kaamer_gpu_t *h, const uint8_t *q_residues, const uint64_t *q_off,
+                     const uint32_t *pair_query, const uint32_t *pair_subject, uint32_t n_pairs,
+                     const kaamer_aln_opts *opts, kaamer_aln *out /* [n_pairs], caller-owned */);
+
+/* ---- device-resident entry points (inputs already in HBM; used by bench.py `value`, by the
+ * multi-GPU drivers and by callers that keep query batches on the device).  All pointers are
+ * device pointers; work is enqueued on `stream` (a cudaStream_t) and is asynchronous. ---- */
+typedef struct kaamer_dev_result {
+  uint32_t *n_hits;      /* [nq]   hits kept per query */
+  uint32_t *hit_base;    /* [nq]   first slot of the query's hits in `pool` */
+  int32_t *size_in_kmer; /* [nq] */
+  uint64_t *pool;        /* [pool_cap] (subject_id | (uint64)kmatch << 32), rank order per query */
+  uint64_t pool_cap;
+  uint64_t *counters;    /* [4]: pool demand, n_lookups, n_increments, status flags */
+} kaamer_dev_result;
+int kaamer_gpu_search_proteins_device(kaamer_gpu_t *h, const uint8_t *d_residues,
+                                      const uint64_t *d_seq_off, uint32_t nq,
+                                      const kaamer_opts *opts, const kaamer_dev_result *d_out,
+                                      void *stream);
+
+/* pinned host buffers for callers that want zero-staging H2D (cgo: C.kaamer_gpu_pinned_alloc) */
+int kaamer_gpu_pinned_alloc(uint64_t bytes, void **out);
+void kaamer_gpu_pinned_free(void *p);
+
+/* per-handle kernel timing (CUDA events around the dominant kernel; bench.py roofline) */
+int kaamer_gpu_profile_enable(kaamer_gpu_t *h, int on);
+int kaamer_gpu_profile_read(kaamer_gpu_t *h, double *kernel_ms_total, uint64_t *kernel_launches,
+                            uint64_t *all_launches, int reset);
+
+const char *kaamer_gpu_last_error(void);
+const char *kaamer_gpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,372 @@
+// api.cu — the extern "C" surface of libkaamer_gpu.so (include/kaamer_gpu.h): handle
+// lifetime, `.kidx` I/O, argument checking.  No torch types, no C++ types in signatures.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "internal.cuh"
+
+namespace kaamer {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+// ---- .kidx container (little-endian; sections 64-byte aligned) ------------------------
+struct KidxHeader {
+  char magic[8];  // "KIDX0001"
+  uint32_t version, k;
+  uint64_t n_keys, n_postings, n_proteins, n_aa, n_kmers;
+  uint32_t max_protein_id, flags;  // flags bit0: protein table present
+  uint64_t n_residues;
+  uint8_t pad[128 - 8 - 8 - 40 - 8 - 8];
+};
+static_assert(sizeof(KidxHeader) == 128, "kidx header is 128 bytes");
+
+static size_t pad64(size_t n) { return (n + 63) & ~(size_t)63; }
+
+static int read_section(FILE *f, void *dst, size_t bytes) {
+  if (bytes && fread(dst, 1, bytes, f) != bytes) {
+    set_error("kidx: short read");
+    return KAAMER_ERR_IO;
+  }
+  size_t skip = pad64(bytes) - bytes;
+  if (skip && fseek(f, (long)skip, SEEK_CUR) != 0) {
+    set_error("kidx: seek failed");
+    return KAAMER_ERR_IO;
+  }
+  return KAAMER_OK;
+}
+static int write_section(FILE *f, const void *src, size_t bytes) {
+  static const char zeros[64] = {0};
+  if (bytes && fwrite(src, 1, bytes, f) != bytes) {
+    set_error("kidx: short write");
+    return KAAMER_ERR_IO;
+  }
+  size_t skip = pad64(bytes) - bytes;
+  if (skip && fwrite(zeros, 1, skip, f) != skip) {
+    set_error("kidx: short write");
+    return KAAMER_ERR_IO;
+  }
+  return KAAMER_OK;
+}
+
+static int new_handle(int device, kaamer_gpu **out) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no CUDA device available (%s); libkaamer_gpu has no CPU fallback",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return KAAMER_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) {
+    set_error("device %d out of range (0..%d)", device, n - 1);
+    return KAAMER_ERR_ARG;
+  }
+  KCUDA(cudaSetDevice(device));
+  auto *h = new kaamer_gpu();
+  h->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    set_error("cudaStreamCreate: %s", cudaGetErrorString(e));
+    delete h;
+    return KAAMER_ERR_CUDA;
+  }
+  *out = h;
+  return KAAMER_OK;
+}
+
+static void destroy_handle(kaamer_gpu *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  index_release(h);
+  h->ws.residues.release();
+  h->ws.seq_off.release();
+  h->ws.n_hits.release();
+  h->ws.hit_base.release();
+  h->ws.lists.release();
+  h->ws.size_in_kmer.release();
+  h->ws.pool.release();
+  h->ws.hit_off.release();
+  h->ws.out_hits.release();
+  h->ws.counters.release();
+  h->ws.ghash.release();
+  h->ws.h_counters.release();
+  for (auto &p : h->prof_pending) {
+    cudaEventDestroy(p.first);
+    cudaEventDestroy(p.second);
+  }
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+}  // namespace kaamer
+
+using namespace kaamer;
+
+extern "C" {
+
+const char *kaamer_gpu_last_error(void) { return g_err; }
+const char *kaamer_gpu_version(void) { return "kaamer_b200 0.1 (sm_100a)"; }
+
+int kaamer_gpu_open_view(const kaamer_index_view *view, int device, kaamer_gpu_t **out) {
+  if (!out || !view) {
+    set_error("null argument");
+    return KAAMER_ERR_ARG;
+  }
+  *out = nullptr;
+  kaamer_gpu *h = nullptr;
+  KCHECK(new_handle(device, &h));
+  int rc = index_from_view(h, view);
+  if (rc != KAAMER_OK) {
+    destroy_handle(h);
+    return rc;
+  }
+  *out = h;
+  return KAAMER_OK;
+}
+
+int kaamer_gpu_open(const char *path, int device, kaamer_gpu_t **out) {
+  if (!out || !path) {
+    set_error("null argument");
+    return KAAMER_ERR_ARG;
+  }
+  *out = nullptr;
+  FILE *f = fopen(path, "rb");
+  if (!f) {
+    set_error("cannot open %s", path);
+    return KAAMER_ERR_IO;
+  }
+  KidxHeader hd;
+  if (fread(&hd, 1, sizeof hd, f) != sizeof hd || memcmp(hd.magic, "KIDX0001", 8) != 0 || hd.version != 1 ||
+      hd.k != KAAMER_KMER_SIZE) {
+    fclose(f);
+    set_error("%s is not a kidx v1 (k=7) file", path);
+    return KAAMER_ERR_FORMAT;
+  }
+  std::vector<uint32_t> keys((size_t)hd.n_keys), postings((size_t)hd.n_postings);
+  std::vector<uint64_t> offsets((size_t)hd.n_keys + 1), poff;
+  std::vector<uint8_t> pres;
+  int rc = read_section(f, keys.data(), keys.size() * 4);
+  if (rc == KAAMER_OK) rc = read_section(f, offsets.data(), offsets.size() * 8);
+  if (rc == KAAMER_OK) rc = read_section(f, postings.data(), postings.size() * 4);
+  if (rc == KAAMER_OK && (hd.flags & 1)) {
+    poff.resize((size_t)hd.max_protein_id + 2);
+    pres.resize((size_t)hd.n_residues);
+    rc = read_section(f, poff.data(), poff.size() * 8);
+    if (rc == KAAMER_OK) rc = read_section(f, pres.data(), pres.size());
+  }
+  fclose(f);
+  if (rc != KAAMER_OK) return rc;
+  kaamer_index_view v{};
+  v.n_keys = hd.n_keys;
+  v.n_postings = hd.n_postings;
+  v.keys = keys.data();
+  v.offsets = offsets.data();
+  v.postings = postings.data();
+  v.n_proteins = hd.n_proteins;
+  v.n_aa = hd.n_aa;
+  v.n_kmers = hd.n_kmers;
+  v.max_protein_id = hd.max_protein_id;
+  if (hd.flags & 1) {
+    v.prot_seq_off = poff.data();
+    v.prot_residues = pres.data();
+  }
+  return kaamer_gpu_open_view(&v, device, out);
+}
+
+int kaamer_gpu_build(const uint8_t *residues, const uint64_t *seq_off, const uint32_t *ids, uint64_t n_records,
+                     int keep_proteins, int device, kaamer_gpu_t **out) {
+  if (!out || (n_records && (!residues || !seq_off || !ids))) {
+    set_error("null argument");
+    return KAAMER_ERR_ARG;
+  }
+  *out = nullptr;
+  kaamer_gpu *h = nullptr;
+  KCHECK(new_handle(device, &h));
+  int rc = index_build(h, residues, seq_off, ids, n_records, keep_proteins);
+  if (rc != KAAMER_OK) {
+    destroy_handle(h);
+    return rc;
+  }
+  *out = h;
+  return KAAMER_OK;
+}
+
+void kaamer_gpu_close(kaamer_gpu_t *h) { destroy_handle(h); }
+
+int kaamer_gpu_dbstats(kaamer_gpu_t *h, uint64_t *n_proteins, uint64_t *n_aa, uint64_t *n_kmers) {
+  if (!h) {
+    set_error("null handle");
+    return KAAMER_ERR_ARG;
+  }
+  if (n_proteins) *n_proteins = h->idx.n_proteins;
+  if (n_aa) *n_aa = h->idx.n_aa;
+  if (n_kmers) *n_kmers = h->idx.n_kmers;
+  return KAAMER_OK;
+}
+
+int kaamer_gpu_index_sizes(kaamer_gpu_t *h, uint64_t *n_keys, uint64_t *n_postings) {
+  if (!h) {
+    set_error("null handle");
+    return KAAMER_ERR_ARG;
+  }
+  if (n_keys) *n_keys = h->idx.n_keys;
+  if (n_postings) *n_postings = h->idx.n_postings;
+  return KAAMER_OK;
+}
+
+int kaamer_gpu_index_copy(kaamer_gpu_t *h, uint32_t *keys, uint64_t *offsets, uint32_t *postings) {
+  if (!h) {
+    set_error("null handle");
+    return KAAMER_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk(h->mu);
+  KCUDA(cudaSetDevice(h->device));
+  DevIndex &ix = h->idx;
+  if (keys && ix.n_keys) KCUDA(cudaMemcpy(keys, ix.keys, (size_t)ix.n_keys * 4, cudaMemcpyDeviceToHost));
+  if (offsets) KCUDA(cudaMemcpy(offsets, ix.offsets, (size_t)(ix.n_keys + 1) * 8, cudaMemcpyDeviceToHost));
+  if (postings && ix.n_postings)
+    KCUDA(cudaMemcpy(postings, ix.postings, (size_t)ix.n_postings * 4, cudaMemcpyDeviceToHost));
+  return KAAMER_OK;
+}
+
+int kaamer_gpu_save(kaamer_gpu_t *h, const char *path) {
+  if (!h || !path) {
+    set_error("null argument");
+    return KAAMER_ERR_ARG;
+  }
+  DevIndex &ix = h->idx;
+  std::vector<uint32_t> keys((size_t)ix.n_keys), postings((size_t)ix.n_postings);
+  std::vector<uint64_t> offsets((size_t)ix.n_keys + 1), poff;
+  std::vector<uint8_t> pres;
+  KCHECK(kaamer_gpu_index_copy(h, keys.data(), offsets.data(), postings.data()));
+  if (ix.has_proteins) {
+    poff.resize((size_t)ix.max_protein_id + 2);
+    pres.resize((size_t)ix.n_prot_res);
+    KCUDA(cudaMemcpy(poff.data(), ix.prot_off, poff.size() * 8, cudaMemcpyDeviceToHost));
+    if (ix.n_prot_res) KCUDA(cudaMemcpy(pres.data(), ix.prot_res, pres.size(), cudaMemcpyDeviceToHost));
+  }
+  KidxHeader hd;
+  memset(&hd, 0, sizeof hd);
+  memcpy(hd.magic, "KIDX0001", 8);
+  hd.version = 1;
+  hd.k = KAAMER_KMER_SIZE;
+  hd.n_keys = ix.n_keys;
+  hd.n_postings = ix.n_postings;
+  hd.n_proteins = ix.n_proteins;
+  hd.n_aa = ix.n_aa;
+  hd.n_kmers = ix.n_kmers;
+  hd.max_protein_id = ix.max_protein_id;
+  hd.flags = ix.has_proteins ? 1u : 0u;
+  hd.n_residues = ix.n_prot_res;
+  FILE *f = fopen(path, "wb");
+  if (!f) {
+    set_error("cannot create %s", path);
+    return KAAMER_ERR_IO;
+  }
+  int rc = fwrite(&hd, 1, sizeof hd, f) == sizeof hd ? KAAMER_OK : KAAMER_ERR_IO;
+  if (rc == KAAMER_OK) rc = write_section(f, keys.data(), keys.size() * 4);
+  if (rc == KAAMER_OK) rc = write_section(f, offsets.data(), offsets.size() * 8);
+  if (rc == KAAMER_OK) rc = write_section(f, postings.data(), postings.size() * 4);
+  if (rc == KAAMER_OK && ix.has_proteins) {
+    rc = write_section(f, poff.data(), poff.size() * 8);
+    if (rc == KAAMER_OK) rc = write_section(f, pres.data(), pres.size());
+  }
+  if (fclose(f) != 0 && rc == KAAMER_OK) rc = KAAMER_ERR_IO;
+  if (rc != KAAMER_OK) set_error("write to %s failed", path);
+  return rc;
+}
+
+static int check_search_args(kaamer_gpu_t *h, const void *a, const void *b, uint32_t n, const kaamer_opts *o,
+                             const void *out) {
+  if (!h || !o || !out || (n && (!a || !b))) {
+    set_error("null argument");
+    return KAAMER_ERR_ARG;
+  }
+  return KAAMER_OK;
+}
+
+int kaamer_gpu_search_proteins(kaamer_gpu_t *h, const uint8_t *residues, const uint64_t *seq_off, uint32_t nq,
+                               const kaamer_opts *opts, kaamer_hits **out) {
+  KCHECK(check_search_args(h, residues, seq_off, nq, opts, out));
+  *out = nullptr;
+  std::lock_guard<std::mutex> lk(h->mu);
+  KCUDA(cudaSetDevice(h->device));
+  return search_proteins_host(h, residues, seq_off, nq, opts, out);
+}
+
+int kaamer_gpu_search_proteins_device(kaamer_gpu_t *h, const uint8_t *d_residues, const uint64_t *d_seq_off,
+                                      uint32_t nq, const kaamer_opts *opts, const kaamer_dev_result *d_out,
+                                      void *stream) {
+  KCHECK(check_search_args(h, d_residues, d_seq_off, nq, opts, d_out));
+  std::lock_guard<std::mutex> lk(h->mu);
+  KCUDA(cudaSetDevice(h->device));
+  return search_proteins_device(h, d_residues, d_seq_off, nq, opts, d_out, (cudaStream_t)stream);
+}
+
+void kaamer_gpu_free_hits(kaamer_hits *hits) {
+  if (!hits) return;
+  delete (HitsOwner *)hits->_owner;
+  delete hits;
+}
+
+int kaamer_gpu_pinned_alloc(uint64_t bytes, void **out) {
+  if (!out) {
+    set_error("null argument");
+    return KAAMER_ERR_ARG;
+  }
+  cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+  if (e != cudaSuccess) {
+    set_error("cudaMallocHost(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    return KAAMER_ERR_NOMEM;
+  }
+  return KAAMER_OK;
+}
+void kaamer_gpu_pinned_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int kaamer_gpu_profile_enable(kaamer_gpu_t *h, int on) {
+  if (!h) {
+    set_error("null handle");
+    return KAAMER_ERR_ARG;
+  }
+  h->profile = on != 0;
+  return KAAMER_OK;
+}
+
+int kaamer_gpu_profile_read(kaamer_gpu_t *h, double *kernel_ms_total, uint64_t *kernel_launches,
+                            uint64_t *all_launches, int reset) {
+  if (!h) {
+    set_error("null handle");
+    return KAAMER_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (auto &p : h->prof_pending) {
+    cudaEventSynchronize(p.second);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) h->prof_ms += ms;
+    cudaEventDestroy(p.first);
+    cudaEventDestroy(p.second);
+  }
+  h->prof_pending.clear();
+  if (kernel_ms_total) *kernel_ms_total = h->prof_ms;
+  if (kernel_launches) *kernel_launches = h->prof_kernel_launches;
+  if (all_launches) *all_launches = h->prof_all_launches;
+  if (reset) {
+    h->prof_ms = 0;
+    h->prof_kernel_launches = 0;
+    h->prof_all_launches = 0;
+  }
+  return KAAMER_OK;
+}
+
+}  // extern "C"

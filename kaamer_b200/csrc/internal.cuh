@@ -1,0 +1,242 @@
+// internal.cuh — shared declarations of libkaamer_gpu (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/kaamer_gpu.h"
+
+namespace kaamer {
+
+// ---- error plumbing -------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+#define KCUDA(call)                                                                         \
+  do {                                                                                      \
+    cudaError_t _e = (call);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::kaamer::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      return KAAMER_ERR_CUDA;                                                               \
+    }                                                                                       \
+  } while (0)
+#define KCHECK(call)          \
+  do {                        \
+    int _r = (call);          \
+    if (_r != KAAMER_OK) return _r; \
+  } while (0)
+
+// ---- k-mer code space -----------------------------------------------------------------
+// EncodeKmer (pkg/kvstore/k_store.go:91-117): key = p01<<23 | p23<<14 | p45<<5 | s6 with
+// pair codes p in {0} U [22,462] and single codes s in [0,20].  The device table is
+// direct-addressed by the DENSE code  d = ((p01'*442 + p23')*442 + p45')*21 + s6,
+// p' = (p==0 ? 0 : p-21) in [0,441]:  442^3*21 = 1,813,366,968 slots.
+constexpr uint32_t PAIR_RADIX = 442;
+constexpr uint64_t DENSE_SPACE = (uint64_t)PAIR_RADIX * PAIR_RADIX * PAIR_RADIX * 21ull;
+constexpr uint32_t CODE_UNKNOWN = 0x80;
+
+// table entry: count:28 | value:36.  count==0 empty; count==1 value = protein id (posting
+// inlined); count>=2 value = first index of the posting list in postings[].
+constexpr int ENTRY_VALUE_BITS = 36;
+constexpr uint64_t ENTRY_VALUE_MASK = (1ull << ENTRY_VALUE_BITS) - 1;
+constexpr uint64_t ENTRY_MAX_COUNT = (1ull << 28) - 1;
+
+#ifdef __CUDACC__
+// residue byte -> code 0..20 ("ACDEFGHIKLMNPQRSTUVWY", k_store.go:41) or CODE_UNKNOWN.
+// Pure ALU (two packed 5-bit tables), no memory lookup.
+__host__ __device__ __forceinline__ uint32_t aa_code(uint32_t c) {
+  //            A  B  C  D  E  F  G  H  I  J  K  L | M   N   O   P   Q   R   S   T   U   V   W   X   Y
+  // code       0  -  1  2  3  4  5  6  7  -  8  9 | 10  11  -   12  13  14  15  16  17  18  19  -   20
+  constexpr uint64_t LO = (0ull) | (31ull << 5) | (1ull << 10) | (2ull << 15) | (3ull << 20) | (4ull << 25) |
+                          (5ull << 30) | (6ull << 35) | (7ull << 40) | (31ull << 45) | (8ull << 50) | (9ull << 55);
+  constexpr uint64_t HI = (10ull) | (11ull << 5) | (31ull << 10) | (12ull << 15) | (13ull << 20) |
+                          (14ull << 25) | (15ull << 30) | (16ull << 35) | (17ull << 40) | (18ull << 45) |
+                          (19ull << 50) | (31ull << 55);  // M..X; 'Y' handled below (25 letters > 2x12 slots)
+  uint32_t i = c - 'A';
+  if (i > 24u) return CODE_UNKNOWN;
+  if (i == 24u) return 20u;
+  uint32_t v = i < 12u ? (uint32_t)(LO >> (5u * i)) & 31u : (uint32_t)(HI >> (5u * (i - 12u))) & 31u;
+  return v == 31u ? CODE_UNKNOWN : v;
+}
+// p' of two codes: 0 if either is unknown (Go map miss -> 0, k_store.go:100-103), else 1+21x+y
+__host__ __device__ __forceinline__ uint32_t pair_dense(uint32_t x, uint32_t y) {
+  return ((x | y) & CODE_UNKNOWN) ? 0u : 1u + 21u * x + y;
+}
+__host__ __device__ __forceinline__ uint32_t single_dense(uint32_t x) {
+  return (x & CODE_UNKNOWN) ? 0u : x;  // unknown last residue aliases 'A' (k_store.go:108-110)
+}
+__host__ __device__ __forceinline__ uint32_t dense_from_codes(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                              uint32_t c3, uint32_t c4, uint32_t c5,
+                                                              uint32_t c6) {
+  return ((pair_dense(c0, c1) * PAIR_RADIX + pair_dense(c2, c3)) * PAIR_RADIX + pair_dense(c4, c5)) * 21u +
+         single_dense(c6);
+}
+// reference u32 key (k_store.go:100-110) from 7 codes
+__host__ __device__ __forceinline__ uint32_t key_from_codes(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                            uint32_t c4, uint32_t c5, uint32_t c6) {
+  uint32_t p0 = pair_dense(c0, c1), p1 = pair_dense(c2, c3), p2 = pair_dense(c4, c5);
+  p0 = p0 ? p0 + 21u : 0u;
+  p1 = p1 ? p1 + 21u : 0u;
+  p2 = p2 ? p2 + 21u : 0u;
+  return (p0 << 23) | (p1 << 14) | (p2 << 5) | single_dense(c6);
+}
+// reference key -> dense code; returns false if the key is not an EncodeKmer output
+__host__ __device__ __forceinline__ bool dense_from_key(uint32_t key, uint32_t *d) {
+  uint32_t p0 = (key >> 23) & 0x1FF, p1 = (key >> 14) & 0x1FF, p2 = (key >> 5) & 0x1FF, s = key & 0x1F;
+  if ((p0 != 0 && (p0 < 22 || p0 > 462)) || (p1 != 0 && (p1 < 22 || p1 > 462)) ||
+      (p2 != 0 && (p2 < 22 || p2 > 462)) || s > 20)
+    return false;
+  p0 = p0 ? p0 - 21u : 0u;
+  p1 = p1 ? p1 - 21u : 0u;
+  p2 = p2 ? p2 - 21u : 0u;
+  *d = ((p0 * PAIR_RADIX + p1) * PAIR_RADIX + p2) * 21u + s;
+  return true;
+}
+__host__ __device__ __forceinline__ uint32_t key_from_dense(uint32_t d) {
+  uint32_t s = d % 21u;
+  d /= 21u;
+  uint32_t p2 = d % PAIR_RADIX;
+  d /= PAIR_RADIX;
+  uint32_t p1 = d % PAIR_RADIX, p0 = d / PAIR_RADIX;
+  p0 = p0 ? p0 + 21u : 0u;
+  p1 = p1 ? p1 + 21u : 0u;
+  p2 = p2 ? p2 + 21u : 0u;
+  return (p0 << 23) | (p1 << 14) | (p2 << 5) | s;
+}
+#endif
+
+// ---- device buffers -------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;  // capacity in elements
+  int ensure(size_t want) {
+    if (want <= n && p) return KAAMER_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    size_t cap = want + want / 4 + 64;
+    cudaError_t e = cudaMalloc((void **)&p, cap * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes): %s", cap * sizeof(T), cudaGetErrorString(e));
+      p = nullptr;
+      return KAAMER_ERR_NOMEM;
+    }
+    n = cap;
+    return KAAMER_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+template <class T>
+struct PinBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  int ensure(size_t want) {
+    if (want <= n && p) return KAAMER_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+    size_t cap = want + want / 4 + 64;
+    cudaError_t e = cudaMallocHost((void **)&p, cap * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error("cudaMallocHost(%zu bytes): %s", cap * sizeof(T), cudaGetErrorString(e));
+      p = nullptr;
+      return KAAMER_ERR_NOMEM;
+    }
+    n = cap;
+    return KAAMER_OK;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+// ---- the resident index ---------------------------------------------------------------
+struct DevIndex {
+  uint64_t *table = nullptr;  // [d_hi - d_lo] direct-address entries
+  uint64_t d_lo = 0, d_hi = 0;
+  uint32_t *postings = nullptr;  // [n_postings]
+  uint64_t n_postings = 0;
+  // sorted form kept for export / save (keys ascending, offsets, postings descending)
+  uint32_t *keys = nullptr;
+  uint64_t *offsets = nullptr;
+  uint64_t n_keys = 0;
+  // protein table (optional)
+  uint64_t *prot_off = nullptr;
+  uint8_t *prot_res = nullptr;
+  uint64_t n_prot_res = 0;
+  uint32_t max_protein_id = 0;
+  bool has_proteins = false;
+  uint64_t n_proteins = 0, n_aa = 0, n_kmers = 0;
+};
+
+struct SearchWorkspace {
+  DevBuf<uint8_t> residues;
+  DevBuf<uint64_t> seq_off;
+  DevBuf<uint32_t> n_hits, hit_base, lists;
+  DevBuf<int32_t> size_in_kmer;
+  DevBuf<uint64_t> pool, hit_off, out_hits;
+  DevBuf<uint64_t> counters;   // see search.cu
+  DevBuf<uint32_t> ghash;      // global-memory hash scratch (class G)
+  PinBuf<uint64_t> h_counters;
+};
+
+// owner of the pinned host buffers behind a kaamer_hits / kaamer_orfs
+struct HitsOwner {
+  std::vector<void *> pinned;
+  ~HitsOwner() {
+    for (void *p : pinned) cudaFreeHost(p);
+  }
+  template <class T>
+  int alloc(T **out, size_t n) {
+    void *p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, (n ? n : 1) * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error("cudaMallocHost: %s", cudaGetErrorString(e));
+      return KAAMER_ERR_NOMEM;
+    }
+    pinned.push_back(p);
+    *out = (T *)p;
+    return KAAMER_OK;
+  }
+};
+
+}  // namespace kaamer
+
+struct kaamer_gpu {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  kaamer::DevIndex idx;
+  kaamer::SearchWorkspace ws;
+  // profiling
+  bool profile = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double prof_ms = 0;
+  uint64_t prof_kernel_launches = 0, prof_all_launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending;
+};
+
+namespace kaamer {
+// index.cu
+int index_from_view(kaamer_gpu *h, const kaamer_index_view *v);
+int index_build(kaamer_gpu *h, const uint8_t *residues, const uint64_t *seq_off, const uint32_t *ids,
+                uint64_t n_records, int keep_proteins);
+void index_release(kaamer_gpu *h);
+// search.cu
+int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint32_t nq,
+                           const kaamer_opts *o, const kaamer_dev_result *out, cudaStream_t st);
+int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off, uint32_t nq,
+                         const kaamer_opts *o, kaamer_hits **out);
+void profile_begin(kaamer_gpu *h, cudaStream_t st);
+void profile_end(kaamer_gpu *h, cudaStream_t st);
+}  // namespace kaamer

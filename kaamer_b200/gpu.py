@@ -1,0 +1,226 @@
+"""Host-side handle on the device-resident index (thin wrapper over the C ABI).
+
+Mirrors the seam of the reference: `KVStoresNew(..., readOnly)` at server start
+(api/server.go:65) -> `GpuIndex.open`; per request `KmerSearch` + `sortMapByValue` +
+`FilterResults` (pkg/search/search.go:132-220,414-440) -> `GpuIndex.search_proteins`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+@dataclass
+class SearchOptions:
+    """The SearchOptions fields that reach the hot path (pkg/search/search.go:56-71).
+    Defaults are the server's (api/server.go:194-207)."""
+
+    max_results: int = 10
+    min_kmatch: int = 10
+    min_kratio: float = 0.05
+    extract_positions: bool = False
+
+    def c(self) -> _lib.Opts:
+        o = _lib.Opts()
+        o.min_kmatch = int(self.min_kmatch)
+        o.min_kratio = float(self.min_kratio)
+        o.max_results = int(self.max_results)
+        o.want_positions = 1 if self.extract_positions else 0
+        return o
+
+
+@dataclass
+class SearchResult:
+    hit_off: np.ndarray       # u64[n_rows+1]
+    subject: np.ndarray       # u32[n_hits]   Hit.Key
+    kmatch: np.ndarray        # u32[n_hits]   Hit.Kmatch
+    size_in_kmer: np.ndarray  # i32[n_rows]   Query.SizeInKmer
+    n_lookups: int
+    n_increments: int
+    pos_off: np.ndarray | None = None
+    pos: np.ndarray | None = None
+    row_contig: np.ndarray | None = None
+    row_start: np.ndarray | None = None
+    row_end: np.ndarray | None = None
+    row_plus: np.ndarray | None = None
+    row_seq_off: np.ndarray | None = None
+    row_seq: np.ndarray | None = None
+
+    @property
+    def n_rows(self) -> int:
+        return len(self.hit_off) - 1
+
+    def hits(self, i: int):
+        b, e = int(self.hit_off[i]), int(self.hit_off[i + 1])
+        return list(zip(self.subject[b:e].tolist(), self.kmatch[b:e].tolist()))
+
+
+def _arr(ptr, n, dtype):
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(int(n),)).astype(dtype, copy=True)
+
+
+def _vp(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _collect_hits(hp) -> SearchResult:
+    h = hp.contents
+    n, nh = h.n_rows, h.n_hits
+    r = SearchResult(
+        hit_off=_arr(h.hit_off, n + 1, np.uint64),
+        subject=_arr(h.subject_id, nh, np.uint32),
+        kmatch=_arr(h.kmatch, nh, np.uint32),
+        size_in_kmer=_arr(h.size_in_kmer, n, np.int32),
+        n_lookups=int(h.n_lookups),
+        n_increments=int(h.n_increments),
+    )
+    if h.pos_off:
+        r.pos_off = _arr(h.pos_off, nh + 1, np.uint64)
+        r.pos = _arr(h.pos, int(r.pos_off[-1]) if nh else 0, np.uint8)
+    if h.row_start:
+        r.row_contig = _arr(h.row_contig, n, np.uint32)
+        r.row_start = _arr(h.row_start, n, np.int64)
+        r.row_end = _arr(h.row_end, n, np.int64)
+        r.row_plus = _arr(h.row_plus, n, np.uint8)
+        r.row_seq_off = _arr(h.row_seq_off, n + 1, np.uint64)
+        r.row_seq = _arr(h.row_seq, int(r.row_seq_off[-1]) if n else 0, np.uint8)
+    _lib.lib().kaamer_gpu_free_hits(hp)
+    return r
+
+
+class GpuIndex:
+    """A k-mer index resident in the HBM of one GPU."""
+
+    def __init__(self, handle, device: int):
+        self._h = handle
+        self.device = device
+
+    # ---- construction ------------------------------------------------------------------
+    @classmethod
+    def open(cls, kidx_path: str, device: int = 0) -> "GpuIndex":
+        h = C.c_void_p()
+        check(_lib.lib().kaamer_gpu_open(kidx_path.encode(), device, C.byref(h)))
+        return cls(h, device)
+
+    @classmethod
+    def from_arrays(cls, keys, offsets, postings, n_proteins=0, n_aa=0, n_kmers=0, max_protein_id=None,
+                    prot_seq_off=None, prot_residues=None, shard=(0, 0), device: int = 0) -> "GpuIndex":
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        postings = np.ascontiguousarray(postings, dtype=np.uint32)
+        v = _lib.IndexView()
+        v.n_keys, v.n_postings = len(keys), len(postings)
+        v.keys, v.offsets, v.postings = _vp(keys), _vp(offsets), _vp(postings)
+        v.n_proteins, v.n_aa, v.n_kmers = int(n_proteins), int(n_aa), int(n_kmers)
+        if max_protein_id is None:
+            max_protein_id = int(postings.max()) if len(postings) else 0
+        v.max_protein_id = int(max_protein_id)
+        keep = [keys, offsets, postings]
+        if prot_seq_off is not None and prot_residues is not None:
+            po = np.ascontiguousarray(prot_seq_off, dtype=np.uint64)
+            pr = np.ascontiguousarray(prot_residues, dtype=np.uint8)
+            assert len(po) == v.max_protein_id + 2
+            v.prot_seq_off, v.prot_residues = _vp(po), _vp(pr)
+            keep += [po, pr]
+        v.shard_lo, v.shard_hi = int(shard[0]), int(shard[1])
+        h = C.c_void_p()
+        check(_lib.lib().kaamer_gpu_open_view(C.byref(v), device, C.byref(h)))
+        return cls(h, device)
+
+    @classmethod
+    def build(cls, residues, seq_off, ids, keep_proteins: bool = True, device: int = 0) -> "GpuIndex":
+        """makedb + indexdb semantics on the GPU (pkg/makedb/inputFASTA.go:195-250,
+        pkg/indexdb/indexdb.go:68-150); ids[i] = protein id of record i."""
+        residues = np.ascontiguousarray(residues, dtype=np.uint8)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        assert len(seq_off) == len(ids) + 1
+        h = C.c_void_p()
+        check(_lib.lib().kaamer_gpu_build(_vp(residues), _vp(seq_off), _vp(ids), len(ids), int(keep_proteins),
+                                          device, C.byref(h)))
+        return cls(h, device)
+
+    def close(self):
+        if self._h:
+            _lib.lib().kaamer_gpu_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- introspection -----------------------------------------------------------------
+    def dbstats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(_lib.lib().kaamer_gpu_dbstats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"NumberOfProteins": a.value, "NumberOfAA": b.value, "NumberOfKmers": c.value}
+
+    def index_arrays(self):
+        nk, npst = C.c_uint64(), C.c_uint64()
+        check(_lib.lib().kaamer_gpu_index_sizes(self._h, C.byref(nk), C.byref(npst)))
+        keys = np.zeros(nk.value, np.uint32)
+        offsets = np.zeros(nk.value + 1, np.uint64)
+        postings = np.zeros(npst.value, np.uint32)
+        check(_lib.lib().kaamer_gpu_index_copy(self._h, _vp(keys), _vp(offsets), _vp(postings)))
+        return keys, offsets, postings
+
+    def save(self, path: str):
+        check(_lib.lib().kaamer_gpu_save(self._h, path.encode()))
+
+    # ---- search ------------------------------------------------------------------------
+    def search_proteins(self, residues, seq_off, opts: SearchOptions | None = None) -> SearchResult:
+        opts = opts or SearchOptions()
+        residues = np.ascontiguousarray(residues, dtype=np.uint8)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        return self.search_proteins_ptr(residues.ctypes.data, seq_off.ctypes.data, len(seq_off) - 1, opts)
+
+    def search_proteins_ptr(self, res_ptr: int, off_ptr: int, nq: int, opts: SearchOptions) -> SearchResult:
+        """Same call with raw host pointers (e.g. pinned buffers)."""
+        o = opts.c()
+        hp = C.POINTER(_lib.Hits)()
+        check(_lib.lib().kaamer_gpu_search_proteins(self._h, C.c_void_p(res_ptr), C.c_void_p(off_ptr), nq,
+                                                    C.byref(o), C.byref(hp)))
+        return _collect_hits(hp)
+
+    def search_proteins_device(self, d_res: int, d_off: int, nq: int, opts: SearchOptions, n_hits: int,
+                               hit_base: int, size_in_kmer: int, pool: int, pool_cap: int, counters: int,
+                               stream: int = 0):
+        """Device-resident, asynchronous on `stream` (all arguments are device pointers)."""
+        o = opts.c()
+        dr = _lib.DevResult(n_hits, hit_base, size_in_kmer, pool, pool_cap, counters)
+        check(_lib.lib().kaamer_gpu_search_proteins_device(self._h, C.c_void_p(d_res), C.c_void_p(d_off), nq,
+                                                           C.byref(o), C.byref(dr), C.c_void_p(stream)))
+
+    def search_nucleotide(self, nt, contig_off, opts: SearchOptions | None = None) -> SearchResult:
+        opts = opts or SearchOptions()
+        nt = np.ascontiguousarray(nt, dtype=np.uint8)
+        contig_off = np.ascontiguousarray(contig_off, dtype=np.uint64)
+        o = opts.c()
+        hp = C.POINTER(_lib.Hits)()
+        check(_lib.lib().kaamer_gpu_search_nucleotide(self._h, _vp(nt), _vp(contig_off), len(contig_off) - 1,
+                                                      C.byref(o), C.byref(hp)))
+        return _collect_hits(hp)
+
+    # ---- profiling ---------------------------------------------------------------------
+    def profile_enable(self, on: bool = True):
+        check(_lib.lib().kaamer_gpu_profile_enable(self._h, int(on)))
+
+    def profile_read(self, reset: bool = True):
+        ms, k, a = C.c_double(), C.c_uint64(), C.c_uint64()
+        check(_lib.lib().kaamer_gpu_profile_read(self._h, C.byref(ms), C.byref(k), C.byref(a), int(reset)))
+        return {"kernel_ms": ms.value, "kernel_launches": k.value, "all_launches": a.value}

@@ -1,0 +1,171 @@
+"""GPU parity tests (through the C ABI) of the protein search path vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from tests.helpers import assert_same_hits
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu_small(small_db):
+    from kaamer_b200 import GpuIndex
+
+    g = GpuIndex.build(small_db["res"], small_db["off"], small_db["ids"], device=0)
+    yield g
+    g.close()
+
+
+def test_device_build_equals_oracle_index(small_db, gpu_small):
+    k, f, p = gpu_small.index_arrays()
+    idx = small_db["idx"]
+    np.testing.assert_array_equal(k, idx.keys)
+    np.testing.assert_array_equal(f, idx.offsets)
+    np.testing.assert_array_equal(p, idx.postings)
+    st = gpu_small.dbstats()
+    assert (st["NumberOfProteins"], st["NumberOfAA"], st["NumberOfKmers"]) == (idx.n_proteins, idx.n_aa, idx.n_kmers)
+
+
+def test_open_view_equals_build(small_db):
+    from kaamer_b200 import GpuIndex, SearchOptions, synth
+    from oracle import oracle as o
+
+    idx = small_db["idx"]
+    q, qo, _ = synth.protein_queries(small_db["res"], small_db["off"], 300, config_index=1, stream=5)
+    ora = o.search_proteins(idx, q, qo, o.opts(), 4)
+    with GpuIndex.from_arrays(idx.keys, idx.offsets, idx.postings, idx.n_proteins, idx.n_aa, idx.n_kmers) as g:
+        r = g.search_proteins(q, qo, SearchOptions())
+    assert_same_hits(r, ora, "open_view")
+
+
+def test_kidx_roundtrip(small_db, gpu_small, tmp_path):
+    from kaamer_b200 import GpuIndex
+
+    path = str(tmp_path / "small.kidx")
+    gpu_small.save(path)
+    with GpuIndex.open(path) as g2:
+        a, b = gpu_small.index_arrays(), g2.index_arrays()
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+        assert g2.dbstats() == gpu_small.dbstats()
+
+
+@pytest.mark.parametrize("opts", [
+    dict(),                                                   # reference defaults 10 / 0.05 / 10
+    dict(min_kmatch=1, min_kratio=0.0, max_results=10),       # everything passes: top-10 of all subjects
+    dict(min_kmatch=1, min_kratio=0.0, max_results=1000),     # slow path: > 64 candidates, bitonic sort
+    dict(min_kmatch=1, min_kratio=0.0, max_results=3),        # radix select through large tie groups
+    dict(min_kmatch=30, min_kratio=0.5, max_results=2),
+    dict(min_kmatch=0, min_kratio=0.31, max_results=5),
+    dict(max_results=0),
+])
+def test_search_parity_options(small_db, gpu_small, opts):
+    from kaamer_b200 import SearchOptions, synth
+    from oracle import oracle as o
+
+    q, qo, _ = synth.protein_queries(small_db["res"], small_db["off"], 500, config_index=1, stream=3)
+    ora = o.search_proteins(small_db["idx"], q, qo, o.opts(**opts), 4)
+    r = gpu_small.search_proteins(q, qo, SearchOptions(max_results=opts.get("max_results", 10),
+                                                       min_kmatch=opts.get("min_kmatch", 10),
+                                                       min_kratio=opts.get("min_kratio", 0.05)))
+    assert_same_hits(r, ora, str(opts))
+    assert r.n_lookups == ora.n_lookups
+    assert r.n_increments == ora.n_increments
+
+
+def test_edge_cases(small_db, gpu_small):
+    """empty / short / ragged queries, unknown residues, trailing '*', lower case, long queries."""
+    from kaamer_b200 import SearchOptions
+    from oracle import oracle as o
+
+    res, off = small_db["res"], small_db["off"]
+    rec = lambda i: res[int(off[i]):int(off[i + 1])].tobytes()
+    long_q = b"".join(rec(i) for i in range(40))           # > 2048 k-mers: class G
+    mid_q = b"".join(rec(i) for i in range(100, 104))      # class M
+    seqs = [
+        b"",                      # empty
+        b"MKT",                   # shorter than k
+        rec(5)[:12],              # SizeInKmer 6 < 7: skipped (search_protein.go:74-76)
+        rec(5)[:13],              # SizeInKmer 7: searched
+        rec(6)[:14] + b"*",       # trailing '*': SizeInKmer - 1
+        rec(7),
+        rec(8).lower(),           # lower case: every residue unknown -> key 0 (no upper-casing on the device)
+        rec(9)[:50] + b"XBZJOU*" + rec(9)[57:],   # unknown letters inside
+        rec(10) + b"*",
+        mid_q,
+        long_q,
+        b"A" * 600,               # low complexity: one k-mer repeated
+        rec(11) * 3,              # repeats: positions counted with multiplicity
+    ]
+    q, qo = o.pack(seqs)
+    for opts in (dict(), dict(min_kmatch=1, min_kratio=0.0, max_results=50)):
+        ora = o.search_proteins(small_db["idx"], q, qo, o.opts(**opts), 2)
+        r = gpu_small.search_proteins(q, qo, SearchOptions(max_results=opts.get("max_results", 10),
+                                                           min_kmatch=opts.get("min_kmatch", 10),
+                                                           min_kratio=opts.get("min_kratio", 0.05)))
+        assert_same_hits(r, ora, f"edge {opts}")
+        assert r.n_lookups == ora.n_lookups and r.n_increments == ora.n_increments
+    assert r.size_in_kmer[:5].tolist() == [-6, -3, 6, 7, 8]
+
+
+def test_empty_batch_and_empty_index(gpu_small):
+    from kaamer_b200 import GpuIndex, SearchOptions
+
+    r = gpu_small.search_proteins(np.zeros(0, np.uint8), np.zeros(1, np.uint64), SearchOptions())
+    assert r.n_rows == 0 and len(r.subject) == 0
+    with GpuIndex.build(np.zeros(0, np.uint8), np.zeros(1, np.uint64), np.zeros(0, np.uint32)) as g:
+        q = np.frombuffer(b"MKTAYIAKQRQISFVKSHFSRQ", np.uint8)
+        r = g.search_proteins(q, np.array([0, len(q)], np.uint64), SearchOptions())
+        assert r.n_rows == 1 and len(r.subject) == 0 and r.size_in_kmer[0] == 16
+
+
+def test_dense_collision_quirk_subjects_with_unknown_letters():
+    """DB proteins with X/B/Z/U: unknown letters collapse to code 0 exactly as EncodeKmer does."""
+    from kaamer_b200 import GpuIndex, SearchOptions
+    from oracle import oracle as o
+
+    seqs = [b"MKTAYIAKQRXISFVKSHFSRQLEERLGLIEV", b"MKTAYIAKQRBISFVKSHFSRQLEERLGLIEV", b"UUUUUUUUUUUUUUUUUUUU",
+            b"AAAAAAAAAAAAAAAAAAAAAAAA"]
+    res, off = o.pack(seqs)
+    ids = np.array([5, 9, 11, 12], np.uint32)
+    idx = o.Index.build(res, off, ids)
+    qs = [b"MKTAYIAKQRZISFVKSHFSRQLEERLGLIEV", b"UUUUUUUUUUUUUUUUUUUUUU", b"XAXAXAXAXAXAXAXAXAXAXA"]
+    q, qo = o.pack(qs)
+    ora = o.search_proteins(idx, q, qo, o.opts(min_kmatch=1, min_kratio=0.0))
+    with GpuIndex.build(res, off, ids) as g:
+        k, f, p = g.index_arrays()
+        np.testing.assert_array_equal(k, idx.keys)
+        np.testing.assert_array_equal(p, idx.postings)
+        r = g.search_proteins(q, qo, SearchOptions(min_kmatch=1, min_kratio=0.0))
+    assert_same_hits(r, ora, "unknown letters")
+    assert len(r.subject) > 0
+
+
+def test_medium_scale_properties():
+    """Size-independent checks at a size the oracle does not index: queries that are exact DB
+    records must rank themselves first with Kmatch == SizeInKmer (every k-mer of the record is
+    in its own posting list), and results are invariant under batch permutation."""
+    from kaamer_b200 import GpuIndex, SearchOptions, synth
+
+    res, off = synth.protein_db(60000, config_index=3)
+    ids = np.arange(len(off) - 1, dtype=np.uint32) + 1
+    q, qo, pick = synth.protein_queries(res, off, 5000, config_index=3, sub_rate=0.0)
+    with GpuIndex.build(res, off, ids) as g:
+        r = g.search_proteins(q, qo, SearchOptions(max_results=5))
+        top = r.hit_off[:-1].astype(np.int64)
+        assert (np.diff(r.hit_off.astype(np.int64)) >= 1).all()
+        assert (r.kmatch[top] == r.size_in_kmer).all()
+        # the query's own id is among the hits tied at the maximum (family members may tie)
+        for i in range(0, 5000, 97):
+            hits = r.hits(i)
+            assert (int(ids[pick[i]]), int(r.size_in_kmer[i])) in hits
+        # permutation invariance
+        perm = np.random.default_rng(1).permutation(5000)
+        lens = np.diff(qo.astype(np.int64))[perm]
+        qo2 = np.zeros(5001, np.uint64)
+        qo2[1:] = np.cumsum(lens)
+        q2 = np.concatenate([q[int(qo[j]):int(qo[j + 1])] for j in perm])
+        r2 = g.search_proteins(q2, qo2, SearchOptions(max_results=5))
+        for n, j in enumerate(perm[:300]):
+            assert r2.hits(n) == r.hits(int(j))
+        assert r2.n_lookups == r.n_lookups and r2.n_increments == r.n_increments

@@ -170,7 +170,8 @@ typedef struct kaamer_dev_result {
   int32_t *size_in_kmer; /* [nq] */
   uint64_t *pool;        /* [pool_cap] (subject_id | (uint64)kmatch << 32), rank order per query */
   uint64_t pool_cap;
-  uint64_t *counters;    /* [4]: pool demand, n_lookups, n_increments, status flags */
+  uint64_t *counters;    /* [16]: pool demand, n_lookups, n_increments, status flags,
+                            [4..6] lookups per size class S/M/G, [8..10] increments per class */
 } kaamer_dev_result;
 int kaamer_gpu_search_proteins_device(kaamer_gpu_t *h, const uint8_t *d_residues,
                                       const uint64_t *d_seq_off, uint32_t nq,
@@ -181,9 +182,11 @@ int kaamer_gpu_search_proteins_device(kaamer_gpu_t *h, const uint8_t *d_residues
 int kaamer_gpu_pinned_alloc(uint64_t bytes, void **out);
 void kaamer_gpu_pinned_free(void *p);
 
-/* per-handle kernel timing (CUDA events around the dominant kernel; bench.py roofline) */
+/* per-handle kernel timing: CUDA events on the launching stream around each search kernel
+ * (size classes S, M, G -> kernel_ms[3], kernel_launches[3]); all_launches counts every
+ * kernel the library launched since the last reset (bench.py roofline / gpu_launches) */
 int kaamer_gpu_profile_enable(kaamer_gpu_t *h, int on);
-int kaamer_gpu_profile_read(kaamer_gpu_t *h, double *kernel_ms_total, uint64_t *kernel_launches,
+int kaamer_gpu_profile_read(kaamer_gpu_t *h, double *kernel_ms, uint64_t *kernel_launches,
                             uint64_t *all_launches, int reset);
 
 const char *kaamer_gpu_last_error(void);

@@ -193,7 +193,7 @@ def lib() -> C.CDLL:
     L.kaamer_gpu_pinned_free.argtypes = [vp]
     L.kaamer_gpu_pinned_free.restype = None
     L.kaamer_gpu_profile_enable.argtypes = [vp, C.c_int]
-    L.kaamer_gpu_profile_read.argtypes = [vp, C.POINTER(C.c_double), u64p, u64p, C.c_int]
+    L.kaamer_gpu_profile_read.argtypes = [vp, vp, vp, u64p, C.c_int]
     for s in SYMBOLS:
         getattr(L, s)  # AttributeError if the .so lacks a declared symbol
     _lib = L

@@ -100,8 +100,8 @@ static void destroy_handle(kaamer_gpu *h) {
   h->ws.ghash.release();
   h->ws.h_counters.release();
   for (auto &p : h->prof_pending) {
-    cudaEventDestroy(p.first);
-    cudaEventDestroy(p.second);
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
   }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -343,27 +343,34 @@ int kaamer_gpu_profile_enable(kaamer_gpu_t *h, int on) {
   return KAAMER_OK;
 }
 
-int kaamer_gpu_profile_read(kaamer_gpu_t *h, double *kernel_ms_total, uint64_t *kernel_launches,
-                            uint64_t *all_launches, int reset) {
+int kaamer_gpu_profile_read(kaamer_gpu_t *h, double *kernel_ms, uint64_t *kernel_launches, uint64_t *all_launches,
+                            int reset) {
   if (!h) {
     set_error("null handle");
     return KAAMER_ERR_ARG;
   }
   std::lock_guard<std::mutex> lk(h->mu);
   for (auto &p : h->prof_pending) {
-    cudaEventSynchronize(p.second);
+    cudaEventSynchronize(p.b);
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) h->prof_ms += ms;
-    cudaEventDestroy(p.first);
-    cudaEventDestroy(p.second);
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      h->prof_ms[p.cls] += ms;
+      h->prof_launches[p.cls]++;
+    }
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
   }
   h->prof_pending.clear();
-  if (kernel_ms_total) *kernel_ms_total = h->prof_ms;
-  if (kernel_launches) *kernel_launches = h->prof_kernel_launches;
+  for (int c = 0; c < 3; ++c) {
+    if (kernel_ms) kernel_ms[c] = h->prof_ms[c];
+    if (kernel_launches) kernel_launches[c] = h->prof_launches[c];
+  }
   if (all_launches) *all_launches = h->prof_all_launches;
   if (reset) {
-    h->prof_ms = 0;
-    h->prof_kernel_launches = 0;
+    for (int c = 0; c < 3; ++c) {
+      h->prof_ms[c] = 0;
+      h->prof_launches[c] = 0;
+    }
     h->prof_all_launches = 0;
   }
   return KAAMER_OK;

@@ -189,6 +189,11 @@ struct SearchWorkspace {
   PinBuf<uint64_t> h_counters;
 };
 
+struct ProfSpan {
+  cudaEvent_t a = nullptr, b = nullptr;
+  int cls = 0;
+};
+
 // owner of the pinned host buffers behind a kaamer_hits / kaamer_orfs
 struct HitsOwner {
   std::vector<void *> pinned;
@@ -221,9 +226,10 @@ struct kaamer_gpu {
   // profiling
   bool profile = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  double prof_ms = 0;
-  uint64_t prof_kernel_launches = 0, prof_all_launches = 0;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending;
+  double prof_ms[3] = {0, 0, 0};  // per size class S, M, G
+  uint64_t prof_launches[3] = {0, 0, 0};
+  uint64_t prof_all_launches = 0;
+  std::vector<kaamer::ProfSpan> prof_pending;
 };
 
 namespace kaamer {
@@ -237,6 +243,6 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
                            const kaamer_opts *o, const kaamer_dev_result *out, cudaStream_t st);
 int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off, uint32_t nq,
                          const kaamer_opts *o, kaamer_hits **out);
-void profile_begin(kaamer_gpu *h, cudaStream_t st);
+void profile_begin(kaamer_gpu *h, cudaStream_t st, int cls);
 void profile_end(kaamer_gpu *h, cudaStream_t st);
 }  // namespace kaamer

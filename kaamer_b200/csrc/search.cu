@@ -21,7 +21,7 @@
 namespace kaamer {
 
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
-enum { CNT_POOL = 0, CNT_LOOKUPS = 1, CNT_INCR = 2, CNT_STATUS = 3 };
+enum { CNT_POOL = 0, CNT_LOOKUPS = 1, CNT_INCR = 2, CNT_STATUS = 3, CNT_CLS_LOOKUPS = 4, CNT_CLS_INCR = 8, CNT_N = 16 };
 enum { ST_POOL_OVERFLOW = 1, ST_GHASH_OVERFLOW = 2 };
 
 // size classes by SizeInKmer
@@ -369,8 +369,14 @@ __global__ void __launch_bounds__(THREADS) k_search(SearchArgs a) {
     my_lookups += __shfl_down_sync(0xFFFFFFFFu, my_lookups, o);
   }
   if ((tid & 31) == 0) {
-    if (my_incr) atomicAdd(&a.counters[CNT_INCR], my_incr);
-    if (my_lookups) atomicAdd(&a.counters[CNT_LOOKUPS], my_lookups);
+    if (my_incr) {
+      atomicAdd(&a.counters[CNT_INCR], my_incr);
+      atomicAdd(&a.counters[CNT_CLS_INCR + CLS], my_incr);
+    }
+    if (my_lookups) {
+      atomicAdd(&a.counters[CNT_LOOKUPS], my_lookups);
+      atomicAdd(&a.counters[CNT_CLS_LOOKUPS + CLS], my_lookups);
+    }
   }
 }
 
@@ -443,8 +449,14 @@ __global__ void __launch_bounds__(G_THREADS) k_search_g(SearchArgs a) {
     my_lookups += __shfl_down_sync(0xFFFFFFFFu, my_lookups, o);
   }
   if ((tid & 31) == 0) {
-    if (my_incr) atomicAdd(&a.counters[CNT_INCR], my_incr);
-    if (my_lookups) atomicAdd(&a.counters[CNT_LOOKUPS], my_lookups);
+    if (my_incr) {
+      atomicAdd(&a.counters[CNT_INCR], my_incr);
+      atomicAdd(&a.counters[CNT_CLS_INCR + 2], my_incr);
+    }
+    if (my_lookups) {
+      atomicAdd(&a.counters[CNT_LOOKUPS], my_lookups);
+      atomicAdd(&a.counters[CNT_CLS_LOOKUPS + 2], my_lookups);
+    }
   }
 }
 
@@ -496,18 +508,18 @@ __global__ void k_gather_hits(const uint32_t *__restrict__ n_hits, const uint32_
 }
 
 // ---- launch ---------------------------------------------------------------------------
-void profile_begin(kaamer_gpu *h, cudaStream_t st) {
+void profile_begin(kaamer_gpu *h, cudaStream_t st, int cls) {
   if (!h->profile) return;
-  cudaEvent_t a, b;
-  cudaEventCreate(&a);
-  cudaEventCreate(&b);
-  h->prof_pending.push_back({a, b});
-  cudaEventRecord(a, st);
+  ProfSpan sp;
+  sp.cls = cls;
+  cudaEventCreate(&sp.a);
+  cudaEventCreate(&sp.b);
+  h->prof_pending.push_back(sp);
+  cudaEventRecord(sp.a, st);
 }
 void profile_end(kaamer_gpu *h, cudaStream_t st) {
   if (!h->profile || h->prof_pending.empty()) return;
-  cudaEventRecord(h->prof_pending.back().second, st);
-  h->prof_kernel_launches++;
+  cudaEventRecord(h->prof_pending.back().b, st);
 }
 
 static uint32_t ghash_slots_for(kaamer_gpu *h) {
@@ -549,16 +561,20 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   KCHECK(ws.ghash.ensure((size_t)g_ctas * 3 * a.ghash_slots));
   a.ghash = ws.ghash.p;
   KCUDA(cudaMemsetAsync(list_count, 0, 4 * sizeof(uint32_t), st));
-  KCUDA(cudaMemsetAsync(out->counters, 0, 4 * sizeof(uint64_t), st));
+  KCUDA(cudaMemsetAsync(out->counters, 0, CNT_N * sizeof(uint64_t), st));
   k_classify<<<(nq + 255) / 256, 256, 0, st>>>(a);
   // persistent grids: a multiple of the SM count, CTAs loop over their class list
   const unsigned s_grid = (unsigned)h->sm_count * 14u;
   const unsigned m_grid = (unsigned)h->sm_count * 3u;
-  profile_begin(h, st);
+  profile_begin(h, st, 0);
   k_search<S_THREADS, S_H, S_MAXK, 0><<<s_grid < nq ? s_grid : nq, S_THREADS, 0, st>>>(a);
   profile_end(h, st);
+  profile_begin(h, st, 1);
   k_search<M_THREADS, M_H, M_MAXK, 1><<<m_grid < nq ? m_grid : nq, M_THREADS, 0, st>>>(a);
+  profile_end(h, st);
+  profile_begin(h, st, 2);
   k_search_g<<<g_ctas, G_THREADS, 0, st>>>(a);
+  profile_end(h, st);
   h->prof_all_launches += 4;
   KCUDA(cudaGetLastError());
   return KAAMER_OK;
@@ -612,8 +628,8 @@ int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off,
   HCHECK(ws.hit_base.ensure(nq));
   HCHECK(ws.size_in_kmer.ensure(nq));
   HCHECK(ws.hit_off.ensure((size_t)nq + 1));
-  HCHECK(ws.counters.ensure(4));
-  HCHECK(ws.h_counters.ensure(8));
+  HCHECK(ws.counters.ensure(CNT_N));
+  HCHECK(ws.h_counters.ensure(CNT_N + 2));
   HCUDA(cudaMemcpyAsync(ws.residues.p, res, (size_t)n_res, cudaMemcpyHostToDevice, st));
   HCUDA(cudaMemcpyAsync(ws.seq_off.p, off, ((size_t)nq + 1) * 8, cudaMemcpyHostToDevice, st));
   uint64_t per_q = o->max_results > 0 ? (uint64_t)(o->max_results < 16 ? o->max_results : 16) : 1;
@@ -630,8 +646,8 @@ int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off,
     HCHECK(search_proteins_device(h, ws.residues.p, ws.seq_off.p, nq, o, &dr, st));
     k_scan_hits<<<1, 1024, 0, st>>>(ws.n_hits.p, nq, ws.hit_off.p);
     h->prof_all_launches += 1;
-    HCUDA(cudaMemcpyAsync(ws.h_counters.p, ws.counters.p, 4 * 8, cudaMemcpyDeviceToHost, st));
-    HCUDA(cudaMemcpyAsync(ws.h_counters.p + 4, ws.hit_off.p + nq, 8, cudaMemcpyDeviceToHost, st));
+    HCUDA(cudaMemcpyAsync(ws.h_counters.p, ws.counters.p, CNT_N * 8, cudaMemcpyDeviceToHost, st));
+    HCUDA(cudaMemcpyAsync(ws.h_counters.p + CNT_N, ws.hit_off.p + nq, 8, cudaMemcpyDeviceToHost, st));
     HCUDA(cudaStreamSynchronize(st));
     uint64_t status = ws.h_counters.p[CNT_STATUS];
     if (status & ST_GHASH_OVERFLOW) {
@@ -649,7 +665,7 @@ int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off,
     }
     break;
   }
-  const uint64_t n_hits = ws.h_counters.p[4];
+  const uint64_t n_hits = ws.h_counters.p[CNT_N];
   hits->n_hits = n_hits;
   hits->n_lookups = ws.h_counters.p[CNT_LOOKUPS];
   hits->n_increments = ws.h_counters.p[CNT_INCR];

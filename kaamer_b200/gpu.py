@@ -221,6 +221,8 @@ class GpuIndex:
         check(_lib.lib().kaamer_gpu_profile_enable(self._h, int(on)))
 
     def profile_read(self, reset: bool = True):
-        ms, k, a = C.c_double(), C.c_uint64(), C.c_uint64()
-        check(_lib.lib().kaamer_gpu_profile_read(self._h, C.byref(ms), C.byref(k), C.byref(a), int(reset)))
-        return {"kernel_ms": ms.value, "kernel_launches": k.value, "all_launches": a.value}
+        ms = (C.c_double * 3)()
+        k = (C.c_uint64 * 3)()
+        a = C.c_uint64()
+        check(_lib.lib().kaamer_gpu_profile_read(self._h, ms, k, C.byref(a), int(reset)))
+        return {"kernel_ms": list(ms), "kernel_launches": list(k), "all_launches": a.value}

@@ -99,6 +99,8 @@ static void destroy_handle(kaamer_gpu *h) {
   h->ws.counters.release();
   h->ws.ghash.release();
   h->ws.h_counters.release();
+  h->ws.h_packed.release();
+  h->ws.kmin.release();
   for (auto &p : h->prof_pending) {
     cudaEventDestroy(p.a);
     cudaEventDestroy(p.b);

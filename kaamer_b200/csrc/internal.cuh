@@ -181,12 +181,12 @@ struct DevIndex {
 struct SearchWorkspace {
   DevBuf<uint8_t> residues;
   DevBuf<uint64_t> seq_off;
-  DevBuf<uint32_t> n_hits, hit_base, lists;
+  DevBuf<uint32_t> n_hits, hit_base, lists, kmin;
   DevBuf<int32_t> size_in_kmer;
   DevBuf<uint64_t> pool, hit_off, out_hits;
   DevBuf<uint64_t> counters;   // see search.cu
   DevBuf<uint32_t> ghash;      // global-memory hash scratch (class G)
-  PinBuf<uint64_t> h_counters;
+  PinBuf<uint64_t> h_counters, h_packed;
 };
 
 struct ProfSpan {

@@ -4,18 +4,23 @@
 // (pkg/search/search_protein.go:94-98), KmerSearch (pkg/search/search.go:414-440),
 // sortMapByValue (:132-152) and FilterResults (:189-220):
 //
-//   k_classify      SizeInKmer per query (search.go:290-293) + size class
-//   k_search<S|M>   one CTA per query: residues -> codes in smem -> dense 7-mer code ->
-//                   ONE 8-byte table probe per k-mer (posting inlined when the list is a
-//                   singleton) -> shared-memory open-addressing histogram keyed by subject
-//                   id -> threshold (MinKMatch / MinKRatio in fp64) -> top-MaxResults by
-//                   (Kmatch desc, id asc) -> hits appended to a pool
-//   k_search_g      same with the histogram in global memory (L2) for queries whose
-//                   subject set outgrows shared memory
-//   k_scan/k_gather CSR compaction of the pool in query order (host API only)
+//   k_classify    SizeInKmer per query (search.go:290-293), the smallest surviving Kmatch
+//                 (FilterResults thresholds, fp64) and the size class
+//   k_search_w    class W (SizeInKmer <= 512): ONE WARP PER QUERY, no block barriers.
+//                 residues -> packed pair/single codes in smem -> dense 7-mer code -> one
+//                 8-byte table probe per k-mer (singleton posting inlined in the entry) ->
+//                 per-warp shared-memory open-addressing histogram keyed by subject id ->
+//                 candidates collected the moment their count reaches the threshold ->
+//                 top-MaxResults by (Kmatch desc, id asc) -> pool
+//   k_search_m    class M (<= 2048): same with one CTA per query and a 4096-slot histogram
+//   k_search_g    class G: histogram in global memory (L2-resident per-CTA scratch)
+//   k_scan/k_gather  CSR compaction of the pool in query order (host API only)
 //
-// HBM traffic per k-mer: 1 B residue + 8 B entry (a 32 B sector) [+ 4 B per posting when
-// the list is not a singleton].  Counts never touch HBM for classes S and M.
+// HBM traffic per k-mer: 1 B residue + one 8 B entry (one 64 B HBM access) [+ 4 B per
+// posting when the list is not a singleton].  Counts never touch HBM for classes W and M.
+// Measured ceiling of the probe stage on B200: 36.5 G random probes/s (profiles/).
+#include <type_traits>
+
 #include "internal.cuh"
 
 namespace kaamer {
@@ -25,10 +30,12 @@ enum { CNT_POOL = 0, CNT_LOOKUPS = 1, CNT_INCR = 2, CNT_STATUS = 3, CNT_CLS_LOOK
 enum { ST_POOL_OVERFLOW = 1, ST_GHASH_OVERFLOW = 2 };
 
 // size classes by SizeInKmer
-constexpr int S_THREADS = 128, S_H = 1024, S_MAXK = 512;
+constexpr int W_H = 512, W_MAXK = 512, W_WARPS = 8, W_CAND = 64;
 constexpr int M_THREADS = 256, M_H = 4096, M_MAXK = 2048;
 constexpr int G_THREADS = 512;
-constexpr int FAST_C = 64;  // candidates ranked by counting below this, bitonic sort above
+constexpr int FAST_C = 64;     // candidates ranked by counting below this, bitonic sort above
+constexpr int BIG_LIST = 32;   // posting lists at least this long are walked by the whole warp
+constexpr int MAX_PROBE = 96;  // linear-probe budget before a histogram is declared full
 
 struct SearchArgs {
   const uint64_t *table;
@@ -42,18 +49,19 @@ struct SearchArgs {
   int max_results;
   uint32_t *n_hits, *hit_base;
   int32_t *size_in_kmer;
+  uint32_t *kmin;
   uint64_t *pool;
   uint64_t pool_cap;
   unsigned long long *counters;
   uint32_t *lists;       // [3][nq]
-  uint32_t *list_count;  // [4]
+  uint32_t *list_count;  // [8]: [0..2] list sizes, [4..6] work cursors (dynamic scheduling)
   uint32_t *ghash;       // class G scratch: per CTA [keys HG][cnt HG][cand HG]
   uint32_t ghash_slots;  // HG (power of two)
 };
 
 __device__ __forceinline__ uint64_t ldg_entry(const uint64_t *p) {
   uint64_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.b64 %0, [%1];" : "=l"(v) : "l"(p));
   return v;
 }
 
@@ -81,53 +89,291 @@ __global__ void k_classify(SearchArgs a) {
   if (q >= a.nq) return;
   uint64_t b = a.off[q], e = a.off[q + 1];
   long long len = (long long)(e - b);
-  long long K = len - KAAMER_KMER_SIZE + 1;          // search.go:290
-  if (len > 0 && a.res[e - 1] == '*') K--;           // search.go:291-293
+  long long K = len - KAAMER_KMER_SIZE + 1;  // search.go:290
+  if (len > 0 && a.res[e - 1] == '*') K--;   // search.go:291-293
   a.size_in_kmer[q] = (int32_t)K;
   a.n_hits[q] = 0;
   a.hit_base[q] = 0;
   if (K < 7) return;  // search_protein.go:74-76 (documented deviation: skipped, not fatal)
-  int cls = K <= S_MAXK ? 0 : (K <= M_MAXK ? 1 : 2);
+  a.kmin[q] = filter_kmin(a.min_kmatch, a.min_kratio, (int32_t)K);
+  int cls = K <= W_MAXK ? 0 : (K <= M_MAXK ? 1 : 2);
   uint32_t slot = atomicAdd(&a.list_count[cls], 1u);
   a.lists[(size_t)cls * a.nq + slot] = q;
 }
 
-struct HashView {
-  uint32_t *keys, *cnt;
+// ---- histograms -------------------------------------------------------------------------
+// add(id) returns the count BEFORE the increment, or 0xFFFFFFFF when the table is full.
+// Shared-memory flavour: keys u32, counts u16 packed two per word (counts <= SizeInKmer <= 2048).
+struct SmemHash {
+  uint32_t *keys;
+  uint32_t *cnt2;  // [slots/2]
   uint32_t mask;
   int shift;  // 32 - log2(slots)
+  __device__ __forceinline__ uint32_t home(uint32_t id) const { return (id * 2654435761u) >> shift; }
+  // claim-or-match: returns the previous key of the slot (EMPTY or id => the slot is ours).
+  // Plain load first: shared-memory atomics are serialised per lane on the SM's atomic unit
+  // (~2 cycles/lane for ADD, twice that for CAS), a repeated subject must not pay the CAS.
+  __device__ __forceinline__ uint32_t cas(uint32_t slot, uint32_t id) const {
+    uint32_t cur = *(volatile uint32_t *)(keys + slot);
+    if (cur == EMPTY) cur = atomicCAS(keys + slot, EMPTY, id);
+    return cur;
+  }
+  __device__ __forceinline__ uint32_t inc(uint32_t slot) const {  // returns the count before
+    uint32_t sh = (slot & 1u) * 16u;
+    uint32_t old = atomicAdd(cnt2 + (slot >> 1), 1u << sh);
+    return (old >> sh) & 0xFFFFu;
+  }
+  __device__ __forceinline__ uint32_t key_at(uint32_t slot) const { return keys[slot]; }
+  __device__ __forceinline__ uint32_t count_at(uint32_t slot) const {
+    return (cnt2[slot >> 1] >> ((slot & 1u) * 16u)) & 0xFFFFu;
+  }
+  static constexpr int kMaxProbe = MAX_PROBE;
+};
+// Global-memory flavour (class G): keys u32, counts u32.
+struct GmemHash {
+  uint32_t *keys;
+  uint32_t *cnt;
+  uint32_t mask;
+  int shift;
+  __device__ __forceinline__ uint32_t home(uint32_t id) const { return (id * 2654435761u) >> shift; }
+  __device__ __forceinline__ uint32_t cas(uint32_t slot, uint32_t id) const { return atomicCAS(keys + slot, EMPTY, id); }
+  __device__ __forceinline__ uint32_t inc(uint32_t slot) const { return atomicAdd(cnt + slot, 1u); }
+  __device__ __forceinline__ uint32_t key_at(uint32_t slot) const { return keys[slot]; }
+  __device__ __forceinline__ uint32_t count_at(uint32_t slot) const { return cnt[slot]; }
+  static constexpr int kMaxProbe = 4 * MAX_PROBE;
 };
 
-struct SelectScratch {
-  uint32_t hist[256];
-  uint32_t ncand, distinct, overflow, kmin, nout;
-  unsigned long long base;
-  unsigned long long prefix;
-  uint32_t remaining;
+// candidate list shared by the lanes/threads that work on one query
+struct CandList {
+  uint32_t *ncand;  // smem counter
+  uint32_t *flags;  // smem: bit0 histogram full, bit1 candidate list full
+  uint16_t *slots16;
+  uint32_t *slots32;
+  uint32_t cap;
 };
 
-// histogram[id]++ ; flags ss.overflow when the table holds more than max_distinct subjects.
-// Callers test ss.overflow before every call, so at most one insertion per thread can land
-// after the flag is raised: max_distinct + THREADS < slots keeps the probe loop finite.
-__device__ __forceinline__ void hash_add(const HashView &hv, uint32_t id, SelectScratch &ss,
-                                         uint32_t max_distinct) {
-  uint32_t slot = (id * 2654435761u) >> hv.shift;
-  for (uint32_t probe = 0; probe <= hv.mask; ++probe) {
-    uint32_t cur = *(volatile uint32_t *)(hv.keys + slot);
-    if (cur == EMPTY) {
-      cur = atomicCAS(hv.keys + slot, EMPTY, id);
-      if (cur == EMPTY) {
-        if (atomicAdd(&ss.distinct, 1u) >= max_distinct) ss.overflow = 1;
-        cur = id;
-      }
-    }
-    if (cur == id) {
-      atomicAdd(hv.cnt + slot, 1u);
+__device__ __forceinline__ void push_candidate(const CandList &cl, uint32_t slot) {
+  uint32_t i = atomicAdd(cl.ncand, 1u);
+  if (i < cl.cap) {
+    if (cl.slots16) cl.slots16[i] = (uint16_t)slot;
+    else cl.slots32[i] = slot;
+  } else {
+    atomicOr(cl.flags, 2u);
+  }
+}
+
+// One increment + candidate bookkeeping (general path: linear probing from `slot`).  The
+// subject becomes a candidate exactly when its count reaches kmin (counts only grow), so no
+// scan of the histogram is needed afterwards.
+template <class Hash>
+__device__ __noinline__ void count_subject_from(const Hash hv, uint32_t id, uint32_t slot, uint32_t kmin,
+                                                const CandList cl) {
+#pragma unroll 1
+  for (int probe = 0; probe < Hash::kMaxProbe; ++probe) {
+    uint32_t cur = hv.cas(slot, id);
+    if (cur == EMPTY || cur == id) {
+      if (hv.inc(slot) + 1 == kmin) push_candidate(cl, slot);
       return;
     }
     slot = (slot + 1) & hv.mask;
   }
-  ss.overflow = 1;
+  atomicOr(cl.flags, 1u);  // histogram full
+}
+template <class Hash>
+__device__ __forceinline__ void count_subject(const Hash &hv, uint32_t id, uint32_t kmin, const CandList &cl) {
+  const uint32_t slot = hv.home(id);
+  const uint32_t cur = hv.cas(slot, id);
+  if (cur == EMPTY || cur == id) {
+    if (hv.inc(slot) + 1 == kmin) push_candidate(cl, slot);
+  } else {
+    count_subject_from(hv, id, (slot + 1) & hv.mask, kmin, cl);
+  }
+}
+
+// ---- warp-private histogram (class W): NO atomics --------------------------------------
+// The table belongs to one warp whose lanes run in lockstep, so duplicates inside a batch of 32
+// ids are merged with __match_any_sync and slots are claimed by write-then-verify.  This
+// removes every shared-memory atomic from the counting loop (ncu: the per-SM atomic unit was
+// the limiter of the atomic version).
+struct WarpHash {
+  uint32_t *keys;   // [W_H]
+  uint16_t *cnt;    // [W_H]
+  __device__ __forceinline__ uint32_t key_at(uint32_t slot) const { return keys[slot]; }
+  __device__ __forceinline__ uint32_t count_at(uint32_t slot) const { return cnt[slot]; }
+};
+
+// all 32 lanes call this together; lanes with valid==false only take part in the votes
+__device__ __forceinline__ void warp_count(const WarpHash &hv, bool valid, uint32_t id, uint32_t kmin,
+                                           const CandList &cl) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned act = __ballot_sync(0xFFFFFFFFu, valid);
+  if (act == 0) return;
+  unsigned peers = 0;
+  if (valid) peers = __match_any_sync(act, id);
+  const uint32_t mult = __popc(peers);
+  bool pending = valid && (lane == (unsigned)(__ffs(peers) - 1));  // one leader per distinct id
+  uint32_t slot = (id * 2654435761u) >> (32 - 9);
+  static_assert(W_H == 512, "hash shift assumes 512 slots");
+#pragma unroll 1
+  for (int probe = 0; probe < MAX_PROBE; ++probe) {
+    if (!__any_sync(0xFFFFFFFFu, pending)) return;
+    uint32_t key = pending ? hv.keys[slot] : 0u;
+    const bool claim = pending && key == EMPTY;
+    if (claim) hv.keys[slot] = id;  // racing leaders with different ids: one store survives
+    __syncwarp();
+    if (claim) key = hv.keys[slot];
+    if (pending) {
+      if (key == id) {
+        const uint32_t c = hv.cnt[slot];
+        hv.cnt[slot] = (uint16_t)(c + mult);
+        if (c < kmin && c + mult >= kmin) push_candidate(cl, slot);
+        pending = false;
+      } else {
+        slot = (slot + 1) & (W_H - 1);
+      }
+    }
+    __syncwarp();
+  }
+  if (__any_sync(0xFFFFFFFFu, pending)) {
+    if (pending) atomicOr(cl.flags, 1u);
+  }
+}
+
+// ---- one warp-round of lookups ------------------------------------------------------------
+// Every lane holds up to U table entries.  Singletons are counted directly; short posting
+// lists (2..BIG_LIST-1) of the whole warp are flattened (warp scan + search by shuffles) so
+// that all 32 lanes fetch and count postings together; long lists are walked cooperatively.
+template <int U, class Hash>
+__device__ __forceinline__ void warp_consume(const SearchArgs &a, const uint64_t (&ent)[U], const Hash &hv,
+                                             uint32_t kmin, const CandList &cl, unsigned long long &q_incr) {
+  const unsigned lane = threadIdx.x & 31;
+  uint32_t m[U];  // postings of this lane's short multi lists
+  uint32_t vlo[U];
+  uint32_t vhi = 0;  // 4 high bits of each value, packed
+  uint32_t mt = 0;
+  bool any_big = false;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint32_t cnt = (uint32_t)(ent[u] >> ENTRY_VALUE_BITS);
+    const uint64_t val = ent[u] & ENTRY_VALUE_MASK;
+    q_incr += cnt;
+    vlo[u] = (uint32_t)val;
+    vhi |= (uint32_t)(val >> 32) << (4 * u);
+    m[u] = (cnt >= 2 && cnt < BIG_LIST) ? cnt : 0u;
+    mt += m[u];
+    any_big |= cnt >= BIG_LIST;
+  }
+  // (1) singletons
+  if constexpr (std::is_same<Hash, WarpHash>::value) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) warp_count(hv, (uint32_t)(ent[u] >> ENTRY_VALUE_BITS) == 1u, vlo[u], kmin, cl);
+  } else {
+    // the first probe of all U entries is issued back to back (independent shared-memory
+    // operations in flight), collisions fall back to the probing loop
+    uint32_t slot[U], cur[U];
+    bool act[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      act[u] = (uint32_t)(ent[u] >> ENTRY_VALUE_BITS) == 1u;
+      slot[u] = hv.home(vlo[u]);
+      cur[u] = act[u] ? hv.cas(slot[u], vlo[u]) : 0u;
+    }
+    uint32_t old[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool mine = act[u] && (cur[u] == EMPTY || cur[u] == vlo[u]);
+      old[u] = mine ? hv.inc(slot[u]) : 0xFFFFFFFEu;
+      act[u] = act[u] && !mine;  // still pending
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (old[u] + 1 == kmin) push_candidate(cl, slot[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (act[u]) count_subject_from(hv, vlo[u], (slot[u] + 1) & hv.mask, kmin, cl);
+  }
+  // (2) short lists, flattened across the warp
+  uint32_t incl = mt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= (unsigned)o) incl += t;
+  }
+  const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  const uint32_t excl = incl - mt;
+#pragma unroll 1
+  for (uint32_t jb = 0; jb < total; jb += 32) {
+    const uint32_t j = jb + lane;
+    uint32_t owner = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      uint32_t v = __shfl_sync(0xFFFFFFFFu, incl, (owner + step - 1) & 31);
+      if (v <= j) owner += step;
+    }
+    owner &= 31;
+    uint32_t r = j - __shfl_sync(0xFFFFFFFFu, excl, owner);
+    const uint32_t ohi = __shfl_sync(0xFFFFFFFFu, vhi, owner);
+    uint32_t sel_lo = 0, sel_hi = 0;
+    bool found = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t mu = __shfl_sync(0xFFFFFFFFu, m[u], owner);
+      uint32_t lo = __shfl_sync(0xFFFFFFFFu, vlo[u], owner);
+      if (!found) {
+        if (r < mu) {
+          sel_lo = lo;
+          sel_hi = (ohi >> (4 * u)) & 0xFu;
+          found = true;
+        } else {
+          r -= mu;
+        }
+      }
+    }
+    uint32_t pid = 0;
+    if (j < total) pid = __ldg(a.postings + (((uint64_t)sel_hi << 32) | sel_lo) + r);
+    if constexpr (std::is_same<Hash, WarpHash>::value) {
+      warp_count(hv, j < total, pid, kmin, cl);
+    } else {
+      if (j < total) count_subject(hv, pid, kmin, cl);
+    }
+  }
+  // (3) long lists: the whole warp walks each of them (coalesced)
+  if (__any_sync(0xFFFFFFFFu, any_big)) {
+#pragma unroll 1
+    for (int u = 0; u < U; ++u) {
+      uint64_t e = ent[0];
+#pragma unroll
+      for (int t = 1; t < U; ++t)
+        if (u == t) e = ent[t];
+      const uint32_t cnt = (uint32_t)(e >> ENTRY_VALUE_BITS);
+      unsigned big = __ballot_sync(0xFFFFFFFFu, cnt >= BIG_LIST);
+      while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t bc = __shfl_sync(0xFFFFFFFFu, cnt, src);
+        const uint64_t bv = __shfl_sync(0xFFFFFFFFu, e & ENTRY_VALUE_MASK, src);
+        if constexpr (std::is_same<Hash, WarpHash>::value) {
+          for (uint32_t ib = 0; ib < bc; ib += 32) {
+            const uint32_t i = ib + lane;
+            warp_count(hv, i < bc, i < bc ? __ldg(a.postings + bv + i) : 0u, kmin, cl);
+          }
+        } else {
+          for (uint32_t i = lane; i < bc; i += 32) {
+            if (*(volatile uint32_t *)cl.flags & 1u) break;
+            count_subject(hv, __ldg(a.postings + bv + i), kmin, cl);
+          }
+        }
+      }
+    }
+  }
+}
+
+// packed per-position code: bits 0..8 pair code p'(c_i, c_i+1), bits 9..13 single code s(c_i)
+__device__ __forceinline__ uint32_t packed_code(uint32_t c0, uint32_t c1) {
+  return pair_dense(c0, c1) | (single_dense(c0) << 9);
+}
+__device__ __forceinline__ uint32_t dense_from_packed(uint32_t w0, uint32_t w2, uint32_t w4, uint32_t w6) {
+  return (((w0 & 511u) * PAIR_RADIX + (w2 & 511u)) * PAIR_RADIX + (w4 & 511u)) * 21u + (w6 >> 9);
 }
 
 // composite sort key: ascending order == (Kmatch desc, subject id asc)
@@ -139,35 +385,181 @@ __device__ __forceinline__ uint64_t decomposite(uint64_t c) {
   return ((uint64_t)cnt << 32) | (uint32_t)c;  // pool format: subject | kmatch << 32
 }
 
-// Candidate c_i lives in hash slot cand[i] (CandT = u16 for smem classes, u32 for class G).
-// Emits the top-N candidates into the pool in rank order and records n_hits / hit_base.
-template <int THREADS, class CandT>
-__device__ void select_and_emit(const SearchArgs &a, uint32_t q, const HashView &hv, const CandT *cand,
+// ---- class W: one warp per query ------------------------------------------------------------
+struct __align__(16) WarpSmem {
+  uint32_t hkeys[W_H];
+  uint16_t hcnt[W_H];
+  uint16_t pp[W_MAXK + 8];
+  uint16_t cand[W_CAND];
+  uint32_t ncand, flags, pad0, pad1;
+};
+
+__global__ void __launch_bounds__(W_WARPS * 32, 5) k_search_w(SearchArgs a) {
+  __shared__ WarpSmem sm[W_WARPS];
+  __shared__ uint8_t lut[256];
+  lut[threadIdx.x] = (uint8_t)aa_code(threadIdx.x);
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  WarpSmem &s = sm[w];
+  const WarpHash hv{s.hkeys, s.hcnt};
+  const CandList cl{&s.ncand, &s.flags, s.cand, nullptr, (uint32_t)W_CAND};
+  const uint32_t count = a.list_count[0];
+  const uint32_t nwarps = gridDim.x * W_WARPS;
+  const uint32_t N = a.max_results > 0 ? (uint32_t)a.max_results : 0u;
+  unsigned long long my_incr = 0, my_lookups = 0;
+  // dynamic scheduling: warps pull the next query from a global cursor (query lengths vary by
+  // 10x, a static split left the SMs idle for ~20 % of the kernel); the next index is
+  // fetched one query ahead so its latency is hidden
+  uint32_t it_next = 0;
+  if (lane == 0) it_next = atomicAdd(&a.list_count[4], 1u);
+  (void)nwarps;
+  for (;;) {
+    const uint32_t it = __shfl_sync(0xFFFFFFFFu, it_next, 0);
+    if (it >= count) break;
+    if (lane == 0) it_next = atomicAdd(&a.list_count[4], 1u);
+    const uint32_t q = a.lists[it];
+    const uint64_t b = a.off[q];
+    const int len = (int)(a.off[q + 1] - b);
+    const int K = a.size_in_kmer[q];
+    const uint32_t kmin = a.kmin[q];
+    // clear the histogram (16-byte stores)
+    {
+      uint4 *hk = reinterpret_cast<uint4 *>(s.hkeys);
+      uint4 *hc = reinterpret_cast<uint4 *>(s.hcnt);
+      const uint4 E = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY), Z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int i = 0; i < W_H / 4 / 32; ++i) hk[i * 32 + lane] = E;
+#pragma unroll
+      for (int i = 0; i < W_H / 8 / 32; ++i) hc[i * 32 + lane] = Z;
+      if (lane == 0) {
+        s.ncand = 0;
+        s.flags = 0;
+      }
+    }
+    // residues -> packed codes
+    const uint8_t *r = a.res + b;
+    const int ncodes = K + KAAMER_KMER_SIZE - 1;
+    for (int i = lane; i < ncodes; i += 32) {
+      uint32_t c0 = lut[r[i]];
+      uint32_t c1 = (i + 1 < len) ? (uint32_t)lut[r[i + 1]] : CODE_UNKNOWN;
+      s.pp[i] = (uint16_t)packed_code(c0, c1);
+    }
+    __syncwarp();
+    unsigned long long q_incr = 0;
+    constexpr int U = 4;
+    // software pipeline: the probes of round r+1 are in flight while round r is counted
+    auto load_round = [&](int base, uint64_t(&e)[U]) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pos = base + u * 32 + (int)lane;
+        e[u] = 0;
+        if (pos < K) {
+          uint32_t d = dense_from_packed(s.pp[pos], s.pp[pos + 2], s.pp[pos + 4], s.pp[pos + 6]);
+          if (d >= a.d_lo && d < a.d_hi) e[u] = ldg_entry(a.table + (d - a.d_lo));
+        }
+      }
+    };
+    uint64_t nxt[U];
+    load_round(0, nxt);
+    for (int base = 0; base < K; base += U * 32) {
+      uint64_t ent[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) ent[u] = nxt[u];
+      if (base + U * 32 < K) load_round(base + U * 32, nxt);
+      warp_consume<U>(a, ent, hv, kmin, cl, q_incr);
+    }
+    __syncwarp();
+    const uint32_t flags = *(volatile uint32_t *)&s.flags;
+    const uint32_t c = *(volatile uint32_t *)&s.ncand;
+    if (flags) {
+      // histogram or candidate list outgrew the warp's shared memory: hand the query to
+      // class M (that kernel starts after this one in stream order)
+      if (lane == 0) {
+        uint32_t slot = atomicAdd(&a.list_count[1], 1u);
+        a.lists[(size_t)a.nq + slot] = q;
+      }
+      __syncwarp();
+      continue;
+    }
+    my_incr += q_incr;
+    if (lane == 0) my_lookups += (unsigned long long)K;
+    const uint32_t nout = c < N ? c : N;
+    if (nout) {
+      // c <= W_CAND = 64: rank by counting, two candidates per lane
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(&a.counters[CNT_POOL], (unsigned long long)nout);
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      const bool fits = base + nout <= a.pool_cap;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t i = lane + 32 * h;
+        if (i < c) {
+          const uint32_t sl = s.cand[i];
+          const uint64_t me = composite(hv.key_at(sl), hv.count_at(sl));
+          uint32_t rank = 0;
+          for (uint32_t j = 0; j < c; ++j) {
+            const uint32_t sj = s.cand[j];
+            rank += composite(hv.key_at(sj), hv.count_at(sj)) < me ? 1u : 0u;
+          }
+          if (rank < nout && fits) a.pool[base + rank] = decomposite(me);
+        }
+      }
+      if (lane == 0) {
+        if (fits) {
+          a.n_hits[q] = nout;
+          a.hit_base[q] = (uint32_t)base;
+        } else {
+          atomicOr(&a.counters[CNT_STATUS], (unsigned long long)ST_POOL_OVERFLOW);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    my_incr += __shfl_down_sync(0xFFFFFFFFu, my_incr, o);
+    my_lookups += __shfl_down_sync(0xFFFFFFFFu, my_lookups, o);
+  }
+  if (lane == 0) {
+    if (my_incr) {
+      atomicAdd(&a.counters[CNT_INCR], my_incr);
+      atomicAdd(&a.counters[CNT_CLS_INCR + 0], my_incr);
+    }
+    if (my_lookups) {
+      atomicAdd(&a.counters[CNT_LOOKUPS], my_lookups);
+      atomicAdd(&a.counters[CNT_CLS_LOOKUPS + 0], my_lookups);
+    }
+  }
+}
+
+// ---- classes M and G: one CTA per query -----------------------------------------------------
+struct SelectScratch {
+  uint32_t hist[256];
+  uint32_t ncand, flags, nout, remaining;
+  unsigned long long base;
+  unsigned long long prefix;
+};
+
+// Candidate i lives in histogram slot cand(i).  Emits the top-N candidates into the pool in
+// rank order and records n_hits / hit_base.
+template <int THREADS, class Hash, class CandAt>
+__device__ void select_and_emit(const SearchArgs &a, uint32_t q, const Hash &hv, CandAt cand, uint32_t c,
                                 SelectScratch &ss) {
   const int tid = threadIdx.x;
-  const uint32_t c = ss.ncand;
   const uint32_t N = a.max_results > 0 ? (uint32_t)a.max_results : 0u;
   const uint32_t nout = c < N ? c : N;
-  if (nout == 0) {
-    if (tid == 0) {
-      a.n_hits[q] = 0;
-      a.hit_base[q] = 0;
-    }
-    return;
-  }
+  if (nout == 0) return;  // n_hits / hit_base were zeroed by k_classify
   if (c <= FAST_C) {
-    // fast path (the common case: a handful of family hits): rank by counting
     if (tid == 0) ss.base = atomicAdd(&a.counters[CNT_POOL], (unsigned long long)nout);
     __syncthreads();
     const unsigned long long base = ss.base;
     const bool fits = base + nout <= a.pool_cap;
     if (tid < (int)c) {
-      uint32_t s = cand[tid];
-      uint64_t me = composite(hv.keys[s], hv.cnt[s]);
+      uint32_t s = cand(tid);
+      uint64_t me = composite(hv.key_at(s), hv.count_at(s));
       uint32_t rank = 0;
       for (uint32_t j = 0; j < c; ++j) {
-        uint32_t sj = cand[j];
-        rank += composite(hv.keys[sj], hv.cnt[sj]) < me ? 1u : 0u;
+        uint32_t sj = cand(j);
+        rank += composite(hv.key_at(sj), hv.count_at(sj)) < me ? 1u : 0u;
       }
       if (rank < nout && fits) a.pool[base + rank] = decomposite(me);
     }
@@ -195,8 +587,8 @@ __device__ void select_and_emit(const SearchArgs &a, uint32_t q, const HashView 
       const unsigned long long prefix = ss.prefix;
       const unsigned long long himask = byte == 7 ? 0ull : (~0ull << (8 * (byte + 1)));
       for (uint32_t i = tid; i < c; i += THREADS) {
-        uint32_t s = cand[i];
-        uint64_t k = composite(hv.keys[s], hv.cnt[s]);
+        uint32_t s = cand(i);
+        uint64_t k = composite(hv.key_at(s), hv.count_at(s));
         if ((k & himask) == prefix) atomicAdd(&ss.hist[(k >> (8 * byte)) & 0xFF], 1u);
       }
       __syncthreads();
@@ -229,8 +621,8 @@ __device__ void select_and_emit(const SearchArgs &a, uint32_t q, const HashView 
   }
   uint64_t *seg = a.pool + base;
   for (uint32_t i = tid; i < c; i += THREADS) {
-    uint32_t s = cand[i];
-    uint64_t k = composite(hv.keys[s], hv.cnt[s]);
+    uint32_t s = cand(i);
+    uint64_t k = composite(hv.key_at(s), hv.count_at(s));
     if (k <= thresh) seg[atomicAdd(&ss.nout, 1u)] = k;
   }
   for (uint32_t i = nout + tid; i < P; i += THREADS) seg[i] = ~0ull;
@@ -258,112 +650,89 @@ __device__ void select_and_emit(const SearchArgs &a, uint32_t q, const HashView 
   }
 }
 
-// Lookup + count for positions [0,K) of one query; codes come from `code_at(pos)`.
-template <int THREADS, class CodeAt>
-__device__ __forceinline__ void lookup_and_count(const SearchArgs &a, int K, CodeAt code_at, const HashView &hv,
-                                                 uint32_t max_distinct, SelectScratch &ss,
-                                                 unsigned long long &q_incr) {
-  const int tid = threadIdx.x;
-  const unsigned lane = tid & 31;
-  constexpr int U = 4;  // independent table probes in flight per thread
-  for (int base = 0; base < K; base += U * THREADS) {
-    uint64_t ent[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      int pos = base + u * THREADS + tid;
-      ent[u] = 0;
-      if (pos < K) {
-        uint32_t d = dense_from_codes(code_at(pos), code_at(pos + 1), code_at(pos + 2), code_at(pos + 3),
-                                      code_at(pos + 4), code_at(pos + 5), code_at(pos + 6));
-        if (d >= a.d_lo && d < a.d_hi) ent[u] = ldg_entry(a.table + (d - a.d_lo));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint32_t cnt = (uint32_t)(ent[u] >> ENTRY_VALUE_BITS);
-      const uint64_t val = ent[u] & ENTRY_VALUE_MASK;
-      q_incr += cnt;
-      if (cnt == 1) {
-        if (!*(volatile uint32_t *)&ss.overflow) hash_add(hv, (uint32_t)val, ss, max_distinct);
-      } else if (cnt > 1 && cnt < 32) {
-        for (uint32_t i = 0; i < cnt; ++i) {
-          if (*(volatile uint32_t *)&ss.overflow) break;
-          hash_add(hv, __ldg(a.postings + val + i), ss, max_distinct);
-        }
-      }
-      // long posting lists: the whole warp walks them together (coalesced)
-      unsigned big = __ballot_sync(0xFFFFFFFFu, cnt >= 32);
-      while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        const uint32_t bc = __shfl_sync(0xFFFFFFFFu, cnt, src);
-        const uint64_t bv = __shfl_sync(0xFFFFFFFFu, val, src);
-        for (uint32_t i = lane; i < bc; i += 32) {
-          if (*(volatile uint32_t *)&ss.overflow) break;
-          hash_add(hv, __ldg(a.postings + bv + i), ss, max_distinct);
-        }
-      }
-    }
-    // warp-uniform early exit (the ballots above need converged warps)
-    if (__any_sync(0xFFFFFFFFu, *(volatile uint32_t *)&ss.overflow != 0)) break;
-  }
-}
-
-template <int THREADS, int H, int MAXK, int CLS>
-__global__ void __launch_bounds__(THREADS) k_search(SearchArgs a) {
-  static_assert((H & (H - 1)) == 0, "H must be a power of two");
-  __shared__ uint32_t hkeys[H];
-  __shared__ uint32_t hcnt[H];
-  __shared__ __align__(16) uint8_t codes[MAXK + 16];
-  __shared__ uint16_t cand[H];
+__global__ void __launch_bounds__(M_THREADS) k_search_m(SearchArgs a) {
+  __shared__ __align__(16) uint32_t hkeys[M_H];
+  __shared__ __align__(16) uint32_t hcnt2[M_H / 2];
+  __shared__ uint16_t pp[M_MAXK + 8];
+  __shared__ uint16_t cand[M_H];  // one entry per slot: can never overflow
+  __shared__ uint8_t lut[256];
   __shared__ SelectScratch ss;
-  constexpr uint32_t MAXD = (H - THREADS - 1) < (3 * H / 4) ? (H - THREADS - 1) : (3 * H / 4);
-  int log2h = 0;
-  while ((1 << log2h) < H) ++log2h;
-  const HashView hv{hkeys, hcnt, (uint32_t)H - 1u, 32 - log2h};
+  constexpr int THREADS = M_THREADS;
   const int tid = threadIdx.x;
-  const uint32_t count = a.list_count[CLS];
+  lut[tid] = (uint8_t)aa_code(tid);
+  __syncthreads();
+  const SmemHash hv{hkeys, hcnt2, (uint32_t)M_H - 1u, 32 - 12};
+  const CandList cl{&ss.ncand, &ss.flags, cand, nullptr, (uint32_t)M_H};
+  const uint32_t count = a.list_count[1];
   unsigned long long my_incr = 0, my_lookups = 0;
-  for (uint32_t it = blockIdx.x; it < count; it += gridDim.x) {
-    const uint32_t q = a.lists[(size_t)CLS * a.nq + it];
+  __shared__ uint32_t s_it;
+  for (;;) {
+    if (tid == 0) s_it = atomicAdd(&a.list_count[5], 1u);
+    __syncthreads();
+    const uint32_t it = s_it;
+    if (it >= count) break;
+    const uint32_t q = a.lists[(size_t)a.nq + it];
     const uint64_t b = a.off[q];
+    const int len = (int)(a.off[q + 1] - b);
     const int K = a.size_in_kmer[q];
-    const int ncodes = K + KAAMER_KMER_SIZE - 1;
-    for (int i = tid; i < H; i += THREADS) {
-      hkeys[i] = EMPTY;
-      hcnt[i] = 0;
+    const uint32_t kmin = a.kmin[q];
+    {
+      uint4 *hk = reinterpret_cast<uint4 *>(hkeys);
+      uint4 *hc = reinterpret_cast<uint4 *>(hcnt2);
+      const uint4 E = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY), Z = make_uint4(0, 0, 0, 0);
+      for (int i = tid; i < M_H / 4; i += THREADS) hk[i] = E;
+      for (int i = tid; i < M_H / 8; i += THREADS) hc[i] = Z;
+      if (tid == 0) {
+        ss.ncand = 0;
+        ss.flags = 0;
+      }
     }
-    for (int i = tid; i < ncodes; i += THREADS) codes[i] = (uint8_t)aa_code(a.res[b + i]);
-    if (tid == 0) {
-      ss.ncand = 0;
-      ss.distinct = 0;
-      ss.overflow = 0;
-      ss.kmin = filter_kmin(a.min_kmatch, a.min_kratio, K);
+    const uint8_t *r = a.res + b;
+    const int ncodes = K + KAAMER_KMER_SIZE - 1;
+    for (int i = tid; i < ncodes; i += THREADS) {
+      uint32_t c0 = lut[r[i]];
+      uint32_t c1 = (i + 1 < len) ? (uint32_t)lut[r[i + 1]] : CODE_UNKNOWN;
+      pp[i] = (uint16_t)packed_code(c0, c1);
     }
     __syncthreads();
     unsigned long long q_incr = 0;
-    lookup_and_count<THREADS>(a, K, [&](int p) -> uint32_t { return codes[p]; }, hv, MAXD, ss, q_incr);
+    constexpr int U = 4;
+    auto load_round = [&](int base, uint64_t(&e)[U]) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pos = base + u * THREADS + tid;
+        e[u] = 0;
+        if (pos < K) {
+          uint32_t d = dense_from_packed(pp[pos], pp[pos + 2], pp[pos + 4], pp[pos + 6]);
+          if (d >= a.d_lo && d < a.d_hi) e[u] = ldg_entry(a.table + (d - a.d_lo));
+        }
+      }
+    };
+    uint64_t nxt[U];
+    load_round(0, nxt);
+    for (int base = 0; base < K; base += U * THREADS) {
+      uint64_t ent[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) ent[u] = nxt[u];
+      if (base + U * THREADS < K) load_round(base + U * THREADS, nxt);
+      warp_consume<U>(a, ent, hv, kmin, cl, q_incr);
+    }
     __syncthreads();
-    if (ss.overflow) {
-      // subject set outgrew this class: hand the query to the next one (stream order
-      // guarantees that kernel has not started yet)
+    if (ss.flags) {
+      // histogram full: class G
       if (tid == 0) {
-        uint32_t slot = atomicAdd(&a.list_count[CLS + 1], 1u);
-        a.lists[(size_t)(CLS + 1) * a.nq + slot] = q;
+        uint32_t slot = atomicAdd(&a.list_count[2], 1u);
+        a.lists[(size_t)2 * a.nq + slot] = q;
       }
       __syncthreads();
       continue;
     }
     my_incr += q_incr;
     if (tid == 0) my_lookups += (unsigned long long)K;
-    const uint32_t kmin = ss.kmin;
-    for (int i = tid; i < H; i += THREADS)
-      if (hkeys[i] != EMPTY && hcnt[i] >= kmin) cand[atomicAdd(&ss.ncand, 1u)] = (uint16_t)i;
-    __syncthreads();
-    select_and_emit<THREADS, uint16_t>(a, q, hv, cand, ss);
+    const uint32_t c = ss.ncand;
+    select_and_emit<THREADS>(a, q, hv, [&](uint32_t i) -> uint32_t { return cand[i]; }, c, ss);
     __syncthreads();
   }
-  // work counters: one atomic per warp
   for (int o = 16; o > 0; o >>= 1) {
     my_incr += __shfl_down_sync(0xFFFFFFFFu, my_incr, o);
     my_lookups += __shfl_down_sync(0xFFFFFFFFu, my_lookups, o);
@@ -371,16 +740,16 @@ __global__ void __launch_bounds__(THREADS) k_search(SearchArgs a) {
   if ((tid & 31) == 0) {
     if (my_incr) {
       atomicAdd(&a.counters[CNT_INCR], my_incr);
-      atomicAdd(&a.counters[CNT_CLS_INCR + CLS], my_incr);
+      atomicAdd(&a.counters[CNT_CLS_INCR + 1], my_incr);
     }
     if (my_lookups) {
       atomicAdd(&a.counters[CNT_LOOKUPS], my_lookups);
-      atomicAdd(&a.counters[CNT_CLS_LOOKUPS + CLS], my_lookups);
+      atomicAdd(&a.counters[CNT_CLS_LOOKUPS + 1], my_lookups);
     }
   }
 }
 
-// class G: histogram in global memory (per-CTA scratch, stays in L2), codes read on the fly
+// class G: histogram in global memory (per-CTA scratch, stays in L2), codes computed on the fly
 __global__ void __launch_bounds__(G_THREADS) k_search_g(SearchArgs a) {
   __shared__ SelectScratch ss;
   __shared__ unsigned long long s_total;
@@ -396,52 +765,63 @@ __global__ void __launch_bounds__(G_THREADS) k_search_g(SearchArgs a) {
     const uint32_t q = a.lists[(size_t)2 * a.nq + it];
     const uint64_t b = a.off[q];
     const int K = a.size_in_kmer[q];
+    const uint32_t kmin = a.kmin[q];
     const uint8_t *s = a.res + b;
-    auto code_at = [&](int p) -> uint32_t { return aa_code(s[p]); };
+    auto dense_at = [&](int pos) -> uint32_t {
+      return dense_from_codes(aa_code(s[pos]), aa_code(s[pos + 1]), aa_code(s[pos + 2]), aa_code(s[pos + 3]),
+                              aa_code(s[pos + 4]), aa_code(s[pos + 5]), aa_code(s[pos + 6]));
+    };
     // pass 1: total postings of the query bounds the number of distinct subjects
     if (tid == 0) s_total = 0;
     __syncthreads();
     unsigned long long tot = 0;
     for (int pos = tid; pos < K; pos += THREADS) {
-      uint32_t d = dense_from_codes(code_at(pos), code_at(pos + 1), code_at(pos + 2), code_at(pos + 3),
-                                    code_at(pos + 4), code_at(pos + 5), code_at(pos + 6));
+      uint32_t d = dense_at(pos);
       if (d >= a.d_lo && d < a.d_hi) tot += ldg_entry(a.table + (d - a.d_lo)) >> ENTRY_VALUE_BITS;
     }
     atomicAdd(&s_total, tot);
     __syncthreads();
-    unsigned long long T = s_total;
+    const unsigned long long T = s_total;
     uint32_t Hq = 1024;
     while (Hq < HG && (unsigned long long)Hq < 2 * T) Hq <<= 1;
     int log2h = 0;
     while ((1u << log2h) < Hq) ++log2h;
-    const HashView hv{gkeys, gcnt, Hq - 1u, 32 - log2h};
+    const GmemHash hv{gkeys, gcnt, Hq - 1u, 32 - log2h};
+    const CandList cl{&ss.ncand, &ss.flags, nullptr, gcand, HG};
     for (uint32_t i = tid; i < Hq; i += THREADS) {
       gkeys[i] = EMPTY;
       gcnt[i] = 0;
     }
     if (tid == 0) {
       ss.ncand = 0;
-      ss.distinct = 0;
-      ss.overflow = 0;
-      ss.kmin = filter_kmin(a.min_kmatch, a.min_kratio, K);
+      ss.flags = 0;
     }
     __syncthreads();
     unsigned long long q_incr = 0;
-    const uint32_t maxd = Hq - THREADS - 1 < (Hq / 4) * 3 ? Hq - THREADS - 1 : (Hq / 4) * 3;
-    lookup_and_count<THREADS>(a, K, code_at, hv, maxd, ss, q_incr);
+    constexpr int U = 4;
+    for (int base = 0; base < K; base += U * THREADS) {
+      uint64_t ent[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pos = base + u * THREADS + tid;
+        ent[u] = 0;
+        if (pos < K) {
+          uint32_t d = dense_at(pos);
+          if (d >= a.d_lo && d < a.d_hi) ent[u] = ldg_entry(a.table + (d - a.d_lo));
+        }
+      }
+      warp_consume<U>(a, ent, hv, kmin, cl, q_incr);
+    }
     __syncthreads();
-    if (ss.overflow) {
+    if (ss.flags) {
       if (tid == 0) atomicOr(&a.counters[CNT_STATUS], (unsigned long long)ST_GHASH_OVERFLOW);
       __syncthreads();
       continue;
     }
     my_incr += q_incr;
     if (tid == 0) my_lookups += (unsigned long long)K;
-    const uint32_t kmin = ss.kmin;
-    for (uint32_t i = tid; i < Hq; i += THREADS)
-      if (gkeys[i] != EMPTY && gcnt[i] >= kmin) gcand[atomicAdd(&ss.ncand, 1u)] = i;
-    __syncthreads();
-    select_and_emit<THREADS, uint32_t>(a, q, hv, gcand, ss);
+    const uint32_t c = ss.ncand;
+    select_and_emit<THREADS>(a, q, hv, [&](uint32_t i) -> uint32_t { return gcand[i]; }, c, ss);
     __syncthreads();
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -535,7 +915,8 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   }
   if (nq == 0) return KAAMER_OK;
   SearchWorkspace &ws = h->ws;
-  KCHECK(ws.lists.ensure((size_t)3 * nq + 8));
+  KCHECK(ws.lists.ensure((size_t)3 * nq + 16));
+  KCHECK(ws.kmin.ensure(nq));
   uint32_t *list_count = ws.lists.p + (size_t)3 * nq;
   SearchArgs a{};
   a.table = h->idx.table;
@@ -551,6 +932,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   a.n_hits = out->n_hits;
   a.hit_base = out->hit_base;
   a.size_in_kmer = out->size_in_kmer;
+  a.kmin = ws.kmin.p;
   a.pool = out->pool;
   a.pool_cap = out->pool_cap;
   a.counters = (unsigned long long *)out->counters;
@@ -560,17 +942,17 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   const int g_ctas = h->sm_count;
   KCHECK(ws.ghash.ensure((size_t)g_ctas * 3 * a.ghash_slots));
   a.ghash = ws.ghash.p;
-  KCUDA(cudaMemsetAsync(list_count, 0, 4 * sizeof(uint32_t), st));
+  KCUDA(cudaMemsetAsync(list_count, 0, 8 * sizeof(uint32_t), st));
   KCUDA(cudaMemsetAsync(out->counters, 0, CNT_N * sizeof(uint64_t), st));
   k_classify<<<(nq + 255) / 256, 256, 0, st>>>(a);
-  // persistent grids: a multiple of the SM count, CTAs loop over their class list
-  const unsigned s_grid = (unsigned)h->sm_count * 14u;
-  const unsigned m_grid = (unsigned)h->sm_count * 3u;
+  // persistent grids: a multiple of the SM count, warps / CTAs loop over their class list
+  const unsigned w_grid = (unsigned)h->sm_count * 5u;
+  const unsigned m_grid = (unsigned)h->sm_count * 4u;
   profile_begin(h, st, 0);
-  k_search<S_THREADS, S_H, S_MAXK, 0><<<s_grid < nq ? s_grid : nq, S_THREADS, 0, st>>>(a);
+  k_search_w<<<w_grid, W_WARPS * 32, 0, st>>>(a);
   profile_end(h, st);
   profile_begin(h, st, 1);
-  k_search<M_THREADS, M_H, M_MAXK, 1><<<m_grid < nq ? m_grid : nq, M_THREADS, 0, st>>>(a);
+  k_search_m<<<m_grid < nq ? m_grid : nq, M_THREADS, 0, st>>>(a);
   profile_end(h, st);
   profile_begin(h, st, 2);
   k_search_g<<<g_ctas, G_THREADS, 0, st>>>(a);
@@ -672,22 +1054,20 @@ int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off,
   HCHECK(owner->alloc(&hits->subject_id, (size_t)n_hits));
   HCHECK(owner->alloc(&hits->kmatch, (size_t)n_hits));
   HCHECK(ws.out_hits.ensure((size_t)n_hits + 1));
-  PinBuf<uint64_t> packed;
-  HCHECK(packed.ensure((size_t)n_hits + 1));
+  HCHECK(ws.h_packed.ensure((size_t)n_hits + 1));
   if (n_hits) {
     unsigned grid = (unsigned)(((uint64_t)nq * 32 + 255) / 256);
     k_gather_hits<<<grid, 256, 0, st>>>(ws.n_hits.p, ws.hit_base.p, ws.hit_off.p, ws.pool.p, nq, ws.out_hits.p);
     h->prof_all_launches += 1;
-    HCUDA(cudaMemcpyAsync(packed.p, ws.out_hits.p, (size_t)n_hits * 8, cudaMemcpyDeviceToHost, st));
+    HCUDA(cudaMemcpyAsync(ws.h_packed.p, ws.out_hits.p, (size_t)n_hits * 8, cudaMemcpyDeviceToHost, st));
   }
   HCUDA(cudaMemcpyAsync(hits->hit_off, ws.hit_off.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st));
   HCUDA(cudaMemcpyAsync(hits->size_in_kmer, ws.size_in_kmer.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
   HCUDA(cudaStreamSynchronize(st));
   for (uint64_t i = 0; i < n_hits; ++i) {
-    hits->subject_id[i] = (uint32_t)packed.p[i];
-    hits->kmatch[i] = (uint32_t)(packed.p[i] >> 32);
+    hits->subject_id[i] = (uint32_t)ws.h_packed.p[i];
+    hits->kmatch[i] = (uint32_t)(ws.h_packed.p[i] >> 32);
   }
-  packed.release();
   *out_hits = hits;
 #undef HCHECK
 #undef HCUDA

@@ -87,20 +87,7 @@ static void destroy_handle(kaamer_gpu *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   index_release(h);
-  h->ws.residues.release();
-  h->ws.seq_off.release();
-  h->ws.n_hits.release();
-  h->ws.hit_base.release();
-  h->ws.lists.release();
-  h->ws.size_in_kmer.release();
-  h->ws.pool.release();
-  h->ws.hit_off.release();
-  h->ws.out_hits.release();
-  h->ws.counters.release();
-  h->ws.ghash.release();
-  h->ws.h_counters.release();
-  h->ws.h_packed.release();
-  h->ws.kmin.release();
+  h->ws.release_all();
   for (auto &p : h->prof_pending) {
     cudaEventDestroy(p.a);
     cudaEventDestroy(p.b);
@@ -312,6 +299,19 @@ int kaamer_gpu_search_proteins_device(kaamer_gpu_t *h, const uint8_t *d_residues
   std::lock_guard<std::mutex> lk(h->mu);
   KCUDA(cudaSetDevice(h->device));
   return search_proteins_device(h, d_residues, d_seq_off, nq, opts, d_out, (cudaStream_t)stream);
+}
+
+int kaamer_gpu_search_nucleotide(kaamer_gpu_t *h, const uint8_t *nt, const uint64_t *contig_off, uint32_t n_contigs,
+                                 const kaamer_opts *opts, kaamer_hits **out) {
+  KCHECK(check_search_args(h, nt, contig_off, n_contigs, opts, out));
+  *out = nullptr;
+  std::lock_guard<std::mutex> lk(h->mu);
+  KCUDA(cudaSetDevice(h->device));
+  if (!h->idx.table) {
+    set_error("no index resident");
+    return KAAMER_ERR_ARG;
+  }
+  return search_nucleotide_host(h, nt, contig_off, n_contigs, opts, out);
 }
 
 void kaamer_gpu_free_hits(kaamer_hits *hits) {

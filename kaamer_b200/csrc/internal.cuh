@@ -186,7 +186,30 @@ struct SearchWorkspace {
   DevBuf<uint64_t> pool, hit_off, out_hits;
   DevBuf<uint64_t> counters;   // see search.cu
   DevBuf<uint32_t> ghash;      // global-memory hash scratch (class G)
+  DevBuf<uint8_t> any0;        // nucleotide mode (search.cu)
   PinBuf<uint64_t> h_counters, h_packed;
+  // finish.cu
+  DevBuf<uint64_t> f_scan;     // [5][nq+1] sizes, scanned in place
+  DevBuf<uint32_t> f_posbits, f_keep, f_trim;
+  DevBuf<uint8_t> f_tmp;
+  void release_all() {
+    residues.release(); seq_off.release(); n_hits.release(); hit_base.release(); lists.release();
+    kmin.release(); size_in_kmer.release(); pool.release(); hit_off.release(); out_hits.release();
+    counters.release(); ghash.release(); any0.release(); h_counters.release(); h_packed.release();
+    f_scan.release(); f_posbits.release(); f_keep.release(); f_trim.release(); f_tmp.release();
+  }
+};
+
+// ORFs of a batch of contigs on the device, in GetORFs order per contig (translate.cu)
+struct OrfSet {
+  uint64_t n = 0, n_seq = 0, n_alts = 0;
+  uint32_t *contig = nullptr;
+  int64_t *start = nullptr, *end = nullptr;
+  uint8_t *plus = nullptr;
+  uint64_t *seq_off = nullptr;   // [n+1]
+  uint8_t *seq = nullptr;        // amino acids
+  uint64_t *alts_off = nullptr;  // [n+1]
+  int32_t *alts = nullptr;       // StartsAlternative
 };
 
 struct ProfSpan {
@@ -240,9 +263,42 @@ int index_build(kaamer_gpu *h, const uint8_t *residues, const uint64_t *seq_off,
 void index_release(kaamer_gpu *h);
 // search.cu
 int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint32_t nq,
-                           const kaamer_opts *o, const kaamer_dev_result *out, cudaStream_t st);
+                           const kaamer_opts *o, const kaamer_dev_result *out, cudaStream_t st, int nt_mode = 0,
+                           uint8_t *d_any0 = nullptr);
+int search_counted(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint32_t nq, const kaamer_opts *o,
+                   int nt_mode, uint8_t *d_any0, cudaStream_t st);
 int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off, uint32_t nq,
                          const kaamer_opts *o, kaamer_hits **out);
+int search_nucleotide_host(kaamer_gpu *h, const uint8_t *nt, const uint64_t *coff, uint32_t nc,
+                           const kaamer_opts *o, kaamer_hits **out);
+#ifdef __CUDACC__
+// smallest Kmatch that survives FilterResults (search.go:195): the hit is dropped when
+// float64(Kmatch)/float64(SizeInKmer) < MinKRatio || Kmatch < MinKMatch; both tests are
+// monotone in Kmatch, so the kept set is {Kmatch >= kmin}.
+__device__ __forceinline__ uint32_t filter_kmin(long long min_kmatch, double ratio, int32_t size) {
+  long long k = min_kmatch > 1 ? min_kmatch : 1;
+  double ds = (double)size;
+  if (ratio != ratio) {
+    // NaN: `x < NaN` is false, the ratio test never drops a hit
+  } else if (ratio > 0.0) {
+    double g = ceil(ratio * ds);
+    if (!(g < 4.0e9)) return 0xFFFFFFFFu;  // nothing can pass (Kmatch <= SizeInKmer < 2^31)
+    long long kr = (long long)g;
+    while (kr > 0 && !((double)(kr - 1) / ds < ratio)) --kr;
+    while ((double)kr / ds < ratio) ++kr;
+    if (kr > k) k = kr;
+  }
+  return k > 0xFFFFFFFEll ? 0xFFFFFFFFu : (uint32_t)k;
+}
+#endif
+// translate.cu
+int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint32_t nc, OrfSet *out,
+                cudaStream_t st);
+void orfset_release(OrfSet *o);
+// finish.cu: positions, SetBestStartCodon, final FilterResults, row assembly, D2H
+int finish_rows(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint32_t nq, const kaamer_opts *o,
+                int nt_mode, const uint8_t *d_any0, const OrfSet *orfs, kaamer_hits *hits, HitsOwner *owner,
+                cudaStream_t st);
 void profile_begin(kaamer_gpu *h, cudaStream_t st, int cls);
 void profile_end(kaamer_gpu *h, cudaStream_t st);
 }  // namespace kaamer

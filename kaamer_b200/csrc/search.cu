@@ -57,31 +57,19 @@ struct SearchArgs {
   uint32_t *list_count;  // [8]: [0..2] list sizes, [4..6] work cursors (dynamic scheduling)
   uint32_t *ghash;       // class G scratch: per CTA [keys HG][cnt HG][cand HG]
   uint32_t ghash_slots;  // HG (power of two)
+  // nucleotide / reads mode (search_nucleotide.go:76-124): queries are ORFs, the candidate
+  // threshold is the gate `Hits[0].Kmatch >= MinKMatch` (:116) — FilterResults runs later with
+  // the SizeInKmer that SetBestStartCodon leaves (finish.cu) — and any0[q] records whether a
+  // hit tied with the best one, other than the first of them, matches at query position 0
+  // (the only thing SetBestStartCodon reads from later tied hits, dna.go:224-237)
+  int nt_mode;
+  uint8_t *any0;
 };
 
 __device__ __forceinline__ uint64_t ldg_entry(const uint64_t *p) {
   uint64_t v;
   asm volatile("ld.global.nc.L1::no_allocate.L2::64B.b64 %0, [%1];" : "=l"(v) : "l"(p));
   return v;
-}
-
-// smallest Kmatch that survives FilterResults (search.go:195): the hit is dropped when
-// float64(Kmatch)/float64(SizeInKmer) < MinKRatio || Kmatch < MinKMatch; both tests are
-// monotone in Kmatch, so the kept set is {Kmatch >= kmin}.
-__device__ uint32_t filter_kmin(long long min_kmatch, double ratio, int32_t size) {
-  long long k = min_kmatch > 1 ? min_kmatch : 1;
-  double ds = (double)size;
-  if (ratio != ratio) {
-    // NaN: `x < NaN` is false, the ratio test never drops a hit
-  } else if (ratio > 0.0) {
-    double g = ceil(ratio * ds);
-    if (!(g < 4.0e9)) return 0xFFFFFFFFu;  // nothing can pass (Kmatch <= SizeInKmer < 2^31)
-    long long kr = (long long)g;
-    while (kr > 0 && !((double)(kr - 1) / ds < ratio)) --kr;
-    while ((double)kr / ds < ratio) ++kr;
-    if (kr > k) k = kr;
-  }
-  return k > 0xFFFFFFFEll ? 0xFFFFFFFFu : (uint32_t)k;
 }
 
 __global__ void k_classify(SearchArgs a) {
@@ -94,8 +82,15 @@ __global__ void k_classify(SearchArgs a) {
   a.size_in_kmer[q] = (int32_t)K;
   a.n_hits[q] = 0;
   a.hit_base[q] = 0;
-  if (K < 7) return;  // search_protein.go:74-76 (documented deviation: skipped, not fatal)
-  a.kmin[q] = filter_kmin(a.min_kmatch, a.min_kratio, (int32_t)K);
+  if (a.nt_mode) {
+    a.any0[q] = 0;
+    if (K < 1) return;  // cannot happen for ORFs (>= 21 residues, dna.go:26)
+    const long long k = a.min_kmatch > 1 ? a.min_kmatch : 1;
+    a.kmin[q] = k > 0xFFFFFFFEll ? 0xFFFFFFFFu : (uint32_t)k;
+  } else {
+    if (K < 7) return;  // search_protein.go:74-76 (documented deviation: skipped, not fatal)
+    a.kmin[q] = filter_kmin(a.min_kmatch, a.min_kratio, (int32_t)K);
+  }
   int cls = K <= W_MAXK ? 0 : (K <= M_MAXK ? 1 : 2);
   uint32_t slot = atomicAdd(&a.list_count[cls], 1u);
   a.lists[(size_t)cls * a.nq + slot] = q;
@@ -198,9 +193,49 @@ __device__ __forceinline__ void count_subject(const Hash &hv, uint32_t id, uint3
 struct WarpHash {
   uint32_t *keys;   // [W_H]
   uint16_t *cnt;    // [W_H]
+  static constexpr uint32_t mask = W_H - 1;
+  static constexpr int kMaxProbe = MAX_PROBE;
+  __device__ __forceinline__ uint32_t home(uint32_t id) const { return (id * 2654435761u) >> (32 - 9); }
   __device__ __forceinline__ uint32_t key_at(uint32_t slot) const { return keys[slot]; }
   __device__ __forceinline__ uint32_t count_at(uint32_t slot) const { return cnt[slot]; }
 };
+
+// count of a subject after the histogram is complete (0 if absent)
+template <class Hash>
+__device__ __forceinline__ uint32_t hist_count(const Hash &hv, uint32_t id) {
+  uint32_t slot = hv.home(id);
+#pragma unroll 1
+  for (int probe = 0; probe < Hash::kMaxProbe; ++probe) {
+    const uint32_t k = hv.key_at(slot);
+    if (k == id) return hv.count_at(slot);
+    if (k == EMPTY) return 0;
+    slot = (slot + 1) & hv.mask;
+  }
+  return 0;
+}
+
+// nucleotide mode, one warp: does a subject tied with the best hit (count T), other than the
+// best hit itself, hold the query's first k-mer (dense code d0)?
+template <class Hash>
+__device__ __noinline__ bool warp_any0(const SearchArgs &a, const Hash &hv, uint32_t d0, uint32_t best_id, uint32_t T) {
+  const unsigned lane = threadIdx.x & 31;
+  bool any = false;
+  if (d0 >= a.d_lo && d0 < a.d_hi) {
+    const uint64_t e = ldg_entry(a.table + (d0 - a.d_lo));
+    const uint32_t cnt = (uint32_t)(e >> ENTRY_VALUE_BITS);
+    const uint64_t val = e & ENTRY_VALUE_MASK;
+    if (cnt == 1) {
+      const uint32_t id = (uint32_t)val;
+      any = id != best_id && hist_count(hv, id) == T;
+    } else {
+      for (uint32_t i = lane; i < cnt; i += 32) {
+        const uint32_t id = __ldg(a.postings + val + i);
+        if (id != best_id && hist_count(hv, id) == T) any = true;
+      }
+    }
+  }
+  return __any_sync(0xFFFFFFFFu, any);
+}
 
 // all 32 lanes call this together; lanes with valid==false only take part in the votes
 __device__ __forceinline__ void warp_count(const WarpHash &hv, bool valid, uint32_t id, uint32_t kmin,
@@ -512,6 +547,13 @@ __global__ void __launch_bounds__(W_WARPS * 32, 5) k_search_w(SearchArgs a) {
           atomicOr(&a.counters[CNT_STATUS], (unsigned long long)ST_POOL_OVERFLOW);
         }
       }
+      if (a.nt_mode && fits) {
+        __syncwarp();
+        const uint64_t top = a.pool[base];  // rank 0, written by this warp
+        const bool any = warp_any0(a, hv, dense_from_packed(s.pp[0], s.pp[2], s.pp[4], s.pp[6]), (uint32_t)top,
+                                   (uint32_t)(top >> 32));
+        if (lane == 0) a.any0[q] = any ? 1 : 0;
+      }
     }
     __syncwarp();
   }
@@ -732,6 +774,15 @@ __global__ void __launch_bounds__(M_THREADS) k_search_m(SearchArgs a) {
     const uint32_t c = ss.ncand;
     select_and_emit<THREADS>(a, q, hv, [&](uint32_t i) -> uint32_t { return cand[i]; }, c, ss);
     __syncthreads();
+    if (a.nt_mode) {
+      if (tid < 32 && a.n_hits[q]) {
+        const uint64_t top = a.pool[a.hit_base[q]];
+        const bool any = warp_any0(a, hv, dense_from_packed(pp[0], pp[2], pp[4], pp[6]), (uint32_t)top,
+                                   (uint32_t)(top >> 32));
+        if (tid == 0) a.any0[q] = any ? 1 : 0;
+      }
+      __syncthreads();
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     my_incr += __shfl_down_sync(0xFFFFFFFFu, my_incr, o);
@@ -823,6 +874,14 @@ __global__ void __launch_bounds__(G_THREADS) k_search_g(SearchArgs a) {
     const uint32_t c = ss.ncand;
     select_and_emit<THREADS>(a, q, hv, [&](uint32_t i) -> uint32_t { return gcand[i]; }, c, ss);
     __syncthreads();
+    if (a.nt_mode) {
+      if (tid < 32 && a.n_hits[q]) {
+        const uint64_t top = a.pool[a.hit_base[q]];
+        const bool any = warp_any0(a, hv, dense_at(0), (uint32_t)top, (uint32_t)(top >> 32));
+        if (tid == 0) a.any0[q] = any ? 1 : 0;
+      }
+      __syncthreads();
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     my_incr += __shfl_down_sync(0xFFFFFFFFu, my_incr, o);
@@ -908,7 +967,8 @@ static uint32_t ghash_slots_for(kaamer_gpu *h) {
 }
 
 int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint32_t nq,
-                           const kaamer_opts *o, const kaamer_dev_result *out, cudaStream_t st) {
+                           const kaamer_opts *o, const kaamer_dev_result *out, cudaStream_t st, int nt_mode,
+                           uint8_t *d_any0) {
   if (!h->idx.table) {
     set_error("no index resident");
     return KAAMER_ERR_ARG;
@@ -939,6 +999,8 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   a.lists = ws.lists.p;
   a.list_count = list_count;
   a.ghash_slots = ghash_slots_for(h);
+  a.nt_mode = nt_mode;
+  a.any0 = d_any0;
   const int g_ctas = h->sm_count;
   KCHECK(ws.ghash.ensure((size_t)g_ctas * 3 * a.ghash_slots));
   a.ghash = ws.ghash.p;
@@ -959,6 +1021,50 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   profile_end(h, st);
   h->prof_all_launches += 4;
   KCUDA(cudaGetLastError());
+  return KAAMER_OK;
+}
+
+// Count pass over queries that are already on the device, with the hit-pool retry loop.
+// Leaves n_hits / hit_base / size_in_kmer / pool in the workspace and the counters in
+// ws.h_counters (host).  Synchronises the stream.
+int search_counted(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint32_t nq, const kaamer_opts *o,
+                   int nt_mode, uint8_t *d_any0, cudaStream_t st) {
+  SearchWorkspace &ws = h->ws;
+  KCHECK(ws.n_hits.ensure(nq));
+  KCHECK(ws.hit_base.ensure(nq));
+  KCHECK(ws.size_in_kmer.ensure(nq));
+  KCHECK(ws.counters.ensure(CNT_N));
+  KCHECK(ws.h_counters.ensure(CNT_N + 2));
+  uint64_t per_q = o->max_results > 0 ? (uint64_t)(o->max_results < 16 ? o->max_results : 16) : 1;
+  uint64_t pool_cap = (uint64_t)nq * per_q + 4096;
+  for (int attempt = 0;; ++attempt) {
+    KCHECK(ws.pool.ensure((size_t)pool_cap));
+    kaamer_dev_result dr{};
+    dr.n_hits = ws.n_hits.p;
+    dr.hit_base = ws.hit_base.p;
+    dr.size_in_kmer = ws.size_in_kmer.p;
+    dr.pool = ws.pool.p;
+    dr.pool_cap = pool_cap;
+    dr.counters = ws.counters.p;
+    KCHECK(search_proteins_device(h, d_res, d_off, nq, o, &dr, st, nt_mode, d_any0));
+    KCUDA(cudaMemcpyAsync(ws.h_counters.p, ws.counters.p, CNT_N * 8, cudaMemcpyDeviceToHost, st));
+    KCUDA(cudaStreamSynchronize(st));
+    uint64_t status = ws.h_counters.p[CNT_STATUS];
+    if (status & ST_GHASH_OVERFLOW) {
+      set_error("a query matched more distinct subjects than the class-G histogram holds (%u slots)",
+                ghash_slots_for(h));
+      return KAAMER_ERR_LIMIT;
+    }
+    if (status & ST_POOL_OVERFLOW) {
+      if (attempt >= 3) {
+        set_error("hit pool overflow after %d attempts", attempt + 1);
+        return KAAMER_ERR_LIMIT;
+      }
+      pool_cap = ws.h_counters.p[CNT_POOL] + 4096;  // exact demand of the failed pass
+      continue;
+    }
+    break;
+  }
   return KAAMER_OK;
 }
 
@@ -991,10 +1097,10 @@ int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off,
     }                                                                                   \
   } while (0)
   hits->n_rows = nq;
-  HCHECK(owner->alloc(&hits->hit_off, (size_t)nq + 1));
-  HCHECK(owner->alloc(&hits->size_in_kmer, (size_t)nq));
-  hits->hit_off[0] = 0;
   if (nq == 0) {
+    HCHECK(owner->alloc(&hits->hit_off, 1));
+    HCHECK(owner->alloc(&hits->size_in_kmer, 1));
+    hits->hit_off[0] = 0;
     HCHECK(owner->alloc(&hits->subject_id, 1));
     HCHECK(owner->alloc(&hits->kmatch, 1));
     *out_hits = hits;
@@ -1006,51 +1112,26 @@ int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off,
   }
   HCHECK(ws.residues.ensure((size_t)n_res + 16));
   HCHECK(ws.seq_off.ensure((size_t)nq + 1));
-  HCHECK(ws.n_hits.ensure(nq));
-  HCHECK(ws.hit_base.ensure(nq));
-  HCHECK(ws.size_in_kmer.ensure(nq));
-  HCHECK(ws.hit_off.ensure((size_t)nq + 1));
-  HCHECK(ws.counters.ensure(CNT_N));
-  HCHECK(ws.h_counters.ensure(CNT_N + 2));
   HCUDA(cudaMemcpyAsync(ws.residues.p, res, (size_t)n_res, cudaMemcpyHostToDevice, st));
   HCUDA(cudaMemcpyAsync(ws.seq_off.p, off, ((size_t)nq + 1) * 8, cudaMemcpyHostToDevice, st));
-  uint64_t per_q = o->max_results > 0 ? (uint64_t)(o->max_results < 16 ? o->max_results : 16) : 1;
-  uint64_t pool_cap = (uint64_t)nq * per_q + 4096;
-  for (int attempt = 0;; ++attempt) {
-    HCHECK(ws.pool.ensure((size_t)pool_cap));
-    kaamer_dev_result dr{};
-    dr.n_hits = ws.n_hits.p;
-    dr.hit_base = ws.hit_base.p;
-    dr.size_in_kmer = ws.size_in_kmer.p;
-    dr.pool = ws.pool.p;
-    dr.pool_cap = pool_cap;
-    dr.counters = ws.counters.p;
-    HCHECK(search_proteins_device(h, ws.residues.p, ws.seq_off.p, nq, o, &dr, st));
-    k_scan_hits<<<1, 1024, 0, st>>>(ws.n_hits.p, nq, ws.hit_off.p);
-    h->prof_all_launches += 1;
-    HCUDA(cudaMemcpyAsync(ws.h_counters.p, ws.counters.p, CNT_N * 8, cudaMemcpyDeviceToHost, st));
-    HCUDA(cudaMemcpyAsync(ws.h_counters.p + CNT_N, ws.hit_off.p + nq, 8, cudaMemcpyDeviceToHost, st));
-    HCUDA(cudaStreamSynchronize(st));
-    uint64_t status = ws.h_counters.p[CNT_STATUS];
-    if (status & ST_GHASH_OVERFLOW) {
-      set_error("a query matched more distinct subjects than the class-G histogram holds (%u slots)",
-                ghash_slots_for(h));
-      return fail(KAAMER_ERR_LIMIT);
-    }
-    if (status & ST_POOL_OVERFLOW) {
-      if (attempt >= 3) {
-        set_error("hit pool overflow after %d attempts", attempt + 1);
-        return fail(KAAMER_ERR_LIMIT);
-      }
-      pool_cap = ws.h_counters.p[CNT_POOL] + 4096;  // exact demand of the failed pass
-      continue;
-    }
-    break;
-  }
-  const uint64_t n_hits = ws.h_counters.p[CNT_N];
-  hits->n_hits = n_hits;
+  HCHECK(search_counted(h, ws.residues.p, ws.seq_off.p, nq, o, 0, nullptr, st));
   hits->n_lookups = ws.h_counters.p[CNT_LOOKUPS];
   hits->n_increments = ws.h_counters.p[CNT_INCR];
+  if (o->want_positions) {
+    // PositionHits wanted (search.go:416,442-452): rows, hits and positions assembled by finish.cu
+    HCHECK(finish_rows(h, ws.residues.p, ws.seq_off.p, nq, o, 0, nullptr, nullptr, hits, owner, st));
+    *out_hits = hits;
+    return KAAMER_OK;
+  }
+  HCHECK(owner->alloc(&hits->hit_off, (size_t)nq + 1));
+  HCHECK(owner->alloc(&hits->size_in_kmer, (size_t)nq));
+  HCHECK(ws.hit_off.ensure((size_t)nq + 1));
+  k_scan_hits<<<1, 1024, 0, st>>>(ws.n_hits.p, nq, ws.hit_off.p);
+  h->prof_all_launches += 1;
+  HCUDA(cudaMemcpyAsync(ws.h_counters.p + CNT_N, ws.hit_off.p + nq, 8, cudaMemcpyDeviceToHost, st));
+  HCUDA(cudaStreamSynchronize(st));
+  const uint64_t n_hits = ws.h_counters.p[CNT_N];
+  hits->n_hits = n_hits;
   HCHECK(owner->alloc(&hits->subject_id, (size_t)n_hits));
   HCHECK(owner->alloc(&hits->kmatch, (size_t)n_hits));
   HCHECK(ws.out_hits.ensure((size_t)n_hits + 1));
@@ -1071,6 +1152,49 @@ int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off,
   *out_hits = hits;
 #undef HCHECK
 #undef HCUDA
+  return KAAMER_OK;
+}
+
+// nucleotide contigs on the host: H2D -> ORFs -> count pass (nt mode) -> finish
+int search_nucleotide_host(kaamer_gpu *h, const uint8_t *nt, const uint64_t *coff, uint32_t nc,
+                           const kaamer_opts *o, kaamer_hits **out_hits) {
+  SearchWorkspace &ws = h->ws;
+  cudaStream_t st = h->stream;
+  const uint64_t zero = 0;
+  if (nc == 0) coff = &zero;
+  if (coff[0] != 0) {
+    set_error("contig_off[0] must be 0");
+    return KAAMER_ERR_ARG;
+  }
+  const uint64_t total = coff[nc];
+  KCHECK(ws.residues.ensure((size_t)total + 16));
+  if (total) KCUDA(cudaMemcpyAsync(ws.residues.p, nt, (size_t)total, cudaMemcpyHostToDevice, st));
+  OrfSet os;
+  KCHECK(orfs_device(h, ws.residues.p, coff, nc, &os, st));
+  auto *hits = new kaamer_hits();
+  memset(hits, 0, sizeof *hits);
+  auto *owner = new HitsOwner();
+  hits->_owner = owner;
+  int rc = KAAMER_OK;
+  if (os.n > 0xFFFFFFFFull) {
+    set_error("too many ORFs in one batch");
+    rc = KAAMER_ERR_LIMIT;
+  }
+  const uint32_t nq = (uint32_t)os.n;
+  if (rc == KAAMER_OK) rc = ws.any0.ensure((size_t)nq + 1);
+  if (rc == KAAMER_OK && nq) rc = search_counted(h, os.seq, os.seq_off, nq, o, 1, ws.any0.p, st);
+  if (rc == KAAMER_OK && nq) {
+    hits->n_lookups = ws.h_counters.p[CNT_LOOKUPS];
+    hits->n_increments = ws.h_counters.p[CNT_INCR];
+  }
+  if (rc == KAAMER_OK) rc = finish_rows(h, os.seq, os.seq_off, nq, o, 1, ws.any0.p, &os, hits, owner, st);
+  orfset_release(&os);
+  if (rc != KAAMER_OK) {
+    delete owner;
+    delete hits;
+    return rc;
+  }
+  *out_hits = hits;
   return KAAMER_OK;
 }
 

@@ -1,0 +1,527 @@
+// translate.cu — six-frame translation and ORF extraction on the device.
+//
+// Replaces GetORFs / GetFrame / ReverseComplement (pkg/search/dna.go:55-196) with table 11
+// (gcodeBacteria, pkg/search/gcode.go:36-101; the geneticCode argument is ignored by the
+// reference, dna.go:106).
+//
+//   k_translate6   one thread per nucleotide position p of a contig: the triple dna[p..p+2]
+//                  is the codon p/3 of plus frame p%3 AND (complemented, reversed) the codon
+//                  (L-3-p)/3 of minus frame (L-3-p)%3.  One byte per codon is written to the
+//                  frame-major codon arrays: bits 0..6 amino-acid letter (0 = codon not in the
+//                  table, i.e. it holds a non-acgt byte: the Go map miss appends nothing,
+//                  dna.go:106,123), bit 7 = start codon.
+//   k_orf_ends     every stop codon and every frame-final codon closes at most one ORF: the
+//                  thread walks back to the previous stop, remembering the left-most start
+//                  codon of the stretch (the frame-initial stretch starts inside an ORF,
+//                  dna.go:98), counts residues and alternative starts, and emits the ORF when
+//                  it has >= 21 residues (dna.go:26,128,155).
+//   radix sort     by (contig, End (+) / Start (-), strand): the order of sort.Slice at
+//                  dna.go:167-177 with ties broken by emission order (ties only occur between
+//                  a plus and a minus ORF, the plus one was emitted first).
+//   k_orf_write    one warp per ORF: residues (empty codons skipped) and StartsAlternative.
+//
+// HBM traffic: 1 B read per nucleotide (+2 halo), 2 B written per nucleotide (six frames x 1/3),
+// the codon arrays are re-read once by k_orf_ends and once by k_orf_write.
+#include <cub/cub.cuh>
+
+#include "internal.cuh"
+
+namespace kaamer {
+
+constexpr int MIN_LEN_CDS = 21;  // dna.go:26
+
+// table 11, codon index = 16*b0 + 4*b1 + b2 with t=0 c=1 a=2 g=3
+__constant__ char c_aas[65] = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+// start codons ttg ctg att atc ata atg gtg (gcode.go:40,56,69-72,88)
+constexpr uint64_t START_MASK = (1ull << 3) | (1ull << 19) | (1ull << 32) | (1ull << 33) | (1ull << 34) |
+                                (1ull << 35) | (1ull << 51);
+
+__device__ __forceinline__ int base_code(uint32_t c) {
+  c |= 0x20u;  // strings.ToLower (dna.go:68) as far as a/c/g/t are concerned
+  return c == 't' ? 0 : c == 'c' ? 1 : c == 'a' ? 2 : c == 'g' ? 3 : -1;
+}
+
+// contig of global nucleotide index g: last c with coff[c] <= g
+__device__ __forceinline__ uint32_t find_contig(const uint64_t *__restrict__ coff, uint32_t nc, uint64_t g) {
+  uint32_t lo = 0, hi = nc;  // invariant coff[lo] <= g < coff[hi]
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (coff[mid] <= g) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+
+struct TranslateArgs {
+  const uint8_t *nt;
+  const uint64_t *coff;   // [nc+1] nucleotide offsets
+  const uint64_t *cbase;  // [nc+1] codon-array offsets: contig c owns 6 frames of stride L/3+1
+  uint32_t nc;
+  uint64_t total_nt;
+  uint8_t *cod;
+  // unsorted ORF records
+  unsigned long long *n_orfs;
+  uint64_t cap;
+  uint64_t *key;      // sort key
+  uint32_t *r_contig;
+  int32_t *r_b, *r_e, *r_cnt, *r_nalt;
+  uint8_t *r_frame;
+};
+
+__global__ void __launch_bounds__(256) k_translate6(TranslateArgs a) {
+  __shared__ char aas[64];
+  if (threadIdx.x < 64) aas[threadIdx.x] = c_aas[threadIdx.x];
+  __syncthreads();
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.total_nt) return;
+  const uint32_t c = find_contig(a.coff, a.nc, g);
+  const uint64_t cb = a.coff[c];
+  const int64_t L = (int64_t)(a.coff[c + 1] - cb);
+  const int64_t p = (int64_t)(g - cb);
+  if (L < 2 || p + 3 > L) return;  // Go would panic on len < 2 (dna.go:183-196): nothing emitted
+  const int b0 = base_code(a.nt[g]), b1 = base_code(a.nt[g + 1]), b2 = base_code(a.nt[g + 2]);
+  const bool ok = (b0 | b1 | b2) >= 0;
+  const int64_t S = L / 3 + 1;
+  uint8_t *cod = a.cod + a.cbase[c];
+  {
+    uint8_t v = 0;
+    if (ok) {
+      const int idx = b0 * 16 + b1 * 4 + b2;
+      v = (uint8_t)aas[idx] | (uint8_t)(((START_MASK >> idx) & 1ull) << 7);
+    }
+    cod[(p % 3) * S + p / 3] = v;
+  }
+  {
+    // reverse complement (dna.go:55-63): only a<->t, c<->g are swapped = code ^ 2
+    const int64_t j = L - 3 - p;
+    uint8_t v = 0;
+    if (ok) {
+      const int idx = (b2 ^ 2) * 16 + (b1 ^ 2) * 4 + (b0 ^ 2);
+      v = (uint8_t)aas[idx] | (uint8_t)(((START_MASK >> idx) & 1ull) << 7);
+    }
+    cod[(3 + j % 3) * S + j / 3] = v;
+  }
+}
+
+__device__ __forceinline__ void orf_close(const TranslateArgs &a, uint32_t c, int64_t L, int frame, int64_t e,
+                                          const uint8_t *__restrict__ fr) {
+  // walk back from e to the previous stop (exclusive) or to the frame start
+  int32_t cnt = 0, nalt = 0, cnt_b = 0, nalt_b = 0;
+  int64_t b = -1, k = e;
+  for (; k >= 0; --k) {
+    const uint8_t v = fr[k];
+    if (k != e && (v & 0x7F) == '*') break;
+    if (v & 0x7F) cnt++;
+    if (v & 0x80) {
+      nalt++;
+      b = k;
+      cnt_b = cnt;
+      nalt_b = nalt;
+    }
+  }
+  if (k < 0) {  // frame-initial stretch: insideORF starts true (dna.go:98)
+    b = 0;
+    cnt_b = cnt;
+    nalt_b = nalt;
+  }
+  if (b < 0 || cnt_b < MIN_LEN_CDS) return;
+  const unsigned long long slot = atomicAdd(a.n_orfs, 1ull);
+  if (slot >= a.cap) return;  // cannot happen (cap = codons/21 + slack); checked on the host
+  int64_t start, end, poskey;
+  if (frame < 3) {
+    start = frame + 3 * b + 1;  // dna.go:84,111
+    end = 3 * e + 3 + frame;    // dna.go:129,156
+    poskey = end;
+  } else {
+    start = L - (frame - 3) - 3 * b;      // dna.go:80-82,112-114
+    end = start - 3 * (int64_t)cnt_b + 1;  // dna.go:131,158
+    poskey = start;
+  }
+  a.key[slot] = ((uint64_t)c << 40) | ((uint64_t)poskey << 1) | (frame >= 3 ? 1ull : 0ull);
+  a.r_contig[slot] = c;
+  a.r_frame[slot] = (uint8_t)frame;
+  a.r_b[slot] = (int32_t)b;
+  a.r_e[slot] = (int32_t)e;
+  a.r_cnt[slot] = cnt_b;
+  a.r_nalt[slot] = nalt_b;
+}
+
+__global__ void __launch_bounds__(256) k_orf_ends(TranslateArgs a) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.total_nt) return;
+  const uint32_t c = find_contig(a.coff, a.nc, g);
+  const uint64_t cb = a.coff[c];
+  const int64_t L = (int64_t)(a.coff[c + 1] - cb);
+  const int64_t p = (int64_t)(g - cb);
+  if (L < 2 || p + 3 > L) return;
+  const int64_t S = L / 3 + 1;
+  const uint8_t *cod = a.cod + a.cbase[c];
+  {
+    const int f = (int)(p % 3);
+    const int64_t k = p / 3, ncod = (L - f) / 3;
+    const uint8_t *fr = cod + f * S;
+    if ((fr[k] & 0x7F) == '*' || k == ncod - 1) orf_close(a, c, L, f, k, fr);
+  }
+  {
+    const int64_t j = L - 3 - p;
+    const int f = (int)(j % 3);
+    const int64_t k = j / 3, ncod = (L - f) / 3;
+    const uint8_t *fr = cod + (3 + f) * S;
+    if ((fr[k] & 0x7F) == '*' || k == ncod - 1) orf_close(a, c, L, 3 + f, k, fr);
+  }
+}
+
+__global__ void k_iota(uint32_t *p, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (uint32_t)i;
+}
+
+struct OrfWriteArgs {
+  const uint8_t *cod;
+  const uint64_t *coff, *cbase;
+  const uint32_t *perm;  // sorted rank -> record slot
+  const uint32_t *r_contig;
+  const int32_t *r_b, *r_e, *r_cnt, *r_nalt;
+  const uint8_t *r_frame;
+  uint64_t n;
+  // outputs (sorted order)
+  uint32_t *contig;
+  int64_t *start, *end;
+  uint8_t *plus;
+  uint64_t *len, *nalt;  // per-ORF sizes (scanned into seq_off / alts_off afterwards)
+  const uint64_t *seq_off, *alts_off;
+  uint8_t *seq;
+  int32_t *alts;
+};
+
+__global__ void k_orf_meta(OrfWriteArgs a) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.n) return;
+  const uint32_t s = a.perm[r];
+  const uint32_t c = a.r_contig[s];
+  const int frame = a.r_frame[s];
+  const int64_t L = (int64_t)(a.coff[c + 1] - a.coff[c]);
+  const int64_t b = a.r_b[s], e = a.r_e[s], cnt = a.r_cnt[s];
+  int64_t start, end;
+  if (frame < 3) {
+    start = frame + 3 * b + 1;
+    end = 3 * e + 3 + frame;
+  } else {
+    start = L - (frame - 3) - 3 * b;
+    end = start - 3 * cnt + 1;
+  }
+  a.contig[r] = c;
+  a.start[r] = start;
+  a.end[r] = end;
+  a.plus[r] = frame < 3 ? 1 : 0;
+  a.len[r] = (uint64_t)cnt;
+  a.nalt[r] = (uint64_t)a.r_nalt[s];
+}
+
+__global__ void __launch_bounds__(256) k_orf_write(OrfWriteArgs a) {
+  const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (r >= a.n) return;
+  const uint32_t s = a.perm[r];
+  const uint32_t c = a.r_contig[s];
+  const int frame = a.r_frame[s];
+  const int64_t L = (int64_t)(a.coff[c + 1] - a.coff[c]);
+  const int64_t S = L / 3 + 1;
+  const uint8_t *fr = a.cod + a.cbase[c] + (int64_t)frame * S;
+  const int64_t b = a.r_b[s], e = a.r_e[s];
+  uint8_t *seq = a.seq + a.seq_off[r];
+  int32_t *alts = a.alts + a.alts_off[r];
+  uint32_t nseq = 0, nal = 0;
+  for (int64_t kb = b; kb <= e; kb += 32) {
+    const int64_t k = kb + lane;
+    const uint8_t v = k <= e ? fr[k] : 0;
+    const unsigned has = __ballot_sync(0xFFFFFFFFu, (v & 0x7F) != 0);
+    const unsigned st = __ballot_sync(0xFFFFFFFFu, (v & 0x80) != 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (v & 0x7F) seq[nseq + __popc(has & below)] = v & 0x7F;
+    if (v & 0x80) alts[nal + __popc(st & below)] = (int32_t)(k - b);  // currentAAPos (dna.go:115,118)
+    nseq += __popc(has);
+    nal += __popc(st);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+template <class T>
+static int dev_alloc(T **p, size_t n) {
+  cudaError_t e = cudaMalloc((void **)p, (n ? n : 1) * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+    *p = nullptr;
+    return KAAMER_ERR_NOMEM;
+  }
+  return KAAMER_OK;
+}
+
+void orfset_release(OrfSet *o) {
+  cudaFree(o->contig);
+  cudaFree(o->start);
+  cudaFree(o->end);
+  cudaFree(o->plus);
+  cudaFree(o->seq_off);
+  cudaFree(o->seq);
+  cudaFree(o->alts_off);
+  cudaFree(o->alts);
+  *o = OrfSet();
+}
+
+// d_nt: nucleotides on the device (+2 readable bytes of slack are NOT required: the last two
+// positions of a contig are never dereferenced beyond the contig end);  h_coff: host copy.
+int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint32_t nc, OrfSet *out,
+                cudaStream_t st) {
+  *out = OrfSet();
+  const uint64_t total_nt = nc ? h_coff[nc] : 0;
+  if (nc >= (1u << 24)) {
+    set_error("too many contigs in one batch (%u >= 2^24)", nc);
+    return KAAMER_ERR_LIMIT;
+  }
+  std::vector<uint64_t> cbase((size_t)nc + 1, 0);
+  for (uint32_t c = 0; c < nc; ++c) {
+    if (h_coff[c + 1] < h_coff[c]) {
+      set_error("contig offsets must be non-decreasing");
+      return KAAMER_ERR_ARG;
+    }
+    const uint64_t L = h_coff[c + 1] - h_coff[c];
+    if (L >= (1ull << 38)) {
+      set_error("contig %u too long", c);
+      return KAAMER_ERR_LIMIT;
+    }
+    cbase[c + 1] = cbase[c] + 6 * (L / 3 + 1);
+  }
+  const uint64_t total_cod = cbase[nc];
+  const uint64_t cap = total_cod / MIN_LEN_CDS + 6ull * nc + 64;
+  uint64_t *d_coff = nullptr, *d_cbase = nullptr, *d_key = nullptr, *d_key2 = nullptr;
+  uint8_t *d_cod = nullptr, *r_frame = nullptr;
+  unsigned long long *d_n = nullptr;
+  uint32_t *r_contig = nullptr, *d_iota = nullptr, *d_perm = nullptr;
+  int32_t *r_b = nullptr, *r_e = nullptr, *r_cnt = nullptr, *r_nalt = nullptr;
+  uint64_t *d_len = nullptr, *d_nalt = nullptr;
+  void *d_tmp = nullptr;
+  int rc = KAAMER_OK;
+  auto cleanup = [&]() {
+    cudaFree(d_coff); cudaFree(d_cbase); cudaFree(d_key); cudaFree(d_key2); cudaFree(d_cod); cudaFree(r_frame);
+    cudaFree(d_n); cudaFree(r_contig); cudaFree(d_iota); cudaFree(d_perm); cudaFree(r_b); cudaFree(r_e);
+    cudaFree(r_cnt); cudaFree(r_nalt); cudaFree(d_len); cudaFree(d_nalt); cudaFree(d_tmp);
+  };
+#define TCHECK(x)                \
+  do {                           \
+    rc = (x);                    \
+    if (rc != KAAMER_OK) {       \
+      cleanup();                 \
+      orfset_release(out);       \
+      return rc;                 \
+    }                            \
+  } while (0)
+#define TCUDA(call)                                                                      \
+  do {                                                                                   \
+    cudaError_t _e = (call);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));   \
+      cleanup();                                                                         \
+      orfset_release(out);                                                               \
+      return KAAMER_ERR_CUDA;                                                            \
+    }                                                                                    \
+  } while (0)
+  TCHECK(dev_alloc(&d_coff, (size_t)nc + 1));
+  TCHECK(dev_alloc(&d_cbase, (size_t)nc + 1));
+  TCHECK(dev_alloc(&d_cod, (size_t)total_cod));
+  TCHECK(dev_alloc(&d_n, 1));
+  TCHECK(dev_alloc(&d_key, (size_t)cap));
+  TCHECK(dev_alloc(&r_contig, (size_t)cap));
+  TCHECK(dev_alloc(&r_frame, (size_t)cap));
+  TCHECK(dev_alloc(&r_b, (size_t)cap));
+  TCHECK(dev_alloc(&r_e, (size_t)cap));
+  TCHECK(dev_alloc(&r_cnt, (size_t)cap));
+  TCHECK(dev_alloc(&r_nalt, (size_t)cap));
+  TCUDA(cudaMemcpyAsync(d_coff, h_coff, ((size_t)nc + 1) * 8, cudaMemcpyHostToDevice, st));
+  TCUDA(cudaMemcpyAsync(d_cbase, cbase.data(), ((size_t)nc + 1) * 8, cudaMemcpyHostToDevice, st));
+  TCUDA(cudaMemsetAsync(d_n, 0, 8, st));
+  TranslateArgs ta{};
+  ta.nt = d_nt;
+  ta.coff = d_coff;
+  ta.cbase = d_cbase;
+  ta.nc = nc;
+  ta.total_nt = total_nt;
+  ta.cod = d_cod;
+  ta.n_orfs = d_n;
+  ta.cap = cap;
+  ta.key = d_key;
+  ta.r_contig = r_contig;
+  ta.r_frame = r_frame;
+  ta.r_b = r_b;
+  ta.r_e = r_e;
+  ta.r_cnt = r_cnt;
+  ta.r_nalt = r_nalt;
+  unsigned long long n_orfs = 0;
+  if (total_nt) {
+    const unsigned grid = (unsigned)((total_nt + 255) / 256);
+    k_translate6<<<grid, 256, 0, st>>>(ta);
+    k_orf_ends<<<grid, 256, 0, st>>>(ta);
+    h->prof_all_launches += 2;
+    TCUDA(cudaGetLastError());
+    TCUDA(cudaMemcpyAsync(&n_orfs, d_n, 8, cudaMemcpyDeviceToHost, st));
+    TCUDA(cudaStreamSynchronize(st));
+  }
+  if (n_orfs > cap) {
+    set_error("internal: ORF record capacity exceeded (%llu > %llu)", n_orfs, (unsigned long long)cap);
+    cleanup();
+    return KAAMER_ERR_LIMIT;
+  }
+  const uint64_t n = n_orfs;
+  out->n = n;
+  TCHECK(dev_alloc(&out->contig, (size_t)n));
+  TCHECK(dev_alloc(&out->start, (size_t)n));
+  TCHECK(dev_alloc(&out->end, (size_t)n));
+  TCHECK(dev_alloc(&out->plus, (size_t)n));
+  TCHECK(dev_alloc(&out->seq_off, (size_t)n + 1));
+  TCHECK(dev_alloc(&out->alts_off, (size_t)n + 1));
+  if (n == 0) {
+    TCUDA(cudaMemsetAsync(out->seq_off, 0, 8, st));
+    TCUDA(cudaMemsetAsync(out->alts_off, 0, 8, st));
+    TCHECK(dev_alloc(&out->seq, 16));
+    TCHECK(dev_alloc(&out->alts, 1));
+    TCUDA(cudaStreamSynchronize(st));
+    cleanup();
+    return KAAMER_OK;
+  }
+  // sort the records
+  TCHECK(dev_alloc(&d_key2, (size_t)n));
+  TCHECK(dev_alloc(&d_iota, (size_t)n));
+  TCHECK(dev_alloc(&d_perm, (size_t)n));
+  TCHECK(dev_alloc(&d_len, (size_t)n + 1));
+  TCHECK(dev_alloc(&d_nalt, (size_t)n + 1));
+  k_iota<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_iota, n);
+  TCUDA(cudaGetLastError());
+  size_t need = 0, need2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, need, d_key, d_key2, d_iota, d_perm, (int64_t)n, 0, 64, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, need2, d_len, out->seq_off, (int64_t)n + 1, st);
+  if (need2 > need) need = need2;
+  TCUDA(cudaMalloc(&d_tmp, need + 16));
+  size_t tb = need;
+  TCUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_key, d_key2, d_iota, d_perm, (int64_t)n, 0, 64, st));
+  OrfWriteArgs wa{};
+  wa.cod = d_cod;
+  wa.coff = d_coff;
+  wa.cbase = d_cbase;
+  wa.perm = d_perm;
+  wa.r_contig = r_contig;
+  wa.r_frame = r_frame;
+  wa.r_b = r_b;
+  wa.r_e = r_e;
+  wa.r_cnt = r_cnt;
+  wa.r_nalt = r_nalt;
+  wa.n = n;
+  wa.contig = out->contig;
+  wa.start = out->start;
+  wa.end = out->end;
+  wa.plus = out->plus;
+  wa.len = d_len;
+  wa.nalt = d_nalt;
+  TCUDA(cudaMemsetAsync(d_len + n, 0, 8, st));
+  TCUDA(cudaMemsetAsync(d_nalt + n, 0, 8, st));
+  k_orf_meta<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(wa);
+  TCUDA(cudaGetLastError());
+  tb = need;
+  TCUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_len, out->seq_off, (int64_t)n + 1, st));
+  tb = need;
+  TCUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_nalt, out->alts_off, (int64_t)n + 1, st));
+  uint64_t tot[2];
+  TCUDA(cudaMemcpyAsync(&tot[0], out->seq_off + n, 8, cudaMemcpyDeviceToHost, st));
+  TCUDA(cudaMemcpyAsync(&tot[1], out->alts_off + n, 8, cudaMemcpyDeviceToHost, st));
+  TCUDA(cudaStreamSynchronize(st));
+  out->n_seq = tot[0];
+  out->n_alts = tot[1];
+  TCHECK(dev_alloc(&out->seq, (size_t)tot[0] + 16));
+  TCHECK(dev_alloc(&out->alts, (size_t)tot[1] + 1));
+  wa.seq_off = out->seq_off;
+  wa.alts_off = out->alts_off;
+  wa.seq = out->seq;
+  wa.alts = out->alts;
+  k_orf_write<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(wa);
+  h->prof_all_launches += 2;
+  TCUDA(cudaGetLastError());
+  TCUDA(cudaStreamSynchronize(st));
+  cleanup();
+#undef TCHECK
+#undef TCUDA
+  return KAAMER_OK;
+}
+
+}  // namespace kaamer
+
+using namespace kaamer;
+
+extern "C" {
+
+int kaamer_gpu_get_orfs(kaamer_gpu_t *h, const uint8_t *nt, const uint64_t *contig_off, uint32_t n_contigs,
+                        kaamer_orfs **out) {
+  if (!h || !out || (n_contigs && (!nt || !contig_off))) {
+    set_error("null argument");
+    return KAAMER_ERR_ARG;
+  }
+  *out = nullptr;
+  std::lock_guard<std::mutex> lk(h->mu);
+  KCUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const uint64_t zero = 0;
+  const uint64_t *coff = n_contigs ? contig_off : &zero;
+  if (coff[0] != 0) {
+    set_error("contig_off[0] must be 0");
+    return KAAMER_ERR_ARG;
+  }
+  const uint64_t total = coff[n_contigs];
+  KCHECK(h->ws.residues.ensure((size_t)total + 16));
+  if (total) KCUDA(cudaMemcpyAsync(h->ws.residues.p, nt, (size_t)total, cudaMemcpyHostToDevice, st));
+  OrfSet os;
+  KCHECK(orfs_device(h, h->ws.residues.p, coff, n_contigs, &os, st));
+  auto *o = new kaamer_orfs();
+  memset(o, 0, sizeof *o);
+  auto *owner = new HitsOwner();
+  o->_owner = owner;
+  o->n_orfs = os.n;
+  int rc = KAAMER_OK;
+  const size_t n = (size_t)os.n;
+  if ((rc = owner->alloc(&o->contig, n)) == KAAMER_OK && (rc = owner->alloc(&o->start, n)) == KAAMER_OK &&
+      (rc = owner->alloc(&o->end, n)) == KAAMER_OK && (rc = owner->alloc(&o->plus, n)) == KAAMER_OK &&
+      (rc = owner->alloc(&o->seq_off, n + 1)) == KAAMER_OK && (rc = owner->alloc(&o->seq, (size_t)os.n_seq)) == KAAMER_OK &&
+      (rc = owner->alloc(&o->alts_off, n + 1)) == KAAMER_OK &&
+      (rc = owner->alloc(&o->alts, (size_t)os.n_alts)) == KAAMER_OK) {
+    cudaError_t e = cudaSuccess;
+    auto cp = [&](void *dst, const void *src, size_t bytes) {
+      if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+    };
+    cp(o->contig, os.contig, n * 4);
+    cp(o->start, os.start, n * 8);
+    cp(o->end, os.end, n * 8);
+    cp(o->plus, os.plus, n);
+    cp(o->seq_off, os.seq_off, (n + 1) * 8);
+    cp(o->seq, os.seq, (size_t)os.n_seq);
+    cp(o->alts_off, os.alts_off, (n + 1) * 8);
+    cp(o->alts, os.alts, (size_t)os.n_alts * 4);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      set_error("get_orfs: D2H failed: %s", cudaGetErrorString(e));
+      rc = KAAMER_ERR_CUDA;
+    }
+  }
+  orfset_release(&os);
+  if (rc != KAAMER_OK) {
+    delete owner;
+    delete o;
+    return rc;
+  }
+  *out = o;
+  return KAAMER_OK;
+}
+
+void kaamer_gpu_free_orfs(kaamer_orfs *o) {
+  if (!o) return;
+  delete (HitsOwner *)o->_owner;
+  delete o;
+}
+
+}  // extern "C"

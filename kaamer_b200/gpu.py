@@ -60,6 +60,30 @@ class SearchResult:
         return list(zip(self.subject[b:e].tolist(), self.kmatch[b:e].tolist()))
 
 
+@dataclass
+class OrfTable:
+    """ORF{Sequence, Location{StartPosition, EndPosition, PlusStrand, StartsAlternative}} rows
+    (pkg/search/dna.go:34-44), contigs concatenated in batch order."""
+
+    contig: np.ndarray
+    start: np.ndarray
+    end: np.ndarray
+    plus: np.ndarray
+    seq_off: np.ndarray
+    seq: np.ndarray
+    alts_off: np.ndarray
+    alts: np.ndarray
+
+    def __len__(self):
+        return len(self.start)
+
+    def sequence(self, i: int) -> bytes:
+        return self.seq[int(self.seq_off[i]):int(self.seq_off[i + 1])].tobytes()
+
+    def starts_alternative(self, i: int):
+        return self.alts[int(self.alts_off[i]):int(self.alts_off[i + 1])].tolist()
+
+
 def _arr(ptr, n, dtype):
     if n == 0 or not ptr:
         return np.zeros(0, dtype=dtype)
@@ -215,6 +239,24 @@ class GpuIndex:
         check(_lib.lib().kaamer_gpu_search_nucleotide(self._h, _vp(nt), _vp(contig_off), len(contig_off) - 1,
                                                       C.byref(o), C.byref(hp)))
         return _collect_hits(hp)
+
+    def get_orfs(self, nt, contig_off) -> "OrfTable":
+        """GetORFs (pkg/search/dna.go:65-181) of every contig of the batch, on the device."""
+        nt = np.ascontiguousarray(nt, dtype=np.uint8)
+        contig_off = np.ascontiguousarray(contig_off, dtype=np.uint64)
+        op = C.POINTER(_lib.Orfs)()
+        check(_lib.lib().kaamer_gpu_get_orfs(self._h, _vp(nt), _vp(contig_off), len(contig_off) - 1, C.byref(op)))
+        o = op.contents
+        n = int(o.n_orfs)
+        seq_off = _arr(o.seq_off, n + 1, np.uint64)
+        alts_off = _arr(o.alts_off, n + 1, np.uint64)
+        t = OrfTable(
+            contig=_arr(o.contig, n, np.uint32), start=_arr(o.start, n, np.int64), end=_arr(o.end, n, np.int64),
+            plus=_arr(o.plus, n, np.uint8), seq_off=seq_off,
+            seq=_arr(o.seq, int(seq_off[-1]) if n else 0, np.uint8), alts_off=alts_off,
+            alts=_arr(o.alts, int(alts_off[-1]) if n else 0, np.int32))
+        _lib.lib().kaamer_gpu_free_orfs(op)
+        return t
 
     # ---- profiling ---------------------------------------------------------------------
     def profile_enable(self, on: bool = True):

@@ -182,9 +182,10 @@ int kaamer_gpu_search_proteins_device(kaamer_gpu_t *h, const uint8_t *d_residues
 int kaamer_gpu_pinned_alloc(uint64_t bytes, void **out);
 void kaamer_gpu_pinned_free(void *p);
 
-/* per-handle kernel timing: CUDA events on the launching stream around each search kernel
- * (size classes S, M, G -> kernel_ms[3], kernel_launches[3]); all_launches counts every
- * kernel the library launched since the last reset (bench.py roofline / gpu_launches) */
+/* per-handle kernel timing: CUDA events on the launching stream around each hot kernel:
+ * kernel_ms[4], kernel_launches[4] = search size classes W, M, G and the Smith-Waterman
+ * kernel; all_launches counts every kernel the library launched since the last reset
+ * (bench.py roofline / gpu_launches) */
 int kaamer_gpu_profile_enable(kaamer_gpu_t *h, int on);
 int kaamer_gpu_profile_read(kaamer_gpu_t *h, double *kernel_ms, uint64_t *kernel_launches,
                             uint64_t *all_launches, int reset);

@@ -363,13 +363,13 @@ int kaamer_gpu_profile_read(kaamer_gpu_t *h, double *kernel_ms, uint64_t *kernel
     cudaEventDestroy(p.b);
   }
   h->prof_pending.clear();
-  for (int c = 0; c < 3; ++c) {
+  for (int c = 0; c < 4; ++c) {
     if (kernel_ms) kernel_ms[c] = h->prof_ms[c];
     if (kernel_launches) kernel_launches[c] = h->prof_launches[c];
   }
   if (all_launches) *all_launches = h->prof_all_launches;
   if (reset) {
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < 4; ++c) {
       h->prof_ms[c] = 0;
       h->prof_launches[c] = 0;
     }

@@ -104,6 +104,7 @@ static int upload_proteins(kaamer_gpu *h, const uint64_t *off, const uint8_t *re
   KCUDA(cudaStreamSynchronize(h->stream));
   ix.n_prot_res = n_res;
   ix.has_proteins = true;
+  ix.h_prot_off.assign(off, off + n_off);
   return KAAMER_OK;
 }
 

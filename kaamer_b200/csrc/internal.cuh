@@ -172,6 +172,7 @@ struct DevIndex {
   // protein table (optional)
   uint64_t *prot_off = nullptr;
   uint8_t *prot_res = nullptr;
+  std::vector<uint64_t> h_prot_off;  // host copy (pair sizing in align.cu)
   uint64_t n_prot_res = 0;
   uint32_t max_protein_id = 0;
   bool has_proteins = false;
@@ -249,8 +250,8 @@ struct kaamer_gpu {
   // profiling
   bool profile = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  double prof_ms[3] = {0, 0, 0};  // per size class S, M, G
-  uint64_t prof_launches[3] = {0, 0, 0};
+  double prof_ms[4] = {0, 0, 0, 0};  // search size classes W, M, G; Smith-Waterman
+  uint64_t prof_launches[4] = {0, 0, 0, 0};
   uint64_t prof_all_launches = 0;
   std::vector<kaamer::ProfSpan> prof_pending;
 };
@@ -291,6 +292,9 @@ __device__ __forceinline__ uint32_t filter_kmin(long long min_kmatch, double rat
   return k > 0xFFFFFFFEll ? 0xFFFFFFFFu : (uint32_t)k;
 }
 #endif
+// align.cu
+int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, const uint32_t *pair_q,
+                const uint32_t *pair_s, uint32_t n_pairs, const kaamer_aln_opts *o, kaamer_aln *out);
 // translate.cu
 int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint32_t nc, OrfSet *out,
                 cudaStream_t st);

@@ -84,6 +84,13 @@ class OrfTable:
         return self.alts[int(self.alts_off[i]):int(self.alts_off[i + 1])].tolist()
 
 
+# kaamer_aln (include/kaamer_gpu.h)
+ALN_DTYPE = np.dtype([("identity", "<f4"), ("similarity", "<f4"), ("length", "<i4"), ("mismatches", "<i4"),
+                      ("gap_openings", "<i4"), ("raw", "<i4"), ("bitscore", "<f8"), ("evalue", "<f8"),
+                      ("query_start", "<i4"), ("query_end", "<i4"), ("subject_start", "<i4"),
+                      ("subject_end", "<i4"), ("dp_score", "<i4"), ("status", "<i4")], align=True)
+
+
 def _arr(ptr, n, dtype):
     if n == 0 or not ptr:
         return np.zeros(0, dtype=dtype)
@@ -258,13 +265,29 @@ class GpuIndex:
         _lib.lib().kaamer_gpu_free_orfs(op)
         return t
 
+    def align(self, q_residues, q_off, pair_query, pair_subject, lambda_: float = 0.267, K: float = 0.041,
+              gap_open: int = 11, gap_extend: int = 1, number_of_aa: int = 0) -> np.ndarray:
+        """align.Align (pkg/align/align.go:46-161) for (query index, subject protein id) pairs;
+        defaults = blosum62_11_1 (pkg/align/matrixScores.go:59).  Returns a structured array
+        with the fields of AlignmentResult (align.go:25-40)."""
+        q_residues = np.ascontiguousarray(q_residues, dtype=np.uint8)
+        q_off = np.ascontiguousarray(q_off, dtype=np.uint64)
+        pq = np.ascontiguousarray(pair_query, dtype=np.uint32)
+        ps = np.ascontiguousarray(pair_subject, dtype=np.uint32)
+        assert len(pq) == len(ps)
+        o = _lib.AlnOpts(lambda_, K, gap_open, gap_extend, number_of_aa)
+        out = np.zeros(len(pq), dtype=ALN_DTYPE)
+        check(_lib.lib().kaamer_gpu_align(self._h, _vp(q_residues), _vp(q_off), _vp(pq), _vp(ps), len(pq),
+                                          C.byref(o), _vp(out)))
+        return out
+
     # ---- profiling ---------------------------------------------------------------------
     def profile_enable(self, on: bool = True):
         check(_lib.lib().kaamer_gpu_profile_enable(self._h, int(on)))
 
     def profile_read(self, reset: bool = True):
-        ms = (C.c_double * 3)()
-        k = (C.c_uint64 * 3)()
+        ms = (C.c_double * 4)()
+        k = (C.c_uint64 * 4)()
         a = C.c_uint64()
         check(_lib.lib().kaamer_gpu_profile_read(self._h, ms, k, C.byref(a), int(reset)))
         return {"kernel_ms": list(ms), "kernel_launches": list(k), "all_launches": a.value}

@@ -1,0 +1,116 @@
+"""GPU parity tests (through the C ABI) of the Smith-Waterman re-alignment stage vs the CPU
+oracle: integer fields bit-exact (DP optimum, raw score, alignment length, mismatches, gap
+openings, coordinates), float32 identity/similarity and float64 bitscore/e-value within 1e-6
+relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6  # stated tolerance for %identity, bitscore, e-value
+INT_FIELDS = ["length", "mismatches", "gap_openings", "raw", "query_start", "query_end", "subject_start",
+              "subject_end", "dp_score"]
+
+
+def _check(gpu_rows, pairs, queries, subjects, prm, what=""):
+    from oracle import oracle as o
+
+    for k, (qi, sid) in enumerate(pairs):
+        exp = o.align(queries[qi], subjects[sid], prm)
+        g = gpu_rows[k]
+        for f in INT_FIELDS:
+            assert int(g[f]) == int(getattr(exp, f)), f"{what} pair {k} (q{qi}, s{sid}): {f} {g[f]} != {getattr(exp, f)}"
+        assert int(g["status"]) == int(exp.illegal), f"{what} pair {k}: status"
+        for f in ("identity", "similarity", "bitscore", "evalue"):
+            a, b = float(g[f]), float(getattr(exp, f))
+            if np.isnan(b):
+                assert np.isnan(a), f"{what} pair {k}: {f} {a} vs NaN"
+            elif np.isinf(b):
+                assert a == b, f"{what} pair {k}: {f} {a} != {b}"
+            else:
+                assert abs(a - b) <= RTOL * abs(b), f"{what} pair {k}: {f} {a} != {b}"
+
+
+def _subjects_by_id(res, off, ids):
+    """protein_store[id] = last accepted record written with that id."""
+    out = {}
+    for i, pid in enumerate(ids.tolist()):
+        s = res[int(off[i]):int(off[i + 1])].tobytes()
+        if len(s) >= 7:
+            out[pid] = s
+    return out
+
+
+def test_align_top_hits_of_a_search(small_db):
+    from kaamer_b200 import GpuIndex, SearchOptions, synth
+    from oracle import oracle as o
+
+    res, off, ids = small_db["res"], small_db["off"], small_db["ids"]
+    subjects = _subjects_by_id(res, off, ids)
+    q, qo, _ = synth.protein_queries(res, off, 120, config_index=1, stream=21)
+    queries = [q[int(qo[i]):int(qo[i + 1])].tobytes() for i in range(len(qo) - 1)]
+    with GpuIndex.build(res, off, ids, keep_proteins=True) as g:
+        r = g.search_proteins(q, qo, SearchOptions(min_kmatch=1, min_kratio=0.0, max_results=4))
+        pairs = [(i, int(s)) for i in range(r.n_rows) for s in r.subject[int(r.hit_off[i]):int(r.hit_off[i + 1])]]
+        assert len(pairs) > 200
+        n_aa = g.dbstats()["NumberOfAA"]
+        out = g.align(q, qo, [p[0] for p in pairs], [p[1] for p in pairs])
+        _check(out, pairs, queries, subjects, o.aln_params(n_aa), "top hits")
+        # a different GapOpen option only changes the `score == -GapOpen` test (align.go:127)
+        out = g.align(q, qo, [p[0] for p in pairs[:60]], [p[1] for p in pairs[:60]], gap_open=10, gap_extend=2,
+                      lambda_=0.3, K=0.1, number_of_aa=12345678)
+        _check(out, pairs[:60], queries, subjects, o.aln_params(12345678, 0.3, 0.1, 10, 2), "opts")
+        assert (out["gap_openings"] == 0).all()
+
+
+def test_align_edge_cases():
+    from kaamer_b200 import GpuIndex
+    from oracle import oracle as o
+
+    rng = np.random.default_rng(5)
+    aa = np.frombuffer(b"ARNDCQEGHILKMFPSTWYV", np.uint8)
+
+    def rnd(n):
+        return aa[rng.integers(0, 20, n)].tobytes()
+
+    def mutate(s, rate, indel=0.02):
+        out = bytearray()
+        for c in s:
+            u = rng.random()
+            if u < indel:
+                continue
+            if u < 2 * indel:
+                out += rnd(int(rng.integers(1, 6)))
+            out.append(c if rng.random() > rate else int(aa[rng.integers(0, 20)]))
+        return bytes(out)
+
+    base = rnd(300)
+    long_a = rnd(1400)
+    subj_list = [
+        base, mutate(base, 0.2), rnd(7), b"MKTAYIAKQRQISFVKSHFSRQLEERLGLIEVQ", b"AAAAAAAAAAAAAAAAAAAAAAAA",
+        b"MKTUUIAKQRQISFuKSHFSRQ*", b"MKTAYIAKQROISFVKSHFSRQ", b"mktayiakqrqisfvkshfsrq", b"MKT-YIAKQ-QISFVKSHFSRQ",
+        long_a, mutate(long_a, 0.3, 0.01), rnd(129), rnd(257), rnd(600), b"WWWWWWWCCCCCCCWWWWWWW",
+        b"BZXJBZXJBZXJ*BZXJ", rnd(5000),
+    ]
+    ids = np.arange(3, 3 + len(subj_list), dtype=np.uint32)
+    res, off = o.pack(subj_list)
+    subjects = {int(i): s for i, s in zip(ids, subj_list)}
+    queries = [
+        base, mutate(base, 0.1), b"", b"A", b"MKTAYIAKQRQISFVKSHFSRQLEERLGLIEVQ", b"MKTAYIAKQRQISFVKSHFSRQ1",
+        b"mktayiakqrqisfvkshfsrq", b"MKTUYIAKQRQISFVKSHFSRQ", b"MKT-YIAKQRQISFVKSHFSRQ", long_a[100:1300],
+        mutate(long_a, 0.15, 0.03), rnd(40), b"WWWWWWWWWWWWWW", b"BZXJBZXJBZXJ*BZXJ", rnd(2500), b"O" * 30,
+    ]
+    q, qo = o.pack(queries)
+    pairs = [(i, int(s)) for i in range(len(queries)) for s in ids]
+    with GpuIndex.build(res, off, ids, keep_proteins=True) as g:
+        out = g.align(q, qo, [p[0] for p in pairs], [p[1] for p in pairs], number_of_aa=3_500_000)
+        _check(out, pairs, queries, subjects, o.aln_params(3_500_000), "edge")
+        assert out["status"].sum() > 0 and (out["gap_openings"] > 0).sum() > 3
+        # empty pair list, unknown subject id, index without proteins
+        assert len(g.align(q, qo, [], [])) == 0
+        from kaamer_b200 import KaamerGpuError
+        with pytest.raises(KaamerGpuError):
+            g.align(q, qo, [0], [10_000])
+    with GpuIndex.build(res, off, ids, keep_proteins=False) as g:
+        with pytest.raises(KaamerGpuError):
+            g.align(q, qo, [0], [3])

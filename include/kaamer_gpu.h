@@ -178,6 +178,36 @@ int kaamer_gpu_search_proteins_device(kaamer_gpu_t *h, const uint8_t *d_residues
                                       const kaamer_opts *opts, const kaamer_dev_result *d_out,
                                       void *stream);
 
+/* ---- key-range sharded search (mode S; new with respect to the single-process
+ * reference: Kmatch is a sum over query k-mers, search.go:431-436, so it decomposes over a
+ * partition of the key space).  Device pointers, asynchronous on `stream`; the all-to-all
+ * exchanges between the steps belong to the caller (NCCL / torch.distributed). ---- */
+uint64_t kaamer_gpu_dense_space(void); /* size of the dense 7-mer code space the fences partition */
+/* step 1, home rank.  fences[n_shards+1] (host): shard s owns dense codes [fences[s], fences[s+1]).
+ * Count pass (d_codes == NULL): d_counts[s*nq + q] = k-mers of query q owned by shard s, and
+ * d_size_in_kmer[q].  Fill pass (d_codes != NULL): d_offsets = exclusive scan of d_counts;
+ * d_codes receives the dense codes in (shard, query) order. */
+int kaamer_gpu_shard_route(kaamer_gpu_t *h, const uint8_t *d_residues, const uint64_t *d_seq_off, uint32_t nq,
+                           const uint64_t *fences, int n_shards, uint32_t *d_counts, const uint64_t *d_offsets,
+                           uint32_t *d_codes, int32_t *d_size_in_kmer, void *stream);
+/* step 2, owner shard.  Segment i = d_codes[d_seg_off[i] .. d_seg_off[i+1]) = one query's k-mers
+ * on this shard.  Emits every (subject | partial count << 32) of the segment into d_pool at
+ * d_part_base[i], d_part_n[i] of them.  d_counters[16]: [0] pool demand, [1] lookups,
+ * [2] increments, [3] status (1 = pool overflow: retry with pool_cap >= demand). */
+int kaamer_gpu_shard_count(kaamer_gpu_t *h, const uint32_t *d_codes, const uint64_t *d_seg_off, uint32_t n_segments,
+                           uint32_t *d_part_n, uint64_t *d_part_base, uint64_t *d_pool, uint64_t pool_cap,
+                           uint64_t *d_counters, void *stream);
+/* pool -> segment order: d_out[d_part_off[i] + j] = pool[d_part_base[i] + j] */
+int kaamer_gpu_shard_gather(kaamer_gpu_t *h, const uint32_t *d_part_n, const uint64_t *d_part_base,
+                            const uint64_t *d_part_off, const uint64_t *d_pool, uint32_t n_segments, uint64_t *d_out,
+                            void *stream);
+/* step 3, home rank.  Partial entries of (shard s, query q) = d_part[d_part_off[s*(nq+1)+q] ..
+ * d_part_off[s*(nq+1)+q+1]).  Sums the partial counts per subject, applies FilterResults
+ * (search.go:189-220) and ranks: same output as kaamer_gpu_search_proteins_device. */
+int kaamer_gpu_shard_merge(kaamer_gpu_t *h, const uint64_t *d_part, const uint64_t *d_part_off, int n_shards,
+                           uint32_t nq, const int32_t *d_size_in_kmer, const kaamer_opts *opts,
+                           const kaamer_dev_result *d_out, void *stream);
+
 /* pinned host buffers for callers that want zero-staging H2D (cgo: C.kaamer_gpu_pinned_alloc) */
 int kaamer_gpu_pinned_alloc(uint64_t bytes, void **out);
 void kaamer_gpu_pinned_free(void *p);

@@ -145,6 +145,11 @@ SYMBOLS = [
     "kaamer_gpu_free_orfs",
     "kaamer_gpu_align",
     "kaamer_gpu_search_proteins_device",
+    "kaamer_gpu_dense_space",
+    "kaamer_gpu_shard_route",
+    "kaamer_gpu_shard_count",
+    "kaamer_gpu_shard_gather",
+    "kaamer_gpu_shard_merge",
     "kaamer_gpu_pinned_alloc",
     "kaamer_gpu_pinned_free",
     "kaamer_gpu_profile_enable",
@@ -189,6 +194,12 @@ def lib() -> C.CDLL:
     L.kaamer_gpu_free_orfs.restype = None
     L.kaamer_gpu_align.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.POINTER(AlnOpts), vp]
     L.kaamer_gpu_search_proteins_device.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(Opts), C.POINTER(DevResult), vp]
+    L.kaamer_gpu_dense_space.restype = C.c_uint64
+    L.kaamer_gpu_dense_space.argtypes = []
+    L.kaamer_gpu_shard_route.argtypes = [vp, vp, vp, C.c_uint32, u64p, C.c_int, vp, vp, vp, vp, vp]
+    L.kaamer_gpu_shard_count.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint64, vp, vp]
+    L.kaamer_gpu_shard_gather.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, vp, vp]
+    L.kaamer_gpu_shard_merge.argtypes = [vp, vp, vp, C.c_int, C.c_uint32, vp, C.POINTER(Opts), C.POINTER(DevResult), vp]
     L.kaamer_gpu_pinned_alloc.argtypes = [C.c_uint64, C.POINTER(vp)]
     L.kaamer_gpu_pinned_free.argtypes = [vp]
     L.kaamer_gpu_pinned_free.restype = None

@@ -23,54 +23,9 @@
 
 #include "internal.cuh"
 
+#include "search_common.cuh"
+
 namespace kaamer {
-
-constexpr uint32_t EMPTY = 0xFFFFFFFFu;
-enum { CNT_POOL = 0, CNT_LOOKUPS = 1, CNT_INCR = 2, CNT_STATUS = 3, CNT_CLS_LOOKUPS = 4, CNT_CLS_INCR = 8, CNT_N = 16 };
-enum { ST_POOL_OVERFLOW = 1, ST_GHASH_OVERFLOW = 2 };
-
-// size classes by SizeInKmer
-constexpr int W_H = 512, W_MAXK = 512, W_WARPS = 8, W_CAND = 64;
-constexpr int M_THREADS = 256, M_H = 4096, M_MAXK = 2048;
-constexpr int G_THREADS = 512;
-constexpr int FAST_C = 64;     // candidates ranked by counting below this, bitonic sort above
-constexpr int BIG_LIST = 32;   // posting lists at least this long are walked by the whole warp
-constexpr int MAX_PROBE = 96;  // linear-probe budget before a histogram is declared full
-
-struct SearchArgs {
-  const uint64_t *table;
-  uint64_t d_lo, d_hi;
-  const uint32_t *postings;
-  const uint8_t *res;
-  const uint64_t *off;
-  uint32_t nq;
-  long long min_kmatch;
-  double min_kratio;
-  int max_results;
-  uint32_t *n_hits, *hit_base;
-  int32_t *size_in_kmer;
-  uint32_t *kmin;
-  uint64_t *pool;
-  uint64_t pool_cap;
-  unsigned long long *counters;
-  uint32_t *lists;       // [3][nq]
-  uint32_t *list_count;  // [8]: [0..2] list sizes, [4..6] work cursors (dynamic scheduling)
-  uint32_t *ghash;       // class G scratch: per CTA [keys HG][cnt HG][cand HG]
-  uint32_t ghash_slots;  // HG (power of two)
-  // nucleotide / reads mode (search_nucleotide.go:76-124): queries are ORFs, the candidate
-  // threshold is the gate `Hits[0].Kmatch >= MinKMatch` (:116) — FilterResults runs later with
-  // the SizeInKmer that SetBestStartCodon leaves (finish.cu) — and any0[q] records whether a
-  // hit tied with the best one, other than the first of them, matches at query position 0
-  // (the only thing SetBestStartCodon reads from later tied hits, dna.go:224-237)
-  int nt_mode;
-  uint8_t *any0;
-};
-
-__device__ __forceinline__ uint64_t ldg_entry(const uint64_t *p) {
-  uint64_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.b64 %0, [%1];" : "=l"(v) : "l"(p));
-  return v;
-}
 
 __global__ void k_classify(SearchArgs a) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,330 +49,6 @@ __global__ void k_classify(SearchArgs a) {
   int cls = K <= W_MAXK ? 0 : (K <= M_MAXK ? 1 : 2);
   uint32_t slot = atomicAdd(&a.list_count[cls], 1u);
   a.lists[(size_t)cls * a.nq + slot] = q;
-}
-
-// ---- histograms -------------------------------------------------------------------------
-// add(id) returns the count BEFORE the increment, or 0xFFFFFFFF when the table is full.
-// Shared-memory flavour: keys u32, counts u16 packed two per word (counts <= SizeInKmer <= 2048).
-struct SmemHash {
-  uint32_t *keys;
-  uint32_t *cnt2;  // [slots/2]
-  uint32_t mask;
-  int shift;  // 32 - log2(slots)
-  __device__ __forceinline__ uint32_t home(uint32_t id) const { return (id * 2654435761u) >> shift; }
-  // claim-or-match: returns the previous key of the slot (EMPTY or id => the slot is ours).
-  // Plain load first: shared-memory atomics are serialised per lane on the SM's atomic unit
-  // (~2 cycles/lane for ADD, twice that for CAS), a repeated subject must not pay the CAS.
-  __device__ __forceinline__ uint32_t cas(uint32_t slot, uint32_t id) const {
-    uint32_t cur = *(volatile uint32_t *)(keys + slot);
-    if (cur == EMPTY) cur = atomicCAS(keys + slot, EMPTY, id);
-    return cur;
-  }
-  __device__ __forceinline__ uint32_t inc(uint32_t slot) const {  // returns the count before
-    uint32_t sh = (slot & 1u) * 16u;
-    uint32_t old = atomicAdd(cnt2 + (slot >> 1), 1u << sh);
-    return (old >> sh) & 0xFFFFu;
-  }
-  __device__ __forceinline__ uint32_t key_at(uint32_t slot) const { return keys[slot]; }
-  __device__ __forceinline__ uint32_t count_at(uint32_t slot) const {
-    return (cnt2[slot >> 1] >> ((slot & 1u) * 16u)) & 0xFFFFu;
-  }
-  static constexpr int kMaxProbe = MAX_PROBE;
-};
-// Global-memory flavour (class G): keys u32, counts u32.
-struct GmemHash {
-  uint32_t *keys;
-  uint32_t *cnt;
-  uint32_t mask;
-  int shift;
-  __device__ __forceinline__ uint32_t home(uint32_t id) const { return (id * 2654435761u) >> shift; }
-  __device__ __forceinline__ uint32_t cas(uint32_t slot, uint32_t id) const { return atomicCAS(keys + slot, EMPTY, id); }
-  __device__ __forceinline__ uint32_t inc(uint32_t slot) const { return atomicAdd(cnt + slot, 1u); }
-  __device__ __forceinline__ uint32_t key_at(uint32_t slot) const { return keys[slot]; }
-  __device__ __forceinline__ uint32_t count_at(uint32_t slot) const { return cnt[slot]; }
-  static constexpr int kMaxProbe = 4 * MAX_PROBE;
-};
-
-// candidate list shared by the lanes/threads that work on one query
-struct CandList {
-  uint32_t *ncand;  // smem counter
-  uint32_t *flags;  // smem: bit0 histogram full, bit1 candidate list full
-  uint16_t *slots16;
-  uint32_t *slots32;
-  uint32_t cap;
-};
-
-__device__ __forceinline__ void push_candidate(const CandList &cl, uint32_t slot) {
-  uint32_t i = atomicAdd(cl.ncand, 1u);
-  if (i < cl.cap) {
-    if (cl.slots16) cl.slots16[i] = (uint16_t)slot;
-    else cl.slots32[i] = slot;
-  } else {
-    atomicOr(cl.flags, 2u);
-  }
-}
-
-// One increment + candidate bookkeeping (general path: linear probing from `slot`).  The
-// subject becomes a candidate exactly when its count reaches kmin (counts only grow), so no
-// scan of the histogram is needed afterwards.
-template <class Hash>
-__device__ __noinline__ void count_subject_from(const Hash hv, uint32_t id, uint32_t slot, uint32_t kmin,
-                                                const CandList cl) {
-#pragma unroll 1
-  for (int probe = 0; probe < Hash::kMaxProbe; ++probe) {
-    uint32_t cur = hv.cas(slot, id);
-    if (cur == EMPTY || cur == id) {
-      if (hv.inc(slot) + 1 == kmin) push_candidate(cl, slot);
-      return;
-    }
-    slot = (slot + 1) & hv.mask;
-  }
-  atomicOr(cl.flags, 1u);  // histogram full
-}
-template <class Hash>
-__device__ __forceinline__ void count_subject(const Hash &hv, uint32_t id, uint32_t kmin, const CandList &cl) {
-  const uint32_t slot = hv.home(id);
-  const uint32_t cur = hv.cas(slot, id);
-  if (cur == EMPTY || cur == id) {
-    if (hv.inc(slot) + 1 == kmin) push_candidate(cl, slot);
-  } else {
-    count_subject_from(hv, id, (slot + 1) & hv.mask, kmin, cl);
-  }
-}
-
-// ---- warp-private histogram (class W): NO atomics --------------------------------------
-// The table belongs to one warp whose lanes run in lockstep, so duplicates inside a batch of 32
-// ids are merged with __match_any_sync and slots are claimed by write-then-verify.  This
-// removes every shared-memory atomic from the counting loop (ncu: the per-SM atomic unit was
-// the limiter of the atomic version).
-struct WarpHash {
-  uint32_t *keys;   // [W_H]
-  uint16_t *cnt;    // [W_H]
-  static constexpr uint32_t mask = W_H - 1;
-  static constexpr int kMaxProbe = MAX_PROBE;
-  __device__ __forceinline__ uint32_t home(uint32_t id) const { return (id * 2654435761u) >> (32 - 9); }
-  __device__ __forceinline__ uint32_t key_at(uint32_t slot) const { return keys[slot]; }
-  __device__ __forceinline__ uint32_t count_at(uint32_t slot) const { return cnt[slot]; }
-};
-
-// count of a subject after the histogram is complete (0 if absent)
-template <class Hash>
-__device__ __forceinline__ uint32_t hist_count(const Hash &hv, uint32_t id) {
-  uint32_t slot = hv.home(id);
-#pragma unroll 1
-  for (int probe = 0; probe < Hash::kMaxProbe; ++probe) {
-    const uint32_t k = hv.key_at(slot);
-    if (k == id) return hv.count_at(slot);
-    if (k == EMPTY) return 0;
-    slot = (slot + 1) & hv.mask;
-  }
-  return 0;
-}
-
-// nucleotide mode, one warp: does a subject tied with the best hit (count T), other than the
-// best hit itself, hold the query's first k-mer (dense code d0)?
-template <class Hash>
-__device__ __noinline__ bool warp_any0(const SearchArgs &a, const Hash &hv, uint32_t d0, uint32_t best_id, uint32_t T) {
-  const unsigned lane = threadIdx.x & 31;
-  bool any = false;
-  if (d0 >= a.d_lo && d0 < a.d_hi) {
-    const uint64_t e = ldg_entry(a.table + (d0 - a.d_lo));
-    const uint32_t cnt = (uint32_t)(e >> ENTRY_VALUE_BITS);
-    const uint64_t val = e & ENTRY_VALUE_MASK;
-    if (cnt == 1) {
-      const uint32_t id = (uint32_t)val;
-      any = id != best_id && hist_count(hv, id) == T;
-    } else {
-      for (uint32_t i = lane; i < cnt; i += 32) {
-        const uint32_t id = __ldg(a.postings + val + i);
-        if (id != best_id && hist_count(hv, id) == T) any = true;
-      }
-    }
-  }
-  return __any_sync(0xFFFFFFFFu, any);
-}
-
-// all 32 lanes call this together; lanes with valid==false only take part in the votes
-__device__ __forceinline__ void warp_count(const WarpHash &hv, bool valid, uint32_t id, uint32_t kmin,
-                                           const CandList &cl) {
-  const unsigned lane = threadIdx.x & 31;
-  const unsigned act = __ballot_sync(0xFFFFFFFFu, valid);
-  if (act == 0) return;
-  unsigned peers = 0;
-  if (valid) peers = __match_any_sync(act, id);
-  const uint32_t mult = __popc(peers);
-  bool pending = valid && (lane == (unsigned)(__ffs(peers) - 1));  // one leader per distinct id
-  uint32_t slot = (id * 2654435761u) >> (32 - 9);
-  static_assert(W_H == 512, "hash shift assumes 512 slots");
-#pragma unroll 1
-  for (int probe = 0; probe < MAX_PROBE; ++probe) {
-    if (!__any_sync(0xFFFFFFFFu, pending)) return;
-    uint32_t key = pending ? hv.keys[slot] : 0u;
-    const bool claim = pending && key == EMPTY;
-    if (claim) hv.keys[slot] = id;  // racing leaders with different ids: one store survives
-    __syncwarp();
-    if (claim) key = hv.keys[slot];
-    if (pending) {
-      if (key == id) {
-        const uint32_t c = hv.cnt[slot];
-        hv.cnt[slot] = (uint16_t)(c + mult);
-        if (c < kmin && c + mult >= kmin) push_candidate(cl, slot);
-        pending = false;
-      } else {
-        slot = (slot + 1) & (W_H - 1);
-      }
-    }
-    __syncwarp();
-  }
-  if (__any_sync(0xFFFFFFFFu, pending)) {
-    if (pending) atomicOr(cl.flags, 1u);
-  }
-}
-
-// ---- one warp-round of lookups ------------------------------------------------------------
-// Every lane holds up to U table entries.  Singletons are counted directly; short posting
-// lists (2..BIG_LIST-1) of the whole warp are flattened (warp scan + search by shuffles) so
-// that all 32 lanes fetch and count postings together; long lists are walked cooperatively.
-template <int U, class Hash>
-__device__ __forceinline__ void warp_consume(const SearchArgs &a, const uint64_t (&ent)[U], const Hash &hv,
-                                             uint32_t kmin, const CandList &cl, unsigned long long &q_incr) {
-  const unsigned lane = threadIdx.x & 31;
-  uint32_t m[U];  // postings of this lane's short multi lists
-  uint32_t vlo[U];
-  uint32_t vhi = 0;  // 4 high bits of each value, packed
-  uint32_t mt = 0;
-  bool any_big = false;
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const uint32_t cnt = (uint32_t)(ent[u] >> ENTRY_VALUE_BITS);
-    const uint64_t val = ent[u] & ENTRY_VALUE_MASK;
-    q_incr += cnt;
-    vlo[u] = (uint32_t)val;
-    vhi |= (uint32_t)(val >> 32) << (4 * u);
-    m[u] = (cnt >= 2 && cnt < BIG_LIST) ? cnt : 0u;
-    mt += m[u];
-    any_big |= cnt >= BIG_LIST;
-  }
-  // (1) singletons
-  if constexpr (std::is_same<Hash, WarpHash>::value) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) warp_count(hv, (uint32_t)(ent[u] >> ENTRY_VALUE_BITS) == 1u, vlo[u], kmin, cl);
-  } else {
-    // the first probe of all U entries is issued back to back (independent shared-memory
-    // operations in flight), collisions fall back to the probing loop
-    uint32_t slot[U], cur[U];
-    bool act[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      act[u] = (uint32_t)(ent[u] >> ENTRY_VALUE_BITS) == 1u;
-      slot[u] = hv.home(vlo[u]);
-      cur[u] = act[u] ? hv.cas(slot[u], vlo[u]) : 0u;
-    }
-    uint32_t old[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const bool mine = act[u] && (cur[u] == EMPTY || cur[u] == vlo[u]);
-      old[u] = mine ? hv.inc(slot[u]) : 0xFFFFFFFEu;
-      act[u] = act[u] && !mine;  // still pending
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (old[u] + 1 == kmin) push_candidate(cl, slot[u]);
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (act[u]) count_subject_from(hv, vlo[u], (slot[u] + 1) & hv.mask, kmin, cl);
-  }
-  // (2) short lists, flattened across the warp
-  uint32_t incl = mt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= (unsigned)o) incl += t;
-  }
-  const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-  const uint32_t excl = incl - mt;
-#pragma unroll 1
-  for (uint32_t jb = 0; jb < total; jb += 32) {
-    const uint32_t j = jb + lane;
-    uint32_t owner = 0;
-#pragma unroll
-    for (int step = 16; step >= 1; step >>= 1) {
-      uint32_t v = __shfl_sync(0xFFFFFFFFu, incl, (owner + step - 1) & 31);
-      if (v <= j) owner += step;
-    }
-    owner &= 31;
-    uint32_t r = j - __shfl_sync(0xFFFFFFFFu, excl, owner);
-    const uint32_t ohi = __shfl_sync(0xFFFFFFFFu, vhi, owner);
-    uint32_t sel_lo = 0, sel_hi = 0;
-    bool found = false;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      uint32_t mu = __shfl_sync(0xFFFFFFFFu, m[u], owner);
-      uint32_t lo = __shfl_sync(0xFFFFFFFFu, vlo[u], owner);
-      if (!found) {
-        if (r < mu) {
-          sel_lo = lo;
-          sel_hi = (ohi >> (4 * u)) & 0xFu;
-          found = true;
-        } else {
-          r -= mu;
-        }
-      }
-    }
-    uint32_t pid = 0;
-    if (j < total) pid = __ldg(a.postings + (((uint64_t)sel_hi << 32) | sel_lo) + r);
-    if constexpr (std::is_same<Hash, WarpHash>::value) {
-      warp_count(hv, j < total, pid, kmin, cl);
-    } else {
-      if (j < total) count_subject(hv, pid, kmin, cl);
-    }
-  }
-  // (3) long lists: the whole warp walks each of them (coalesced)
-  if (__any_sync(0xFFFFFFFFu, any_big)) {
-#pragma unroll 1
-    for (int u = 0; u < U; ++u) {
-      uint64_t e = ent[0];
-#pragma unroll
-      for (int t = 1; t < U; ++t)
-        if (u == t) e = ent[t];
-      const uint32_t cnt = (uint32_t)(e >> ENTRY_VALUE_BITS);
-      unsigned big = __ballot_sync(0xFFFFFFFFu, cnt >= BIG_LIST);
-      while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        const uint32_t bc = __shfl_sync(0xFFFFFFFFu, cnt, src);
-        const uint64_t bv = __shfl_sync(0xFFFFFFFFu, e & ENTRY_VALUE_MASK, src);
-        if constexpr (std::is_same<Hash, WarpHash>::value) {
-          for (uint32_t ib = 0; ib < bc; ib += 32) {
-            const uint32_t i = ib + lane;
-            warp_count(hv, i < bc, i < bc ? __ldg(a.postings + bv + i) : 0u, kmin, cl);
-          }
-        } else {
-          for (uint32_t i = lane; i < bc; i += 32) {
-            if (*(volatile uint32_t *)cl.flags & 1u) break;
-            count_subject(hv, __ldg(a.postings + bv + i), kmin, cl);
-          }
-        }
-      }
-    }
-  }
-}
-
-// packed per-position code: bits 0..8 pair code p'(c_i, c_i+1), bits 9..13 single code s(c_i)
-__device__ __forceinline__ uint32_t packed_code(uint32_t c0, uint32_t c1) {
-  return pair_dense(c0, c1) | (single_dense(c0) << 9);
-}
-__device__ __forceinline__ uint32_t dense_from_packed(uint32_t w0, uint32_t w2, uint32_t w4, uint32_t w6) {
-  return (((w0 & 511u) * PAIR_RADIX + (w2 & 511u)) * PAIR_RADIX + (w4 & 511u)) * 21u + (w6 >> 9);
-}
-
-// composite sort key: ascending order == (Kmatch desc, subject id asc)
-__device__ __forceinline__ uint64_t composite(uint32_t id, uint32_t cnt) {
-  return ((uint64_t)(0xFFFFFFFFu - cnt) << 32) | id;
-}
-__device__ __forceinline__ uint64_t decomposite(uint64_t c) {
-  uint32_t cnt = 0xFFFFFFFFu - (uint32_t)(c >> 32);
-  return ((uint64_t)cnt << 32) | (uint32_t)c;  // pool format: subject | kmatch << 32
 }
 
 // ---- class W: one warp per query ------------------------------------------------------------
@@ -570,125 +201,6 @@ __global__ void __launch_bounds__(W_WARPS * 32, 5) k_search_w(SearchArgs a) {
       atomicAdd(&a.counters[CNT_LOOKUPS], my_lookups);
       atomicAdd(&a.counters[CNT_CLS_LOOKUPS + 0], my_lookups);
     }
-  }
-}
-
-// ---- classes M and G: one CTA per query -----------------------------------------------------
-struct SelectScratch {
-  uint32_t hist[256];
-  uint32_t ncand, flags, nout, remaining;
-  unsigned long long base;
-  unsigned long long prefix;
-};
-
-// Candidate i lives in histogram slot cand(i).  Emits the top-N candidates into the pool in
-// rank order and records n_hits / hit_base.
-template <int THREADS, class Hash, class CandAt>
-__device__ void select_and_emit(const SearchArgs &a, uint32_t q, const Hash &hv, CandAt cand, uint32_t c,
-                                SelectScratch &ss) {
-  const int tid = threadIdx.x;
-  const uint32_t N = a.max_results > 0 ? (uint32_t)a.max_results : 0u;
-  const uint32_t nout = c < N ? c : N;
-  if (nout == 0) return;  // n_hits / hit_base were zeroed by k_classify
-  if (c <= FAST_C) {
-    if (tid == 0) ss.base = atomicAdd(&a.counters[CNT_POOL], (unsigned long long)nout);
-    __syncthreads();
-    const unsigned long long base = ss.base;
-    const bool fits = base + nout <= a.pool_cap;
-    if (tid < (int)c) {
-      uint32_t s = cand(tid);
-      uint64_t me = composite(hv.key_at(s), hv.count_at(s));
-      uint32_t rank = 0;
-      for (uint32_t j = 0; j < c; ++j) {
-        uint32_t sj = cand(j);
-        rank += composite(hv.key_at(sj), hv.count_at(sj)) < me ? 1u : 0u;
-      }
-      if (rank < nout && fits) a.pool[base + rank] = decomposite(me);
-    }
-    if (tid == 0) {
-      if (fits) {
-        a.n_hits[q] = nout;
-        a.hit_base[q] = (uint32_t)base;
-      } else {
-        atomicOr(&a.counters[CNT_STATUS], (unsigned long long)ST_POOL_OVERFLOW);
-      }
-    }
-    return;
-  }
-  // slow path: (1) radix-select the N-th smallest composite when c > N, (2) write the kept
-  // composites to a power-of-two pool segment padded with +inf, (3) bitonic sort in place.
-  unsigned long long thresh = ~0ull;
-  if (c > N) {
-    if (tid == 0) {
-      ss.prefix = 0;
-      ss.remaining = N;  // N >= 1 here
-    }
-    for (int byte = 7; byte >= 0; --byte) {
-      for (int i = tid; i < 256; i += THREADS) ss.hist[i] = 0;
-      __syncthreads();
-      const unsigned long long prefix = ss.prefix;
-      const unsigned long long himask = byte == 7 ? 0ull : (~0ull << (8 * (byte + 1)));
-      for (uint32_t i = tid; i < c; i += THREADS) {
-        uint32_t s = cand(i);
-        uint64_t k = composite(hv.key_at(s), hv.count_at(s));
-        if ((k & himask) == prefix) atomicAdd(&ss.hist[(k >> (8 * byte)) & 0xFF], 1u);
-      }
-      __syncthreads();
-      if (tid == 0) {
-        uint32_t rem = ss.remaining, acc = 0;
-        int b = 0;
-        for (; b < 256; ++b) {
-          if (acc + ss.hist[b] >= rem) break;
-          acc += ss.hist[b];
-        }
-        ss.remaining = rem - acc;
-        ss.prefix = prefix | ((unsigned long long)b << (8 * byte));
-      }
-      __syncthreads();
-    }
-    thresh = ss.prefix;  // exactly N composites are <= thresh (keys are unique)
-  }
-  uint32_t P = 1;
-  while (P < nout) P <<= 1;
-  if (tid == 0) {
-    ss.base = atomicAdd(&a.counters[CNT_POOL], (unsigned long long)P);
-    ss.nout = 0;
-  }
-  __syncthreads();
-  const unsigned long long base = ss.base;
-  const bool fits = base + P <= a.pool_cap;
-  if (!fits) {
-    if (tid == 0) atomicOr(&a.counters[CNT_STATUS], (unsigned long long)ST_POOL_OVERFLOW);
-    return;
-  }
-  uint64_t *seg = a.pool + base;
-  for (uint32_t i = tid; i < c; i += THREADS) {
-    uint32_t s = cand(i);
-    uint64_t k = composite(hv.key_at(s), hv.count_at(s));
-    if (k <= thresh) seg[atomicAdd(&ss.nout, 1u)] = k;
-  }
-  for (uint32_t i = nout + tid; i < P; i += THREADS) seg[i] = ~0ull;
-  __syncthreads();
-  for (uint32_t k = 2; k <= P; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t i = tid; i < P; i += THREADS) {
-        uint32_t l = i ^ j;
-        if (l > i) {
-          uint64_t x = seg[i], y = seg[l];
-          bool up = (i & k) == 0;
-          if ((x > y) == up) {
-            seg[i] = y;
-            seg[l] = x;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-  for (uint32_t i = tid; i < nout; i += THREADS) seg[i] = decomposite(seg[i]);
-  if (tid == 0) {
-    a.n_hits[q] = nout;
-    a.hit_base[q] = (uint32_t)base;
   }
 }
 

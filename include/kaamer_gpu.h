@@ -212,10 +212,11 @@ int kaamer_gpu_shard_merge(kaamer_gpu_t *h, const uint64_t *d_part, const uint64
 int kaamer_gpu_pinned_alloc(uint64_t bytes, void **out);
 void kaamer_gpu_pinned_free(void *p);
 
-/* per-handle kernel timing: CUDA events on the launching stream around each hot kernel:
- * kernel_ms[4], kernel_launches[4] = search size classes W, M, G and the Smith-Waterman
- * kernel; all_launches counts every kernel the library launched since the last reset
- * (bench.py roofline / gpu_launches) */
+/* per-handle timing: CUDA events on the launching stream around each hot stage.
+ * kernel_ms[8], kernel_launches[8]: [0..2] search size classes W, M, G; [3] Smith-Waterman;
+ * [4] host->device copies of a host-buffer call; [5] CSR compaction + device->host; [6] reserved;
+ * [7] translation / ORF kernels.  all_launches counts every kernel the library launched since
+ * the last reset (bench.py roofline / gpu_launches) */
 int kaamer_gpu_profile_enable(kaamer_gpu_t *h, int on);
 int kaamer_gpu_profile_read(kaamer_gpu_t *h, double *kernel_ms, uint64_t *kernel_launches,
                             uint64_t *all_launches, int reset);

@@ -17,6 +17,60 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+// ---- pinned block cache ------------------------------------------------------------------
+static std::mutex g_pin_mu;
+static std::vector<std::pair<void *, size_t>> g_pin_free;
+static size_t g_pin_cached = 0;
+constexpr size_t PIN_CACHE_MAX = 4ull << 30;
+
+void *pinned_get(size_t bytes, size_t *cap) {
+  size_t c = 4096;
+  while (c < bytes) c <<= 1;
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (size_t i = 0; i < g_pin_free.size(); ++i)
+      if (g_pin_free[i].second == c) {
+        void *p = g_pin_free[i].first;
+        g_pin_free[i] = g_pin_free.back();
+        g_pin_free.pop_back();
+        g_pin_cached -= c;
+        *cap = c;
+        return p;
+      }
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, c, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    // drop the cache and retry once
+    {
+      std::lock_guard<std::mutex> lk(g_pin_mu);
+      for (auto &b : g_pin_free) cudaFreeHost(b.first);
+      g_pin_free.clear();
+      g_pin_cached = 0;
+    }
+    e = cudaHostAlloc(&p, c, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+      set_error("cudaHostAlloc(%zu bytes): %s", c, cudaGetErrorString(e));
+      return nullptr;
+    }
+  }
+  *cap = c;
+  return p;
+}
+
+void pinned_put(void *p, size_t cap) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (g_pin_cached + cap <= PIN_CACHE_MAX) {
+      g_pin_free.emplace_back(p, cap);
+      g_pin_cached += cap;
+      return;
+    }
+  }
+  cudaFreeHost(p);
+}
+
 // ---- .kidx container (little-endian; sections 64-byte aligned) ------------------------
 struct KidxHeader {
   char magic[8];  // "KIDX0001"
@@ -74,6 +128,9 @@ static int new_handle(int device, kaamer_gpu **out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->chunk_ev[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->done_ev, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     set_error("cudaStreamCreate: %s", cudaGetErrorString(e));
     delete h;
@@ -93,6 +150,10 @@ static void destroy_handle(kaamer_gpu *h) {
     cudaEventDestroy(p.b);
   }
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int i = 0; i < 8; ++i)
+    if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
+  if (h->done_ev) cudaEventDestroy(h->done_ev);
   delete h;
 }
 
@@ -363,13 +424,13 @@ int kaamer_gpu_profile_read(kaamer_gpu_t *h, double *kernel_ms, uint64_t *kernel
     cudaEventDestroy(p.b);
   }
   h->prof_pending.clear();
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 8; ++c) {
     if (kernel_ms) kernel_ms[c] = h->prof_ms[c];
     if (kernel_launches) kernel_launches[c] = h->prof_launches[c];
   }
   if (all_launches) *all_launches = h->prof_all_launches;
   if (reset) {
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 8; ++c) {
       h->prof_ms[c] = 0;
       h->prof_launches[c] = 0;
     }

@@ -218,21 +218,23 @@ struct ProfSpan {
   int cls = 0;
 };
 
+// process-wide cache of pinned host blocks (api.cu): cudaHostAlloc / cudaFreeHost cost
+// hundreds of microseconds each, result buffers are recycled instead
+void *pinned_get(size_t bytes, size_t *cap);
+void pinned_put(void *p, size_t cap);
+
 // owner of the pinned host buffers behind a kaamer_hits / kaamer_orfs
 struct HitsOwner {
-  std::vector<void *> pinned;
+  std::vector<std::pair<void *, size_t>> pinned;
   ~HitsOwner() {
-    for (void *p : pinned) cudaFreeHost(p);
+    for (auto &p : pinned) pinned_put(p.first, p.second);
   }
   template <class T>
   int alloc(T **out, size_t n) {
-    void *p = nullptr;
-    cudaError_t e = cudaMallocHost(&p, (n ? n : 1) * sizeof(T));
-    if (e != cudaSuccess) {
-      set_error("cudaMallocHost: %s", cudaGetErrorString(e));
-      return KAAMER_ERR_NOMEM;
-    }
-    pinned.push_back(p);
+    size_t cap = 0;
+    void *p = pinned_get((n ? n : 1) * sizeof(T), &cap);
+    if (!p) return KAAMER_ERR_NOMEM;  // error text set by pinned_get
+    pinned.emplace_back(p, cap);
     *out = (T *)p;
     return KAAMER_OK;
   }
@@ -250,8 +252,14 @@ struct kaamer_gpu {
   // profiling
   bool profile = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  double prof_ms[4] = {0, 0, 0, 0};  // search size classes W, M, G; Smith-Waterman
-  uint64_t prof_launches[4] = {0, 0, 0, 0};
+  // [0..2] search size classes W, M, G; [3] Smith-Waterman; [4] H2D of a host call; [5] CSR
+  // compaction + D2H; [6] reserved; [7] translation/ORF kernels
+  double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t prof_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // host-call pipeline: H2D of chunk c+1 on copy_stream overlaps the search of chunk c
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t done_ev = nullptr;
   uint64_t prof_all_launches = 0;
   std::vector<kaamer::ProfSpan> prof_pending;
 };
@@ -265,7 +273,7 @@ void index_release(kaamer_gpu *h);
 // search.cu
 int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint32_t nq,
                            const kaamer_opts *o, const kaamer_dev_result *out, cudaStream_t st, int nt_mode = 0,
-                           uint8_t *d_any0 = nullptr);
+                           uint8_t *d_any0 = nullptr, const uint64_t *d_prev_counters = nullptr);
 int search_counted(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint32_t nq, const kaamer_opts *o,
                    int nt_mode, uint8_t *d_any0, cudaStream_t st);
 int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off, uint32_t nq,

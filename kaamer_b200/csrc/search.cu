@@ -19,6 +19,7 @@
 // HBM traffic per k-mer: 1 B residue + one 8 B entry (one 64 B HBM access) [+ 4 B per
 // posting when the list is not a singleton].  Counts never touch HBM for classes W and M.
 // Measured ceiling of the probe stage on B200: 36.5 G random probes/s (profiles/).
+#include <algorithm>
 #include <type_traits>
 
 #include "internal.cuh"
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(W_WARPS * 32, 5) k_search_w(SearchArgs a) {
   const WarpHash hv{s.hkeys, s.hcnt};
   const CandList cl{&s.ncand, &s.flags, s.cand, nullptr, (uint32_t)W_CAND};
   const uint32_t count = a.list_count[0];
+  const uint8_t *res_end = a.res + a.off[a.nq];
   const uint32_t nwarps = gridDim.x * W_WARPS;
   const uint32_t N = a.max_results > 0 ? (uint32_t)a.max_results : 0u;
   unsigned long long my_incr = 0, my_lookups = 0;
@@ -88,6 +90,20 @@ __global__ void __launch_bounds__(W_WARPS * 32, 5) k_search_w(SearchArgs a) {
     const int len = (int)(a.off[q + 1] - b);
     const int K = a.size_in_kmer[q];
     const uint32_t kmin = a.kmin[q];
+    // residues -> packed codes; the raw bytes are staged in the (not yet cleared) histogram
+    {
+      uint8_t *raw = reinterpret_cast<uint8_t *>(s.hkeys);
+      const int head = stage_bytes<32>(raw, a.res + b, len, res_end, (int)lane);
+      __syncwarp();
+      const uint8_t *r = raw + head;
+      const int ncodes = K + KAAMER_KMER_SIZE - 1;
+      for (int i = lane; i < ncodes; i += 32) {
+        uint32_t c0 = lut[r[i]];
+        uint32_t c1 = (i + 1 < len) ? (uint32_t)lut[r[i + 1]] : CODE_UNKNOWN;
+        s.pp[i] = (uint16_t)packed_code(c0, c1);
+      }
+      __syncwarp();
+    }
     // clear the histogram (16-byte stores)
     {
       uint4 *hk = reinterpret_cast<uint4 *>(s.hkeys);
@@ -101,14 +117,6 @@ __global__ void __launch_bounds__(W_WARPS * 32, 5) k_search_w(SearchArgs a) {
         s.ncand = 0;
         s.flags = 0;
       }
-    }
-    // residues -> packed codes
-    const uint8_t *r = a.res + b;
-    const int ncodes = K + KAAMER_KMER_SIZE - 1;
-    for (int i = lane; i < ncodes; i += 32) {
-      uint32_t c0 = lut[r[i]];
-      uint32_t c1 = (i + 1 < len) ? (uint32_t)lut[r[i + 1]] : CODE_UNKNOWN;
-      s.pp[i] = (uint16_t)packed_code(c0, c1);
     }
     __syncwarp();
     unsigned long long q_incr = 0;
@@ -204,11 +212,11 @@ __global__ void __launch_bounds__(W_WARPS * 32, 5) k_search_w(SearchArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(M_THREADS) k_search_m(SearchArgs a) {
+__global__ void __launch_bounds__(M_THREADS, 5) k_search_m(SearchArgs a) {
   __shared__ __align__(16) uint32_t hkeys[M_H];
   __shared__ __align__(16) uint32_t hcnt2[M_H / 2];
   __shared__ uint16_t pp[M_MAXK + 8];
-  __shared__ uint16_t cand[M_H];  // one entry per slot: can never overflow
+  __shared__ __align__(16) uint16_t cand[M_H];  // one entry per slot: can never overflow
   __shared__ uint8_t lut[256];
   __shared__ SelectScratch ss;
   constexpr int THREADS = M_THREADS;
@@ -218,6 +226,7 @@ __global__ void __launch_bounds__(M_THREADS) k_search_m(SearchArgs a) {
   const SmemHash hv{hkeys, hcnt2, (uint32_t)M_H - 1u, 32 - 12};
   const CandList cl{&ss.ncand, &ss.flags, cand, nullptr, (uint32_t)M_H};
   const uint32_t count = a.list_count[1];
+  const uint8_t *res_end = a.res + a.off[a.nq];
   unsigned long long my_incr = 0, my_lookups = 0;
   __shared__ uint32_t s_it;
   for (;;) {
@@ -241,7 +250,11 @@ __global__ void __launch_bounds__(M_THREADS) k_search_m(SearchArgs a) {
         ss.flags = 0;
       }
     }
-    const uint8_t *r = a.res + b;
+    // raw residues staged in the (idle) candidate list with aligned 16-byte loads
+    uint8_t *raw = reinterpret_cast<uint8_t *>(cand);
+    const int head = stage_bytes<THREADS>(raw, a.res + b, len, res_end, tid);
+    __syncthreads();
+    const uint8_t *r = raw + head;
     const int ncodes = K + KAAMER_KMER_SIZE - 1;
     for (int i = tid; i < ncodes; i += THREADS) {
       uint32_t c0 = lut[r[i]];
@@ -313,7 +326,9 @@ __global__ void __launch_bounds__(M_THREADS) k_search_m(SearchArgs a) {
 }
 
 // class G: histogram in global memory (per-CTA scratch, stays in L2), codes computed on the fly
+constexpr int G_STAGE = 40 * 1024;
 __global__ void __launch_bounds__(G_THREADS) k_search_g(SearchArgs a) {
+  __shared__ __align__(16) uint8_t s_res[G_STAGE];
   __shared__ SelectScratch ss;
   __shared__ unsigned long long s_total;
   constexpr int THREADS = G_THREADS;
@@ -323,13 +338,22 @@ __global__ void __launch_bounds__(G_THREADS) k_search_g(SearchArgs a) {
   uint32_t *gcnt = gkeys + HG;
   uint32_t *gcand = gcnt + HG;
   const uint32_t count = a.list_count[2];
+  const uint8_t *res_end = a.res + a.off[a.nq];
   unsigned long long my_incr = 0, my_lookups = 0;
   for (uint32_t it = blockIdx.x; it < count; it += gridDim.x) {
     const uint32_t q = a.lists[(size_t)2 * a.nq + it];
     const uint64_t b = a.off[q];
     const int K = a.size_in_kmer[q];
     const uint32_t kmin = a.kmin[q];
-    const uint8_t *s = a.res + b;
+    // stage the query in shared memory (it is read 14 times per position below, and may live in
+    // pinned host memory when the caller's buffer is used without a copy)
+    const int len = (int)(a.off[q + 1] - b);
+    const bool staged = len + 31 <= G_STAGE;
+    __syncthreads();
+    int head = 0;
+    if (staged) head = stage_bytes<THREADS>(s_res, a.res + b, len, res_end, tid);
+    __syncthreads();
+    const uint8_t *s = staged ? s_res + head : a.res + b;
     auto dense_at = [&](int pos) -> uint32_t {
       return dense_from_codes(aa_code(s[pos]), aa_code(s[pos + 1]), aa_code(s[pos + 2]), aa_code(s[pos + 3]),
                               aa_code(s[pos + 4]), aa_code(s[pos + 5]), aa_code(s[pos + 6]));
@@ -449,13 +473,17 @@ __global__ void __launch_bounds__(1024) k_scan_hits(const uint32_t *__restrict__
 
 __global__ void k_gather_hits(const uint32_t *__restrict__ n_hits, const uint32_t *__restrict__ hit_base,
                               const uint64_t *__restrict__ hit_off, const uint64_t *__restrict__ pool,
-                              uint32_t nq, uint64_t *out) {
+                              uint32_t nq, uint32_t *subject, uint32_t *kmatch) {
   // one warp per query
   uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= nq) return;
   uint32_t n = n_hits[q];
   uint64_t src = hit_base[q], dst = hit_off[q];
-  for (uint32_t i = threadIdx.x & 31; i < n; i += 32) out[dst + i] = pool[src + i];
+  for (uint32_t i = threadIdx.x & 31; i < n; i += 32) {
+    const uint64_t v = pool[src + i];
+    subject[dst + i] = (uint32_t)v;
+    kmatch[dst + i] = (uint32_t)(v >> 32);
+  }
 }
 
 // ---- launch ---------------------------------------------------------------------------
@@ -480,7 +508,7 @@ static uint32_t ghash_slots_for(kaamer_gpu *h) {
 
 int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint32_t nq,
                            const kaamer_opts *o, const kaamer_dev_result *out, cudaStream_t st, int nt_mode,
-                           uint8_t *d_any0) {
+                           uint8_t *d_any0, const uint64_t *d_prev_counters) {
   if (!h->idx.table) {
     set_error("no index resident");
     return KAAMER_ERR_ARG;
@@ -518,6 +546,8 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   a.ghash = ws.ghash.p;
   KCUDA(cudaMemsetAsync(list_count, 0, 8 * sizeof(uint32_t), st));
   KCUDA(cudaMemsetAsync(out->counters, 0, CNT_N * sizeof(uint64_t), st));
+  if (d_prev_counters)  // chunked host call: the pool cursor continues where the previous chunk stopped
+    KCUDA(cudaMemcpyAsync(out->counters + CNT_POOL, d_prev_counters + CNT_POOL, 8, cudaMemcpyDeviceToDevice, st));
   k_classify<<<(nq + 255) / 256, 256, 0, st>>>(a);
   // persistent grids: a multiple of the SM count, warps / CTAs loop over their class list
   const unsigned w_grid = (unsigned)h->sm_count * 5u;
@@ -622,44 +652,121 @@ int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off,
     set_error("seq_off[0] must be 0");
     return fail(KAAMER_ERR_ARG);
   }
-  HCHECK(ws.residues.ensure((size_t)n_res + 16));
   HCHECK(ws.seq_off.ensure((size_t)nq + 1));
-  HCUDA(cudaMemcpyAsync(ws.residues.p, res, (size_t)n_res, cudaMemcpyHostToDevice, st));
-  HCUDA(cudaMemcpyAsync(ws.seq_off.p, off, ((size_t)nq + 1) * 8, cudaMemcpyHostToDevice, st));
-  HCHECK(search_counted(h, ws.residues.p, ws.seq_off.p, nq, o, 0, nullptr, st));
-  hits->n_lookups = ws.h_counters.p[CNT_LOOKUPS];
-  hits->n_increments = ws.h_counters.p[CNT_INCR];
+  // Residues: a pinned (page-locked, device-mapped) caller buffer — kaamer_gpu_pinned_alloc, or
+  // any cudaHostAlloc/cudaHostRegister memory — is read by the kernels IN PLACE over PCIe: every
+  // residue is needed exactly once, so the transfer overlaps the table probes instead of
+  // preceding them.  Pageable memory is staged with one H2D copy.
+  const uint8_t *d_res = nullptr;
+  {
+    cudaPointerAttributes at;
+    if (n_res && cudaPointerGetAttributes(&at, res) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+      d_res = (const uint8_t *)at.devicePointer;
+    else
+      cudaGetLastError();
+  }
+  const int n_chunks = 1;
+  uint32_t cq[9];
+  cq[0] = 0;
+  cq[n_chunks] = nq;
+  profile_begin(h, h->copy_stream, 4);
+  HCUDA(cudaMemcpyAsync(ws.seq_off.p, off, ((size_t)nq + 1) * 8, cudaMemcpyHostToDevice, h->copy_stream));
+  if (!d_res) {
+    HCHECK(ws.residues.ensure((size_t)n_res + 16));
+    if (n_res) HCUDA(cudaMemcpyAsync(ws.residues.p, res, (size_t)n_res, cudaMemcpyHostToDevice, h->copy_stream));
+    d_res = ws.residues.p;
+  }
+  HCUDA(cudaEventRecord(h->chunk_ev[0], h->copy_stream));
+  profile_end(h, h->copy_stream);
   if (o->want_positions) {
     // PositionHits wanted (search.go:416,442-452): rows, hits and positions assembled by finish.cu
-    HCHECK(finish_rows(h, ws.residues.p, ws.seq_off.p, nq, o, 0, nullptr, nullptr, hits, owner, st));
+    HCUDA(cudaStreamWaitEvent(st, h->chunk_ev[0], 0));
+    HCHECK(search_counted(h, d_res, ws.seq_off.p, nq, o, 0, nullptr, st));
+    hits->n_lookups = ws.h_counters.p[CNT_LOOKUPS];
+    hits->n_increments = ws.h_counters.p[CNT_INCR];
+    HCHECK(finish_rows(h, d_res, ws.seq_off.p, nq, o, 0, nullptr, nullptr, hits, owner, st));
     *out_hits = hits;
     return KAAMER_OK;
   }
+  // count pass + CSR offsets in one stream pass, one host sync for (status, counters, total)
+  HCHECK(ws.n_hits.ensure(nq));
+  HCHECK(ws.hit_base.ensure(nq));
+  HCHECK(ws.size_in_kmer.ensure(nq));
+  HCHECK(ws.counters.ensure(CNT_N * 8));
+  HCHECK(ws.h_counters.ensure(CNT_N * 8 + 2));
+  HCHECK(ws.hit_off.ensure((size_t)nq + 1));
   HCHECK(owner->alloc(&hits->hit_off, (size_t)nq + 1));
   HCHECK(owner->alloc(&hits->size_in_kmer, (size_t)nq));
-  HCHECK(ws.hit_off.ensure((size_t)nq + 1));
-  k_scan_hits<<<1, 1024, 0, st>>>(ws.n_hits.p, nq, ws.hit_off.p);
-  h->prof_all_launches += 1;
-  HCUDA(cudaMemcpyAsync(ws.h_counters.p + CNT_N, ws.hit_off.p + nq, 8, cudaMemcpyDeviceToHost, st));
-  HCUDA(cudaStreamSynchronize(st));
-  const uint64_t n_hits = ws.h_counters.p[CNT_N];
+  uint64_t per_q = o->max_results > 0 ? (uint64_t)(o->max_results < 16 ? o->max_results : 16) : 1;
+  uint64_t pool_cap = (uint64_t)nq * per_q + 4096;
+  if (ws.pool.n > pool_cap) pool_cap = ws.pool.n;  // a previous batch already grew the pool
+  for (int attempt = 0;; ++attempt) {
+    HCHECK(ws.pool.ensure((size_t)pool_cap));
+    for (int c = 0; c < n_chunks; ++c) {
+      const uint32_t qb = cq[c], nqc = cq[c + 1] - cq[c];
+      if (attempt == 0) HCUDA(cudaStreamWaitEvent(st, h->chunk_ev[c], 0));
+      kaamer_dev_result dr{};
+      dr.n_hits = ws.n_hits.p + qb;
+      dr.hit_base = ws.hit_base.p + qb;
+      dr.size_in_kmer = ws.size_in_kmer.p + qb;
+      dr.pool = ws.pool.p;
+      dr.pool_cap = pool_cap;
+      dr.counters = ws.counters.p + (size_t)c * CNT_N;
+      if (nqc == 0) {
+        HCUDA(cudaMemsetAsync(dr.counters, 0, CNT_N * 8, st));
+        if (c) HCUDA(cudaMemcpyAsync(dr.counters + CNT_POOL, dr.counters - CNT_N + CNT_POOL, 8, cudaMemcpyDeviceToDevice, st));
+        continue;
+      }
+      HCHECK(search_proteins_device(h, d_res, ws.seq_off.p + qb, nqc, o, &dr, st, 0, nullptr,
+                                    c ? ws.counters.p + (size_t)(c - 1) * CNT_N : nullptr));
+    }
+    profile_begin(h, st, 5);
+    k_scan_hits<<<1, 1024, 0, st>>>(ws.n_hits.p, nq, ws.hit_off.p);
+    h->prof_all_launches += 1;
+    HCUDA(cudaMemcpyAsync(ws.h_counters.p, ws.counters.p, (size_t)n_chunks * CNT_N * 8, cudaMemcpyDeviceToHost, st));
+    HCUDA(cudaMemcpyAsync(ws.h_counters.p + CNT_N * 8, ws.hit_off.p + nq, 8, cudaMemcpyDeviceToHost, st));
+    HCUDA(cudaMemcpyAsync(hits->hit_off, ws.hit_off.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st));
+    HCUDA(cudaMemcpyAsync(hits->size_in_kmer, ws.size_in_kmer.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    profile_end(h, st);
+    HCUDA(cudaStreamSynchronize(st));
+    uint64_t status = 0, lookups = 0, incr = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+      status |= ws.h_counters.p[(size_t)c * CNT_N + CNT_STATUS];
+      lookups += ws.h_counters.p[(size_t)c * CNT_N + CNT_LOOKUPS];
+      incr += ws.h_counters.p[(size_t)c * CNT_N + CNT_INCR];
+    }
+    if (status & ST_GHASH_OVERFLOW) {
+      set_error("a query matched more distinct subjects than the class-G histogram holds (%u slots)",
+                ghash_slots_for(h));
+      return fail(KAAMER_ERR_LIMIT);
+    }
+    if (status & ST_POOL_OVERFLOW) {
+      if (attempt >= 3) {
+        set_error("hit pool overflow after %d attempts", attempt + 1);
+        return fail(KAAMER_ERR_LIMIT);
+      }
+      pool_cap = ws.h_counters.p[(size_t)(n_chunks - 1) * CNT_N + CNT_POOL] + 4096;  // exact demand of the failed pass
+      continue;
+    }
+    hits->n_lookups = lookups;
+    hits->n_increments = incr;
+    break;
+  }
+  const uint64_t n_hits = ws.h_counters.p[CNT_N * 8];
   hits->n_hits = n_hits;
   HCHECK(owner->alloc(&hits->subject_id, (size_t)n_hits));
   HCHECK(owner->alloc(&hits->kmatch, (size_t)n_hits));
-  HCHECK(ws.out_hits.ensure((size_t)n_hits + 1));
-  HCHECK(ws.h_packed.ensure((size_t)n_hits + 1));
   if (n_hits) {
+    HCHECK(ws.out_hits.ensure((size_t)n_hits + 1));  // subject u32[n_hits] | kmatch u32[n_hits]
+    uint32_t *d_subj = reinterpret_cast<uint32_t *>(ws.out_hits.p), *d_km = d_subj + n_hits;
     unsigned grid = (unsigned)(((uint64_t)nq * 32 + 255) / 256);
-    k_gather_hits<<<grid, 256, 0, st>>>(ws.n_hits.p, ws.hit_base.p, ws.hit_off.p, ws.pool.p, nq, ws.out_hits.p);
+    profile_begin(h, st, 5);
+    k_gather_hits<<<grid, 256, 0, st>>>(ws.n_hits.p, ws.hit_base.p, ws.hit_off.p, ws.pool.p, nq, d_subj, d_km);
     h->prof_all_launches += 1;
-    HCUDA(cudaMemcpyAsync(ws.h_packed.p, ws.out_hits.p, (size_t)n_hits * 8, cudaMemcpyDeviceToHost, st));
-  }
-  HCUDA(cudaMemcpyAsync(hits->hit_off, ws.hit_off.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st));
-  HCUDA(cudaMemcpyAsync(hits->size_in_kmer, ws.size_in_kmer.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
-  HCUDA(cudaStreamSynchronize(st));
-  for (uint64_t i = 0; i < n_hits; ++i) {
-    hits->subject_id[i] = (uint32_t)ws.h_packed.p[i];
-    hits->kmatch[i] = (uint32_t)(ws.h_packed.p[i] >> 32);
+    HCUDA(cudaMemcpyAsync(hits->subject_id, d_subj, (size_t)n_hits * 4, cudaMemcpyDeviceToHost, st));
+    HCUDA(cudaMemcpyAsync(hits->kmatch, d_km, (size_t)n_hits * 4, cudaMemcpyDeviceToHost, st));
+    profile_end(h, st);
+    HCUDA(cudaStreamSynchronize(st));
   }
   *out_hits = hits;
 #undef HCHECK

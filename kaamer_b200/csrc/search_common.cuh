@@ -48,6 +48,34 @@ struct SearchArgs {
   uint8_t *any0;
 };
 
+// Copy src[0, len) into shared memory with aligned 16-byte loads (one request per 16 residues:
+// coalesced into full lines from HBM and into large read requests when the source is pinned
+// host memory read in place over PCIe).  dst must be 16-byte aligned with room for len + 31
+// bytes; returns `head`: the sequence starts at dst + head.  Bytes outside [src, src_end) are
+// never dereferenced past src_end (the chunk that would cross it is read bytewise).
+template <int NT>
+__device__ __forceinline__ int stage_bytes(uint8_t *dst, const uint8_t *src, int len, const uint8_t *src_end,
+                                           int tid) {
+  const uintptr_t base = reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15;
+  const int head = (int)(reinterpret_cast<uintptr_t>(src) - base);
+  const int nchunks = (head + len + 15) >> 4;
+  const uint4 *g = reinterpret_cast<const uint4 *>(base);
+  for (int c = tid; c < nchunks; c += NT) {
+    if (reinterpret_cast<const uint8_t *>(g + c + 1) <= src_end) {
+      uint4 v;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                   : "l"(g + c));
+      reinterpret_cast<uint4 *>(dst)[c] = v;
+    } else {
+      const uint8_t *p = reinterpret_cast<const uint8_t *>(g + c);
+      for (int k = 0; k < 16; ++k)
+        if (p + k < src_end && p + k >= src) dst[c * 16 + k] = p[k];
+    }
+  }
+  return head;
+}
+
 __device__ __forceinline__ uint64_t ldg_entry(const uint64_t *p) {
   uint64_t v;
   asm volatile("ld.global.nc.L1::no_allocate.L2::64B.b64 %0, [%1];" : "=l"(v) : "l"(p));

@@ -286,8 +286,8 @@ class GpuIndex:
         check(_lib.lib().kaamer_gpu_profile_enable(self._h, int(on)))
 
     def profile_read(self, reset: bool = True):
-        ms = (C.c_double * 4)()
-        k = (C.c_uint64 * 4)()
+        ms = (C.c_double * 8)()
+        k = (C.c_uint64 * 8)()
         a = C.c_uint64()
         check(_lib.lib().kaamer_gpu_profile_read(self._h, ms, k, C.byref(a), int(reset)))
         return {"kernel_ms": list(ms), "kernel_launches": list(k), "all_launches": a.value}

@@ -169,3 +169,25 @@ def test_medium_scale_properties():
         for n, j in enumerate(perm[:300]):
             assert r2.hits(n) == r.hits(int(j))
         assert r2.n_lookups == r.n_lookups and r2.n_increments == r.n_increments
+
+
+def test_pinned_host_buffers_are_read_in_place(small_db, gpu_small):
+    """Page-locked caller buffers take the zero-copy path of kaamer_gpu_search_proteins (kernels
+    read the residues over PCIe); results must equal the staged (pageable) path and the oracle."""
+    import torch
+
+    from kaamer_b200 import SearchOptions, synth
+    from oracle import oracle as o
+
+    q, qo, _ = synth.protein_queries(small_db["res"], small_db["off"], 3000, config_index=1, stream=17)
+    seqs = [q[int(qo[i]):int(qo[i + 1])].tobytes() for i in range(len(qo) - 1)]
+    seqs += [small_db["res"][:6000].tobytes(), small_db["res"][:50_000].tobytes(), b"", b"MKT*"]  # class G, > smem stage
+    q, qo = o.pack(seqs)
+    ora = o.search_proteins(small_db["idx"], q, qo, o.opts(), 4)
+    hq = torch.from_numpy(q).pin_memory()
+    ho = torch.from_numpy(qo.astype(np.int64)).pin_memory()
+    r = gpu_small.search_proteins_ptr(hq.data_ptr(), ho.data_ptr(), len(qo) - 1, SearchOptions())
+    assert_same_hits(r, ora, "pinned / zero-copy")
+    assert r.n_lookups == ora.n_lookups and r.n_increments == ora.n_increments
+    r2 = gpu_small.search_proteins(q, qo, SearchOptions())
+    assert_same_hits(r2, ora, "pageable / staged")

@@ -1,0 +1,226 @@
+#!/usr/bin/env python
+"""bench_stages.py — per-stage measurements of the other SURVEY §8 rows (bench.py measures the
+headline C3 protein search).  One JSON line per workload, same conventions as bench.py: CUDA-event
+kernel times from the library's own timers, algorithmic bytes / cell updates for the roofline, the
+CPU restatement (oracle/) timed beside it on a bounded sample.
+
+    python bench_stages.py --workload c2        translated search: 5 Mb contigs vs the 10k-protein DB
+    python bench_stages.py --workload c5        Smith-Waterman re-alignment of the hits of a C3 batch
+    torchrun ... bench_stages.py --workload sharded   mode S (key-range shards + NCCL all-to-all)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def c2(a):
+    import torch
+
+    from kaamer_b200 import GpuIndex, SearchOptions, synth
+    from kaamer_b200.makedb import fasta_protein_ids
+    from oracle import oracle as o
+
+    res, off = synth.protein_db(10_000, config_index=1)
+    ids = fasta_protein_ids(len(off) - 1)
+    nt, noff = synth.nucleotide_contigs(res, off, a.contigs, 5_000_000, config_index=2)
+    threads = os.cpu_count() or 1
+    with GpuIndex.build(res, off, ids, keep_proteins=False) as g:
+        opts = SearchOptions()
+        for _ in range(a.warmup):
+            r = g.search_nucleotide(nt, noff, opts)
+        g.profile_enable(True)
+        g.profile_read(reset=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            r = g.search_nucleotide(nt, noff, opts)
+        dt = (time.perf_counter() - t0) / a.steps
+        prof = g.profile_read(reset=True)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            t = g.get_orfs(nt, noff)
+        dt_orf = (time.perf_counter() - t0) / a.steps
+    k_ms = [x / a.steps for x in prof["kernel_ms"]]
+    n_nt = int(noff[-1])
+    tr_ms = k_ms[7]  # k_translate6 + k_orf_ends (+ sort, write)
+    # CPU restatement on one contig
+    idx = o.Index.build(res, off, ids, threads)
+    one = nt[:int(noff[1])]
+    t0 = time.perf_counter()
+    ro = o.search_nucleotide(idx, one, noff[:2], o.opts(), threads)
+    cpu_s = time.perf_counter() - t0
+    line = {
+        "workload": f"C2 translated search: {a.contigs} x 5 Mb synthetic contigs (~88 % coding) vs 10 000-protein DB, default options",
+        "metric": "query residues/sec", "unit": "nt/s", "value": n_nt / dt, "ms_per_step": 1e3 * dt,
+        "e2e": {"value": n_nt / dt, "unit": "nt/s", "note": "kaamer_gpu_search_nucleotide on host buffers (pageable), H2D + ORFs + search + positions/start-codon + D2H"},
+        "orfs": int(len(t)), "rows": int(r.n_rows), "hits": int(len(r.subject)), "orf_kmer_lookups": int(r.n_lookups),
+        "get_orfs_ms_host_call": 1e3 * dt_orf,
+        "stage_ms": {"translate_orf_kernels": tr_ms, "search_W": k_ms[0], "search_M": k_ms[1], "search_G": k_ms[2]},
+        "roofline": {"bound": "hbm", "kernel": "k_translate6+k_orf_ends+k_orf_write (incl. cub sort/scan)",
+                     "algorithmic_bytes_per_nt": 3.0, "achieved": 3.0 * n_nt / (tr_ms * 1e-3) / 1e9 if tr_ms else None,
+                     "peak": peaks(), "unit": "GB/s", "frac": (3.0 * n_nt / (tr_ms * 1e-3) / 1e9) / peaks() if tr_ms else None},
+        "cpu_baseline": {"value": int(noff[1]) / cpu_s, "unit": "nt/s", "cores": threads, "kind": "port",
+                         "sample": "one 5 Mb contig, CPU restatement (oracle/): GetORFs serial per contig as in the reference, ORF searches on all threads",
+                         "rows": int(ro.n_rows)},
+    }
+    print(json.dumps(line))
+
+
+def c5(a):
+    import torch
+
+    from kaamer_b200 import GpuIndex, SearchOptions, synth
+    from kaamer_b200.makedb import fasta_protein_ids
+    from oracle import oracle as o
+
+    res, off = synth.protein_db(a.db_proteins, config_index=3)
+    ids = fasta_protein_ids(len(off) - 1)
+    q, qo, _ = synth.protein_queries(res, off, a.queries, config_index=3, stream=100)
+    threads = os.cpu_count() or 1
+    with GpuIndex.build(res, off, ids, keep_proteins=True) as g:
+        r = g.search_proteins(q, qo, SearchOptions())
+        nh = np.diff(r.hit_off.astype(np.int64))
+        pq = np.repeat(np.arange(len(nh), dtype=np.uint32), nh)
+        ps = r.subject
+        n_aa = g.dbstats()["NumberOfAA"]
+        qlen = np.diff(qo.astype(np.int64))
+        # subject lengths by id: protein table semantics of the builder (last record with the id)
+        slen_by_id = np.zeros(int(ids.max()) + 1, np.int64)
+        slen_by_id[ids] = np.diff(off.astype(np.int64))
+        cells = int((qlen[pq] * slen_by_id[ps]).sum())
+        for _ in range(a.warmup):
+            out = g.align(q, qo, pq, ps, number_of_aa=n_aa)
+        g.profile_enable(True)
+        g.profile_read(reset=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            out = g.align(q, qo, pq, ps, number_of_aa=n_aa)
+        dt = (time.perf_counter() - t0) / a.steps
+        prof = g.profile_read(reset=True)
+    k_ms = prof["kernel_ms"][3] / a.steps
+    # CPU restatement on a bounded sample of the same pairs
+    rng = np.random.default_rng(1)
+    sample = rng.choice(len(pq), size=min(a.cpu_pairs, len(pq)), replace=False)
+    subj = {}
+    for i in range(len(ids)):
+        subj[int(ids[i])] = (int(off[i]), int(off[i + 1]))
+    prm = o.aln_params(n_aa)
+    import concurrent.futures as cf
+
+    def one(k):
+        qi, sid = int(pq[k]), int(ps[k])
+        b, e = subj[sid]
+        x = o.align(q[int(qo[qi]):int(qo[qi + 1])].tobytes(), res[b:e].tobytes(), prm)
+        return int(x.dp_score), int(x.raw)
+
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(threads) as ex:  # ko_align releases the GIL inside ctypes
+        ref = list(ex.map(one, sample.tolist()))
+    cpu_s = time.perf_counter() - t0
+    cpu_cells = int((qlen[pq[sample]] * slen_by_id[ps[sample]]).sum())
+    ok = all(int(out["dp_score"][k]) == ref[i][0] and int(out["raw"][k]) == ref[i][1] for i, k in enumerate(sample.tolist()))
+    line = {
+        "workload": f"C5 re-alignment: all {len(pq)} (query, hit) pairs of one C3 batch ({a.queries} queries, {a.db_proteins}-protein DB), BLOSUM62 11/1",
+        "metric": "cell updates/sec", "unit": "GCUPS", "value": cells / (k_ms * 1e-3) / 1e9 if k_ms else None,
+        "pairs": int(len(pq)), "cells": cells, "kernel_ms": k_ms,
+        "e2e": {"value": cells / dt / 1e9, "unit": "GCUPS", "ms_per_step": 1e3 * dt,
+                "note": "kaamer_gpu_align on host buffers: H2D queries + pair list, chunked kernels, D2H of 64 B per pair"},
+        "roofline": {"bound": "integer ALU / shared memory (no dense contraction, no HBM roofline; SURVEY §8d)",
+                     "achieved": cells / (k_ms * 1e-3) / 1e9 if k_ms else None, "unit": "GCUPS",
+                     "traceback_bytes_per_cell": 1.0},
+        "parity_spot_check": {"pairs": int(len(sample)), "dp_score_and_raw_equal_oracle": bool(ok)},
+        "cpu_baseline": {"value": cpu_cells / cpu_s / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
+                         "sample": f"{len(sample)} of the pairs, CPU restatement (oracle/) of align.Align on {threads} threads"},
+    }
+    print(json.dumps(line))
+
+
+def sharded(a):
+    import torch
+    import torch.distributed as dist
+
+    from kaamer_b200 import GpuIndex, SearchOptions, synth
+    from kaamer_b200.makedb import fasta_protein_ids
+    from kaamer_b200.sharded import CudaShardBackend, ShardedSearch, SingleComm, TorchComm, make_fences, shard_arrays
+
+    rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(lr)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    res, off = synth.protein_db(a.db_proteins, config_index=3)
+    ids = fasta_protein_ids(len(off) - 1)
+    # full index once on this GPU (device build), exported, re-opened as this rank's key range
+    with GpuIndex.build(res, off, ids, keep_proteins=False, device=lr) as g0:
+        keys, offsets, postings = g0.index_arrays()
+    fences = make_fences(keys, offsets, world)
+    k, fo, p = shard_arrays(keys, offsets, postings, int(fences[rank]), int(fences[rank + 1]))
+    del keys, offsets, postings
+    nq = a.queries  # per rank (weak scaling, as bench.py)
+    q, qo, _ = synth.protein_queries(res, off, nq, config_index=3, stream=100 + rank)
+    dev = torch.device("cuda", lr)
+    d_res = torch.from_numpy(q).to(dev)
+    d_off = torch.from_numpy(qo.astype(np.int64)).to(dev)
+    opts = SearchOptions()
+    with GpuIndex.from_arrays(k, fo, p, shard=(int(fences[rank]), int(fences[rank + 1])), device=lr) as g:
+        s = ShardedSearch(CudaShardBackend(g), fences, TorchComm() if world > 1 else SingleComm())
+        for _ in range(a.warmup):
+            r = s.search(d_res, d_off, nq, opts)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            r = s.search(d_res, d_off, nq, opts)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.steps
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        tot = torch.tensor([float(qo[-1]), float(r.n_lookups), float(r.a2a_bytes), float(int(r.n_hits.sum().item()))],
+                           dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            line = {"workload": f"mode S: {a.db_proteins}-protein DB key-range sharded over {world} GPU(s), {nq} queries per rank",
+                    "metric": "query residues/sec", "unit": "residues/s", "n_gpus": world, "scaling": "weak",
+                    "value": tot[0].item() / (t.item() * 1e-3), "ms_per_step": t.item(),
+                    "kmer_lookups_per_sec": tot[1].item() / (t.item() * 1e-3),
+                    "all_to_all_bytes_per_step": tot[2].item(), "hits": tot[3].item(),
+                    "note": "device-resident queries; includes route, 2 x (counts + payload) all-to-all over NCCL, partial counts, merge; "
+                            "host syncs for the split sizes are inside the timed region"}
+            print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", required=True, choices=["c2", "c5", "sharded"])
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--contigs", type=int, default=2)
+    ap.add_argument("--db-proteins", type=int, default=570_000)
+    ap.add_argument("--queries", type=int, default=100_000)
+    ap.add_argument("--cpu-pairs", type=int, default=2000)
+    a = ap.parse_args()
+    {"c2": c2, "c5": c5, "sharded": sharded}[a.workload](a)

@@ -22,6 +22,8 @@
 #include <algorithm>
 #include <type_traits>
 
+#include <cub/cub.cuh>
+
 #include "internal.cuh"
 
 #include "search_common.cuh"
@@ -29,27 +31,40 @@
 namespace kaamer {
 
 __global__ void k_classify(SearchArgs a) {
-  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= a.nq) return;
-  uint64_t b = a.off[q], e = a.off[q + 1];
-  long long len = (long long)(e - b);
-  long long K = len - KAAMER_KMER_SIZE + 1;  // search.go:290
-  if (len > 0 && a.res[e - 1] == '*') K--;   // search.go:291-293
-  a.size_in_kmer[q] = (int32_t)K;
-  a.n_hits[q] = 0;
-  a.hit_base[q] = 0;
-  if (a.nt_mode) {
-    a.any0[q] = 0;
-    if (K < 1) return;  // cannot happen for ORFs (>= 21 residues, dna.go:26)
-    const long long k = a.min_kmatch > 1 ? a.min_kmatch : 1;
-    a.kmin[q] = k > 0xFFFFFFFEll ? 0xFFFFFFFFu : (uint32_t)k;
-  } else {
-    if (K < 7) return;  // search_protein.go:74-76 (documented deviation: skipped, not fatal)
-    a.kmin[q] = filter_kmin(a.min_kmatch, a.min_kratio, (int32_t)K);
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31;
+  int cls = -1;
+  if (q < a.nq) {
+    uint64_t b = a.off[q], e = a.off[q + 1];
+    long long len = (long long)(e - b);
+    long long K = len - KAAMER_KMER_SIZE + 1;  // search.go:290
+    if (len > 0 && a.res[e - 1] == '*') K--;   // search.go:291-293
+    a.size_in_kmer[q] = (int32_t)K;
+    a.n_hits[q] = 0;
+    a.hit_base[q] = 0;
+    bool go;
+    if (a.nt_mode) {
+      a.any0[q] = 0;
+      go = K >= 1;  // always true for ORFs (>= 21 residues, dna.go:26)
+      const long long k = a.min_kmatch > 1 ? a.min_kmatch : 1;
+      if (go) a.kmin[q] = k > 0xFFFFFFFEll ? 0xFFFFFFFFu : (uint32_t)k;
+    } else {
+      go = K >= 7;  // search_protein.go:74-76 (documented deviation: skipped, not fatal)
+      if (go) a.kmin[q] = filter_kmin(a.min_kmatch, a.min_kratio, (int32_t)K);
+    }
+    if (go) cls = K <= W_MAXK ? 0 : (K <= M_MAXK ? 1 : 2);
   }
-  int cls = K <= W_MAXK ? 0 : (K <= M_MAXK ? 1 : 2);
-  uint32_t slot = atomicAdd(&a.list_count[cls], 1u);
-  a.lists[(size_t)cls * a.nq + slot] = q;
+  // warp-aggregated append to the class lists (one atomic per warp and class)
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, cls == c);
+    if (mask == 0) continue;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(&a.list_count[c], (uint32_t)__popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (cls == c) a.lists[(size_t)c * a.nq + base + __popc(mask & ((1u << lane) - 1u))] = q;
+  }
 }
 
 // ---- class W: one warp per query ------------------------------------------------------------
@@ -436,41 +451,9 @@ __global__ void __launch_bounds__(G_THREADS) k_search_g(SearchArgs a) {
 }
 
 // ---- CSR compaction (host API) ----------------------------------------------------------
-// single-CTA exclusive scan of n_hits -> hit_off[nq+1]
-__global__ void __launch_bounds__(1024) k_scan_hits(const uint32_t *__restrict__ n_hits, uint32_t nq,
-                                                    uint64_t *hit_off) {
-  __shared__ uint64_t warp_sum[32];
-  __shared__ uint64_t carry;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid == 0) carry = 0;
-  __syncthreads();
-  for (uint32_t base = 0; base < nq; base += 1024) {
-    uint32_t i = base + tid;
-    uint64_t v = i < nq ? n_hits[i] : 0, x = v;
-    for (int o = 1; o < 32; o <<= 1) {
-      uint64_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) warp_sum[w] = x;
-    __syncthreads();
-    if (w == 0) {
-      uint64_t s = warp_sum[lane], t = s;
-      for (int o = 1; o < 32; o <<= 1) {
-        uint64_t y = __shfl_up_sync(0xFFFFFFFFu, t, o);
-        if (lane >= o) t += y;
-      }
-      warp_sum[lane] = t - s;  // exclusive
-    }
-    __syncthreads();
-    uint64_t excl = carry + warp_sum[w] + x - v;
-    if (i < nq) hit_off[i] = excl;
-    __syncthreads();
-    if (tid == 1023) carry = excl + v;
-    __syncthreads();
-  }
-  if (tid == 0) hit_off[nq] = carry;
-}
-
+struct WidenU32 {
+  __host__ __device__ uint64_t operator()(uint32_t x) const { return x; }
+};
 __global__ void k_gather_hits(const uint32_t *__restrict__ n_hits, const uint32_t *__restrict__ hit_base,
                               const uint64_t *__restrict__ hit_off, const uint64_t *__restrict__ pool,
                               uint32_t nq, uint32_t *subject, uint32_t *kmatch) {
@@ -689,9 +672,15 @@ int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off,
     return KAAMER_OK;
   }
   // count pass + CSR offsets in one stream pass, one host sync for (status, counters, total)
-  HCHECK(ws.n_hits.ensure(nq));
+  HCHECK(ws.n_hits.ensure((size_t)nq + 1));
   HCHECK(ws.hit_base.ensure(nq));
   HCHECK(ws.size_in_kmer.ensure(nq));
+  size_t scan_tmp = 0;
+  {
+    cub::TransformInputIterator<uint64_t, WidenU32, const uint32_t *> in(ws.n_hits.p, WidenU32());
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, in, ws.hit_off.p, (int64_t)nq + 1, st);
+    HCHECK(ws.f_tmp.ensure(scan_tmp + 16));
+  }
   HCHECK(ws.counters.ensure(CNT_N * 8));
   HCHECK(ws.h_counters.ensure(CNT_N * 8 + 2));
   HCHECK(ws.hit_off.ensure((size_t)nq + 1));
@@ -721,8 +710,14 @@ int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off,
                                     c ? ws.counters.p + (size_t)(c - 1) * CNT_N : nullptr));
     }
     profile_begin(h, st, 5);
-    k_scan_hits<<<1, 1024, 0, st>>>(ws.n_hits.p, nq, ws.hit_off.p);
-    h->prof_all_launches += 1;
+    {
+      // hit_off[0..nq] = exclusive sum of n_hits[0..nq) (+ one zero): total lands in hit_off[nq]
+      HCUDA(cudaMemsetAsync(ws.n_hits.p + nq, 0, 4, st));
+      cub::TransformInputIterator<uint64_t, WidenU32, const uint32_t *> in(ws.n_hits.p, WidenU32());
+      size_t tb = scan_tmp;
+      HCUDA(cub::DeviceScan::ExclusiveSum(ws.f_tmp.p, tb, in, ws.hit_off.p, (int64_t)nq + 1, st));
+      h->prof_all_launches += 2;
+    }
     HCUDA(cudaMemcpyAsync(ws.h_counters.p, ws.counters.p, (size_t)n_chunks * CNT_N * 8, cudaMemcpyDeviceToHost, st));
     HCUDA(cudaMemcpyAsync(ws.h_counters.p + CNT_N * 8, ws.hit_off.p + nq, 8, cudaMemcpyDeviceToHost, st));
     HCUDA(cudaMemcpyAsync(hits->hit_off, ws.hit_off.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st));

@@ -359,8 +359,10 @@ int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint
   unsigned long long n_orfs = 0;
   if (total_nt) {
     const unsigned grid = (unsigned)((total_nt + 255) / 256);
+    profile_begin(h, st, 7);
     k_translate6<<<grid, 256, 0, st>>>(ta);
     k_orf_ends<<<grid, 256, 0, st>>>(ta);
+    profile_end(h, st);
     h->prof_all_launches += 2;
     TCUDA(cudaGetLastError());
     TCUDA(cudaMemcpyAsync(&n_orfs, d_n, 8, cudaMemcpyDeviceToHost, st));
@@ -394,6 +396,7 @@ int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint
   TCHECK(dev_alloc(&d_perm, (size_t)n));
   TCHECK(dev_alloc(&d_len, (size_t)n + 1));
   TCHECK(dev_alloc(&d_nalt, (size_t)n + 1));
+  profile_begin(h, st, 7);
   k_iota<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_iota, n);
   TCUDA(cudaGetLastError());
   size_t need = 0, need2 = 0;
@@ -442,6 +445,7 @@ int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint
   wa.seq = out->seq;
   wa.alts = out->alts;
   k_orf_write<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(wa);
+  profile_end(h, st);
   h->prof_all_launches += 2;
   TCUDA(cudaGetLastError());
   TCUDA(cudaStreamSynchronize(st));

@@ -27,13 +27,14 @@
 // integer max/add work, reported in GCUPS (cell updates per second).
 #include <algorithm>
 #include <cmath>
+#include <type_traits>
 
 #include "internal.cuh"
 
 namespace kaamer {
 
 constexpr int ALN_WARPS = 4;
-constexpr int PROF_COLS = 256;  // 32 lanes x CW(max 8)
+constexpr int PROF_COLS = 512;  // 32 lanes x CW(max 16)
 constexpr int GAP_OPEN_DP = -11;  // align.go:64 (hard-coded in the reference, options ignored)
 
 // NCBI BLOSUM62, 24-letter order ARNDCQEGHILKMFPSTWYVBZX*, + the J (I/L) row of BLAST+.
@@ -120,24 +121,81 @@ struct AlnArgs {
 
 __device__ __forceinline__ uint8_t fix_u(uint8_t c) { return (c == 'u' || c == 'U') ? (uint8_t)'*' : c; }  // align.go:54-55
 
-struct WarpShared {
-  int8_t prof[26 * PROF_COLS];  // prof[a][col] = B62[a][s_col] of the current column block
-};
 
 // region layout: [nblocks][n+31 steps][32 lanes][CW bytes], then 3 x int32[n] block-boundary column
 __device__ __forceinline__ size_t block_stride(int n, int cw) { return (size_t)(n + 31) * 32 * cw; }
 
-template <int CW>
+// One DP cell, in PTX so that every traceback bit costs one predicated add (the compiler turned the
+// C++ form into branches and moves).
+//   m = max(diag + sc, 0); u = max(Mup - 11, Uup); l = max(left_m - 11, left_l); b = max(m, u, l)
+//   byte CC of w += best layer (M, then U, then L on ties) | M==0 <<2 | U opened <<3 | L opened <<4
+//   (bs, br): running column maximum of M and the last row that reached it
+template <int CC>
+__device__ __forceinline__ void sw_cell(int diag, int sc, int Mup, int Uup, int left_m, int left_l, int r, int &m,
+                                        int &u, int &l, int &b, uint32_t &w, int &bs, int &br) {
+  asm("{\n\t"
+      ".reg .pred pu, pl, p1, p2, pz, pt;\n\t"
+      ".reg .s32 uo, lo, mu, dd;\n\t"
+      ".reg .u32 f;\n\t"
+      "add.s32 dd, %7, %8;\n\t"
+      "max.s32 %0, dd, 0;\n\t"
+      "add.s32 uo, %9, -11;\n\t"
+      "setp.ge.s32 pu, uo, %10;\n\t"
+      "max.s32 %1, uo, %10;\n\t"
+      "add.s32 lo, %11, -11;\n\t"
+      "setp.ge.s32 pl, lo, %12;\n\t"
+      "max.s32 %2, lo, %12;\n\t"
+      "setp.ge.s32 p1, %0, %1;\n\t"
+      "max.s32 mu, %0, %1;\n\t"
+      "setp.ge.s32 p2, mu, %2;\n\t"
+      "max.s32 %3, mu, %2;\n\t"
+      "setp.eq.s32 pz, %0, 0;\n\t"
+      "selp.u32 f, 0, %13, p1;\n\t"
+      "selp.u32 f, f, %14, p2;\n\t"
+      "@pz add.u32 f, f, %15;\n\t"
+      "@pu add.u32 f, f, %16;\n\t"
+      "@pl add.u32 f, f, %17;\n\t"
+      "add.u32 %4, %4, f;\n\t"
+      "setp.ge.s32 pt, %0, %5;\n\t"
+      "max.s32 %5, %5, %0;\n\t"
+      "@pt mov.s32 %6, %18;\n\t"
+      "}"
+      : "=&r"(m), "=&r"(u), "=&r"(l), "=&r"(b), "+r"(w), "+r"(bs), "+r"(br)
+      : "r"(diag), "r"(sc), "r"(Mup), "r"(Uup), "r"(left_m), "r"(left_l), "n"(1u << (8 * CC)), "n"(2u << (8 * CC)),
+        "n"(4u << (8 * CC)), "n"(8u << (8 * CC)), "n"(16u << (8 * CC)), "r"(r));
+}
+
+template <class F>
+__device__ __forceinline__ void static_for4(F f) {
+  f(std::integral_constant<int, 0>());
+  f(std::integral_constant<int, 1>());
+  f(std::integral_constant<int, 2>());
+  f(std::integral_constant<int, 3>());
+}
+
+// One column block (32*CW subject columns) swept over all query rows by one warp.
+// bnd_in / bnd_out: the values crossing the block boundary, one entry per row (M, L and
+// max(M,U,L) of the block's last column).  In the multi-warp kernel the previous block is being
+// produced by another warp of the CTA at the same time: prog_in counts its finished rows,
+// prog_out publishes ours (shared memory, volatile; data in global memory, fenced).
+template <int CW, bool PIPE, int PCOLS>
 __device__ __forceinline__ void dp_block(const int8_t *prof, const int8_t *lidx, const uint8_t *q, int n, int blk,
-                                         int nblk, uint8_t *dirs, int *bndM, int *bndL, int *bndB, int &out_s,
+                                         uint8_t *dirs, const int *bnd_in, int *bnd_out,
+                                         const volatile int *prog_in, volatile int *prog_out, int &out_s,
                                          uint32_t &out_pos) {
   const unsigned lane = threadIdx.x & 31;
-  int best_s = 0;
-  uint32_t best_pos = 0;
+  // per-column running maximum of M and the last row that reached it (">=": the last row wins);
+  // 1 as the initial maximum implements the `M > 0` condition of the end-cell rule
+  int bs[CW], br[CW];
   int Mup[CW], Uup[CW], Bup[CW];
 #pragma unroll
-  for (int c = 0; c < CW; ++c) Mup[c] = Uup[c] = Bup[c] = 0;
+  for (int c = 0; c < CW; ++c) {
+    Mup[c] = Uup[c] = Bup[c] = 0;
+    bs[c] = 1;
+    br[c] = -1;
+  }
   int pubM = 0, pubL = 0, pubB = 0, prevB = 0;
+  int avail = (PIPE && prog_in) ? 0 : n;  // rows of the previous block known to be finished
   const int j0 = blk * 32 * CW + (int)lane * CW;  // first column (0-based) of this lane
   const int steps = n + 31;
   for (int t = 0; t < steps; ++t) {
@@ -148,78 +206,102 @@ __device__ __forceinline__ void dp_block(const int8_t *prof, const int8_t *lidx,
     int inB = __shfl_up_sync(0xFFFFFFFFu, pubB, 1);
     if (lane == 0) {
       inM = inL = inB = 0;
-      if (blk > 0 && active) {
-        inM = bndM[r];
-        inL = bndL[r];
-        inB = bndB[r];
+      if (bnd_in && active) {
+        if constexpr (PIPE) {
+          if (avail <= r) {
+            do avail = *prog_in;
+            while (avail <= r);
+            __threadfence_block();
+          }
+        }
+        inM = __ldcg(bnd_in + (uint32_t)r);
+        inL = __ldcg(bnd_in + (uint32_t)(n + r));
+        inB = __ldcg(bnd_in + (uint32_t)(2 * n + r));
       }
     }
     int diag = prevB;  // max(M,U,L)[r-1][j0-1]
     prevB = inB;
     if (active) {
       const int qi = lidx[fix_u(q[r])];
-      int sc[CW];
-      if constexpr (CW == 8) {
-        const uint2 p = *reinterpret_cast<const uint2 *>(prof + qi * PROF_COLS + lane * 8);
+      uint32_t pw[CW / 4];
+      {
+        const uint32_t *pp = reinterpret_cast<const uint32_t *>(prof + qi * PCOLS + lane * CW);
+        if constexpr (CW == 16) {
+          const uint4 p = *reinterpret_cast<const uint4 *>(pp);
+          pw[0] = p.x;
+          pw[1] = p.y;
+          pw[2] = p.z;
+          pw[3] = p.w;
+        } else if constexpr (CW == 8) {
+          const uint2 p = *reinterpret_cast<const uint2 *>(pp);
+          pw[0] = p.x;
+          pw[1] = p.y;
+        } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          sc[c] = (int)(int8_t)(p.x >> (8 * c));
-          sc[4 + c] = (int)(int8_t)(p.y >> (8 * c));
+          for (int g = 0; g < CW / 4; ++g) pw[g] = pp[g];
         }
-      } else {
-        const uint32_t p = *reinterpret_cast<const uint32_t *>(prof + qi * PROF_COLS + lane * 4);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) sc[c] = (int)(int8_t)(p >> (8 * c));
       }
       int left_m = inM, left_l = inL;
-      uint32_t flags[CW];
+      uint32_t fw[CW / 4];
 #pragma unroll
-      for (int c = 0; c < CW; ++c) {
-        const int d = diag + sc[c];
-        const int m = d > 0 ? d : 0;
-        const int uo = Mup[c] + GAP_OPEN_DP;
-        const int u = uo > Uup[c] ? uo : Uup[c];
-        const int lo = left_m + GAP_OPEN_DP;
-        const int l = lo > left_l ? lo : left_l;
-        // traceback state of this cell
-        uint32_t f = (m >= u && m >= l) ? 0u : (u >= l ? 1u : 2u);
-        f |= (m == 0 ? 4u : 0u) | (u == uo ? 8u : 0u) | (l == lo ? 16u : 0u);
-        flags[c] = f;
-        const int b = max(m, max(u, l));
-        if (m > 0 && m >= best_s) {  // row-major visiting order inside the lane: last maximum wins
-          best_s = m;
-          best_pos = ((uint32_t)(r + 1) << 16) | (uint32_t)(j0 + c + 1);
-        }
-        diag = Bup[c];
-        Mup[c] = m;
-        Uup[c] = u;
-        Bup[c] = b;
-        left_m = m;
-        left_l = l;
+      for (int g = 0; g < CW / 4; ++g) {
+        uint32_t w = 0;
+        static_for4([&](auto CC) {
+          constexpr int cc = decltype(CC)::value;
+          const int c = g * 4 + cc;
+          const int sc = (int)(pw[g] << (24 - 8 * cc)) >> 24;  // sign-extended byte cc
+          // One cell, in PTX so that every traceback bit costs one predicated add (the compiler
+          // turned the C++ form into branches).
+          //   m = max(diag + sc, 0); u = max(Mup - 11, Uup); l = max(left_m - 11, left_l)
+          //   byte = best layer (M, then U, then L on ties) | M==0 <<2 | U opened <<3 | L opened <<4
+          int m, u, l, b;
+          sw_cell<cc>(diag, sc, Mup[c], Uup[c], left_m, left_l, r, m, u, l, b, w, bs[c], br[c]);
+          diag = Bup[c];
+          Mup[c] = m;
+          Uup[c] = u;
+          Bup[c] = b;
+          left_m = m;
+          left_l = l;
+        });
+        fw[g] = w;
       }
       pubM = left_m;
       pubL = left_l;
       pubB = Bup[CW - 1];
-      if constexpr (CW == 8) {
-        uint2 w;
-        w.x = flags[0] | (flags[1] << 8) | (flags[2] << 16) | (flags[3] << 24);
-        w.y = flags[4] | (flags[5] << 8) | (flags[6] << 16) | (flags[7] << 24);
-        *reinterpret_cast<uint2 *>(dirs + ((size_t)t * 32 + lane) * 8) = w;
-      } else {
-        const uint32_t w = flags[0] | (flags[1] << 8) | (flags[2] << 16) | (flags[3] << 24);
-        *reinterpret_cast<uint32_t *>(dirs + ((size_t)t * 32 + lane) * 4) = w;
+      {
+        uint32_t *dp = reinterpret_cast<uint32_t *>(dirs + ((uint32_t)t * 32u + lane) * (uint32_t)CW);
+        if constexpr (CW == 16) {
+          *reinterpret_cast<uint4 *>(dp) = make_uint4(fw[0], fw[1], fw[2], fw[3]);
+        } else if constexpr (CW == 8) {
+          *reinterpret_cast<uint2 *>(dp) = make_uint2(fw[0], fw[1]);
+        } else {
+#pragma unroll
+          for (int g = 0; g < CW / 4; ++g) dp[g] = fw[g];
+        }
       }
-      if (lane == 31 && blk + 1 < nblk) {
-        bndM[r] = pubM;
-        bndL[r] = pubL;
-        bndB[r] = pubB;
+      if (lane == 31 && bnd_out) {
+        bnd_out[(uint32_t)r] = pubM;
+        bnd_out[(uint32_t)(n + r)] = pubL;
+        bnd_out[(uint32_t)(2 * n + r)] = pubB;
+        if constexpr (PIPE) {
+          if (prog_out) {
+            __threadfence_block();
+            *prog_out = r + 1;
+          }
+        }
       }
     }
   }
-  // merge with the earlier column blocks: higher score, then later in row-major order
-  if (best_s > out_s || (best_s == out_s && best_pos > out_pos)) {
-    out_s = best_s;
-    out_pos = best_pos;
+  // this lane's end-cell candidate, then the merge with the earlier column blocks: higher score,
+  // then later in row-major order
+#pragma unroll
+  for (int c = 0; c < CW; ++c) {
+    if (br[c] < 0) continue;
+    const uint32_t pos = ((uint32_t)(br[c] + 1) << 16) | (uint32_t)(j0 + c + 1);
+    if (bs[c] > out_s || (bs[c] == out_s && pos > out_pos)) {
+      out_s = bs[c];
+      out_pos = pos;
+    }
   }
 }
 
@@ -232,17 +314,174 @@ __device__ __forceinline__ uint32_t dir_at(const uint8_t *scratch, int n, int cw
   return scratch[(size_t)blk * block_stride(n, cw) + ((size_t)(r + lane) * 32 + lane) * cw + c];
 }
 
-__global__ void __launch_bounds__(ALN_WARPS * 32) k_sw_affine(AlnArgs a) {
-  __shared__ __align__(16) WarpShared ws[ALN_WARPS];
-  __shared__ int8_t s_b62[26 * 32];
-  __shared__ int8_t s_lidx[256];
-  __shared__ int8_t s_apos[256];
+// block profile: prof[a][col] = B62[a][s_col]; columns past the subject end score -100 so that
+// nothing positive ever lives there
+template <int PCOLS>
+__device__ __forceinline__ void build_profile(int8_t *prof, const int8_t *b62, const int8_t *lidx, const uint8_t *s,
+                                              int m, int blk, int bw) {
+  const unsigned lane = threadIdx.x & 31;
+  for (int col = lane; col < bw; col += 32) {
+    const int j = blk * bw + col;
+    const int sj = j < m ? (int)lidx[fix_u(s[j])] : -1;
+#pragma unroll 1
+    for (int aa = 0; aa < 26; ++aa) prof[aa * PCOLS + col] = sj >= 0 ? b62[aa * 32 + sj] : (int8_t)-100;
+  }
+}
+
+// Traceback + the post-processing of align.go:72-157, executed by one whole warp: the 32 lanes
+// fetch a window of 32 traceback bytes (and residues) ahead of the path in its current direction
+// (diagonal, up or left) with ONE memory round trip; the path is then followed through
+// shuffles and a new window is fetched only when the layer changes or the window is used up.
+__device__ __forceinline__ void traceback_and_emit(const AlnArgs &a, const AlnPair &pr, const uint8_t *scratch,
+                                                   const uint8_t *q, int n, const uint8_t *s, int cw, int best_s,
+                                                   uint32_t best_pos, bool bad, const int8_t *s_b62,
+                                                   const int8_t *s_lidx, const int8_t *s_apos) {
+  const unsigned lane = threadIdx.x & 31;
+  float identity = 0.f, similarity = 0.f, nb_pos = 0.f;
+  int mismatches = 0, raw = 0, gap_openings = 0, aln_len = 0;
+  int q_start = 0, q_end = 0, s_start = 0, s_end = 0;
+  if (best_s > 0) {
+    int i = (int)(best_pos >> 16), j = (int)(best_pos & 0xFFFFu);
+    q_end = i;
+    s_end = j;
+    int layer = 0, cur_kind = -1, cur_score = 0, cur_lq = 0, cur_ls = 0;
+    auto flush = [&]() {
+      if (cur_kind < 0) return;
+      raw += cur_score;
+      if (cur_score == -a.gap_open_opt) {  // align.go:127: the test is on the score VALUE
+        gap_openings += 1;
+        const int gl = cur_lq > cur_ls ? cur_lq : cur_ls;
+        raw -= (gl - 1) * a.gap_extend_opt;
+      }
+      cur_kind = -1;
+    };
+    auto open_seg = [&](int kind) {
+      if (cur_kind != kind) {
+        flush();
+        cur_kind = kind;
+        cur_score = 0;
+        cur_lq = cur_ls = 0;
+      }
+    };
+    bool done = false;
+    while (!done) {
+      const int di = layer == 2 ? 0 : 1, dj = layer == 1 ? 0 : 1;
+      const int wi = i - di * (int)lane, wj = j - dj * (int)lane;
+      uint32_t F = 0, QA = 0, SB = 0;
+      if (wi > 0 && wj > 0) {
+        F = dir_at(scratch, n, cw, wi, wj);
+        QA = fix_u(q[wi - 1]);
+        SB = fix_u(s[wj - 1]);
+      }
+      const int layer0 = layer;
+      for (int k = 0; k < 31; ++k) {  // window cell k == current cell (i, j); k+1 stays inside the window
+        const uint32_t f = __shfl_sync(0xFFFFFFFFu, F, k);
+        const uint32_t ca = __shfl_sync(0xFFFFFFFFu, QA, k), cb = __shfl_sync(0xFFFFFFFFu, SB, k);
+        if (layer == 0) {
+          if (f & 4u) {
+            done = true;
+            break;
+          }
+          open_seg(0);
+          cur_score += s_b62[s_lidx[ca] * 32 + s_lidx[cb]];
+          cur_lq++;
+          cur_ls++;
+          if (cb == ca) {  // align.go:82-86
+            identity += 1.f;
+            similarity += 1.f;
+          } else {
+            if (cb != '-' && ca != '-') mismatches += 1;                      // align.go:88-90
+            if (s_b62[s_apos[cb] * 32 + s_apos[ca]] > 0) similarity += 1.f;  // GetAlnScoreAA (:91)
+          }
+          nb_pos += 1.f;
+          aln_len++;
+          --i;
+          --j;
+          if (i == 0 || j == 0) {
+            done = true;
+            break;
+          }
+          layer = (int)(__shfl_sync(0xFFFFFFFFu, F, k + 1) & 3u);
+        } else if (layer == 1) {
+          open_seg(1);
+          cur_lq++;
+          if (ca == '-') {  // a literal '-' residue equals the gap character (align.go:82)
+            identity += 1.f;
+            similarity += 1.f;
+          }
+          nb_pos += 1.f;
+          aln_len++;
+          if (f & 8u) {
+            cur_score += GAP_OPEN_DP;
+            layer = 0;
+          }
+          --i;
+          if (i == 0) {
+            done = true;
+            break;
+          }
+        } else {
+          open_seg(2);
+          cur_ls++;
+          if (cb == '-') {
+            identity += 1.f;
+            similarity += 1.f;
+          }
+          nb_pos += 1.f;
+          aln_len++;
+          if (f & 16u) {
+            cur_score += GAP_OPEN_DP;
+            layer = 0;
+          }
+          --j;
+          if (j == 0) {
+            done = true;
+            break;
+          }
+        }
+        if (layer != layer0) break;  // the path turned: fetch a window in the new direction
+      }
+    }
+    flush();
+    q_start = i;
+    s_start = j;
+  }
+  if (lane != 0) return;
+  kaamer_aln r;
+  r.identity = __fmul_rn(__fdiv_rn(identity, nb_pos), 100.f);  // NaN for an empty alignment, as in Go
+  r.similarity = __fmul_rn(__fdiv_rn(similarity, nb_pos), 100.f);
+  r.length = aln_len;
+  r.mismatches = mismatches;
+  r.gap_openings = gap_openings;
+  r.raw = raw;
+  r.bitscore = __ddiv_rn(__dsub_rn(__dmul_rn(a.lambda, (double)raw), log(a.K)), log(2.0));  // align.go:136
+  r.evalue = __ddiv_rn(__dmul_rn((double)n, a.number_of_aa), pow(2.0, r.bitscore));         // align.go:141
+  r.query_start = q_start + 1;  // align.go:153-156
+  r.query_end = q_end;
+  r.subject_start = s_start + 1;
+  r.subject_end = s_end;
+  r.dp_score = best_s;
+  r.status = bad ? 1 : 0;
+  a.out[pr.out_index] = r;
+}
+
+__device__ __forceinline__ void load_tables(int8_t *s_b62, int8_t *s_lidx, int8_t *s_apos) {
   for (int i = threadIdx.x; i < 26 * 32; i += blockDim.x) s_b62[i] = c_aln.b62[i];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     s_lidx[i] = c_aln.letter_index[i];
     s_apos[i] = c_aln.aa_pos[i];
   }
   __syncthreads();
+}
+
+// ---- one warp per pair (pairs below BIG_CELLS) ------------------------------------------------
+constexpr size_t WARP_SMEM = (size_t)ALN_WARPS * 26 * PROF_COLS;
+__global__ void __launch_bounds__(ALN_WARPS * 32) k_sw_affine(AlnArgs a) {
+  extern __shared__ __align__(16) int8_t warp_prof[];  // [ALN_WARPS][26 * PROF_COLS]
+  __shared__ int8_t s_b62[26 * 32];
+  __shared__ int8_t s_lidx[256];
+  __shared__ int8_t s_apos[256];
+  load_tables(s_b62, s_lidx, s_apos);
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t pi = blockIdx.x * ALN_WARPS + w;
   if (pi >= a.n_pairs) return;
@@ -263,22 +502,19 @@ __global__ void __launch_bounds__(ALN_WARPS * 32) k_sw_affine(AlnArgs a) {
   if (!bad && n > 0 && m > 0) {
     const int bw = 32 * cw;
     const int nblk = (m + bw - 1) / bw;
-    int *bnd = reinterpret_cast<int *>(scratch + (size_t)nblk * block_stride(n, cw));
-    int8_t *prof = ws[w].prof;
+    int *bnd = reinterpret_cast<int *>(scratch + (size_t)nblk * block_stride(n, cw));  // in place: 3 x int[n]
+    int8_t *prof = warp_prof + (size_t)w * 26 * PROF_COLS;
     for (int blk = 0; blk < nblk; ++blk) {
       __syncwarp();
-      // block profile: prof[a][col] = B62[a][s_col]; columns past the subject end score -100 so
-      // that nothing positive ever lives there
-      for (int col = lane; col < bw; col += 32) {
-        const int j = blk * bw + col;
-        const int sj = j < m ? (int)s_lidx[fix_u(s[j])] : -1;
-#pragma unroll 1
-        for (int aa = 0; aa < 26; ++aa) prof[aa * PROF_COLS + col] = sj >= 0 ? s_b62[aa * 32 + sj] : (int8_t)-100;
-      }
+      build_profile<PROF_COLS>(prof, s_b62, s_lidx, s, m, blk, bw);
       __syncwarp();
       uint8_t *dirs = scratch + (size_t)blk * block_stride(n, cw);
-      if (cw == 8) dp_block<8>(prof, s_lidx, q, n, blk, nblk, dirs, bnd, bnd + n, bnd + 2 * n, best_s, best_pos);
-      else dp_block<4>(prof, s_lidx, q, n, blk, nblk, dirs, bnd, bnd + n, bnd + 2 * n, best_s, best_pos);
+      const int *bin = blk > 0 ? bnd : nullptr;
+      int *bout = blk + 1 < nblk ? bnd : nullptr;
+      if (cw == 16) dp_block<16, false, PROF_COLS>(prof, s_lidx, q, n, blk, dirs, bin, bout, nullptr, nullptr, best_s, best_pos);
+      else if (cw == 12) dp_block<12, false, PROF_COLS>(prof, s_lidx, q, n, blk, dirs, bin, bout, nullptr, nullptr, best_s, best_pos);
+      else if (cw == 8) dp_block<8, false, PROF_COLS>(prof, s_lidx, q, n, blk, dirs, bin, bout, nullptr, nullptr, best_s, best_pos);
+      else dp_block<4, false, PROF_COLS>(prof, s_lidx, q, n, blk, dirs, bin, bout, nullptr, nullptr, best_s, best_pos);
     }
     // end cell: maximum score, then last in row-major order (larger i, then larger j)
     for (int o = 16; o > 0; o >>= 1) {
@@ -291,131 +527,112 @@ __global__ void __launch_bounds__(ALN_WARPS * 32) k_sw_affine(AlnArgs a) {
     }
   }
   __syncwarp();
-  if (lane != 0) return;
-  // ---- traceback + align.go post-processing (lane 0) --------------------------------------
-  float identity = 0.f, similarity = 0.f, nb_pos = 0.f;
-  int mismatches = 0, raw = 0, gap_openings = 0, aln_len = 0;
-  int q_start = 0, q_end = 0, s_start = 0, s_end = 0;
-  if (best_s > 0) {
-    int i = (int)(best_pos >> 16), j = (int)(best_pos & 0xFFFFu);
-    q_end = i;
-    s_end = j;
-    int layer = 0, cur_kind = -1, cur_score = 0, cur_lq = 0, cur_ls = 0;
-    auto flush = [&]() {
-      if (cur_kind < 0) return;
-      raw += cur_score;
-      if (cur_score == -a.gap_open_opt) {  // align.go:127: the test is on the score VALUE
-        gap_openings += 1;
-        const int gl = cur_lq > cur_ls ? cur_lq : cur_ls;
-        raw -= (gl - 1) * a.gap_extend_opt;
-      }
-      cur_kind = -1;
-    };
-    uint32_t f = dir_at(scratch, n, cw, i, j);
-    while (i > 0 && j > 0) {
-      if (layer == 0) {
-        if (f & 4u) break;
-        const uint8_t ca = fix_u(q[i - 1]), cb = fix_u(s[j - 1]);
-        if (cur_kind != 0) {
-          flush();
-          cur_kind = 0;
-          cur_score = 0;
-          cur_lq = cur_ls = 0;
-        }
-        cur_score += s_b62[s_lidx[ca] * 32 + s_lidx[cb]];
-        cur_lq++;
-        cur_ls++;
-        if (cb == ca) {  // align.go:82-86
-          identity += 1.f;
-          similarity += 1.f;
-        } else {
-          if (cb != '-' && ca != '-') mismatches += 1;                      // align.go:88-90
-          if (s_b62[s_apos[cb] * 32 + s_apos[ca]] > 0) similarity += 1.f;  // GetAlnScoreAA (:91)
-        }
-        nb_pos += 1.f;
-        aln_len++;
-        --i;
-        --j;
-        if (i > 0 && j > 0) {
-          f = dir_at(scratch, n, cw, i, j);
-          layer = (int)(f & 3u);
-        }
-      } else if (layer == 1) {
-        if (cur_kind != 1) {
-          flush();
-          cur_kind = 1;
-          cur_score = 0;
-          cur_lq = cur_ls = 0;
-        }
-        cur_lq++;
-        if (fix_u(q[i - 1]) == '-') {  // a literal '-' residue equals the gap character (align.go:82)
-          identity += 1.f;
-          similarity += 1.f;
-        }
-        nb_pos += 1.f;
-        aln_len++;
-        if (f & 8u) {
-          cur_score += GAP_OPEN_DP;
-          layer = 0;
-        }
-        --i;
-        if (i > 0) f = dir_at(scratch, n, cw, i, j);
-      } else {
-        if (cur_kind != 2) {
-          flush();
-          cur_kind = 2;
-          cur_score = 0;
-          cur_lq = cur_ls = 0;
-        }
-        cur_ls++;
-        if (fix_u(s[j - 1]) == '-') {
-          identity += 1.f;
-          similarity += 1.f;
-        }
-        nb_pos += 1.f;
-        aln_len++;
-        if (f & 16u) {
-          cur_score += GAP_OPEN_DP;
-          layer = 0;
-        }
-        --j;
-        if (j > 0) f = dir_at(scratch, n, cw, i, j);
+  traceback_and_emit(a, pr, scratch, q, n, s, cw, best_s, best_pos, bad, s_b62, s_lidx, s_apos);
+}
+
+// ---- one CTA per pair (long pairs): the column blocks are pipelined over the warps --------------
+// Warp w sweeps blocks w, w+BIG_WARPS, ...; block b starts as soon as block b-1 has produced its
+// first boundary rows, so up to BIG_WARPS*32 lanes form one wavefront over the DP table.
+constexpr int BIG_WARPS = 4;
+constexpr int BIG_MAX_BLOCKS = 256;  // 65535 columns / 256
+constexpr int BIG_PCOLS = 256;       // 32 lanes x 8 columns
+constexpr size_t BIG_SMEM = (size_t)BIG_WARPS * 26 * BIG_PCOLS;
+
+__global__ void __launch_bounds__(BIG_WARPS * 32, 4) k_sw_affine_cta(AlnArgs a) {
+  extern __shared__ __align__(16) int8_t big_prof[];  // [BIG_WARPS][26 * BIG_PCOLS]
+  __shared__ int8_t s_b62[26 * 32];
+  __shared__ int8_t s_lidx[256];
+  __shared__ int8_t s_apos[256];
+  __shared__ volatile int prog[BIG_MAX_BLOCKS];
+  __shared__ int s_best[BIG_WARPS];
+  __shared__ uint32_t s_pos[BIG_WARPS];
+  __shared__ int s_bad;
+  load_tables(s_b62, s_lidx, s_apos);
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const AlnPair pr = a.pairs[blockIdx.x];
+  const uint8_t *q = a.q_res + a.q_off[pr.q];
+  const int n = (int)(a.q_off[pr.q + 1] - a.q_off[pr.q]);
+  const uint8_t *s = a.p_res + a.p_off[pr.s];
+  const int m = (int)(a.p_off[pr.s + 1] - a.p_off[pr.s]);
+  if (threadIdx.x == 0) s_bad = 0;
+  for (int i = threadIdx.x; i < BIG_MAX_BLOCKS; i += blockDim.x) prog[i] = 0;
+  __syncthreads();
+  bool bad = false;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) bad |= s_lidx[fix_u(q[i])] < 0;
+  for (int j = threadIdx.x; j < m; j += blockDim.x) bad |= s_lidx[fix_u(s[j])] < 0;
+  if (bad) s_bad = 1;
+  __syncthreads();
+  bad = s_bad != 0;
+  constexpr int cw = 8, bw = 256;
+  uint8_t *scratch = a.scratch + pr.scratch;
+  int best_s = 0;
+  uint32_t best_pos = 0;
+  if (!bad && n > 0 && m > 0) {
+    const int nblk = (m + bw - 1) / bw;
+    int *bnd = reinterpret_cast<int *>(scratch + (size_t)nblk * block_stride(n, cw));  // [nblk][3][n]
+    int8_t *prof = big_prof + (size_t)w * 26 * BIG_PCOLS;
+    for (int blk = (int)w; blk < nblk; blk += BIG_WARPS) {
+      __syncwarp();
+      build_profile<BIG_PCOLS>(prof, s_b62, s_lidx, s, m, blk, bw);
+      __syncwarp();
+      uint8_t *dirs = scratch + (size_t)blk * block_stride(n, cw);
+      const int *bin = blk > 0 ? bnd + (size_t)(blk - 1) * 3 * n : nullptr;
+      int *bout = blk + 1 < nblk ? bnd + (size_t)blk * 3 * n : nullptr;
+      dp_block<8, true, BIG_PCOLS>(prof, s_lidx, q, n, blk, dirs, bin, bout, blk > 0 ? &prog[blk - 1] : nullptr,
+                  blk + 1 < nblk ? &prog[blk] : nullptr, best_s, best_pos);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const int os = __shfl_xor_sync(0xFFFFFFFFu, best_s, o);
+      const uint32_t op = __shfl_xor_sync(0xFFFFFFFFu, best_pos, o);
+      if (os > best_s || (os == best_s && op > best_pos)) {
+        best_s = os;
+        best_pos = op;
       }
     }
-    flush();
-    q_start = i;
-    s_start = j;
   }
-  kaamer_aln r;
-  r.identity = __fmul_rn(__fdiv_rn(identity, nb_pos), 100.f);  // NaN for an empty alignment, as in Go
-  r.similarity = __fmul_rn(__fdiv_rn(similarity, nb_pos), 100.f);
-  r.length = aln_len;
-  r.mismatches = mismatches;
-  r.gap_openings = gap_openings;
-  r.raw = raw;
-  r.bitscore = __ddiv_rn(__dsub_rn(__dmul_rn(a.lambda, (double)raw), log(a.K)), log(2.0));  // align.go:136
-  r.evalue = __ddiv_rn(__dmul_rn((double)n, a.number_of_aa), pow(2.0, r.bitscore));         // align.go:141
-  r.query_start = q_start + 1;  // align.go:153-156
-  r.query_end = q_end;
-  r.subject_start = s_start + 1;
-  r.subject_end = s_end;
-  r.dp_score = best_s;
-  r.status = bad ? 1 : 0;
-  a.out[pr.out_index] = r;
+  if (lane == 0) {
+    s_best[w] = best_s;
+    s_pos[w] = best_pos;
+  }
+  __threadfence();  // traceback bytes of every warp visible before warp 0 walks them
+  __syncthreads();
+  if (w != 0) return;
+  for (int k = 1; k < BIG_WARPS; ++k) {
+    const int os = s_best[k];
+    const uint32_t op = s_pos[k];
+    if (os > best_s || (os == best_s && op > best_pos)) {
+      best_s = os;
+      best_pos = op;
+    }
+  }
+  traceback_and_emit(a, pr, scratch, q, n, s, cw, best_s, best_pos, bad, s_b62, s_lidx, s_apos);
 }
 
 // ---------------------------------------------------------------------------------------
 static bool g_tables_ready[64] = {false};
+constexpr uint64_t BIG_CELLS = 2ull << 20;  // pairs at least this large get a whole CTA
 
+// columns per lane of the warp-per-pair kernel: the cost of a pair is
+// blocks x (rows + 31) x (per-step overhead + CW x per-cell work), ~40 and ~22.5 instructions
 static int choose_cw(uint64_t m) {
-  const uint64_t p8 = (m + 255) / 256 * 256, p4 = (m + 127) / 128 * 128;
-  return p4 < p8 ? 4 : 8;
+  int best = 4;
+  double best_cost = 1e300;
+  for (int cw = 4; cw <= 16; cw += 4) {
+    const uint64_t bw = 32ull * cw, nblk = (m + bw - 1) / bw;
+    const double cost = (double)nblk * (40.0 + 22.5 * cw);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = cw;
+    }
+  }
+  return best;
 }
 
-static uint64_t pair_scratch_bytes(uint64_t n, uint64_t m, int cw) {
+static uint64_t pair_scratch_bytes(uint64_t n, uint64_t m, int cw, bool big) {
   const uint64_t bw = 32ull * cw;
   const uint64_t nblk = (m + bw - 1) / bw;
-  uint64_t b = nblk * (n + 31) * 32 * cw + 3 * 4 * n;
+  // traceback bytes + boundary columns (one per block in the pipelined kernel, one in place otherwise)
+  uint64_t b = nblk * (n + 31) * 32 * cw + (big ? nblk : 1) * 3 * 4 * n;
   return (b + 255) & ~255ull;
 }
 
@@ -464,18 +681,17 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
     std::vector<uint32_t> cur(bucket_start.begin(), bucket_start.end() - 1);
     for (uint32_t i = 0; i < n_pairs; ++i) order[cur[bucket_of(cost[i])]++] = i;
   }
+  // the long pairs (one CTA each) first, exactly
+  std::stable_partition(order.begin(), order.end(), [&](uint32_t i) { return cost[i] >= BIG_CELLS; });
   // device buffers
+  // device buffers live in the handle's workspace (allocating tens of GB per call costs more than
+  // the kernels)
+  SearchWorkspace &ws = h->ws;
   uint8_t *d_q = nullptr, *d_scratch = nullptr;
   uint64_t *d_qoff = nullptr;
   AlnPair *d_pairs = nullptr;
   kaamer_aln *d_out = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(d_q);
-    cudaFree(d_qoff);
-    cudaFree(d_pairs);
-    cudaFree(d_out);
-    cudaFree(d_scratch);
-  };
+  auto cleanup = [&]() {};
 #define ACUDA(call)                                                                      \
   do {                                                                                   \
     cudaError_t _e = (call);                                                             \
@@ -485,26 +701,32 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
       return KAAMER_ERR_CUDA;                                                            \
     }                                                                                    \
   } while (0)
-  ACUDA(cudaMalloc((void **)&d_q, (size_t)n_qres + 16));
-  ACUDA(cudaMalloc((void **)&d_qoff, ((size_t)nq + 1) * 8));
-  ACUDA(cudaMalloc((void **)&d_pairs, (size_t)n_pairs * sizeof(AlnPair)));
-  ACUDA(cudaMalloc((void **)&d_out, (size_t)n_pairs * sizeof(kaamer_aln)));
+  KCHECK(ws.residues.ensure((size_t)n_qres + 16));
+  KCHECK(ws.seq_off.ensure((size_t)nq + 1));
+  KCHECK(ws.a_pairs.ensure((size_t)n_pairs * sizeof(AlnPair)));
+  KCHECK(ws.a_out.ensure((size_t)n_pairs * sizeof(kaamer_aln)));
+  d_q = ws.residues.p;
+  d_qoff = ws.seq_off.p;
+  d_pairs = reinterpret_cast<AlnPair *>(ws.a_pairs.p);
+  d_out = reinterpret_cast<kaamer_aln *>(ws.a_out.p);
   ACUDA(cudaMemcpyAsync(d_q, q_res, (size_t)n_qres, cudaMemcpyHostToDevice, st));
   ACUDA(cudaMemcpyAsync(d_qoff, q_off, ((size_t)nq + 1) * 8, cudaMemcpyHostToDevice, st));
   // chunks under the traceback-memory budget
   size_t free_b = 0, total_b = 0;
   ACUDA(cudaMemGetInfo(&free_b, &total_b));
-  uint64_t budget = free_b / 2;
-  if (budget > (24ull << 30)) budget = 24ull << 30;
+  uint64_t budget = (free_b + ws.a_scratch.n) / 2;
+  if (budget > (16ull << 30)) budget = 16ull << 30;
   std::vector<AlnPair> pairs(n_pairs);
   std::vector<uint32_t> chunk_end;
   uint64_t used = 0, max_used = 0;
+  uint32_t n_big = 0;
   for (uint32_t k = 0; k < n_pairs; ++k) {
     const uint32_t i = order[k];
     const uint64_t n = q_off[pair_q[i] + 1] - q_off[pair_q[i]];
     const uint64_t m = ix.h_prot_off[pair_s[i] + 1] - ix.h_prot_off[pair_s[i]];
-    const int cw = choose_cw(m);
-    const uint64_t b = pair_scratch_bytes(n, m, cw);
+    const bool big = n * m >= BIG_CELLS;
+    const int cw = big ? 8 : choose_cw(m);
+    const uint64_t b = pair_scratch_bytes(n, m, cw, big);
     if (b > budget) {
       set_error("pair %u (%llu x %llu) needs %llu bytes of traceback state, more than the device has free", i,
                 (unsigned long long)n, (unsigned long long)m, (unsigned long long)b);
@@ -515,12 +737,14 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
       chunk_end.push_back(k);
       used = 0;
     }
+    if (big) n_big = k + 1;  // cost-ordered: the long pairs are a prefix
     pairs[k] = AlnPair{i, pair_q[i], pair_s[i], (uint32_t)cw, used};
     used += b;
     max_used = used > max_used ? used : max_used;
   }
   chunk_end.push_back(n_pairs);
-  ACUDA(cudaMalloc((void **)&d_scratch, (size_t)max_used + 256));
+  KCHECK(ws.a_scratch.ensure((size_t)max_used + 256));
+  d_scratch = ws.a_scratch.p;
   ACUDA(cudaMemcpyAsync(d_pairs, pairs.data(), (size_t)n_pairs * sizeof(AlnPair), cudaMemcpyHostToDevice, st));
   AlnArgs a{};
   a.q_res = d_q;
@@ -534,19 +758,41 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
   a.gap_open_opt = o->gap_open;
   a.gap_extend_opt = o->gap_extend;
   a.number_of_aa = (double)(o->number_of_aa ? o->number_of_aa : ix.n_aa);
+  static bool attr_done = false;
+  if (!attr_done) {
+    ACUDA(cudaFuncSetAttribute(k_sw_affine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WARP_SMEM));
+    ACUDA(cudaFuncSetAttribute(k_sw_affine_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM));
+    attr_done = true;
+  }
+  // Per chunk: the long pairs (one CTA each) on `st`, the rest (one warp each) on the second
+  // stream so that both kernels share the GPU; the chunk's scratch is reused only after both end.
+  cudaStream_t st2 = h->copy_stream;
   uint32_t begin = 0;
+  profile_begin(h, st, 3);
   for (uint32_t end : chunk_end) {
     if (end > begin) {
-      a.pairs = d_pairs + begin;
-      a.n_pairs = end - begin;
-      profile_begin(h, st, 3);
-      k_sw_affine<<<(a.n_pairs + ALN_WARPS - 1) / ALN_WARPS, ALN_WARPS * 32, 0, st>>>(a);
-      profile_end(h, st);
-      h->prof_all_launches += 1;
+      const uint32_t big_end = n_big > begin ? (n_big < end ? n_big : end) : begin;
+      ACUDA(cudaEventRecord(h->chunk_ev[0], st));
+      ACUDA(cudaStreamWaitEvent(st2, h->chunk_ev[0], 0));
+      if (big_end > begin) {
+        a.pairs = d_pairs + begin;
+        a.n_pairs = big_end - begin;
+        k_sw_affine_cta<<<a.n_pairs, BIG_WARPS * 32, BIG_SMEM, st>>>(a);
+        h->prof_all_launches += 1;
+      }
+      if (end > big_end) {
+        a.pairs = d_pairs + big_end;
+        a.n_pairs = end - big_end;
+        k_sw_affine<<<(a.n_pairs + ALN_WARPS - 1) / ALN_WARPS, ALN_WARPS * 32, WARP_SMEM, st2>>>(a);
+        h->prof_all_launches += 1;
+      }
       ACUDA(cudaGetLastError());
+      ACUDA(cudaEventRecord(h->chunk_ev[1], st2));
+      ACUDA(cudaStreamWaitEvent(st, h->chunk_ev[1], 0));
     }
     begin = end;
   }
+  profile_end(h, st);
   ACUDA(cudaMemcpyAsync(out, d_out, (size_t)n_pairs * sizeof(kaamer_aln), cudaMemcpyDeviceToHost, st));
   ACUDA(cudaStreamSynchronize(st));
   cleanup();

@@ -193,11 +193,13 @@ struct SearchWorkspace {
   DevBuf<uint64_t> f_scan;     // [5][nq+1] sizes, scanned in place
   DevBuf<uint32_t> f_posbits, f_keep, f_trim;
   DevBuf<uint8_t> f_tmp;
+  DevBuf<uint8_t> a_pairs, a_out, a_scratch;  // align.cu
   void release_all() {
     residues.release(); seq_off.release(); n_hits.release(); hit_base.release(); lists.release();
     kmin.release(); size_in_kmer.release(); pool.release(); hit_off.release(); out_hits.release();
     counters.release(); ghash.release(); any0.release(); h_counters.release(); h_packed.release();
     f_scan.release(); f_posbits.release(); f_keep.release(); f_trim.release(); f_tmp.release();
+    a_pairs.release(); a_out.release(); a_scratch.release();
   }
 };
 

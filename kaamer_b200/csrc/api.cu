@@ -145,6 +145,7 @@ static void destroy_handle(kaamer_gpu *h) {
   cudaSetDevice(h->device);
   index_release(h);
   h->ws.release_all();
+  h->arena.release();
   for (auto &p : h->prof_pending) {
     cudaEventDestroy(p.a);
     cudaEventDestroy(p.b);

@@ -357,7 +357,7 @@ int finish_rows(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint
   size_t o_rso = cur; cur += up(n_rows * 8);
   size_t o_rseq = cur; cur += up(n_seq);
   uint8_t *stage = nullptr;
-  KCUDA(cudaMalloc((void **)&stage, cur + 64));
+  KCHECK(h->arena.get(&stage, cur + 64));
   a.hit_off = (uint64_t *)(stage + o_hit_off);
   a.out_size = (int32_t *)(stage + o_size);
   a.subject = (uint32_t *)(stage + o_subj);
@@ -393,7 +393,6 @@ int finish_rows(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint
     cp(hits->row_seq, a.row_seq, n_seq);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(stage);
   if (e != cudaSuccess) {
     set_error("finish_rows: %s", cudaGetErrorString(e));
     return KAAMER_ERR_CUDA;

@@ -159,6 +159,49 @@ struct PinBuf {
   }
 };
 
+// bump allocator over device slabs that persist for the life of the handle: the temporaries of a
+// call (translation, row assembly) are carved out of it and the whole arena is reset at the start
+// of the next call, so steady-state calls do no cudaMalloc / cudaFree at all
+struct Arena {
+  struct Slab {
+    uint8_t *p;
+    size_t cap, used;
+  };
+  std::vector<Slab> slabs;
+  void reset() {
+    for (auto &s : slabs) s.used = 0;
+  }
+  void *alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    for (auto &s : slabs)
+      if (s.cap - s.used >= bytes) {
+        void *r = s.p + s.used;
+        s.used += bytes;
+        return r;
+      }
+    size_t cap = bytes + bytes / 4;
+    if (cap < ((size_t)16 << 20)) cap = (size_t)16 << 20;
+    uint8_t *p = nullptr;
+    cudaError_t e = cudaMalloc((void **)&p, cap);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes): %s", cap, cudaGetErrorString(e));
+      return nullptr;
+    }
+    slabs.push_back(Slab{p, cap, bytes});
+    return p;
+  }
+  template <class T>
+  int get(T **out, size_t n) {
+    *out = (T *)alloc((n ? n : 1) * sizeof(T));
+    return *out ? KAAMER_OK : KAAMER_ERR_NOMEM;
+  }
+  void release() {
+    for (auto &s : slabs) cudaFree(s.p);
+    slabs.clear();
+  }
+};
+
 // ---- the resident index ---------------------------------------------------------------
 struct DevIndex {
   uint64_t *table = nullptr;  // [d_hi - d_lo] direct-address entries
@@ -251,6 +294,7 @@ struct kaamer_gpu {
   std::mutex mu;
   kaamer::DevIndex idx;
   kaamer::SearchWorkspace ws;
+  kaamer::Arena arena;
   // profiling
   bool profile = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

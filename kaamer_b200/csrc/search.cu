@@ -663,6 +663,7 @@ int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off,
   profile_end(h, h->copy_stream);
   if (o->want_positions) {
     // PositionHits wanted (search.go:416,442-452): rows, hits and positions assembled by finish.cu
+    h->arena.reset();
     HCUDA(cudaStreamWaitEvent(st, h->chunk_ev[0], 0));
     HCHECK(search_counted(h, d_res, ws.seq_off.p, nq, o, 0, nullptr, st));
     hits->n_lookups = ws.h_counters.p[CNT_LOOKUPS];
@@ -781,6 +782,7 @@ int search_nucleotide_host(kaamer_gpu *h, const uint8_t *nt, const uint64_t *cof
     return KAAMER_ERR_ARG;
   }
   const uint64_t total = coff[nc];
+  h->arena.reset();
   KCHECK(ws.residues.ensure((size_t)total + 16));
   if (total) KCUDA(cudaMemcpyAsync(ws.residues.p, nt, (size_t)total, cudaMemcpyHostToDevice, st));
   OrfSet os;

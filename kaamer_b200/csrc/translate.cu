@@ -103,72 +103,133 @@ __global__ void __launch_bounds__(256) k_translate6(TranslateArgs a) {
   }
 }
 
-__device__ __forceinline__ void orf_close(const TranslateArgs &a, uint32_t c, int64_t L, int frame, int64_t e,
-                                          const uint8_t *__restrict__ fr) {
-  // walk back from e to the previous stop (exclusive) or to the frame start
+struct OrfRec {
+  int64_t b, e;
+  int32_t cnt, nalt;
+  bool valid;
+};
+
+__device__ __forceinline__ OrfRec orf_close(int64_t e, const uint8_t *__restrict__ fr) {
+  // Walk back from e to the previous stop (exclusive) or to the frame start, eight codons per
+  // aligned 64-bit load; the bytes are classified with SWAR arithmetic (all codon bytes have
+  // their letter in bits 0..6, so `x + 0x7f` sets bit 7 exactly for non-zero letters).
+  constexpr unsigned long long LO7 = 0x7F7F7F7F7F7F7F7Full, HI1 = 0x8080808080808080ull,
+                               STOPS = 0x2A2A2A2A2A2A2A2Aull;  // '*'
   int32_t cnt = 0, nalt = 0, cnt_b = 0, nalt_b = 0;
   int64_t b = -1, k = e;
-  for (; k >= 0; --k) {
-    const uint8_t v = fr[k];
-    if (k != e && (v & 0x7F) == '*') break;
-    if (v & 0x7F) cnt++;
-    if (v & 0x80) {
-      nalt++;
-      b = k;
-      cnt_b = cnt;
-      nalt_b = nalt;
+  bool hit_stop = false;
+  while (k >= 0) {
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(fr + k);
+    const int hi = (int)(addr & 7);          // byte of codon k inside its aligned word
+    const int64_t k0 = k - hi;               // codon of byte 0
+    const int lo = k0 < 0 ? (int)(-k0) : 0;  // bytes below belong to another array
+    unsigned long long w = *reinterpret_cast<const unsigned long long *>(addr - hi);
+    unsigned long long valid = (hi == 7 ? ~0ull : ((1ull << (8 * (hi + 1))) - 1ull)) & (~0ull << (8 * lo));
+    w &= valid;
+    unsigned long long aa = w & LO7;
+    unsigned long long stopm = ~((aa ^ STOPS) + LO7) & HI1 & valid;
+    if (k == e) stopm &= ~(0x80ull << (8 * hi));  // the closing codon itself is not a boundary
+    if (stopm) {                                  // nearest stop below k: keep only the bytes above it
+      const int js = (63 - __clzll((long long)stopm)) >> 3;
+      const unsigned long long above = js == 7 ? 0ull : (~0ull << (8 * (js + 1)));
+      w &= above;
+      aa &= above;
+      hit_stop = true;
     }
+    const unsigned long long nz = (aa + LO7) & HI1;
+    const unsigned long long st = w & HI1;
+    const int nst = __popcll(st);
+    if (st) {  // left-most start codon seen so far
+      const int jb = (__ffsll((long long)st) - 1) >> 3;
+      b = k0 + jb;
+      cnt_b = cnt + __popcll(nz >> (8 * jb));
+      nalt_b = nalt + nst;
+    }
+    cnt += __popcll(nz);
+    nalt += nst;
+    if (hit_stop) break;
+    k = k0 - 1;
   }
-  if (k < 0) {  // frame-initial stretch: insideORF starts true (dna.go:98)
+  if (!hit_stop) {  // frame-initial stretch: insideORF starts true (dna.go:98)
     b = 0;
     cnt_b = cnt;
     nalt_b = nalt;
   }
-  if (b < 0 || cnt_b < MIN_LEN_CDS) return;
-  const unsigned long long slot = atomicAdd(a.n_orfs, 1ull);
+  OrfRec r;
+  r.b = b;
+  r.e = e;
+  r.cnt = cnt_b;
+  r.nalt = nalt_b;
+  r.valid = b >= 0 && cnt_b >= MIN_LEN_CDS;
+  return r;
+}
+
+// warp-aggregated append of the ORF records (one atomic per warp instead of one per ORF: 200 k
+// same-address atomics were the whole cost of the kernel)
+__device__ __forceinline__ void orf_emit(const TranslateArgs &a, const OrfRec &r, uint32_t c, int64_t L, int frame) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned mask = __ballot_sync(0xFFFFFFFFu, r.valid);
+  if (mask == 0) return;
+  const int leader = __ffs(mask) - 1;
+  unsigned long long base = 0;
+  if ((int)lane == leader) base = atomicAdd(a.n_orfs, (unsigned long long)__popc(mask));
+  base = __shfl_sync(0xFFFFFFFFu, base, leader);
+  if (!r.valid) return;
+  const unsigned long long slot = base + __popc(mask & ((1u << lane) - 1u));
   if (slot >= a.cap) return;  // cannot happen (cap = codons/21 + slack); checked on the host
   int64_t start, end, poskey;
   if (frame < 3) {
-    start = frame + 3 * b + 1;  // dna.go:84,111
-    end = 3 * e + 3 + frame;    // dna.go:129,156
+    start = frame + 3 * r.b + 1;  // dna.go:84,111
+    end = 3 * r.e + 3 + frame;    // dna.go:129,156
     poskey = end;
   } else {
-    start = L - (frame - 3) - 3 * b;      // dna.go:80-82,112-114
-    end = start - 3 * (int64_t)cnt_b + 1;  // dna.go:131,158
+    start = L - (frame - 3) - 3 * r.b;       // dna.go:80-82,112-114
+    end = start - 3 * (int64_t)r.cnt + 1;   // dna.go:131,158
     poskey = start;
   }
+  (void)end;
   a.key[slot] = ((uint64_t)c << 40) | ((uint64_t)poskey << 1) | (frame >= 3 ? 1ull : 0ull);
   a.r_contig[slot] = c;
   a.r_frame[slot] = (uint8_t)frame;
-  a.r_b[slot] = (int32_t)b;
-  a.r_e[slot] = (int32_t)e;
-  a.r_cnt[slot] = cnt_b;
-  a.r_nalt[slot] = nalt_b;
+  a.r_b[slot] = (int32_t)r.b;
+  a.r_e[slot] = (int32_t)r.e;
+  a.r_cnt[slot] = r.cnt;
+  a.r_nalt[slot] = r.nalt;
 }
 
 __global__ void __launch_bounds__(256) k_orf_ends(TranslateArgs a) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= a.total_nt) return;
-  const uint32_t c = find_contig(a.coff, a.nc, g);
-  const uint64_t cb = a.coff[c];
-  const int64_t L = (int64_t)(a.coff[c + 1] - cb);
-  const int64_t p = (int64_t)(g - cb);
-  if (L < 2 || p + 3 > L) return;
-  const int64_t S = L / 3 + 1;
-  const uint8_t *cod = a.cod + a.cbase[c];
-  {
-    const int f = (int)(p % 3);
-    const int64_t k = p / 3, ncod = (L - f) / 3;
-    const uint8_t *fr = cod + f * S;
-    if ((fr[k] & 0x7F) == '*' || k == ncod - 1) orf_close(a, c, L, f, k, fr);
+  OrfRec rp, rm;
+  rp.valid = rm.valid = false;
+  uint32_t c = 0;
+  int64_t L = 0;
+  int fp = 0, fm = 3;
+  if (g < a.total_nt) {
+    c = find_contig(a.coff, a.nc, g);
+    const uint64_t cb = a.coff[c];
+    L = (int64_t)(a.coff[c + 1] - cb);
+    const int64_t p = (int64_t)(g - cb);
+    if (L >= 2 && p + 3 <= L) {
+      const int64_t S = L / 3 + 1;
+      const uint8_t *cod = a.cod + a.cbase[c];
+      {
+        fp = (int)(p % 3);
+        const int64_t k = p / 3, ncod = (L - fp) / 3;
+        const uint8_t *fr = cod + fp * S;
+        if ((fr[k] & 0x7F) == '*' || k == ncod - 1) rp = orf_close(k, fr);
+      }
+      {
+        const int64_t j = L - 3 - p;
+        const int f = (int)(j % 3);
+        fm = 3 + f;
+        const int64_t k = j / 3, ncod = (L - f) / 3;
+        const uint8_t *fr = cod + (3 + f) * S;
+        if ((fr[k] & 0x7F) == '*' || k == ncod - 1) rm = orf_close(k, fr);
+      }
+    }
   }
-  {
-    const int64_t j = L - 3 - p;
-    const int f = (int)(j % 3);
-    const int64_t k = j / 3, ncod = (L - f) / 3;
-    const uint8_t *fr = cod + (3 + f) * S;
-    if ((fr[k] & 0x7F) == '*' || k == ncod - 1) orf_close(a, c, L, 3 + f, k, fr);
-  }
+  orf_emit(a, rp, c, L, fp);
+  orf_emit(a, rm, c, L, fm);
 }
 
 __global__ void k_iota(uint32_t *p, uint64_t n) {
@@ -246,28 +307,8 @@ __global__ void __launch_bounds__(256) k_orf_write(OrfWriteArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-template <class T>
-static int dev_alloc(T **p, size_t n) {
-  cudaError_t e = cudaMalloc((void **)p, (n ? n : 1) * sizeof(T));
-  if (e != cudaSuccess) {
-    set_error("cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
-    *p = nullptr;
-    return KAAMER_ERR_NOMEM;
-  }
-  return KAAMER_OK;
-}
-
-void orfset_release(OrfSet *o) {
-  cudaFree(o->contig);
-  cudaFree(o->start);
-  cudaFree(o->end);
-  cudaFree(o->plus);
-  cudaFree(o->seq_off);
-  cudaFree(o->seq);
-  cudaFree(o->alts_off);
-  cudaFree(o->alts);
-  *o = OrfSet();
-}
+// the ORF arrays live in the handle's arena (valid until the next call resets it)
+void orfset_release(OrfSet *o) { *o = OrfSet(); }
 
 // d_nt: nucleotides on the device (+2 readable bytes of slack are NOT required: the last two
 // positions of a contig are never dereferenced beyond the contig end);  h_coff: host copy.
@@ -302,11 +343,7 @@ int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint
   uint64_t *d_len = nullptr, *d_nalt = nullptr;
   void *d_tmp = nullptr;
   int rc = KAAMER_OK;
-  auto cleanup = [&]() {
-    cudaFree(d_coff); cudaFree(d_cbase); cudaFree(d_key); cudaFree(d_key2); cudaFree(d_cod); cudaFree(r_frame);
-    cudaFree(d_n); cudaFree(r_contig); cudaFree(d_iota); cudaFree(d_perm); cudaFree(r_b); cudaFree(r_e);
-    cudaFree(r_cnt); cudaFree(r_nalt); cudaFree(d_len); cudaFree(d_nalt); cudaFree(d_tmp);
-  };
+  auto cleanup = [&]() {};
 #define TCHECK(x)                \
   do {                           \
     rc = (x);                    \
@@ -326,17 +363,17 @@ int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint
       return KAAMER_ERR_CUDA;                                                            \
     }                                                                                    \
   } while (0)
-  TCHECK(dev_alloc(&d_coff, (size_t)nc + 1));
-  TCHECK(dev_alloc(&d_cbase, (size_t)nc + 1));
-  TCHECK(dev_alloc(&d_cod, (size_t)total_cod));
-  TCHECK(dev_alloc(&d_n, 1));
-  TCHECK(dev_alloc(&d_key, (size_t)cap));
-  TCHECK(dev_alloc(&r_contig, (size_t)cap));
-  TCHECK(dev_alloc(&r_frame, (size_t)cap));
-  TCHECK(dev_alloc(&r_b, (size_t)cap));
-  TCHECK(dev_alloc(&r_e, (size_t)cap));
-  TCHECK(dev_alloc(&r_cnt, (size_t)cap));
-  TCHECK(dev_alloc(&r_nalt, (size_t)cap));
+  TCHECK(h->arena.get(&d_coff, (size_t)nc + 1));
+  TCHECK(h->arena.get(&d_cbase, (size_t)nc + 1));
+  TCHECK(h->arena.get(&d_cod, (size_t)total_cod));
+  TCHECK(h->arena.get(&d_n, 1));
+  TCHECK(h->arena.get(&d_key, (size_t)cap));
+  TCHECK(h->arena.get(&r_contig, (size_t)cap));
+  TCHECK(h->arena.get(&r_frame, (size_t)cap));
+  TCHECK(h->arena.get(&r_b, (size_t)cap));
+  TCHECK(h->arena.get(&r_e, (size_t)cap));
+  TCHECK(h->arena.get(&r_cnt, (size_t)cap));
+  TCHECK(h->arena.get(&r_nalt, (size_t)cap));
   TCUDA(cudaMemcpyAsync(d_coff, h_coff, ((size_t)nc + 1) * 8, cudaMemcpyHostToDevice, st));
   TCUDA(cudaMemcpyAsync(d_cbase, cbase.data(), ((size_t)nc + 1) * 8, cudaMemcpyHostToDevice, st));
   TCUDA(cudaMemsetAsync(d_n, 0, 8, st));
@@ -375,27 +412,27 @@ int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint
   }
   const uint64_t n = n_orfs;
   out->n = n;
-  TCHECK(dev_alloc(&out->contig, (size_t)n));
-  TCHECK(dev_alloc(&out->start, (size_t)n));
-  TCHECK(dev_alloc(&out->end, (size_t)n));
-  TCHECK(dev_alloc(&out->plus, (size_t)n));
-  TCHECK(dev_alloc(&out->seq_off, (size_t)n + 1));
-  TCHECK(dev_alloc(&out->alts_off, (size_t)n + 1));
+  TCHECK(h->arena.get(&out->contig, (size_t)n));
+  TCHECK(h->arena.get(&out->start, (size_t)n));
+  TCHECK(h->arena.get(&out->end, (size_t)n));
+  TCHECK(h->arena.get(&out->plus, (size_t)n));
+  TCHECK(h->arena.get(&out->seq_off, (size_t)n + 1));
+  TCHECK(h->arena.get(&out->alts_off, (size_t)n + 1));
   if (n == 0) {
     TCUDA(cudaMemsetAsync(out->seq_off, 0, 8, st));
     TCUDA(cudaMemsetAsync(out->alts_off, 0, 8, st));
-    TCHECK(dev_alloc(&out->seq, 16));
-    TCHECK(dev_alloc(&out->alts, 1));
+    TCHECK(h->arena.get(&out->seq, 16));
+    TCHECK(h->arena.get(&out->alts, 1));
     TCUDA(cudaStreamSynchronize(st));
     cleanup();
     return KAAMER_OK;
   }
   // sort the records
-  TCHECK(dev_alloc(&d_key2, (size_t)n));
-  TCHECK(dev_alloc(&d_iota, (size_t)n));
-  TCHECK(dev_alloc(&d_perm, (size_t)n));
-  TCHECK(dev_alloc(&d_len, (size_t)n + 1));
-  TCHECK(dev_alloc(&d_nalt, (size_t)n + 1));
+  TCHECK(h->arena.get(&d_key2, (size_t)n));
+  TCHECK(h->arena.get(&d_iota, (size_t)n));
+  TCHECK(h->arena.get(&d_perm, (size_t)n));
+  TCHECK(h->arena.get(&d_len, (size_t)n + 1));
+  TCHECK(h->arena.get(&d_nalt, (size_t)n + 1));
   profile_begin(h, st, 7);
   k_iota<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_iota, n);
   TCUDA(cudaGetLastError());
@@ -403,7 +440,7 @@ int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint
   cub::DeviceRadixSort::SortPairs(nullptr, need, d_key, d_key2, d_iota, d_perm, (int64_t)n, 0, 64, st);
   cub::DeviceScan::ExclusiveSum(nullptr, need2, d_len, out->seq_off, (int64_t)n + 1, st);
   if (need2 > need) need = need2;
-  TCUDA(cudaMalloc(&d_tmp, need + 16));
+  TCHECK(h->arena.get((uint8_t **)&d_tmp, need + 16));
   size_t tb = need;
   TCUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_key, d_key2, d_iota, d_perm, (int64_t)n, 0, 64, st));
   OrfWriteArgs wa{};
@@ -438,8 +475,8 @@ int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint
   TCUDA(cudaStreamSynchronize(st));
   out->n_seq = tot[0];
   out->n_alts = tot[1];
-  TCHECK(dev_alloc(&out->seq, (size_t)tot[0] + 16));
-  TCHECK(dev_alloc(&out->alts, (size_t)tot[1] + 1));
+  TCHECK(h->arena.get(&out->seq, (size_t)tot[0] + 16));
+  TCHECK(h->arena.get(&out->alts, (size_t)tot[1] + 1));
   wa.seq_off = out->seq_off;
   wa.alts_off = out->alts_off;
   wa.seq = out->seq;
@@ -471,6 +508,7 @@ int kaamer_gpu_get_orfs(kaamer_gpu_t *h, const uint8_t *nt, const uint64_t *cont
   std::lock_guard<std::mutex> lk(h->mu);
   KCUDA(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
+  h->arena.reset();
   const uint64_t zero = 0;
   const uint64_t *coff = n_contigs ? contig_off : &zero;
   if (coff[0] != 0) {

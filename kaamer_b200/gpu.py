@@ -101,28 +101,62 @@ def _vp(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
+class _HitsOwner:
+    """Keeps a library-owned kaamer_hits alive while numpy views of its pinned buffers exist."""
+
+    def __init__(self, hp):
+        self.hp = hp
+
+    def __del__(self):
+        try:
+            if self.hp:
+                _lib.lib().kaamer_gpu_free_hits(self.hp)
+                self.hp = None
+        except Exception:
+            pass
+
+
+def _view(ptr, n, dtype, owner):
+    """zero-copy numpy view of a library-owned buffer (released when the last view dies)"""
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    a = np.ctypeslib.as_array(ptr, shape=(int(n),))
+    a = a.view(dtype) if a.dtype != np.dtype(dtype) else a
+    v = a.view(_OwnedArray)
+    v._owner = owner
+    return v
+
+
+class _OwnedArray(np.ndarray):
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self._owner = getattr(obj, "_owner", None)
+
+
 def _collect_hits(hp) -> SearchResult:
     h = hp.contents
     n, nh = h.n_rows, h.n_hits
+    own = _HitsOwner(hp)
     r = SearchResult(
-        hit_off=_arr(h.hit_off, n + 1, np.uint64),
-        subject=_arr(h.subject_id, nh, np.uint32),
-        kmatch=_arr(h.kmatch, nh, np.uint32),
-        size_in_kmer=_arr(h.size_in_kmer, n, np.int32),
+        hit_off=_view(h.hit_off, n + 1, np.uint64, own),
+        subject=_view(h.subject_id, nh, np.uint32, own),
+        kmatch=_view(h.kmatch, nh, np.uint32, own),
+        size_in_kmer=_view(h.size_in_kmer, n, np.int32, own),
         n_lookups=int(h.n_lookups),
         n_increments=int(h.n_increments),
     )
     if h.pos_off:
-        r.pos_off = _arr(h.pos_off, nh + 1, np.uint64)
-        r.pos = _arr(h.pos, int(r.pos_off[-1]) if nh else 0, np.uint8)
+        r.pos_off = _view(h.pos_off, nh + 1, np.uint64, own)
+        r.pos = _view(h.pos, int(r.pos_off[-1]) if nh else 0, np.uint8, own)
     if h.row_start:
-        r.row_contig = _arr(h.row_contig, n, np.uint32)
-        r.row_start = _arr(h.row_start, n, np.int64)
-        r.row_end = _arr(h.row_end, n, np.int64)
-        r.row_plus = _arr(h.row_plus, n, np.uint8)
-        r.row_seq_off = _arr(h.row_seq_off, n + 1, np.uint64)
-        r.row_seq = _arr(h.row_seq, int(r.row_seq_off[-1]) if n else 0, np.uint8)
-    _lib.lib().kaamer_gpu_free_hits(hp)
+        r.row_contig = _view(h.row_contig, n, np.uint32, own)
+        r.row_start = _view(h.row_start, n, np.int64, own)
+        r.row_end = _view(h.row_end, n, np.int64, own)
+        r.row_plus = _view(h.row_plus, n, np.uint8, own)
+        r.row_seq_off = _view(h.row_seq_off, n + 1, np.uint64, own)
+        r.row_seq = _view(h.row_seq, int(r.row_seq_off[-1]) if n else 0, np.uint8, own)
     return r
 
 

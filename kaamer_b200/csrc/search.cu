@@ -52,11 +52,15 @@ __global__ void k_classify(SearchArgs a) {
       go = K >= 7;  // search_protein.go:74-76 (documented deviation: skipped, not fatal)
       if (go) a.kmin[q] = filter_kmin(a.min_kmatch, a.min_kratio, (int32_t)K);
     }
+    // Class W2 (warp-per-query with a 1024-slot table for 512 < K <= 2048) was measured and is not
+    // used: the warp-per-query kernels are bound by the per-warp counting work, W2's larger
+    // per-warp state halves the resident warps and it ran at 10 G lookups/s against 24 G/s for
+    // the CTA-per-query class M (profiles/r1_notes.md).
     if (go) cls = K <= W_MAXK ? 0 : (K <= M_MAXK ? 1 : 2);
   }
   // warp-aggregated append to the class lists (one atomic per warp and class)
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
+  for (int c = 0; c < 4; ++c) {
     const unsigned mask = __ballot_sync(0xFFFFFFFFu, cls == c);
     if (mask == 0) continue;
     const int leader = __ffs(mask) - 1;
@@ -68,39 +72,42 @@ __global__ void k_classify(SearchArgs a) {
 }
 
 // ---- class W: one warp per query ------------------------------------------------------------
-struct __align__(16) WarpSmem {
-  uint32_t hkeys[W_H];
-  uint16_t hcnt[W_H];
-  uint16_t pp[W_MAXK + 8];
+template <int H, int MAXK>
+struct __align__(16) WarpSmemT {
+  uint32_t hkeys[H];
+  uint16_t hcnt[H];
+  uint16_t pp[MAXK + 8];
   uint16_t cand[W_CAND];
   uint32_t ncand, flags, pad0, pad1;
 };
 
-__global__ void __launch_bounds__(W_WARPS * 32, 5) k_search_w(SearchArgs a) {
-  __shared__ WarpSmem sm[W_WARPS];
+// CLS: index of the class list / counters (0 = W, 3 = W2)
+template <int H, int MAXK, int WARPS, int MINB, int CLS>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_search_wt(SearchArgs a) {
+  __shared__ WarpSmemT<H, MAXK> sm[WARPS];
   __shared__ uint8_t lut[256];
-  lut[threadIdx.x] = (uint8_t)aa_code(threadIdx.x);
+  for (int i = threadIdx.x; i < 256; i += WARPS * 32) lut[i] = (uint8_t)aa_code(i);
   __syncthreads();
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  WarpSmem &s = sm[w];
-  const WarpHash hv{s.hkeys, s.hcnt};
+  WarpSmemT<H, MAXK> &s = sm[w];
+  const WarpHashT<H> hv{s.hkeys, s.hcnt};
   const CandList cl{&s.ncand, &s.flags, s.cand, nullptr, (uint32_t)W_CAND};
-  const uint32_t count = a.list_count[0];
+  const uint32_t count = a.list_count[CLS];
   const uint8_t *res_end = a.res + a.off[a.nq];
-  const uint32_t nwarps = gridDim.x * W_WARPS;
+  const uint32_t nwarps = gridDim.x * WARPS;
   const uint32_t N = a.max_results > 0 ? (uint32_t)a.max_results : 0u;
   unsigned long long my_incr = 0, my_lookups = 0;
   // dynamic scheduling: warps pull the next query from a global cursor (query lengths vary by
   // 10x, a static split left the SMs idle for ~20 % of the kernel); the next index is
   // fetched one query ahead so its latency is hidden
   uint32_t it_next = 0;
-  if (lane == 0) it_next = atomicAdd(&a.list_count[4], 1u);
+  if (lane == 0) it_next = atomicAdd(&a.list_count[4 + CLS], 1u);
   (void)nwarps;
   for (;;) {
     const uint32_t it = __shfl_sync(0xFFFFFFFFu, it_next, 0);
     if (it >= count) break;
-    if (lane == 0) it_next = atomicAdd(&a.list_count[4], 1u);
-    const uint32_t q = a.lists[it];
+    if (lane == 0) it_next = atomicAdd(&a.list_count[4 + CLS], 1u);
+    const uint32_t q = a.lists[(size_t)CLS * a.nq + it];
     const uint64_t b = a.off[q];
     const int len = (int)(a.off[q + 1] - b);
     const int K = a.size_in_kmer[q];
@@ -125,9 +132,9 @@ __global__ void __launch_bounds__(W_WARPS * 32, 5) k_search_w(SearchArgs a) {
       uint4 *hc = reinterpret_cast<uint4 *>(s.hcnt);
       const uint4 E = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY), Z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int i = 0; i < W_H / 4 / 32; ++i) hk[i * 32 + lane] = E;
+      for (int i = 0; i < H / 4 / 32; ++i) hk[i * 32 + lane] = E;
 #pragma unroll
-      for (int i = 0; i < W_H / 8 / 32; ++i) hc[i * 32 + lane] = Z;
+      for (int i = 0; i < H / 8 / 32; ++i) hc[i * 32 + lane] = Z;
       if (lane == 0) {
         s.ncand = 0;
         s.flags = 0;
@@ -218,11 +225,11 @@ __global__ void __launch_bounds__(W_WARPS * 32, 5) k_search_w(SearchArgs a) {
   if (lane == 0) {
     if (my_incr) {
       atomicAdd(&a.counters[CNT_INCR], my_incr);
-      atomicAdd(&a.counters[CNT_CLS_INCR + 0], my_incr);
+      atomicAdd(&a.counters[CNT_CLS_INCR + CLS], my_incr);
     }
     if (my_lookups) {
       atomicAdd(&a.counters[CNT_LOOKUPS], my_lookups);
-      atomicAdd(&a.counters[CNT_CLS_LOOKUPS + 0], my_lookups);
+      atomicAdd(&a.counters[CNT_CLS_LOOKUPS + CLS], my_lookups);
     }
   }
 }
@@ -498,9 +505,9 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   }
   if (nq == 0) return KAAMER_OK;
   SearchWorkspace &ws = h->ws;
-  KCHECK(ws.lists.ensure((size_t)3 * nq + 16));
+  KCHECK(ws.lists.ensure((size_t)4 * nq + 16));
   KCHECK(ws.kmin.ensure(nq));
-  uint32_t *list_count = ws.lists.p + (size_t)3 * nq;
+  uint32_t *list_count = ws.lists.p + (size_t)4 * nq;
   SearchArgs a{};
   a.table = h->idx.table;
   a.d_lo = h->idx.d_lo;
@@ -536,7 +543,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   const unsigned w_grid = (unsigned)h->sm_count * 5u;
   const unsigned m_grid = (unsigned)h->sm_count * 4u;
   profile_begin(h, st, 0);
-  k_search_w<<<w_grid, W_WARPS * 32, 0, st>>>(a);
+  k_search_wt<W_H, W_MAXK, W_WARPS, 5, 0><<<w_grid, W_WARPS * 32, 0, st>>>(a);
   profile_end(h, st);
   profile_begin(h, st, 1);
   k_search_m<<<m_grid < nq ? m_grid : nq, M_THREADS, 0, st>>>(a);

@@ -13,6 +13,8 @@ enum { ST_POOL_OVERFLOW = 1, ST_GHASH_OVERFLOW = 2 };
 
 // size classes by SizeInKmer
 constexpr int W_H = 512, W_MAXK = 512, W_WARPS = 8, W_CAND = 64;
+// class W2: the same warp-per-query kernel with a larger table for 512 < SizeInKmer <= 2048
+constexpr int W2_H = 1024, W2_MAXK = 2048, W2_WARPS = 4;
 constexpr int M_THREADS = 256, M_H = 4096, M_MAXK = 2048;
 constexpr int G_THREADS = 512;
 constexpr int FAST_C = 64;     // candidates ranked by counting below this, bitonic sort above
@@ -35,8 +37,8 @@ struct SearchArgs {
   uint64_t *pool;
   uint64_t pool_cap;
   unsigned long long *counters;
-  uint32_t *lists;       // [3][nq]
-  uint32_t *list_count;  // [8]: [0..2] list sizes, [4..6] work cursors (dynamic scheduling)
+  uint32_t *lists;       // [4][nq]: W, M, G, W2
+  uint32_t *list_count;  // [8]: [0..3] list sizes (W, M, G, W2), [4..7] work cursors (dynamic scheduling)
   uint32_t *ghash;       // class G scratch: per CTA [keys HG][cnt HG][cand HG]
   uint32_t ghash_slots;  // HG (power of two)
   // nucleotide / reads mode (search_nucleotide.go:76-124): queries are ORFs, the candidate
@@ -86,6 +88,7 @@ __device__ __forceinline__ uint64_t ldg_entry(const uint64_t *p) {
 // add(id) returns the count BEFORE the increment, or 0xFFFFFFFF when the table is full.
 // Shared-memory flavour: keys u32, counts u16 packed two per word (counts <= SizeInKmer <= 2048).
 struct SmemHash {
+  static constexpr bool kWarp = false;
   uint32_t *keys;
   uint32_t *cnt2;  // [slots/2]
   uint32_t mask;
@@ -113,6 +116,7 @@ struct SmemHash {
 };
 // Global-memory flavour (class G): keys u32, counts u32.
 struct GmemHash {
+  static constexpr bool kWarp = false;
   uint32_t *keys;
   uint32_t *cnt;
   uint32_t mask;
@@ -178,12 +182,15 @@ __device__ __forceinline__ void count_subject(const Hash &hv, uint32_t id, uint3
 // ids are merged with __match_any_sync and slots are claimed by write-then-verify.  This
 // removes every shared-memory atomic from the counting loop (ncu: the per-SM atomic unit was
 // the limiter of the atomic version).
-struct WarpHash {
-  uint32_t *keys;   // [W_H]
-  uint16_t *cnt;    // [W_H]
-  static constexpr uint32_t mask = W_H - 1;
+constexpr int ilog2_c(int x) { return x <= 1 ? 0 : 1 + ilog2_c(x / 2); }
+template <int H>
+struct WarpHashT {
+  uint32_t *keys;   // [H]
+  uint16_t *cnt;    // [H]
+  static constexpr bool kWarp = true;
+  static constexpr uint32_t mask = H - 1;
   static constexpr int kMaxProbe = MAX_PROBE;
-  __device__ __forceinline__ uint32_t home(uint32_t id) const { return (id * 2654435761u) >> (32 - 9); }
+  __device__ __forceinline__ uint32_t home(uint32_t id) const { return (id * 2654435761u) >> (32 - ilog2_c(H)); }
   __device__ __forceinline__ uint32_t key_at(uint32_t slot) const { return keys[slot]; }
   __device__ __forceinline__ uint32_t count_at(uint32_t slot) const { return cnt[slot]; }
 };
@@ -226,7 +233,8 @@ __device__ __noinline__ bool warp_any0(const SearchArgs &a, const Hash &hv, uint
 }
 
 // all 32 lanes call this together; lanes with valid==false only take part in the votes
-__device__ __forceinline__ void warp_count(const WarpHash &hv, bool valid, uint32_t id, uint32_t kmin,
+template <int H>
+__device__ __forceinline__ void warp_count(const WarpHashT<H> &hv, bool valid, uint32_t id, uint32_t kmin,
                                            const CandList &cl) {
   const unsigned lane = threadIdx.x & 31;
   const unsigned act = __ballot_sync(0xFFFFFFFFu, valid);
@@ -234,32 +242,31 @@ __device__ __forceinline__ void warp_count(const WarpHash &hv, bool valid, uint3
   unsigned peers = 0;
   if (valid) peers = __match_any_sync(act, id);
   const uint32_t mult = __popc(peers);
-  bool pending = valid && (lane == (unsigned)(__ffs(peers) - 1));  // one leader per distinct id
-  uint32_t slot = (id * 2654435761u) >> (32 - 9);
-  static_assert(W_H == 512, "hash shift assumes 512 slots");
+  // One leader per distinct id walks its probe sequence on its own (no warp-wide votes or
+  // barriers inside the loop: they were a quarter of the kernel's instructions and most of its
+  // stalls).  A slot is claimed with a CAS only when it is seen EMPTY, i.e. once per distinct
+  // subject of the query; counts are plain read-modify-writes by the single leader of that id.
+  if (valid && lane == (unsigned)(__ffs(peers) - 1)) {
+    uint32_t slot = hv.home(id);
+    int probe = 0;
 #pragma unroll 1
-  for (int probe = 0; probe < MAX_PROBE; ++probe) {
-    if (!__any_sync(0xFFFFFFFFu, pending)) return;
-    uint32_t key = pending ? hv.keys[slot] : 0u;
-    const bool claim = pending && key == EMPTY;
-    if (claim) hv.keys[slot] = id;  // racing leaders with different ids: one store survives
-    __syncwarp();
-    if (claim) key = hv.keys[slot];
-    if (pending) {
+    for (; probe < MAX_PROBE; ++probe) {
+      uint32_t key = *(volatile uint32_t *)(hv.keys + slot);
+      if (key == EMPTY) {
+        key = atomicCAS(hv.keys + slot, EMPTY, id);
+        if (key == EMPTY) key = id;
+      }
       if (key == id) {
         const uint32_t c = hv.cnt[slot];
         hv.cnt[slot] = (uint16_t)(c + mult);
         if (c < kmin && c + mult >= kmin) push_candidate(cl, slot);
-        pending = false;
-      } else {
-        slot = (slot + 1) & (W_H - 1);
+        break;
       }
+      slot = (slot + 1) & (H - 1);
     }
-    __syncwarp();
+    if (probe == MAX_PROBE) atomicOr(cl.flags, 1u);
   }
-  if (__any_sync(0xFFFFFFFFu, pending)) {
-    if (pending) atomicOr(cl.flags, 1u);
-  }
+  __syncwarp();
 }
 
 // ---- one warp-round of lookups ------------------------------------------------------------
@@ -287,7 +294,7 @@ __device__ __forceinline__ void warp_consume(const SearchArgs &a, const uint64_t
     any_big |= cnt >= BIG_LIST;
   }
   // (1) singletons
-  if constexpr (std::is_same<Hash, WarpHash>::value) {
+  if constexpr (Hash::kWarp) {
 #pragma unroll
     for (int u = 0; u < U; ++u) warp_count(hv, (uint32_t)(ent[u] >> ENTRY_VALUE_BITS) == 1u, vlo[u], kmin, cl);
   } else {
@@ -355,7 +362,7 @@ __device__ __forceinline__ void warp_consume(const SearchArgs &a, const uint64_t
     }
     uint32_t pid = 0;
     if (j < total) pid = __ldg(a.postings + (((uint64_t)sel_hi << 32) | sel_lo) + r);
-    if constexpr (std::is_same<Hash, WarpHash>::value) {
+    if constexpr (Hash::kWarp) {
       warp_count(hv, j < total, pid, kmin, cl);
     } else {
       if (j < total) count_subject(hv, pid, kmin, cl);
@@ -376,7 +383,7 @@ __device__ __forceinline__ void warp_consume(const SearchArgs &a, const uint64_t
         big &= big - 1;
         const uint32_t bc = __shfl_sync(0xFFFFFFFFu, cnt, src);
         const uint64_t bv = __shfl_sync(0xFFFFFFFFu, e & ENTRY_VALUE_MASK, src);
-        if constexpr (std::is_same<Hash, WarpHash>::value) {
+        if constexpr (Hash::kWarp) {
           for (uint32_t ib = 0; ib < bc; ib += 32) {
             const uint32_t i = ib + lane;
             warp_count(hv, i < bc, i < bc ? __ldg(a.postings + bv + i) : 0u, kmin, cl);

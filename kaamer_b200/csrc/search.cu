@@ -126,21 +126,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_search_wt(SearchArgs a) {
       }
       __syncwarp();
     }
-    // clear the histogram (16-byte stores)
-    {
-      uint4 *hk = reinterpret_cast<uint4 *>(s.hkeys);
-      uint4 *hc = reinterpret_cast<uint4 *>(s.hcnt);
-      const uint4 E = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY), Z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int i = 0; i < H / 4 / 32; ++i) hk[i * 32 + lane] = E;
-#pragma unroll
-      for (int i = 0; i < H / 8 / 32; ++i) hc[i * 32 + lane] = Z;
-      if (lane == 0) {
-        s.ncand = 0;
-        s.flags = 0;
-      }
-    }
-    __syncwarp();
     unsigned long long q_incr = 0;
     constexpr int U = 4;
     // software pipeline: the probes of round r+1 are in flight while round r is counted
@@ -157,6 +142,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_search_wt(SearchArgs a) {
     };
     uint64_t nxt[U];
     load_round(0, nxt);
+    // (the first probes are in flight while the histogram is cleared)
+    {
+      uint4 *hk = reinterpret_cast<uint4 *>(s.hkeys);
+      uint4 *hc = reinterpret_cast<uint4 *>(s.hcnt);
+      const uint4 E = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY), Z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int i = 0; i < H / 4 / 32; ++i) hk[i * 32 + lane] = E;
+#pragma unroll
+      for (int i = 0; i < H / 8 / 32; ++i) hc[i * 32 + lane] = Z;
+      if (lane == 0) {
+        s.ncand = 0;
+        s.flags = 0;
+      }
+    }
+    __syncwarp();
     for (int base = 0; base < K; base += U * 32) {
       uint64_t ent[U];
 #pragma unroll
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_search_wt(SearchArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(M_THREADS, 5) k_search_m(SearchArgs a) {
+__global__ void __launch_bounds__(M_THREADS, M_CTAS) k_search_m(SearchArgs a) {
   __shared__ __align__(16) uint32_t hkeys[M_H];
   __shared__ __align__(16) uint32_t hcnt2[M_H / 2];
   __shared__ uint16_t pp[M_MAXK + 8];
@@ -243,9 +243,9 @@ __global__ void __launch_bounds__(M_THREADS, 5) k_search_m(SearchArgs a) {
   __shared__ SelectScratch ss;
   constexpr int THREADS = M_THREADS;
   const int tid = threadIdx.x;
-  lut[tid] = (uint8_t)aa_code(tid);
+  for (int i = tid; i < 256; i += THREADS) lut[i] = (uint8_t)aa_code(i);
   __syncthreads();
-  const SmemHash hv{hkeys, hcnt2, (uint32_t)M_H - 1u, 32 - 12};
+  const SmemHash hv{hkeys, hcnt2, (uint32_t)M_H - 1u, 32 - ilog2_c(M_H)};
   const CandList cl{&ss.ncand, &ss.flags, cand, nullptr, (uint32_t)M_H};
   const uint32_t count = a.list_count[1];
   const uint8_t *res_end = a.res + a.off[a.nq];
@@ -261,17 +261,6 @@ __global__ void __launch_bounds__(M_THREADS, 5) k_search_m(SearchArgs a) {
     const int len = (int)(a.off[q + 1] - b);
     const int K = a.size_in_kmer[q];
     const uint32_t kmin = a.kmin[q];
-    {
-      uint4 *hk = reinterpret_cast<uint4 *>(hkeys);
-      uint4 *hc = reinterpret_cast<uint4 *>(hcnt2);
-      const uint4 E = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY), Z = make_uint4(0, 0, 0, 0);
-      for (int i = tid; i < M_H / 4; i += THREADS) hk[i] = E;
-      for (int i = tid; i < M_H / 8; i += THREADS) hc[i] = Z;
-      if (tid == 0) {
-        ss.ncand = 0;
-        ss.flags = 0;
-      }
-    }
     // raw residues staged in the (idle) candidate list with aligned 16-byte loads
     uint8_t *raw = reinterpret_cast<uint8_t *>(cand);
     const int head = stage_bytes<THREADS>(raw, a.res + b, len, res_end, tid);
@@ -299,6 +288,19 @@ __global__ void __launch_bounds__(M_THREADS, 5) k_search_m(SearchArgs a) {
     };
     uint64_t nxt[U];
     load_round(0, nxt);
+    // (the first probes are in flight while the histogram is cleared)
+    {
+      uint4 *hk = reinterpret_cast<uint4 *>(hkeys);
+      uint4 *hc = reinterpret_cast<uint4 *>(hcnt2);
+      const uint4 E = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY), Z = make_uint4(0, 0, 0, 0);
+      for (int i = tid; i < M_H / 4; i += THREADS) hk[i] = E;
+      for (int i = tid; i < M_H / 8; i += THREADS) hc[i] = Z;
+      if (tid == 0) {
+        ss.ncand = 0;
+        ss.flags = 0;
+      }
+    }
+    __syncthreads();
     for (int base = 0; base < K; base += U * THREADS) {
       uint64_t ent[U];
 #pragma unroll
@@ -310,8 +312,8 @@ __global__ void __launch_bounds__(M_THREADS, 5) k_search_m(SearchArgs a) {
     if (ss.flags) {
       // histogram full: class G
       if (tid == 0) {
-        uint32_t slot = atomicAdd(&a.list_count[2], 1u);
-        a.lists[(size_t)2 * a.nq + slot] = q;
+        uint32_t slot = atomicAdd(&a.list_count[3], 1u);  // list 3: hand-offs to class G (second G launch)
+        a.lists[(size_t)3 * a.nq + slot] = q;
       }
       __syncthreads();
       continue;
@@ -359,11 +361,11 @@ __global__ void __launch_bounds__(G_THREADS) k_search_g(SearchArgs a) {
   uint32_t *gkeys = a.ghash + (size_t)blockIdx.x * 3 * HG;
   uint32_t *gcnt = gkeys + HG;
   uint32_t *gcand = gcnt + HG;
-  const uint32_t count = a.list_count[2];
+  const uint32_t count = a.list_count[a.g_list];
   const uint8_t *res_end = a.res + a.off[a.nq];
   unsigned long long my_incr = 0, my_lookups = 0;
   for (uint32_t it = blockIdx.x; it < count; it += gridDim.x) {
-    const uint32_t q = a.lists[(size_t)2 * a.nq + it];
+    const uint32_t q = a.lists[(size_t)a.g_list * a.nq + it];
     const uint64_t b = a.off[q];
     const int K = a.size_in_kmer[q];
     const uint32_t kmin = a.kmin[q];
@@ -532,7 +534,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   a.nt_mode = nt_mode;
   a.any0 = d_any0;
   const int g_ctas = h->sm_count;
-  KCHECK(ws.ghash.ensure((size_t)g_ctas * 3 * a.ghash_slots));
+  KCHECK(ws.ghash.ensure((size_t)2 * g_ctas * 3 * a.ghash_slots));
   a.ghash = ws.ghash.p;
   KCUDA(cudaMemsetAsync(list_count, 0, 8 * sizeof(uint32_t), st));
   KCUDA(cudaMemsetAsync(out->counters, 0, CNT_N * sizeof(uint64_t), st));
@@ -541,17 +543,29 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   k_classify<<<(nq + 255) / 256, 256, 0, st>>>(a);
   // persistent grids: a multiple of the SM count, warps / CTAs loop over their class list
   const unsigned w_grid = (unsigned)h->sm_count * 5u;
-  const unsigned m_grid = (unsigned)h->sm_count * 4u;
+  const unsigned m_grid = (unsigned)h->sm_count * (unsigned)M_CTAS;
+  // Class G holds a handful of very long queries, one CTA each: its kernel is a long tail on a few
+  // SMs.  It is launched first, on the side stream, so that it runs underneath W and M; a second
+  // (normally empty) G launch after M takes the queries whose histograms outgrew class M.
+  cudaStream_t side = h->copy_stream;
+  KCUDA(cudaEventRecord(h->chunk_ev[6], st));
+  KCUDA(cudaStreamWaitEvent(side, h->chunk_ev[6], 0));
+  profile_begin(h, side, 2);
+  a.g_list = 2;
+  k_search_g<<<g_ctas, G_THREADS, 0, side>>>(a);
+  profile_end(h, side);
+  KCUDA(cudaEventRecord(h->chunk_ev[7], side));
   profile_begin(h, st, 0);
   k_search_wt<W_H, W_MAXK, W_WARPS, 5, 0><<<w_grid, W_WARPS * 32, 0, st>>>(a);
   profile_end(h, st);
   profile_begin(h, st, 1);
   k_search_m<<<m_grid < nq ? m_grid : nq, M_THREADS, 0, st>>>(a);
   profile_end(h, st);
-  profile_begin(h, st, 2);
+  a.g_list = 3;
+  a.ghash = ws.ghash.p + (size_t)g_ctas * 3 * a.ghash_slots;  // own scratch: the first G launch may still run
   k_search_g<<<g_ctas, G_THREADS, 0, st>>>(a);
-  profile_end(h, st);
-  h->prof_all_launches += 4;
+  KCUDA(cudaStreamWaitEvent(st, h->chunk_ev[7], 0));
+  h->prof_all_launches += 5;
   KCUDA(cudaGetLastError());
   return KAAMER_OK;
 }

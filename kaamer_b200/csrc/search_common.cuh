@@ -15,7 +15,7 @@ enum { ST_POOL_OVERFLOW = 1, ST_GHASH_OVERFLOW = 2 };
 constexpr int W_H = 512, W_MAXK = 512, W_WARPS = 8, W_CAND = 64;
 // class W2: the same warp-per-query kernel with a larger table for 512 < SizeInKmer <= 2048
 constexpr int W2_H = 1024, W2_MAXK = 2048, W2_WARPS = 4;
-constexpr int M_THREADS = 256, M_H = 4096, M_MAXK = 2048;
+constexpr int M_THREADS = 256, M_H = 4096, M_MAXK = 2048, M_CTAS = 5;
 constexpr int G_THREADS = 512;
 constexpr int FAST_C = 64;     // candidates ranked by counting below this, bitonic sort above
 constexpr int BIG_LIST = 32;   // posting lists at least this long are walked by the whole warp
@@ -48,6 +48,7 @@ struct SearchArgs {
   // (the only thing SetBestStartCodon reads from later tied hits, dna.go:224-237)
   int nt_mode;
   uint8_t *any0;
+  int g_list;  // class list processed by k_search_g (2: classified, 3: hand-offs from class M)
 };
 
 // Copy src[0, len) into shared memory with aligned 16-byte loads (one request per 16 residues:

@@ -191,3 +191,34 @@ def test_pinned_host_buffers_are_read_in_place(small_db, gpu_small):
     assert r.n_lookups == ora.n_lookups and r.n_increments == ora.n_increments
     r2 = gpu_small.search_proteins(q, qo, SearchOptions())
     assert_same_hits(r2, ora, "pageable / staged")
+
+
+def test_handle_is_thread_safe(small_db, gpu_small):
+    """Several host threads share one handle (calls are serialised inside the library, as the
+    goroutines of one kaamer request share the read-only stores, api/server.go:65)."""
+    import threading
+
+    from kaamer_b200 import SearchOptions, synth
+    from oracle import oracle as o
+
+    batches = []
+    for t in range(4):
+        q, qo, _ = synth.protein_queries(small_db["res"], small_db["off"], 400, config_index=1, stream=40 + t)
+        batches.append((q, qo, o.search_proteins(small_db["idx"], q, qo, o.opts(), 2)))
+    errors = []
+
+    def work(t):
+        try:
+            q, qo, ora = batches[t]
+            for _ in range(5):
+                r = gpu_small.search_proteins(q, qo, SearchOptions())
+                assert_same_hits(r, ora, f"thread {t}")
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errors, errors

@@ -159,7 +159,7 @@ def sharded(a):
 
     from kaamer_b200 import GpuIndex, SearchOptions, synth
     from kaamer_b200.makedb import fasta_protein_ids
-    from kaamer_b200.sharded import CudaShardBackend, ShardedSearch, SingleComm, TorchComm, make_fences, shard_arrays
+    from kaamer_b200.sharded import CudaShardBackend, ShardedSearch, SingleComm, TorchComm, fences_from_sample
 
     rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(lr)
@@ -167,19 +167,19 @@ def sharded(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     res, off = synth.protein_db(a.db_proteins, config_index=3)
     ids = fasta_protein_ids(len(off) - 1)
-    # full index once on this GPU (device build), exported, re-opened as this rank's key range
-    with GpuIndex.build(res, off, ids, keep_proteins=False, device=lr) as g0:
-        keys, offsets, postings = g0.index_arrays()
-    fences = make_fences(keys, offsets, world)
-    k, fo, p = shard_arrays(keys, offsets, postings, int(fences[rank]), int(fences[rank + 1]))
-    del keys, offsets, postings
+    # every rank builds its own key range on its GPU from the full record set; the fences come
+    # from the posting mass of a sample of the records (identical on every rank)
+    fences = fences_from_sample(res, off, world, device=lr)
+    t_build = time.perf_counter()
     nq = a.queries  # per rank (weak scaling, as bench.py)
     q, qo, _ = synth.protein_queries(res, off, nq, config_index=3, stream=100 + rank)
     dev = torch.device("cuda", lr)
     d_res = torch.from_numpy(q).to(dev)
     d_off = torch.from_numpy(qo.astype(np.int64)).to(dev)
     opts = SearchOptions()
-    with GpuIndex.from_arrays(k, fo, p, shard=(int(fences[rank]), int(fences[rank + 1])), device=lr) as g:
+    with GpuIndex.build(res, off, ids, keep_proteins=False, device=lr,
+                        shard=(int(fences[rank]), int(fences[rank + 1]))) as g:
+        t_build = time.perf_counter() - t_build
         s = ShardedSearch(CudaShardBackend(g), fences, TorchComm() if world > 1 else SingleComm())
         for _ in range(a.warmup):
             r = s.search(d_res, d_off, nq, opts)
@@ -205,6 +205,7 @@ def sharded(a):
                     "value": tot[0].item() / (t.item() * 1e-3), "ms_per_step": t.item(),
                     "kmer_lookups_per_sec": tot[1].item() / (t.item() * 1e-3),
                     "all_to_all_bytes_per_step": tot[2].item(), "hits": tot[3].item(),
+                    "db_residues": int(off[-1]), "shard_build_s_rank0": t_build,
                     "note": "device-resident queries; includes route, 2 x (counts + payload) all-to-all over NCCL, partial counts, merge; "
                             "host syncs for the split sizes are inside the timed region"}
             print(json.dumps(line))

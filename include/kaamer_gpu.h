@@ -67,6 +67,12 @@ int kaamer_gpu_open_view(const kaamer_index_view *view, int device, kaamer_gpu_t
  * (k-mer, protein id) -> CSR, built on the GPU.  ids[i] is the protein id of record i. */
 int kaamer_gpu_build(const uint8_t *residues, const uint64_t *seq_off, const uint32_t *ids,
                      uint64_t n_records, int keep_proteins, int device, kaamer_gpu_t **out);
+/* same, keeping only the k-mers whose dense code lies in [shard_lo, shard_hi) (mode S: every rank
+ * builds its own key range from the full record set; 0,0 = whole key space).  KStats cover the
+ * whole input. */
+int kaamer_gpu_build_shard(const uint8_t *residues, const uint64_t *seq_off, const uint32_t *ids,
+                           uint64_t n_records, int keep_proteins, int device, uint64_t shard_lo,
+                           uint64_t shard_hi, kaamer_gpu_t **out);
 void kaamer_gpu_close(kaamer_gpu_t *h);
 
 /* KStats (api/server.go:125-132 /api/dbinfo; feeds the e-value, pkg/align/align.go:141) */

@@ -133,6 +133,7 @@ SYMBOLS = [
     "kaamer_gpu_open",
     "kaamer_gpu_open_view",
     "kaamer_gpu_build",
+    "kaamer_gpu_build_shard",
     "kaamer_gpu_close",
     "kaamer_gpu_dbstats",
     "kaamer_gpu_index_sizes",
@@ -178,6 +179,7 @@ def lib() -> C.CDLL:
     L.kaamer_gpu_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.kaamer_gpu_open_view.argtypes = [C.POINTER(IndexView), C.c_int, C.POINTER(vp)]
     L.kaamer_gpu_build.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(vp)]
+    L.kaamer_gpu_build_shard.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(vp)]
     L.kaamer_gpu_close.argtypes = [vp]
     L.kaamer_gpu_close.restype = None
     u64p = C.POINTER(C.c_uint64)

@@ -235,6 +235,11 @@ int kaamer_gpu_open(const char *path, int device, kaamer_gpu_t **out) {
 
 int kaamer_gpu_build(const uint8_t *residues, const uint64_t *seq_off, const uint32_t *ids, uint64_t n_records,
                      int keep_proteins, int device, kaamer_gpu_t **out) {
+  return kaamer_gpu_build_shard(residues, seq_off, ids, n_records, keep_proteins, device, 0, 0, out);
+}
+
+int kaamer_gpu_build_shard(const uint8_t *residues, const uint64_t *seq_off, const uint32_t *ids, uint64_t n_records,
+                           int keep_proteins, int device, uint64_t shard_lo, uint64_t shard_hi, kaamer_gpu_t **out) {
   if (!out || (n_records && (!residues || !seq_off || !ids))) {
     set_error("null argument");
     return KAAMER_ERR_ARG;
@@ -242,7 +247,7 @@ int kaamer_gpu_build(const uint8_t *residues, const uint64_t *seq_off, const uin
   *out = nullptr;
   kaamer_gpu *h = nullptr;
   KCHECK(new_handle(device, &h));
-  int rc = index_build(h, residues, seq_off, ids, n_records, keep_proteins);
+  int rc = index_build(h, residues, seq_off, ids, n_records, keep_proteins, shard_lo, shard_hi);
   if (rc != KAAMER_OK) {
     destroy_handle(h);
     return rc;

@@ -155,11 +155,11 @@ int index_from_view(kaamer_gpu *h, const kaamer_index_view *v) {
 // ---------------------------------------------------------------------------------------
 // on-device build (makedb + indexdb semantics)
 // ---------------------------------------------------------------------------------------
-// one thread per residue position: window i of record r -> (key << 32 | id)
+// one warp per record (records average ~350 residues); lanes stride over the windows.  Only
+// windows whose dense code lies in [d_lo, d_hi) are kept (key-range shards build their own part).
 __global__ void k_emit_pairs(const uint8_t *__restrict__ res, const uint64_t *__restrict__ seq_off,
                              const uint64_t *__restrict__ win_off, const uint32_t *__restrict__ ids,
-                             uint64_t n_records, uint64_t *pairs) {
-  // one warp per record (records average ~350 residues); lanes stride over windows
+                             uint64_t n_records, uint64_t d_lo, uint64_t d_hi, uint64_t *pairs) {
   uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   uint32_t lane = threadIdx.x & 31;
   if (warp >= n_records) return;
@@ -170,26 +170,60 @@ __global__ void k_emit_pairs(const uint8_t *__restrict__ res, const uint64_t *__
   uint64_t wo = win_off[warp];
   uint64_t id = ids[warp];
   const uint8_t *s = res + b;
-  for (uint64_t i = lane; i < nwin; i += 32) {
-    uint32_t c[7];
+  for (uint64_t i0 = 0; i0 < nwin; i0 += 32) {
+    const uint64_t i = i0 + lane;
+    bool in = false;
+    uint32_t key = 0;
+    if (i < nwin) {
+      uint32_t c[7];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) c[j] = aa_code(s[i + j]);
-    uint32_t key = key_from_codes(c[0], c[1], c[2], c[3], c[4], c[5], c[6]);
-    pairs[wo + i] = ((uint64_t)key << 32) | id;
+      for (int j = 0; j < 7; ++j) c[j] = aa_code(s[i + j]);
+      const uint32_t d = dense_from_codes(c[0], c[1], c[2], c[3], c[4], c[5], c[6]);
+      in = d >= d_lo && d < d_hi;
+      key = key_from_codes(c[0], c[1], c[2], c[3], c[4], c[5], c[6]);
+    }
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, in);
+    if (in) pairs[wo + __popc(mask & ((1u << lane) - 1u))] = ((uint64_t)key << 32) | id;
+    wo += __popc(mask);
   }
 }
 
-__global__ void k_window_counts(const uint64_t *__restrict__ seq_off, uint64_t n_records, uint64_t *win,
+// windows of each record inside the shard's code range + KStats of the WHOLE input
+__global__ void k_window_counts(const uint8_t *__restrict__ res, const uint64_t *__restrict__ seq_off,
+                                uint64_t n_records, uint64_t d_lo, uint64_t d_hi, uint64_t *win,
                                 unsigned long long *stats) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_records) return;
-  uint64_t len = seq_off[i + 1] - seq_off[i];
-  uint64_t w = len >= KAAMER_KMER_SIZE ? len - KAAMER_KMER_SIZE + 1 : 0;
-  win[i] = w;
-  if (w) {
-    atomicAdd(stats + 0, 1ull);                      // NumberOfProteins
-    atomicAdd(stats + 1, (unsigned long long)len);   // NumberOfAA   (inputFASTA.go:142-145)
-    atomicAdd(stats + 2, (unsigned long long)w);     // NumberOfKmers
+  uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint32_t lane = threadIdx.x & 31;
+  if (warp >= n_records) return;
+  uint64_t b = seq_off[warp];
+  uint64_t len = seq_off[warp + 1] - b;
+  uint64_t nwin = len >= KAAMER_KMER_SIZE ? len - KAAMER_KMER_SIZE + 1 : 0;
+  uint64_t cnt = 0;
+  const uint8_t *s = res + b;
+  const bool whole = d_lo == 0 && d_hi >= DENSE_SPACE;
+  if (whole) {
+    cnt = nwin;
+  } else {
+    for (uint64_t i0 = 0; i0 < nwin; i0 += 32) {
+      const uint64_t i = i0 + lane;
+      bool in = false;
+      if (i < nwin) {
+        uint32_t c[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) c[j] = aa_code(s[i + j]);
+        const uint32_t d = dense_from_codes(c[0], c[1], c[2], c[3], c[4], c[5], c[6]);
+        in = d >= d_lo && d < d_hi;
+      }
+      cnt += __popc(__ballot_sync(0xFFFFFFFFu, in));
+    }
+  }
+  if (lane == 0) {
+    win[warp] = cnt;
+    if (nwin) {
+      atomicAdd(stats + 0, 1ull);                       // NumberOfProteins
+      atomicAdd(stats + 1, (unsigned long long)len);    // NumberOfAA   (inputFASTA.go:142-145)
+      atomicAdd(stats + 2, (unsigned long long)nwin);   // NumberOfKmers
+    }
   }
 }
 
@@ -223,7 +257,12 @@ __global__ void k_write_postings(const uint64_t *__restrict__ pairs, const uint6
 }
 
 int index_build(kaamer_gpu *h, const uint8_t *residues, const uint64_t *seq_off, const uint32_t *ids,
-                uint64_t n_records, int keep_proteins) {
+                uint64_t n_records, int keep_proteins, uint64_t shard_lo, uint64_t shard_hi) {
+  if (shard_lo == 0 && shard_hi == 0) shard_hi = DENSE_SPACE;
+  if (shard_hi > DENSE_SPACE || shard_lo >= shard_hi) {
+    set_error("build: bad shard range");
+    return KAAMER_ERR_ARG;
+  }
   DevIndex &ix = h->idx;
   cudaStream_t st = h->stream;
   uint64_t n_res = n_records ? seq_off[n_records] : 0;
@@ -261,7 +300,8 @@ int index_build(kaamer_gpu *h, const uint8_t *residues, const uint64_t *seq_off,
     BCUDA(cudaMemcpyAsync(d_res, residues, (size_t)n_res, cudaMemcpyHostToDevice, st));
     BCUDA(cudaMemcpyAsync(d_off, seq_off, (size_t)(n_records + 1) * 8, cudaMemcpyHostToDevice, st));
     BCUDA(cudaMemcpyAsync(d_ids, ids, (size_t)n_records * 4, cudaMemcpyHostToDevice, st));
-    k_window_counts<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(d_off, n_records, d_win, d_stats);
+    k_window_counts<<<(unsigned)((n_records * 32 + 255) / 256), 256, 0, st>>>(d_res, d_off, n_records, shard_lo, shard_hi,
+                                                                             d_win, d_stats);
     BCUDA(cudaGetLastError());
   } else {
     BCUDA(cudaMemsetAsync(d_off, 0, 8, st));
@@ -290,7 +330,7 @@ int index_build(kaamer_gpu *h, const uint8_t *residues, const uint64_t *seq_off,
   if (n_pairs) {
     uint64_t warps = n_records;
     unsigned grid = (unsigned)((warps * 32 + 255) / 256);
-    k_emit_pairs<<<grid, 256, 0, st>>>(d_res, d_off, d_woff, d_ids, n_records, d_pairs);
+    k_emit_pairs<<<grid, 256, 0, st>>>(d_res, d_off, d_woff, d_ids, n_records, shard_lo, shard_hi, d_pairs);
     BCUDA(cudaGetLastError());
     // radix sort (key,id) as one u64
     need = 0;
@@ -365,7 +405,7 @@ int index_build(kaamer_gpu *h, const uint8_t *residues, const uint64_t *seq_off,
   cudaFree(d_rank); d_rank = nullptr;
   cudaFree(d_head); d_head = nullptr;
   cudaFree(d_tmp); d_tmp = nullptr;
-  rc = alloc_table(h, 0, DENSE_SPACE);
+  rc = alloc_table(h, shard_lo, shard_hi);
   if (rc == KAAMER_OK) rc = fill_table(h);
   if (rc == KAAMER_OK && keep_proteins && n_records) {
     // protein table indexed by id (later records with the same id overwrite earlier ones,

@@ -314,7 +314,7 @@ namespace kaamer {
 // index.cu
 int index_from_view(kaamer_gpu *h, const kaamer_index_view *v);
 int index_build(kaamer_gpu *h, const uint8_t *residues, const uint64_t *seq_off, const uint32_t *ids,
-                uint64_t n_records, int keep_proteins);
+                uint64_t n_records, int keep_proteins, uint64_t shard_lo = 0, uint64_t shard_hi = 0);
 void index_release(kaamer_gpu *h);
 // search.cu
 int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint32_t nq,

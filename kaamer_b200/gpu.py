@@ -200,16 +200,17 @@ class GpuIndex:
         return cls(h, device)
 
     @classmethod
-    def build(cls, residues, seq_off, ids, keep_proteins: bool = True, device: int = 0) -> "GpuIndex":
+    def build(cls, residues, seq_off, ids, keep_proteins: bool = True, device: int = 0, shard=(0, 0)) -> "GpuIndex":
         """makedb + indexdb semantics on the GPU (pkg/makedb/inputFASTA.go:195-250,
-        pkg/indexdb/indexdb.go:68-150); ids[i] = protein id of record i."""
+        pkg/indexdb/indexdb.go:68-150); ids[i] = protein id of record i.  `shard` = dense-code
+        range [lo, hi) to keep (mode S), (0, 0) = everything."""
         residues = np.ascontiguousarray(residues, dtype=np.uint8)
         seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         assert len(seq_off) == len(ids) + 1
         h = C.c_void_p()
-        check(_lib.lib().kaamer_gpu_build(_vp(residues), _vp(seq_off), _vp(ids), len(ids), int(keep_proteins),
-                                          device, C.byref(h)))
+        check(_lib.lib().kaamer_gpu_build_shard(_vp(residues), _vp(seq_off), _vp(ids), len(ids), int(keep_proteins),
+                                                device, int(shard[0]), int(shard[1]), C.byref(h)))
         return cls(h, device)
 
     def close(self):

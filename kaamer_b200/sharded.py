@@ -65,6 +65,26 @@ def make_fences(keys: np.ndarray, offsets: np.ndarray, n_shards: int) -> np.ndar
     return np.maximum.accumulate(fences)
 
 
+def fences_from_sample(residues: np.ndarray, seq_off: np.ndarray, n_shards: int, device: int = 0,
+                       sample_records: int = 50_000) -> np.ndarray:
+    """Fences without the full index: the posting mass of an evenly spaced sample of the records
+    (indexed on the GPU) stands for the whole database.  Every rank computes the same fences."""
+    n = len(seq_off) - 1
+    if n_shards == 1 or n == 0:
+        return make_fences(np.zeros(0, np.uint32), np.zeros(1, np.uint64), n_shards)
+    step = max(1, n // sample_records)
+    pick = np.arange(0, n, step)
+    lens = (seq_off[pick + 1] - seq_off[pick]).astype(np.int64)
+    so = np.zeros(len(pick) + 1, dtype=np.uint64)
+    so[1:] = np.cumsum(lens)
+    pos = np.arange(int(so[-1]), dtype=np.int64) - np.repeat(so[:-1].astype(np.int64), lens)
+    sres = residues[np.repeat(seq_off[pick].astype(np.int64), lens) + pos]
+    with GpuIndex.build(sres, so, np.arange(1, len(pick) + 1, dtype=np.uint32), keep_proteins=False,
+                        device=device) as g:
+        keys, offsets, _ = g.index_arrays()
+    return make_fences(keys, offsets, n_shards)
+
+
 def shard_arrays(keys, offsets, postings, lo: int, hi: int):
     """The part of a flat index (keys, offsets, postings) whose dense codes lie in [lo, hi)."""
     d = dense_from_keys(keys)

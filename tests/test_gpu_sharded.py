@@ -99,3 +99,27 @@ def test_sharded_nccl_two_gpus():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "sharded nccl ok" in out.stdout
+
+
+def test_build_shard_equals_slice_of_full_index(small_db):
+    """kaamer_gpu_build_shard: every rank builds its own key range; the result is the slice of the
+    full index (oracle) for that range, and sample-based fences balance the posting mass."""
+    from kaamer_b200 import GpuIndex
+    from kaamer_b200.sharded import fences_from_sample, shard_arrays
+
+    idx = small_db["idx"]
+    fences = fences_from_sample(small_db["res"], small_db["off"], 3, sample_records=500)
+    assert fences[0] == 0 and len(fences) == 4
+    masses = []
+    for r in range(3):
+        lo, hi = int(fences[r]), int(fences[r + 1])
+        with GpuIndex.build(small_db["res"], small_db["off"], small_db["ids"], keep_proteins=False, shard=(lo, hi)) as g:
+            k, fo, p = g.index_arrays()
+            st = g.dbstats()
+        ek, efo, ep = shard_arrays(idx.keys, idx.offsets, idx.postings, lo, hi)
+        np.testing.assert_array_equal(k, ek)
+        np.testing.assert_array_equal(fo, efo)
+        np.testing.assert_array_equal(p, ep)
+        assert (st["NumberOfProteins"], st["NumberOfAA"], st["NumberOfKmers"]) == (idx.n_proteins, idx.n_aa, idx.n_kmers)
+        masses.append(len(k) + len(p))
+    assert max(masses) < 1.25 * sum(masses) / 3

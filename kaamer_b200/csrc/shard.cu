@@ -81,9 +81,116 @@ struct ShardArgs {
   uint32_t nseg;
   uint32_t *part_n;
   uint64_t *part_base;
-  uint32_t *work;  // [0] cursor, [1] overflow count, [2] cursor of the overflow pass
+  uint32_t *work;  // [0] CTA-tier cursor, [1] global-tier count, [3] warp-tier cursor, [4] CTA-tier count
   uint32_t *ovf;   // [nseg] segments that need the global-memory histogram
+  uint32_t *mid;   // [nseg] segments the warp tier passed on to the CTA tier
 };
+
+// ---- warp tier: one warp per segment, warp-private 512-slot histogram ------------------------
+// With 8 shards a 350-residue query leaves ~43 k-mers per segment: a CTA per segment spends its
+// time in barriers and table sweeps.  Here the candidate mechanism of the search kernels is
+// reused with kmin = 1: a slot enters the list when its subject is first seen, so the list IS the
+// set of distinct subjects and no sweep is needed.
+constexpr int SWP_H = 512, SWP_WARPS = 8, SWP_MAXN = 256;
+struct __align__(16) ShardWarpSmem {
+  uint32_t hkeys[SWP_H];
+  uint16_t hcnt[SWP_H];
+  uint16_t cand[SWP_H];
+  uint32_t ncand, flags, pad0, pad1;
+};
+
+__device__ __forceinline__ void swp_clear(ShardWarpSmem &s, unsigned lane) {
+  uint4 *hk = reinterpret_cast<uint4 *>(s.hkeys);
+  uint4 *hc = reinterpret_cast<uint4 *>(s.hcnt);
+  const uint4 E = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY), Z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int i = 0; i < SWP_H / 4 / 32; ++i) hk[i * 32 + lane] = E;
+#pragma unroll
+  for (int i = 0; i < SWP_H / 8 / 32; ++i) hc[i * 32 + lane] = Z;
+  if (lane == 0) {
+    s.ncand = 0;
+    s.flags = 0;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(SWP_WARPS * 32, 6) k_shard_count_w(ShardArgs a) {
+  __shared__ ShardWarpSmem sm[SWP_WARPS];
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  ShardWarpSmem &s = sm[w];
+  const WarpHashT<SWP_H> hv{s.hkeys, s.hcnt};
+  const CandList cl{&s.ncand, &s.flags, s.cand, nullptr, (uint32_t)SWP_H};
+  unsigned long long my_incr = 0, my_lookups = 0;
+  uint32_t it_next = 0;
+  if (lane == 0) it_next = atomicAdd(&a.work[3], 1u);
+  for (;;) {
+    const uint32_t seg = __shfl_sync(0xFFFFFFFFu, it_next, 0);
+    if (seg >= a.nseg) break;
+    if (lane == 0) it_next = atomicAdd(&a.work[3], 1u);
+    const uint64_t b = a.seg_off[seg];
+    const uint64_t n64 = a.seg_off[seg + 1] - b;
+    if (n64 == 0) {
+      if (lane == 0) {
+        a.part_n[seg] = 0;
+        a.part_base[seg] = 0;
+      }
+      continue;
+    }
+    if (n64 > SWP_MAXN) {
+      if (lane == 0) a.mid[atomicAdd(&a.work[4], 1u)] = seg;
+      continue;
+    }
+    const int n = (int)n64;
+    swp_clear(s, lane);
+    unsigned long long incr = 0;
+    constexpr int U = 4;
+    for (int base = 0; base < n; base += U * 32) {
+      uint64_t ent[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pos = base + u * 32 + (int)lane;
+        ent[u] = 0;
+        if (pos < n) {
+          const uint32_t d = a.codes[b + pos];
+          if (d >= a.sa.d_lo && d < a.sa.d_hi) ent[u] = ldg_entry(a.sa.table + (d - a.sa.d_lo));
+        }
+      }
+      warp_consume<U>(a.sa, ent, hv, 1u, cl, incr);
+    }
+    __syncwarp();
+    if (*(volatile uint32_t *)&s.flags) {
+      if (lane == 0) a.mid[atomicAdd(&a.work[4], 1u)] = seg;
+      __syncwarp();
+      continue;
+    }
+    const uint32_t c = *(volatile uint32_t *)&s.ncand;
+    unsigned long long pbase = 0;
+    if (lane == 0 && c) pbase = atomicAdd(&a.sa.counters[CNT_POOL], (unsigned long long)c);
+    pbase = __shfl_sync(0xFFFFFFFFu, pbase, 0);
+    const bool fits = pbase + c <= a.sa.pool_cap;
+    if (fits)
+      for (uint32_t i = lane; i < c; i += 32) {
+        const uint32_t sl = s.cand[i];
+        a.sa.pool[pbase + i] = (uint64_t)hv.key_at(sl) | ((uint64_t)hv.count_at(sl) << 32);
+      }
+    if (lane == 0) {
+      a.part_n[seg] = fits ? c : 0;
+      a.part_base[seg] = fits ? pbase : 0;
+      if (!fits) atomicOr(&a.sa.counters[CNT_STATUS], (unsigned long long)ST_POOL_OVERFLOW);
+    }
+    my_incr += incr;
+    if (lane == 0) my_lookups += (unsigned long long)n;
+    __syncwarp();
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    my_incr += __shfl_down_sync(0xFFFFFFFFu, my_incr, o);
+    my_lookups += __shfl_down_sync(0xFFFFFFFFu, my_lookups, o);
+  }
+  if (lane == 0) {
+    if (my_incr) atomicAdd(&a.sa.counters[CNT_INCR], my_incr);
+    if (my_lookups) atomicAdd(&a.sa.counters[CNT_LOOKUPS], my_lookups);
+  }
+}
 
 template <class Hash>
 __device__ __forceinline__ void hash_add(const Hash &hv, uint32_t id, uint32_t c, uint32_t *flags) {
@@ -175,9 +282,10 @@ __global__ void __launch_bounds__(SH_THREADS) k_shard_count(ShardArgs a) {
   for (;;) {
     if (tid == 0) s_seg = atomicAdd(&a.work[0], 1u);
     __syncthreads();
-    const uint32_t seg = s_seg;
+    const uint32_t it = s_seg;
     __syncthreads();
-    if (seg >= a.nseg) break;
+    if (it >= a.work[4]) break;
+    const uint32_t seg = a.mid[it];
     const uint64_t b = a.seg_off[seg];
     const uint64_t n64 = a.seg_off[seg + 1] - b;
     if (n64 == 0) {
@@ -312,9 +420,128 @@ struct MergeArgs {
   const uint64_t *part;      // (subject | count << 32)
   const uint64_t *part_off;  // [n_shards][nq+1] absolute offsets into part
   int n_shards;
-  uint32_t *work;            // [0] cursor, [1] overflow count
+  uint32_t *work;            // [0] CTA-tier cursor, [1] global-tier count, [3] warp-tier cursor, [4] CTA-tier count
   uint32_t *ovf;
+  uint32_t *mid;
 };
+
+// add `c` to the count of `id`; duplicates of an id inside the batch of 32 are summed first
+template <int H>
+__device__ __forceinline__ void warp_add(const WarpHashT<H> &hv, bool valid, uint32_t id, uint32_t c, uint32_t kmin,
+                                         const CandList &cl) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned act = __ballot_sync(0xFFFFFFFFu, valid);
+  if (act == 0) return;
+  unsigned peers = 0;
+  uint32_t mult = 0;
+  if (valid) {
+    peers = __match_any_sync(act, id);
+    mult = __reduce_add_sync(peers, c);
+  }
+  if (valid && lane == (unsigned)(__ffs(peers) - 1)) {
+    uint32_t slot = hv.home(id);
+    int probe = 0;
+#pragma unroll 1
+    for (; probe < MAX_PROBE; ++probe) {
+      uint32_t key = *(volatile uint32_t *)(hv.keys + slot);
+      if (key == EMPTY) {
+        key = atomicCAS(hv.keys + slot, EMPTY, id);
+        if (key == EMPTY) key = id;
+      }
+      if (key == id) {
+        const uint32_t old = hv.cnt[slot];
+        hv.cnt[slot] = (uint16_t)(old + mult);
+        if (old < kmin && old + mult >= kmin) push_candidate(cl, slot);
+        break;
+      }
+      slot = (slot + 1) & (H - 1);
+    }
+    if (probe == MAX_PROBE) atomicOr(cl.flags, 1u);
+  }
+  __syncwarp();
+}
+
+// warp tier of the merge: queries whose partial lists hold <= SWP_MAXN entries in total
+__global__ void __launch_bounds__(SWP_WARPS * 32, 6) k_shard_merge_w(MergeArgs a) {
+  __shared__ ShardWarpSmem sm[SWP_WARPS];
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  ShardWarpSmem &s = sm[w];
+  const WarpHashT<SWP_H> hv{s.hkeys, s.hcnt};
+  const CandList cl{&s.ncand, &s.flags, s.cand, nullptr, (uint32_t)SWP_H};
+  const uint32_t N = a.sa.max_results > 0 ? (uint32_t)a.sa.max_results : 0u;
+  uint32_t it_next = 0;
+  if (lane == 0) it_next = atomicAdd(&a.work[3], 1u);
+  for (;;) {
+    const uint32_t q = __shfl_sync(0xFFFFFFFFu, it_next, 0);
+    if (q >= a.sa.nq) break;
+    if (lane == 0) it_next = atomicAdd(&a.work[3], 1u);
+    const int K = a.sa.size_in_kmer[q];
+    if (lane == 0) {
+      a.sa.n_hits[q] = 0;
+      a.sa.hit_base[q] = 0;
+    }
+    if (K < 7) continue;  // search_protein.go:74-76
+    uint64_t total = 0;
+    for (int sh = 0; sh < a.n_shards; ++sh) {
+      const uint64_t *po = a.part_off + (size_t)sh * (a.sa.nq + 1) + q;
+      total += po[1] - po[0];
+    }
+    if (total == 0) continue;
+    if (total > SWP_MAXN || (uint32_t)K > SEG_MAX_U16) {
+      if (lane == 0) a.mid[atomicAdd(&a.work[4], 1u)] = q;
+      continue;
+    }
+    const uint32_t kmin = filter_kmin(a.sa.min_kmatch, a.sa.min_kratio, K);
+    swp_clear(s, lane);
+    for (int sh = 0; sh < a.n_shards; ++sh) {
+      const uint64_t *po = a.part_off + (size_t)sh * (a.sa.nq + 1) + q;
+      const uint64_t b = po[0], e = po[1];
+      for (uint64_t i0 = b; i0 < e; i0 += 32) {
+        const uint64_t i = i0 + lane;
+        const uint64_t v = i < e ? a.part[i] : 0ull;
+        warp_add(hv, i < e, (uint32_t)v, (uint32_t)(v >> 32), kmin, cl);
+      }
+    }
+    __syncwarp();
+    const uint32_t c = *(volatile uint32_t *)&s.ncand;
+    if (*(volatile uint32_t *)&s.flags || c > (uint32_t)W_CAND) {  // the CTA tier ranks large candidate sets
+      if (lane == 0) a.mid[atomicAdd(&a.work[4], 1u)] = q;
+      __syncwarp();
+      continue;
+    }
+    const uint32_t nout = c < N ? c : N;
+    if (nout) {
+      // c <= 64: rank by counting, two candidates per lane (same as the search kernels)
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(&a.sa.counters[CNT_POOL], (unsigned long long)nout);
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      const bool fits = base + nout <= a.sa.pool_cap;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const uint32_t i = lane + 32 * hh;
+        if (i < c) {
+          const uint32_t sl = s.cand[i];
+          const uint64_t me = composite(hv.key_at(sl), hv.count_at(sl));
+          uint32_t rank = 0;
+          for (uint32_t j = 0; j < c; ++j) {
+            const uint32_t sj = s.cand[j];
+            rank += composite(hv.key_at(sj), hv.count_at(sj)) < me ? 1u : 0u;
+          }
+          if (rank < nout && fits) a.sa.pool[base + rank] = decomposite(me);
+        }
+      }
+      if (lane == 0) {
+        if (fits) {
+          a.sa.n_hits[q] = nout;
+          a.sa.hit_base[q] = (uint32_t)base;
+        } else {
+          atomicOr(&a.sa.counters[CNT_STATUS], (unsigned long long)ST_POOL_OVERFLOW);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
 
 template <int THREADS, class Hash, class CandPush>
 __device__ __forceinline__ void merge_query(const MergeArgs &a, uint32_t q, const Hash &hv, uint32_t slots,
@@ -347,21 +574,16 @@ __global__ void __launch_bounds__(SH_THREADS) k_shard_merge(MergeArgs a) {
   for (;;) {
     if (tid == 0) s_q = atomicAdd(&a.work[0], 1u);
     __syncthreads();
-    const uint32_t q = s_q;
+    const uint32_t it = s_q;
     __syncthreads();
-    if (q >= a.sa.nq) break;
+    if (it >= a.work[4]) break;
+    const uint32_t q = a.mid[it];
     const int K = a.sa.size_in_kmer[q];
-    if (tid == 0) {
-      a.sa.n_hits[q] = 0;
-      a.sa.hit_base[q] = 0;
-    }
-    if (K < 7) continue;  // search_protein.go:74-76
     uint64_t total = 0;
     for (int s = 0; s < a.n_shards; ++s) {
       const uint64_t *po = a.part_off + (size_t)s * (a.sa.nq + 1) + q;
       total += po[1] - po[0];
     }
-    if (total == 0) continue;
     if (total > SH_H / 2 || (uint32_t)K > SEG_MAX_U16) {
       if (tid == 0) a.ovf[atomicAdd(&a.work[1], 1u)] = q;
       continue;
@@ -527,7 +749,7 @@ int kaamer_gpu_shard_count(kaamer_gpu_t *h, const uint32_t *d_codes, const uint6
   KCUDA(cudaMemsetAsync(d_counters, 0, CNT_N * sizeof(uint64_t), st));
   if (n_segments == 0) return KAAMER_OK;
   SearchWorkspace &ws = h->ws;
-  KCHECK(ws.lists.ensure((size_t)n_segments + 16));
+  KCHECK(ws.lists.ensure((size_t)2 * n_segments + 16));
   const uint32_t HG = 1u << 20;
   const int g_ctas = h->sm_count;
   KCHECK(ws.ghash.ensure((size_t)g_ctas * 3 * HG));
@@ -547,15 +769,20 @@ int kaamer_gpu_shard_count(kaamer_gpu_t *h, const uint32_t *d_codes, const uint6
   a.part_n = d_part_n;
   a.part_base = d_part_base;
   a.ovf = ws.lists.p;
-  a.work = ws.lists.p + n_segments;
+  a.mid = ws.lists.p + n_segments;
+  a.work = ws.lists.p + (size_t)2 * n_segments;
   KCUDA(cudaMemsetAsync(a.work, 0, 8 * sizeof(uint32_t), st));
   unsigned grid = (unsigned)h->sm_count * 4u;
-  if (grid > n_segments) grid = n_segments;
+  unsigned wgrid = (unsigned)h->sm_count * 6u;
+  if (wgrid > (n_segments + SWP_WARPS - 1) / SWP_WARPS) wgrid = (n_segments + SWP_WARPS - 1) / SWP_WARPS;
   profile_begin(h, st, 0);
+  k_shard_count_w<<<wgrid, SWP_WARPS * 32, 0, st>>>(a);
+  profile_end(h, st);
+  profile_begin(h, st, 1);
   k_shard_count<<<grid, SH_THREADS, COUNT_SMEM, st>>>(a);
   profile_end(h, st);
   k_shard_count_g<<<g_ctas, SH_THREADS, 0, st>>>(a);
-  h->prof_all_launches += 2;
+  h->prof_all_launches += 3;
   KCUDA(cudaGetLastError());
   return KAAMER_OK;
 }
@@ -595,7 +822,7 @@ int kaamer_gpu_shard_merge(kaamer_gpu_t *h, const uint64_t *d_part, const uint64
   KCUDA(cudaMemsetAsync(d_out->counters, 0, CNT_N * sizeof(uint64_t), st));
   if (nq == 0) return KAAMER_OK;
   SearchWorkspace &ws = h->ws;
-  KCHECK(ws.kmin.ensure((size_t)nq + 16));  // overflow list + work counters (lists may be in use by a shard pass)
+  KCHECK(ws.kmin.ensure((size_t)2 * nq + 16));  // tier lists + work counters (ws.lists may be in use by a shard pass)
   const uint32_t HG = 1u << 20;
   const int g_ctas = h->sm_count;
   KCHECK(ws.ghash.ensure((size_t)g_ctas * 3 * HG));
@@ -616,13 +843,16 @@ int kaamer_gpu_shard_merge(kaamer_gpu_t *h, const uint64_t *d_part, const uint64
   a.part_off = d_part_off;
   a.n_shards = n_shards;
   a.ovf = ws.kmin.p;
-  a.work = ws.kmin.p + nq;
+  a.mid = ws.kmin.p + nq;
+  a.work = ws.kmin.p + (size_t)2 * nq;
   KCUDA(cudaMemsetAsync(a.work, 0, 8 * sizeof(uint32_t), st));
   unsigned grid = (unsigned)h->sm_count * 3u;
-  if (grid > nq) grid = nq;
+  unsigned wgrid = (unsigned)h->sm_count * 6u;
+  if (wgrid > (nq + SWP_WARPS - 1) / SWP_WARPS) wgrid = (nq + SWP_WARPS - 1) / SWP_WARPS;
+  k_shard_merge_w<<<wgrid, SWP_WARPS * 32, 0, st>>>(a);
   k_shard_merge<<<grid, SH_THREADS, MERGE_SMEM, st>>>(a);
   k_shard_merge_g<<<g_ctas, SH_THREADS, 0, st>>>(a);
-  h->prof_all_launches += 2;
+  h->prof_all_launches += 3;
   KCUDA(cudaGetLastError());
   return KAAMER_OK;
 }

@@ -60,8 +60,12 @@ struct TranslateArgs {
   uint64_t total_nt;
   uint8_t *cod;
   // unsorted ORF records
-  unsigned long long *n_orfs;
+  unsigned long long *n_orfs;  // [0] ORF records, [1] end codons seen, [2] end list overflowed
   uint64_t cap;
+  // compacted list of "end" codons (stops and frame-final codons) as global codon indices: the ORF
+  // walk runs one thread per END instead of one per codon (5 % of them), with all lanes busy
+  uint32_t *ends;
+  uint64_t ends_cap;
   uint64_t *key;      // sort key
   uint32_t *r_contig;
   int32_t *r_b, *r_e, *r_cnt, *r_nalt;
@@ -73,12 +77,18 @@ __global__ void __launch_bounds__(256) k_translate6(TranslateArgs a) {
   if (threadIdx.x < 64) aas[threadIdx.x] = c_aas[threadIdx.x];
   __syncthreads();
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= a.total_nt) return;
-  const uint32_t c = find_contig(a.coff, a.nc, g);
-  const uint64_t cb = a.coff[c];
-  const int64_t L = (int64_t)(a.coff[c + 1] - cb);
-  const int64_t p = (int64_t)(g - cb);
-  if (L < 2 || p + 3 > L) return;  // Go would panic on len < 2 (dna.go:183-196): nothing emitted
+  bool end_p = false, end_m = false;
+  uint64_t gi_p = 0, gi_m = 0;
+  uint32_t c = 0;
+  int64_t L = 0, p = 0;
+  if (g < a.total_nt) {
+    c = find_contig(a.coff, a.nc, g);
+    const uint64_t cb = a.coff[c];
+    L = (int64_t)(a.coff[c + 1] - cb);
+    p = (int64_t)(g - cb);
+  }
+  // Go would panic on len < 2 (dna.go:183-196): nothing emitted
+  if (g < a.total_nt && L >= 2 && p + 3 <= L) {
   const int b0 = base_code(a.nt[g]), b1 = base_code(a.nt[g + 1]), b2 = base_code(a.nt[g + 2]);
   const bool ok = (b0 | b1 | b2) >= 0;
   const int64_t S = L / 3 + 1;
@@ -90,6 +100,8 @@ __global__ void __launch_bounds__(256) k_translate6(TranslateArgs a) {
       v = (uint8_t)aas[idx] | (uint8_t)(((START_MASK >> idx) & 1ull) << 7);
     }
     cod[(p % 3) * S + p / 3] = v;
+    end_p = (v & 0x7F) == '*' || p / 3 == (L - p % 3) / 3 - 1;
+    gi_p = a.cbase[c] + (uint64_t)((p % 3) * S + p / 3);
   }
   {
     // reverse complement (dna.go:55-63): only a<->t, c<->g are swapped = code ^ 2
@@ -100,6 +112,42 @@ __global__ void __launch_bounds__(256) k_translate6(TranslateArgs a) {
       v = (uint8_t)aas[idx] | (uint8_t)(((START_MASK >> idx) & 1ull) << 7);
     }
     cod[(3 + j % 3) * S + j / 3] = v;
+    end_m = (v & 0x7F) == '*' || j / 3 == (L - j % 3) / 3 - 1;
+    gi_m = a.cbase[c] + (uint64_t)((3 + j % 3) * S + j / 3);
+  }
+  }
+  // CTA-aggregated append of the end codons: one global atomic per block (one per warp made
+  // the kernel 3.5x slower: ~600 k atomics on one address)
+  __shared__ uint32_t s_cnt[2][8];
+  __shared__ unsigned long long s_base;
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned mp = __ballot_sync(0xFFFFFFFFu, end_p), mm = __ballot_sync(0xFFFFFFFFu, end_m);
+  if (lane == 0) {
+    s_cnt[0][w] = __popc(mp);
+    s_cnt[1][w] = __popc(mm);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tot = 0;
+    for (int t = 0; t < 2; ++t)
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t c2 = s_cnt[t][i];
+        s_cnt[t][i] = tot;  // exclusive offset of (strand t, warp i) inside the block
+        tot += c2;
+      }
+    s_base = tot ? atomicAdd(a.n_orfs + 1, (unsigned long long)tot) : 0ull;
+  }
+  __syncthreads();
+  const unsigned below = (1u << lane) - 1u;
+  if (end_p) {
+    const unsigned long long slot = s_base + s_cnt[0][w] + __popc(mp & below);
+    if (slot < a.ends_cap) a.ends[slot] = (uint32_t)gi_p;
+    else a.n_orfs[2] = 1;
+  }
+  if (end_m) {
+    const unsigned long long slot = s_base + s_cnt[1][w] + __popc(mm & below);
+    if (slot < a.ends_cap) a.ends[slot] = (uint32_t)gi_m;
+    else a.n_orfs[2] = 1;
   }
 }
 
@@ -197,7 +245,31 @@ __device__ __forceinline__ void orf_emit(const TranslateArgs &a, const OrfRec &r
   a.r_nalt[slot] = r.nalt;
 }
 
+// one thread per end codon of the compacted list
+__global__ void __launch_bounds__(256) k_orf_ends_list(TranslateArgs a) {
+  if (a.n_orfs[2]) return;  // list overflowed: the dense kernel below does the work
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  OrfRec r;
+  r.valid = false;
+  uint32_t c = 0;
+  int64_t L = 0;
+  int frame = 0;
+  if (i < a.n_orfs[1]) {
+    const uint64_t gi = a.ends[i];
+    c = find_contig(a.cbase, a.nc, gi);  // cbase is increasing like coff
+    L = (int64_t)(a.coff[c + 1] - a.coff[c]);
+    const int64_t S = L / 3 + 1;
+    const uint64_t o = gi - a.cbase[c];
+    frame = (int)(o / (uint64_t)S);
+    const int64_t k = (int64_t)(o % (uint64_t)S);
+    r = orf_close(k, a.cod + a.cbase[c] + (int64_t)frame * S);
+  }
+  orf_emit(a, r, c, L, frame);
+}
+
+// one thread per codon (fallback when the end list overflowed: > 12.5 % of the codons are ends)
 __global__ void __launch_bounds__(256) k_orf_ends(TranslateArgs a) {
+  if (!a.n_orfs[2]) return;
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   OrfRec rp, rm;
   rp.valid = rm.valid = false;
@@ -366,7 +438,14 @@ int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint
   TCHECK(h->arena.get(&d_coff, (size_t)nc + 1));
   TCHECK(h->arena.get(&d_cbase, (size_t)nc + 1));
   TCHECK(h->arena.get(&d_cod, (size_t)total_cod));
-  TCHECK(h->arena.get(&d_n, 1));
+  TCHECK(h->arena.get(&d_n, 4));
+  if (total_cod >= (1ull << 32)) {
+    set_error("batch too large: %llu codons (split the contigs over several calls)", (unsigned long long)total_cod);
+    return KAAMER_ERR_LIMIT;
+  }
+  const uint64_t ends_cap = total_cod / 8 + 1024;
+  uint32_t *d_ends = nullptr;
+  TCHECK(h->arena.get(&d_ends, (size_t)ends_cap));
   TCHECK(h->arena.get(&d_key, (size_t)cap));
   TCHECK(h->arena.get(&r_contig, (size_t)cap));
   TCHECK(h->arena.get(&r_frame, (size_t)cap));
@@ -376,7 +455,7 @@ int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint
   TCHECK(h->arena.get(&r_nalt, (size_t)cap));
   TCUDA(cudaMemcpyAsync(d_coff, h_coff, ((size_t)nc + 1) * 8, cudaMemcpyHostToDevice, st));
   TCUDA(cudaMemcpyAsync(d_cbase, cbase.data(), ((size_t)nc + 1) * 8, cudaMemcpyHostToDevice, st));
-  TCUDA(cudaMemsetAsync(d_n, 0, 8, st));
+  TCUDA(cudaMemsetAsync(d_n, 0, 32, st));
   TranslateArgs ta{};
   ta.nt = d_nt;
   ta.coff = d_coff;
@@ -386,6 +465,8 @@ int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint
   ta.cod = d_cod;
   ta.n_orfs = d_n;
   ta.cap = cap;
+  ta.ends = d_ends;
+  ta.ends_cap = ends_cap;
   ta.key = d_key;
   ta.r_contig = r_contig;
   ta.r_frame = r_frame;
@@ -398,9 +479,10 @@ int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint
     const unsigned grid = (unsigned)((total_nt + 255) / 256);
     profile_begin(h, st, 7);
     k_translate6<<<grid, 256, 0, st>>>(ta);
+    k_orf_ends_list<<<(unsigned)((ends_cap + 255) / 256), 256, 0, st>>>(ta);
     k_orf_ends<<<grid, 256, 0, st>>>(ta);
     profile_end(h, st);
-    h->prof_all_launches += 2;
+    h->prof_all_launches += 3;
     TCUDA(cudaGetLastError());
     TCUDA(cudaMemcpyAsync(&n_orfs, d_n, 8, cudaMemcpyDeviceToHost, st));
     TCUDA(cudaStreamSynchronize(st));

@@ -64,6 +64,21 @@ def test_orfs_edge_contigs(gpu_small):
     assert_same_orfs(t, _oracle_orfs(contigs))
 
 
+def test_orfs_stop_dense_contig_takes_the_dense_fallback(gpu_small):
+    """more than 12.5 % of the codons are stops: the compacted end list overflows and the
+    one-thread-per-codon kernel must produce the same ORFs"""
+    from oracle import oracle as o
+
+    rng = np.random.default_rng(3)
+    acgt = np.frombuffer(b"acgt", np.uint8)
+    contigs = [b"taa" * 4000, b"taa" * 700 + acgt[rng.integers(0, 4, 900)].tobytes() + b"tag" * 500 + b"a",
+               b"ttaa" * 3000]
+    nt, off = o.pack(contigs)
+    t = gpu_small.get_orfs(nt, off)
+    assert len(t) > 3
+    assert_same_orfs(t, _oracle_orfs(contigs))
+
+
 def test_orfs_synthetic_contigs(small_db, gpu_small):
     from kaamer_b200 import synth
 

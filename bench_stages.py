@@ -83,6 +83,48 @@ def c2(a):
     print(json.dumps(line))
 
 
+def reads(a):
+    """FASTQ-like batch: many short reads through the nucleotide path (search_fastq.go:78-140 is the
+    per-ORF loop of the nucleotide search applied to every read)."""
+    from kaamer_b200 import GpuIndex, SearchOptions, synth
+    from kaamer_b200.makedb import fasta_protein_ids
+    from oracle import oracle as o
+
+    res, off = synth.protein_db(10_000, config_index=1)
+    ids = fasta_protein_ids(len(off) - 1)
+    nt, noff = synth.nucleotide_contigs(res, off, 2, 5_000_000, config_index=2)
+    rng = np.random.default_rng(7)
+    n_reads, rl = a.reads, 150
+    start = rng.integers(0, len(nt) - rl, n_reads)
+    rd = nt[(start[:, None] + np.arange(rl)[None, :]).reshape(-1)]
+    roff = (np.arange(n_reads + 1, dtype=np.uint64) * rl)
+    threads = os.cpu_count() or 1
+    with GpuIndex.build(res, off, ids, keep_proteins=False) as g:
+        opts = SearchOptions()
+        for _ in range(a.warmup):
+            r = g.search_nucleotide(rd, roff, opts)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            r = g.search_nucleotide(rd, roff, opts)
+        dt = (time.perf_counter() - t0) / a.steps
+    idx = o.Index.build(res, off, ids, threads)
+    ns = min(n_reads, 50_000)
+    t0 = time.perf_counter()
+    ro = o.search_nucleotide(idx, rd[:ns * rl], roff[:ns + 1], o.opts(), threads)
+    cpu_s = time.perf_counter() - t0
+    # parity on the CPU sample: the first rows of the GPU result are the rows of the first `ns` reads
+    k = int(np.searchsorted(r.row_contig, ns))
+    ok = (k == ro.n_rows and np.array_equal(r.subject[:int(r.hit_off[k])], ro.subject)
+          and np.array_equal(r.row_start[:k], ro.row_start))
+    print(json.dumps({
+        "workload": f"reads: {n_reads} x {rl} nt sampled from 2 x 5 Mb synthetic contigs vs 10 000-protein DB, default options",
+        "metric": "query residues/sec", "unit": "nt/s", "value": n_reads * rl / dt, "ms_per_step": 1e3 * dt,
+        "rows": int(r.n_rows), "hits": int(len(r.subject)), "orf_kmer_lookups": int(r.n_lookups),
+        "parity_sample": {"reads": ns, "rows_hits_locations_equal_oracle": bool(ok)},
+        "cpu_baseline": {"value": ns * rl / cpu_s, "unit": "nt/s", "cores": threads, "kind": "port",
+                         "sample": f"{ns} reads, CPU restatement (oracle/): reads serial, ORF searches of one read on all threads"}}))
+
+
 def c5(a):
     import torch
 
@@ -216,7 +258,8 @@ def sharded(a):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["c2", "c5", "sharded"])
+    ap.add_argument("--workload", required=True, choices=["c2", "c5", "sharded", "reads"])
+    ap.add_argument("--reads", type=int, default=1_000_000)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--contigs", type=int, default=2)
@@ -224,4 +267,4 @@ if __name__ == "__main__":
     ap.add_argument("--queries", type=int, default=100_000)
     ap.add_argument("--cpu-pairs", type=int, default=2000)
     a = ap.parse_args()
-    {"c2": c2, "c5": c5, "sharded": sharded}[a.workload](a)
+    {"c2": c2, "c5": c5, "sharded": sharded, "reads": reads}[a.workload](a)

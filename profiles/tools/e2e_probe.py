@@ -1,5 +1,5 @@
 import ctypes as C, sys, time
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.join(__import__('os').path.dirname(__import__('os').path.abspath(__file__)), '..', '..'))
 import numpy as np, torch
 from kaamer_b200 import GpuIndex, SearchOptions, synth, _lib
 from kaamer_b200.makedb import fasta_protein_ids

@@ -222,3 +222,40 @@ def test_handle_is_thread_safe(small_db, gpu_small):
     for x in th:
         x.join()
     assert not errors, errors
+
+
+def test_c1_fasta_pipeline(tmp_path):
+    """BASELINE.json configs[0]: `kaamer-db -make` on a synthetic 10 k-protein FASTA, then 1 k protein
+    queries with the default options — FASTA -> records/ids (host) -> device index -> search, against
+    the oracle's makedb + indexdb + search on the same file."""
+    from kaamer_b200 import GpuIndex, SearchOptions, makedb, synth
+    from oracle import oracle as o
+
+    res, off = synth.protein_db(10_000, config_index=1)
+    names = [f"sp|S{i:06d}|SYN_{i} synthetic protein {i}" for i in range(1, 10_001)]
+    fa = str(tmp_path / "c1.fa")
+    synth.write_fasta(fa, names, res, off)
+    _, _, r_res, r_off, r_ids = makedb.read_fasta(fa)
+    q, qo, pick = synth.protein_queries(res, off, 1000, config_index=1, stream=1)
+    idx = o.Index.build(r_res, r_off, r_ids, 8)
+    ora = o.search_proteins(idx, q, qo, o.opts(), 8)
+    with GpuIndex.build(r_res, r_off, r_ids, keep_proteins=True) as g:
+        k, f, p = g.index_arrays()
+        np.testing.assert_array_equal(k, idx.keys)
+        np.testing.assert_array_equal(f, idx.offsets)
+        np.testing.assert_array_equal(p, idx.postings)
+        assert g.dbstats() == {"NumberOfProteins": idx.n_proteins, "NumberOfAA": idx.n_aa, "NumberOfKmers": idx.n_kmers}
+        r = g.search_proteins(q, qo, SearchOptions())
+        assert_same_hits(r, ora, "C1")
+        assert r.n_lookups == ora.n_lookups and r.n_increments == ora.n_increments
+        # the source record of every query is its best hit (ids follow the FASTA id quirk)
+        has = np.diff(r.hit_off.astype(np.int64)) > 0
+        assert has.mean() > 0.99
+        top = r.subject[r.hit_off[:-1].astype(np.int64)[has]]
+        assert (top == r_ids[pick][has]).mean() > 0.98
+        # .kidx round trip of the C1 index
+        path = str(tmp_path / "c1.kidx")
+        g.save(path)
+    with GpuIndex.open(path) as g2:
+        r2 = g2.search_proteins(q, qo, SearchOptions())
+        assert_same_hits(r2, ora, "C1 from .kidx")

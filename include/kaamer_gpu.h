@@ -169,7 +169,9 @@ int kaamer_gpu_align(kaamer_gpu_t *h, const uint8_t *q_residues, const uint64_t 
 
 /* ---- device-resident entry points (inputs already in HBM; used by bench.py `value`, by the
  * multi-GPU drivers and by callers that keep query batches on the device).  All pointers are
- * device pointers; work is enqueued on `stream` (a cudaStream_t) and is asynchronous. ---- */
+ * device pointers; work is enqueued on `stream` (a cudaStream_t) and is asynchronous.  The
+ * handle's scratch buffers are shared by these calls: enqueue all device-resident calls of one
+ * handle on ONE stream (or order them with events); use one handle per stream otherwise. ---- */
 typedef struct kaamer_dev_result {
   uint32_t *n_hits;      /* [nq]   hits kept per query */
   uint32_t *hit_base;    /* [nq]   first slot of the query's hits in `pool` */

@@ -7,6 +7,7 @@ CPU restatement (oracle/) timed beside it on a bounded sample.
     python bench_stages.py --workload c2        translated search: 5 Mb contigs vs the 10k-protein DB
     python bench_stages.py --workload c5        Smith-Waterman re-alignment of the hits of a C3 batch
     torchrun ... bench_stages.py --workload sharded   mode S (key-range shards + NCCL all-to-all)
+    torchrun ... bench_stages.py --workload peer      mode P (key-range shards peer-mapped, NVLink probes)
 """
 from __future__ import annotations
 
@@ -256,9 +257,103 @@ def sharded(a):
         dist.destroy_process_group()
 
 
+def peer(a):
+    """mode P: key-range shards mapped into every rank (CUDA IPC), probed through NVLink by the
+    ordinary search kernels; same database, fences and per-rank query batches as `sharded`."""
+    import torch
+    import torch.distributed as dist
+
+    from kaamer_b200 import SearchOptions, synth
+    from kaamer_b200 import GpuIndex
+    from kaamer_b200.makedb import fasta_protein_ids
+    from kaamer_b200.peer import attach_distributed
+    from kaamer_b200.sharded import fences_from_sample
+
+    rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(lr)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    res, off = synth.protein_db(a.db_proteins, config_index=3)
+    ids = fasta_protein_ids(len(off) - 1)
+    fences = fences_from_sample(res, off, world, device=lr)
+    nq = a.queries  # per rank (weak scaling)
+    q, qo, _ = synth.protein_queries(res, off, nq, config_index=3, stream=100 + rank)
+    dev = torch.device("cuda", lr)
+    d_res = torch.from_numpy(q).to(dev)
+    d_off = torch.from_numpy(qo.astype(np.int64)).to(dev)
+    opts = SearchOptions()
+    t_build = time.perf_counter()
+    g = GpuIndex.build(res, off, ids, keep_proteins=False, device=lr, shard=(int(fences[rank]), int(fences[rank + 1])))
+    t_build = time.perf_counter() - t_build
+    if world > 1:
+        attach_distributed(g)
+    else:
+        g.attach_shards([g.export_shard()])
+    pool_cap = nq * 16 + 4096
+    d_nhits = torch.zeros(nq, dtype=torch.int32, device=dev)
+    d_base = torch.zeros(nq, dtype=torch.int32, device=dev)
+    d_size = torch.zeros(nq, dtype=torch.int32, device=dev)
+    d_pool = torch.zeros(pool_cap, dtype=torch.int64, device=dev)
+    d_cnt = torch.zeros(16, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        g.search_proteins_device(d_res.data_ptr(), d_off.data_ptr(), nq, opts, d_nhits.data_ptr(), d_base.data_ptr(),
+                                 d_size.data_ptr(), d_pool.data_ptr(), pool_cap, d_cnt.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, a.warmup)):
+        step()
+    barrier()
+    g.profile_enable(True)
+    g.profile_read(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(a.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1) / a.steps
+    prof = g.profile_read(reset=True)
+    c = d_cnt.cpu().numpy().astype(np.uint64)
+    assert int(c[3]) == 0, "status flags set"
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(qo[-1]), float(c[1]), float(c[2]), float(int(d_nhits.sum().item()))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        lookups = tot[1].item()
+        pbar = tot[2].item() / max(1.0, lookups)
+        remote = (world - 1) / world
+        line = {"workload": f"mode P: {a.db_proteins}-protein DB key-range sharded over {world} GPU(s), shards peer-mapped (CUDA IPC) "
+                            f"and probed through NVLink, {nq} queries per rank",
+                "metric": "query residues/sec", "unit": "residues/s", "n_gpus": world, "scaling": "weak",
+                "value": tot[0].item() / (t.item() * 1e-3), "ms_per_step": t.item(),
+                "kmer_lookups_per_sec": lookups / (t.item() * 1e-3),
+                "postings_per_lookup": pbar, "hits": tot[3].item(), "db_residues": int(off[-1]),
+                "remote_probe_fraction_expected": remote,
+                "nvlink_payload_bytes_per_step_est": lookups * remote * (8.0 + 4.0 * max(0.0, pbar - 0.94)),
+                "kernel_ms_rank0": {n: prof["kernel_ms"][i] / max(1, prof["kernel_launches"][i]) for i, n in enumerate(["W", "M", "G"])},
+                "shard_build_s_rank0": t_build,
+                "note": "device-resident queries; no data-path collective: remote table entries and posting lists are "
+                        "read by the search kernels with peer loads (sector-granular NVLink reads)"}
+        print(json.dumps(line))
+    barrier()
+    g.detach_shards()
+    barrier()
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["c2", "c5", "sharded", "reads"])
+    ap.add_argument("--workload", required=True, choices=["c2", "c5", "sharded", "peer", "reads"])
     ap.add_argument("--reads", type=int, default=1_000_000)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
@@ -267,4 +362,4 @@ if __name__ == "__main__":
     ap.add_argument("--queries", type=int, default=100_000)
     ap.add_argument("--cpu-pairs", type=int, default=2000)
     a = ap.parse_args()
-    {"c2": c2, "c5": c5, "sharded": sharded, "reads": reads}[a.workload](a)
+    {"c2": c2, "c5": c5, "sharded": sharded, "peer": peer, "reads": reads}[a.workload](a)

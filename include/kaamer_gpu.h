@@ -216,6 +216,34 @@ int kaamer_gpu_shard_merge(kaamer_gpu_t *h, const uint64_t *d_part, const uint64
                            uint32_t nq, const int32_t *d_size_in_kmer, const kaamer_opts *opts,
                            const kaamer_dev_result *d_out, void *stream);
 
+/* ---- peer-mapped shards (mode P): the key-range shards of all GPUs of one NVSwitch
+ * domain form ONE index.  Every rank builds (or loads) its own range, exports it, and attaches the
+ * exports of all ranks; from then on the ordinary entry points of the handle
+ * (kaamer_gpu_search_proteins[_device], _search_nucleotide) see the whole key space: the search
+ * kernels resolve the owner of each k-mer and read its table entry and posting list from that
+ * GPU's HBM through NVLink (peer loads inside the kernel; no all-to-all, no merge step — Kmatch
+ * is accumulated at the query's home GPU exactly as in the single-GPU path, search.go:431-436).
+ * A kaamer_shard_handle is plain bytes: ship it between processes with any transport
+ * (torch.distributed all_gather_object, a pipe, a file).  Same-process shards (one Go process
+ * driving several GPUs) are attached by pointer with peer access enabled; shards of other
+ * processes through cudaIpcOpenMemHandle. ---- */
+typedef struct kaamer_shard_handle {
+  uint64_t shard_lo, shard_hi; /* dense-code range [lo, hi) held by the exporting handle */
+  uint64_t n_postings;
+  uint64_t table_ptr, postings_ptr; /* device pointers in the exporting process */
+  int32_t device;                   /* CUDA ordinal in the exporting process */
+  int32_t pid;                      /* exporting process */
+  uint8_t table_ipc[64];            /* cudaIpcMemHandle_t of the table */
+  uint8_t postings_ipc[64];         /* cudaIpcMemHandle_t of the postings */
+} kaamer_shard_handle;
+#define KAAMER_MAX_PEER_SHARDS 8
+int kaamer_gpu_shard_export(kaamer_gpu_t *h, kaamer_shard_handle *out);
+/* shards[n_shards]: the exports of ALL ranks (this handle's own included), in any order; their
+ * ranges must tile [0, kaamer_gpu_dense_space()).  The exporting handles must stay open while
+ * attached.  Re-attaching replaces the previous set. */
+int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards, int n_shards);
+int kaamer_gpu_detach_shards(kaamer_gpu_t *h);
+
 /* pinned host buffers for callers that want zero-staging H2D (cgo: C.kaamer_gpu_pinned_alloc) */
 int kaamer_gpu_pinned_alloc(uint64_t bytes, void **out);
 void kaamer_gpu_pinned_free(void *p);

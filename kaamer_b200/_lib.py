@@ -128,6 +128,21 @@ class DevResult(C.Structure):
     ]
 
 
+class ShardHandle(C.Structure):
+    """kaamer_shard_handle: plain bytes, picklable through bytes(handle)."""
+    _fields_ = [
+        ("shard_lo", C.c_uint64),
+        ("shard_hi", C.c_uint64),
+        ("n_postings", C.c_uint64),
+        ("table_ptr", C.c_uint64),
+        ("postings_ptr", C.c_uint64),
+        ("device", C.c_int32),
+        ("pid", C.c_int32),
+        ("table_ipc", C.c_uint8 * 64),
+        ("postings_ipc", C.c_uint8 * 64),
+    ]
+
+
 # every symbol include/kaamer_gpu.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "kaamer_gpu_open",
@@ -151,6 +166,9 @@ SYMBOLS = [
     "kaamer_gpu_shard_count",
     "kaamer_gpu_shard_gather",
     "kaamer_gpu_shard_merge",
+    "kaamer_gpu_shard_export",
+    "kaamer_gpu_attach_shards",
+    "kaamer_gpu_detach_shards",
     "kaamer_gpu_pinned_alloc",
     "kaamer_gpu_pinned_free",
     "kaamer_gpu_profile_enable",
@@ -202,6 +220,9 @@ def lib() -> C.CDLL:
     L.kaamer_gpu_shard_count.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint64, vp, vp]
     L.kaamer_gpu_shard_gather.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, vp, vp]
     L.kaamer_gpu_shard_merge.argtypes = [vp, vp, vp, C.c_int, C.c_uint32, vp, C.POINTER(Opts), C.POINTER(DevResult), vp]
+    L.kaamer_gpu_shard_export.argtypes = [vp, C.POINTER(ShardHandle)]
+    L.kaamer_gpu_attach_shards.argtypes = [vp, C.POINTER(ShardHandle), C.c_int]
+    L.kaamer_gpu_detach_shards.argtypes = [vp]
     L.kaamer_gpu_pinned_alloc.argtypes = [C.c_uint64, C.POINTER(vp)]
     L.kaamer_gpu_pinned_free.argtypes = [vp]
     L.kaamer_gpu_pinned_free.restype = None

@@ -4,6 +4,9 @@
 #include <cstdio>
 #include <cstring>
 
+#include <algorithm>
+#include <unistd.h>
+
 #include "internal.cuh"
 
 namespace kaamer {
@@ -143,6 +146,10 @@ static int new_handle(int device, kaamer_gpu **out) {
 static void destroy_handle(kaamer_gpu *h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  for (void *p : h->idx.ipc_open) cudaIpcCloseMemHandle(p);
+  h->idx.ipc_open.clear();
+  if (h->idx.d_peer) cudaFree(h->idx.d_peer);
+  h->idx.d_peer = nullptr;
   index_release(h);
   h->ws.release_all();
   h->arena.release();
@@ -257,6 +264,150 @@ int kaamer_gpu_build_shard(const uint8_t *residues, const uint64_t *seq_off, con
 }
 
 void kaamer_gpu_close(kaamer_gpu_t *h) { destroy_handle(h); }
+
+// ---- peer-mapped shards (mode P) -----------------------------------------------------------
+int kaamer_gpu_shard_export(kaamer_gpu_t *h, kaamer_shard_handle *out) {
+  if (!h || !out) {
+    set_error("null argument");
+    return KAAMER_ERR_ARG;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) <= 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::lock_guard<std::mutex> lk(h->mu);
+  KCUDA(cudaSetDevice(h->device));
+  if (!h->idx.table) {
+    set_error("no index resident");
+    return KAAMER_ERR_ARG;
+  }
+  memset(out, 0, sizeof *out);
+  out->shard_lo = h->idx.d_lo;
+  out->shard_hi = h->idx.d_hi;
+  out->n_postings = h->idx.n_postings;
+  out->table_ptr = (uint64_t)(uintptr_t)h->idx.table;
+  out->postings_ptr = (uint64_t)(uintptr_t)h->idx.postings;
+  out->device = h->device;
+  out->pid = (int32_t)getpid();
+  if (h->idx.n_postings > PEER_LOCAL_MASK) {
+    set_error("shard holds %llu postings: more than 2^%d per shard cannot be peer-mapped",
+              (unsigned long long)h->idx.n_postings, PEER_SHARD_SHIFT);
+    return KAAMER_ERR_LIMIT;
+  }
+  KCUDA(cudaStreamSynchronize(h->stream));  // the build is complete before anyone maps it
+  cudaIpcMemHandle_t ht, hp;
+  KCUDA(cudaIpcGetMemHandle(&ht, h->idx.table));
+  KCUDA(cudaIpcGetMemHandle(&hp, h->idx.postings));
+  memcpy(out->table_ipc, &ht, sizeof ht);
+  memcpy(out->postings_ipc, &hp, sizeof hp);
+  return KAAMER_OK;
+}
+
+static void detach_shards_locked(kaamer_gpu *h) {
+  for (void *p : h->idx.ipc_open) cudaIpcCloseMemHandle(p);
+  h->idx.ipc_open.clear();
+  h->idx.peer = PeerView{};
+}
+
+int kaamer_gpu_detach_shards(kaamer_gpu_t *h) {
+  if (!h) {
+    set_error("null handle");
+    return KAAMER_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk(h->mu);
+  KCUDA(cudaSetDevice(h->device));
+  KCUDA(cudaStreamSynchronize(h->stream));
+  detach_shards_locked(h);
+  return KAAMER_OK;
+}
+
+int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards, int n_shards) {
+  if (!h || !shards) {
+    set_error("null argument");
+    return KAAMER_ERR_ARG;
+  }
+  if (n_shards < 1 || n_shards > MAX_PEER_SHARDS) {
+    set_error("n_shards %d out of range (1..%d)", n_shards, MAX_PEER_SHARDS);
+    return KAAMER_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk(h->mu);
+  KCUDA(cudaSetDevice(h->device));
+  KCUDA(cudaStreamSynchronize(h->stream));
+  detach_shards_locked(h);
+  // order by shard_lo and check that the ranges tile the dense code space
+  std::vector<int> order(n_shards);
+  for (int i = 0; i < n_shards; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int x, int y) { return shards[x].shard_lo < shards[y].shard_lo; });
+  uint64_t expect = 0;
+  for (int i = 0; i < n_shards; ++i) {
+    const kaamer_shard_handle &s = shards[order[i]];
+    if (s.shard_lo != expect || s.shard_hi <= s.shard_lo) {
+      set_error("shard ranges do not tile the key space: shard %d covers [%llu, %llu), expected to start at %llu", i,
+                (unsigned long long)s.shard_lo, (unsigned long long)s.shard_hi, (unsigned long long)expect);
+      return KAAMER_ERR_ARG;
+    }
+    expect = s.shard_hi;
+  }
+  if (expect != DENSE_SPACE) {
+    set_error("shard ranges end at %llu, not at the end of the key space (%llu)", (unsigned long long)expect,
+              (unsigned long long)DENSE_SPACE);
+    return KAAMER_ERR_ARG;
+  }
+  PeerView pv{};
+  for (int i = 0; i <= MAX_PEER_SHARDS; ++i) pv.fence[i] = 0xFFFFFFFFu;
+  pv.n = n_shards;
+  const int32_t me = (int32_t)getpid();
+  for (int i = 0; i < n_shards; ++i) {
+    const kaamer_shard_handle &s = shards[order[i]];
+    pv.fence[i] = (uint32_t)s.shard_lo;
+    if (s.n_postings > PEER_LOCAL_MASK) {
+      set_error("shard %d holds more than 2^%d postings", i, PEER_SHARD_SHIFT);
+      detach_shards_locked(h);
+      return KAAMER_ERR_LIMIT;
+    }
+    if (s.pid == me) {
+      // same process: the pointers are valid here; another device needs peer access
+      if (s.device != h->device) {
+        int can = 0;
+        KCUDA(cudaDeviceCanAccessPeer(&can, h->device, s.device));
+        if (!can) {
+          set_error("device %d cannot access device %d (no NVLink / P2P path)", h->device, s.device);
+          detach_shards_locked(h);
+          return KAAMER_ERR_CUDA;
+        }
+        cudaError_t e = cudaDeviceEnablePeerAccess(s.device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) {
+          cudaGetLastError();
+        } else if (e != cudaSuccess) {
+          set_error("cudaDeviceEnablePeerAccess(%d): %s", s.device, cudaGetErrorString(e));
+          detach_shards_locked(h);
+          return KAAMER_ERR_CUDA;
+        }
+      }
+      pv.table[i] = (const uint64_t *)(uintptr_t)s.table_ptr;
+      pv.postings[i] = (const uint32_t *)(uintptr_t)s.postings_ptr;
+    } else {
+      cudaIpcMemHandle_t ht, hp;
+      memcpy(&ht, s.table_ipc, sizeof ht);
+      memcpy(&hp, s.postings_ipc, sizeof hp);
+      void *pt = nullptr, *pp = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&pt, ht, cudaIpcMemLazyEnablePeerAccess);
+      if (e == cudaSuccess) {
+        h->idx.ipc_open.push_back(pt);
+        e = cudaIpcOpenMemHandle(&pp, hp, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) h->idx.ipc_open.push_back(pp);
+      }
+      if (e != cudaSuccess) {
+        set_error("cudaIpcOpenMemHandle (shard %d of process %d): %s", i, s.pid, cudaGetErrorString(e));
+        detach_shards_locked(h);
+        return KAAMER_ERR_CUDA;
+      }
+      pv.table[i] = (const uint64_t *)pt;
+      pv.postings[i] = (const uint32_t *)pp;
+    }
+  }
+  if (!h->idx.d_peer) KCUDA(cudaMalloc((void **)&h->idx.d_peer, sizeof(PeerView)));
+  KCUDA(cudaMemcpy(h->idx.d_peer, &pv, sizeof pv, cudaMemcpyHostToDevice));
+  h->idx.peer = pv;
+  return KAAMER_OK;
+}
 
 int kaamer_gpu_dbstats(kaamer_gpu_t *h, uint64_t *n_proteins, uint64_t *n_aa, uint64_t *n_kmers) {
   if (!h) {

@@ -25,6 +25,7 @@ struct FinishArgs {
   const uint64_t *table;
   uint64_t d_lo, d_hi;
   const uint32_t *postings;
+  const PeerView *peer;  // mode P: shards of all ranks (nullptr otherwise)
   // queries + count-pass results
   const uint8_t *res;
   const uint64_t *off;
@@ -118,12 +119,23 @@ __global__ void __launch_bounds__(256) k_positions(FinishArgs a) {
       const int32_t k = kb + (int32_t)lane;
       uint32_t cnt = 0;
       uint64_t val = 0;
+      const uint32_t *post = a.postings;
       if (k < K) {
         const uint8_t *s = seq + k;
         const uint32_t d = dense_from_codes(aa_code(s[0]), aa_code(s[1]), aa_code(s[2]), aa_code(s[3]),
                                             aa_code(s[4]), aa_code(s[5]), aa_code(s[6]));
-        if (d >= a.d_lo && d < a.d_hi) {
-          const uint64_t e = ldg_entry_f(a.table + (d - a.d_lo));
+        const uint64_t *tab = a.table;
+        uint64_t lo = a.d_lo, hi = a.d_hi;
+        if (a.peer) {  // owner shard of d: its table and postings, local or behind NVLink
+          uint32_t sh = 0;
+          for (int i = 1; i < MAX_PEER_SHARDS; ++i) sh += d >= a.peer->fence[i] ? 1u : 0u;
+          tab = a.peer->table[sh];
+          post = a.peer->postings[sh];
+          lo = a.peer->fence[sh];
+          hi = DENSE_SPACE;
+        }
+        if (d >= lo && d < hi) {
+          const uint64_t e = ldg_entry_f(tab + (d - lo));
           cnt = (uint32_t)(e >> ENTRY_VALUE_BITS);
           val = e & ENTRY_VALUE_MASK;
         }
@@ -132,7 +144,7 @@ __global__ void __launch_bounds__(256) k_positions(FinishArgs a) {
         const uint32_t id = __shfl_sync(0xFFFFFFFFu, my_id, hh);
         bool m = false;
         if (cnt == 1) m = (uint32_t)val == id;
-        else if (cnt >= 2) m = list_contains(a.postings + val, cnt, id);
+        else if (cnt >= 2) m = list_contains(post + val, cnt, id);
         const unsigned w = __ballot_sync(0xFFFFFFFFu, m);
         if (lane == 0) words[(size_t)(h0 + hh) * wpr + (uint32_t)kb / 32] = w;
         if (h0 + hh == 0 && p1 < 0 && w) p1 = kb + __ffs(w) - 1;
@@ -253,6 +265,7 @@ int finish_rows(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint
   a.d_lo = h->idx.d_lo;
   a.d_hi = h->idx.d_hi;
   a.postings = h->idx.postings;
+  a.peer = h->idx.peer.n > 0 ? h->idx.d_peer : nullptr;
   a.res = d_res;
   a.off = d_off;
   a.nq = nq;

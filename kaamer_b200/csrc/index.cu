@@ -42,12 +42,21 @@ __global__ void k_fill_table(const uint32_t *__restrict__ keys, const uint64_t *
   table[d - d_lo] = (cnt << ENTRY_VALUE_BITS) | val;
 }
 
+// The postings get an allocation of their own of at least 2 MiB: smaller cudaMalloc blocks are
+// carved out of shared 2 MiB pages, and the shard may be exported to other processes as a CUDA IPC
+// handle (kaamer_gpu_shard_export), which must cover this array and nothing else.
+static size_t postings_alloc_bytes(uint64_t n_postings) {
+  const size_t b = (size_t)(n_postings + 1) * sizeof(uint32_t);
+  return b < ((size_t)2 << 20) ? ((size_t)2 << 20) : b;
+}
+
 static int alloc_table(kaamer_gpu *h, uint64_t d_lo, uint64_t d_hi) {
   DevIndex &ix = h->idx;
   ix.d_lo = d_lo;
   ix.d_hi = d_hi;
   size_t bytes = (size_t)(d_hi - d_lo) * sizeof(uint64_t);
-  cudaError_t e = cudaMalloc((void **)&ix.table, bytes);
+  const size_t alloc = bytes < ((size_t)2 << 20) ? ((size_t)2 << 20) : bytes;  // see postings_alloc_bytes
+  cudaError_t e = cudaMalloc((void **)&ix.table, alloc);
   if (e != cudaSuccess) {
     set_error("cudaMalloc(table, %zu bytes): %s", bytes, cudaGetErrorString(e));
     return KAAMER_ERR_NOMEM;
@@ -138,7 +147,7 @@ int index_from_view(kaamer_gpu *h, const kaamer_index_view *v) {
   KCHECK(alloc_table(h, lo, hi));
   KCUDA(cudaMalloc((void **)&ix.keys, (size_t)(v->n_keys + 1) * sizeof(uint32_t)));
   KCUDA(cudaMalloc((void **)&ix.offsets, (size_t)(v->n_keys + 1) * sizeof(uint64_t)));
-  KCUDA(cudaMalloc((void **)&ix.postings, (size_t)(v->n_postings + 1) * sizeof(uint32_t)));
+  KCUDA(cudaMalloc((void **)&ix.postings, postings_alloc_bytes(v->n_postings)));
   if (v->n_keys) {
     KCUDA(cudaMemcpyAsync(ix.keys, v->keys, (size_t)v->n_keys * 4, cudaMemcpyHostToDevice, h->stream));
     KCUDA(cudaMemcpyAsync(ix.offsets, v->offsets, (size_t)(v->n_keys + 1) * 8, cudaMemcpyHostToDevice, h->stream));
@@ -389,7 +398,7 @@ int index_build(kaamer_gpu *h, const uint8_t *residues, const uint64_t *seq_off,
   ix.n_postings = n_uniq;
   BCUDA(cudaMalloc((void **)&ix.keys, (size_t)(n_keys + 1) * 4));
   BCUDA(cudaMalloc((void **)&ix.offsets, (size_t)(n_keys + 1) * 8));
-  BCUDA(cudaMalloc((void **)&ix.postings, (size_t)(n_uniq + 1) * 4));
+  BCUDA(cudaMalloc((void **)&ix.postings, postings_alloc_bytes(n_uniq)));
   if (n_uniq) {
     unsigned grid = (unsigned)((n_uniq + 255) / 256);
     k_write_keys<<<grid, 256, 0, st>>>(d_pairs, d_head, d_rank, n_uniq, ix.keys, ix.offsets, n_keys);

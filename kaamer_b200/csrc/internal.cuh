@@ -202,6 +202,23 @@ struct Arena {
   }
 };
 
+// ---- peer-mapped shards (mode P) ------------------------------------------
+// The dense code space is tiled by up to MAX_PEER_SHARDS key ranges; shard s lives in the HBM of
+// the GPU that built it and is mapped into this process (same process: plain pointers with
+// peer access enabled; other process: cudaIpcOpenMemHandle).  The search kernels resolve the
+// owner of a dense code with MAX_PEER_SHARDS-1 compares and read the 8-byte entry (and the
+// posting list) straight through NVLink.  A posting-list reference carries its shard in the top
+// bits of the 36-bit entry value, so per-shard posting indices are limited to 2^33.
+constexpr int MAX_PEER_SHARDS = 8;
+constexpr int PEER_SHARD_SHIFT = 33;
+constexpr uint64_t PEER_LOCAL_MASK = (1ull << PEER_SHARD_SHIFT) - 1;
+struct PeerView {
+  uint32_t fence[MAX_PEER_SHARDS + 1];  // fence[s] = first dense code of shard s; unused = 0xFFFFFFFF
+  int32_t n;
+  const uint64_t *table[MAX_PEER_SHARDS];
+  const uint32_t *postings[MAX_PEER_SHARDS];
+};
+
 // ---- the resident index ---------------------------------------------------------------
 struct DevIndex {
   uint64_t *table = nullptr;  // [d_hi - d_lo] direct-address entries
@@ -220,6 +237,10 @@ struct DevIndex {
   uint32_t max_protein_id = 0;
   bool has_proteins = false;
   uint64_t n_proteins = 0, n_aa = 0, n_kmers = 0;
+  // mode P: the shards of the other ranks, mapped into this process (api.cu kaamer_gpu_attach_shards)
+  PeerView peer{};               // host copy; peer.n == 0: not attached
+  PeerView *d_peer = nullptr;    // device copy read by the kernels
+  std::vector<void *> ipc_open;  // pointers to close with cudaIpcCloseMemHandle
 };
 
 struct SearchWorkspace {

@@ -82,10 +82,16 @@ struct __align__(16) WarpSmemT {
 };
 
 // CLS: index of the class list / counters (0 = W, 3 = W2)
-template <int H, int MAXK, int WARPS, int MINB, int CLS>
+template <int H, int MAXK, int WARPS, int MINB, int CLS, bool PEER>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_search_wt(SearchArgs a) {
   __shared__ WarpSmemT<H, MAXK> sm[WARPS];
   __shared__ uint8_t lut[256];
+  const PeerView *pv = nullptr;
+  if constexpr (PEER) {
+    __shared__ PeerView s_peer;
+    load_peer_view(&s_peer, a.peer, threadIdx.x, WARPS * 32);
+    pv = &s_peer;
+  }
   for (int i = threadIdx.x; i < 256; i += WARPS * 32) lut[i] = (uint8_t)aa_code(i);
   __syncthreads();
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -135,8 +141,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_search_wt(SearchArgs a) {
         const int pos = base + u * 32 + (int)lane;
         e[u] = 0;
         if (pos < K) {
-          uint32_t d = dense_from_packed(s.pp[pos], s.pp[pos + 2], s.pp[pos + 4], s.pp[pos + 6]);
-          if (d >= a.d_lo && d < a.d_hi) e[u] = ldg_entry(a.table + (d - a.d_lo));
+          e[u] = probe_entry<PEER>(a, pv, dense_from_packed(s.pp[pos], s.pp[pos + 2], s.pp[pos + 4], s.pp[pos + 6]));
         }
       }
     };
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_search_wt(SearchArgs a) {
 #pragma unroll
       for (int u = 0; u < U; ++u) ent[u] = nxt[u];
       if (base + U * 32 < K) load_round(base + U * 32, nxt);
-      warp_consume<U>(a, ent, hv, kmin, cl, q_incr);
+      warp_consume<U, PEER>(a, ent, hv, kmin, cl, q_incr, pv);
     }
     __syncwarp();
     const uint32_t flags = *(volatile uint32_t *)&s.flags;
@@ -211,8 +216,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_search_wt(SearchArgs a) {
       if (a.nt_mode && fits) {
         __syncwarp();
         const uint64_t top = a.pool[base];  // rank 0, written by this warp
-        const bool any = warp_any0(a, hv, dense_from_packed(s.pp[0], s.pp[2], s.pp[4], s.pp[6]), (uint32_t)top,
-                                   (uint32_t)(top >> 32));
+        const bool any = warp_any0<PEER>(a, pv, hv, dense_from_packed(s.pp[0], s.pp[2], s.pp[4], s.pp[6]),
+                                         (uint32_t)top, (uint32_t)(top >> 32));
         if (lane == 0) a.any0[q] = any ? 1 : 0;
       }
     }
@@ -234,6 +239,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_search_wt(SearchArgs a) {
   }
 }
 
+template <bool PEER>
 __global__ void __launch_bounds__(M_THREADS, M_CTAS) k_search_m(SearchArgs a) {
   __shared__ __align__(16) uint32_t hkeys[M_H];
   __shared__ __align__(16) uint32_t hcnt2[M_H / 2];
@@ -243,6 +249,12 @@ __global__ void __launch_bounds__(M_THREADS, M_CTAS) k_search_m(SearchArgs a) {
   __shared__ SelectScratch ss;
   constexpr int THREADS = M_THREADS;
   const int tid = threadIdx.x;
+  const PeerView *pv = nullptr;
+  if constexpr (PEER) {
+    __shared__ PeerView s_peer;
+    load_peer_view(&s_peer, a.peer, tid, THREADS);
+    pv = &s_peer;
+  }
   for (int i = tid; i < 256; i += THREADS) lut[i] = (uint8_t)aa_code(i);
   __syncthreads();
   const SmemHash hv{hkeys, hcnt2, (uint32_t)M_H - 1u, 32 - ilog2_c(M_H)};
@@ -281,8 +293,7 @@ __global__ void __launch_bounds__(M_THREADS, M_CTAS) k_search_m(SearchArgs a) {
         const int pos = base + u * THREADS + tid;
         e[u] = 0;
         if (pos < K) {
-          uint32_t d = dense_from_packed(pp[pos], pp[pos + 2], pp[pos + 4], pp[pos + 6]);
-          if (d >= a.d_lo && d < a.d_hi) e[u] = ldg_entry(a.table + (d - a.d_lo));
+          e[u] = probe_entry<PEER>(a, pv, dense_from_packed(pp[pos], pp[pos + 2], pp[pos + 4], pp[pos + 6]));
         }
       }
     };
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(M_THREADS, M_CTAS) k_search_m(SearchArgs a) {
 #pragma unroll
       for (int u = 0; u < U; ++u) ent[u] = nxt[u];
       if (base + U * THREADS < K) load_round(base + U * THREADS, nxt);
-      warp_consume<U>(a, ent, hv, kmin, cl, q_incr);
+      warp_consume<U, PEER>(a, ent, hv, kmin, cl, q_incr, pv);
     }
     __syncthreads();
     if (ss.flags) {
@@ -326,8 +337,8 @@ __global__ void __launch_bounds__(M_THREADS, M_CTAS) k_search_m(SearchArgs a) {
     if (a.nt_mode) {
       if (tid < 32 && a.n_hits[q]) {
         const uint64_t top = a.pool[a.hit_base[q]];
-        const bool any = warp_any0(a, hv, dense_from_packed(pp[0], pp[2], pp[4], pp[6]), (uint32_t)top,
-                                   (uint32_t)(top >> 32));
+        const bool any = warp_any0<PEER>(a, pv, hv, dense_from_packed(pp[0], pp[2], pp[4], pp[6]), (uint32_t)top,
+                                         (uint32_t)(top >> 32));
         if (tid == 0) a.any0[q] = any ? 1 : 0;
       }
       __syncthreads();
@@ -351,12 +362,19 @@ __global__ void __launch_bounds__(M_THREADS, M_CTAS) k_search_m(SearchArgs a) {
 
 // class G: histogram in global memory (per-CTA scratch, stays in L2), codes computed on the fly
 constexpr int G_STAGE = 40 * 1024;
+template <bool PEER>
 __global__ void __launch_bounds__(G_THREADS) k_search_g(SearchArgs a) {
   __shared__ __align__(16) uint8_t s_res[G_STAGE];
   __shared__ SelectScratch ss;
   __shared__ unsigned long long s_total;
   constexpr int THREADS = G_THREADS;
   const int tid = threadIdx.x;
+  const PeerView *pv = nullptr;
+  if constexpr (PEER) {
+    __shared__ PeerView s_peer;
+    load_peer_view(&s_peer, a.peer, tid, THREADS);
+    pv = &s_peer;  // (the first use is behind the __syncthreads() of the query loop)
+  }
   const uint32_t HG = a.ghash_slots;
   uint32_t *gkeys = a.ghash + (size_t)blockIdx.x * 3 * HG;
   uint32_t *gcnt = gkeys + HG;
@@ -387,8 +405,7 @@ __global__ void __launch_bounds__(G_THREADS) k_search_g(SearchArgs a) {
     __syncthreads();
     unsigned long long tot = 0;
     for (int pos = tid; pos < K; pos += THREADS) {
-      uint32_t d = dense_at(pos);
-      if (d >= a.d_lo && d < a.d_hi) tot += ldg_entry(a.table + (d - a.d_lo)) >> ENTRY_VALUE_BITS;
+      tot += probe_entry<PEER>(a, pv, dense_at(pos)) >> ENTRY_VALUE_BITS;
     }
     atomicAdd(&s_total, tot);
     __syncthreads();
@@ -416,12 +433,9 @@ __global__ void __launch_bounds__(G_THREADS) k_search_g(SearchArgs a) {
       for (int u = 0; u < U; ++u) {
         const int pos = base + u * THREADS + tid;
         ent[u] = 0;
-        if (pos < K) {
-          uint32_t d = dense_at(pos);
-          if (d >= a.d_lo && d < a.d_hi) ent[u] = ldg_entry(a.table + (d - a.d_lo));
-        }
+        if (pos < K) ent[u] = probe_entry<PEER>(a, pv, dense_at(pos));
       }
-      warp_consume<U>(a, ent, hv, kmin, cl, q_incr);
+      warp_consume<U, PEER>(a, ent, hv, kmin, cl, q_incr, pv);
     }
     __syncthreads();
     if (ss.flags) {
@@ -437,7 +451,7 @@ __global__ void __launch_bounds__(G_THREADS) k_search_g(SearchArgs a) {
     if (a.nt_mode) {
       if (tid < 32 && a.n_hits[q]) {
         const uint64_t top = a.pool[a.hit_base[q]];
-        const bool any = warp_any0(a, hv, dense_at(0), (uint32_t)top, (uint32_t)(top >> 32));
+        const bool any = warp_any0<PEER>(a, pv, hv, dense_at(0), (uint32_t)top, (uint32_t)(top >> 32));
         if (tid == 0) a.any0[q] = any ? 1 : 0;
       }
       __syncthreads();
@@ -505,6 +519,13 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
     set_error("no index resident");
     return KAAMER_ERR_ARG;
   }
+  const bool peer = h->idx.peer.n > 0;
+  if (!peer && (h->idx.d_lo != 0 || h->idx.d_hi != DENSE_SPACE)) {
+    set_error("this handle holds the key-range shard [%llu, %llu) only: attach the other shards "
+              "(kaamer_gpu_attach_shards) or use the kaamer_gpu_shard_* steps",
+              (unsigned long long)h->idx.d_lo, (unsigned long long)h->idx.d_hi);
+    return KAAMER_ERR_ARG;
+  }
   if (nq == 0) return KAAMER_OK;
   SearchWorkspace &ws = h->ws;
   KCHECK(ws.lists.ensure((size_t)4 * nq + 16));
@@ -533,6 +554,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   a.ghash_slots = ghash_slots_for(h);
   a.nt_mode = nt_mode;
   a.any0 = d_any0;
+  a.peer = h->idx.d_peer;
   const int g_ctas = h->sm_count;
   KCHECK(ws.ghash.ensure((size_t)2 * g_ctas * 3 * a.ghash_slots));
   a.ghash = ws.ghash.p;
@@ -552,18 +574,22 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   KCUDA(cudaStreamWaitEvent(side, h->chunk_ev[6], 0));
   profile_begin(h, side, 2);
   a.g_list = 2;
-  k_search_g<<<g_ctas, G_THREADS, 0, side>>>(a);
+  if (peer) k_search_g<true><<<g_ctas, G_THREADS, 0, side>>>(a);
+  else k_search_g<false><<<g_ctas, G_THREADS, 0, side>>>(a);
   profile_end(h, side);
   KCUDA(cudaEventRecord(h->chunk_ev[7], side));
   profile_begin(h, st, 0);
-  k_search_wt<W_H, W_MAXK, W_WARPS, 5, 0><<<w_grid, W_WARPS * 32, 0, st>>>(a);
+  if (peer) k_search_wt<W_H, W_MAXK, W_WARPS, 5, 0, true><<<w_grid, W_WARPS * 32, 0, st>>>(a);
+  else k_search_wt<W_H, W_MAXK, W_WARPS, 5, 0, false><<<w_grid, W_WARPS * 32, 0, st>>>(a);
   profile_end(h, st);
   profile_begin(h, st, 1);
-  k_search_m<<<m_grid < nq ? m_grid : nq, M_THREADS, 0, st>>>(a);
+  if (peer) k_search_m<true><<<m_grid < nq ? m_grid : nq, M_THREADS, 0, st>>>(a);
+  else k_search_m<false><<<m_grid < nq ? m_grid : nq, M_THREADS, 0, st>>>(a);
   profile_end(h, st);
   a.g_list = 3;
   a.ghash = ws.ghash.p + (size_t)g_ctas * 3 * a.ghash_slots;  // own scratch: the first G launch may still run
-  k_search_g<<<g_ctas, G_THREADS, 0, st>>>(a);
+  if (peer) k_search_g<true><<<g_ctas, G_THREADS, 0, st>>>(a);
+  else k_search_g<false><<<g_ctas, G_THREADS, 0, st>>>(a);
   KCUDA(cudaStreamWaitEvent(st, h->chunk_ev[7], 0));
   h->prof_all_launches += 5;
   KCUDA(cudaGetLastError());

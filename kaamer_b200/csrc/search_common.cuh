@@ -49,6 +49,7 @@ struct SearchArgs {
   int nt_mode;
   uint8_t *any0;
   int g_list;  // class list processed by k_search_g (2: classified, 3: hand-offs from class M)
+  const PeerView *peer;  // mode P (kernels instantiated with PEER = true): shards of all ranks
 };
 
 // Copy src[0, len) into shared memory with aligned 16-byte loads (one request per 16 residues:
@@ -83,6 +84,41 @@ __device__ __forceinline__ uint64_t ldg_entry(const uint64_t *p) {
   uint64_t v;
   asm volatile("ld.global.nc.L1::no_allocate.L2::64B.b64 %0, [%1];" : "=l"(v) : "l"(p));
   return v;
+}
+
+// ---- table probe / posting access -----------------------------------------------------------
+// PEER = false: the handle's own table over [d_lo, d_hi).  PEER = true (mode P): the dense code
+// space is tiled by the shards of pv (a shared-memory copy of SearchArgs::peer); the owner is found
+// with MAX_PEER_SHARDS-1 compares and the entry is read from its HBM — local or through NVLink.
+// A multi-posting entry gets its shard folded into the value so that post_ptr finds the list.
+template <bool PEER>
+__device__ __forceinline__ uint64_t probe_entry(const SearchArgs &a, const PeerView *pv, uint32_t d) {
+  if constexpr (!PEER) {
+    (void)pv;
+    return (d >= a.d_lo && d < a.d_hi) ? ldg_entry(a.table + (d - a.d_lo)) : 0ull;
+  } else {
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 1; i < MAX_PEER_SHARDS; ++i) s += d >= pv->fence[i] ? 1u : 0u;
+    uint64_t e = ldg_entry(pv->table[s] + (d - pv->fence[s]));
+    if ((e >> ENTRY_VALUE_BITS) >= 2ull) e |= (uint64_t)s << PEER_SHARD_SHIFT;
+    return e;
+  }
+}
+template <bool PEER>
+__device__ __forceinline__ const uint32_t *post_ptr(const SearchArgs &a, const PeerView *pv, uint64_t val) {
+  if constexpr (!PEER) {
+    (void)pv;
+    return a.postings + val;
+  } else {
+    return pv->postings[val >> PEER_SHARD_SHIFT] + (val & PEER_LOCAL_MASK);
+  }
+}
+// CTA-wide copy of the peer view into shared memory (callers barrier afterwards)
+__device__ __forceinline__ void load_peer_view(PeerView *dst, const PeerView *src, int tid, int nthreads) {
+  const uint32_t *s = reinterpret_cast<const uint32_t *>(src);
+  uint32_t *d = reinterpret_cast<uint32_t *>(dst);
+  for (int i = tid; i < (int)(sizeof(PeerView) / 4); i += nthreads) d[i] = s[i];
 }
 
 // ---- histograms -------------------------------------------------------------------------
@@ -209,22 +245,22 @@ __device__ __forceinline__ uint32_t hist_count(const Hash &hv, uint32_t id) {
 
 // nucleotide mode, one warp: does a subject tied with the best hit (count T), other than the
 // best hit itself, hold the query's first k-mer (dense code d0)?
-template <class Hash>
-__device__ __noinline__ bool warp_any0(const SearchArgs &a, const Hash &hv, uint32_t d0, uint32_t best_id, uint32_t T) {
+template <bool PEER = false, class Hash>
+__device__ __noinline__ bool warp_any0(const SearchArgs &a, const PeerView *pv, const Hash &hv, uint32_t d0,
+                                       uint32_t best_id, uint32_t T) {
   const unsigned lane = threadIdx.x & 31;
   bool any = false;
-  if (d0 >= a.d_lo && d0 < a.d_hi) {
-    const uint64_t e = ldg_entry(a.table + (d0 - a.d_lo));
-    const uint32_t cnt = (uint32_t)(e >> ENTRY_VALUE_BITS);
-    const uint64_t val = e & ENTRY_VALUE_MASK;
-    if (cnt == 1) {
-      const uint32_t id = (uint32_t)val;
-      any = id != best_id && hist_count(hv, id) == T;
-    } else {
-      for (uint32_t i = lane; i < cnt; i += 32) {
-        const uint32_t id = __ldg(a.postings + val + i);
-        if (id != best_id && hist_count(hv, id) == T) any = true;
-      }
+  const uint64_t e = probe_entry<PEER>(a, pv, d0);
+  const uint32_t cnt = (uint32_t)(e >> ENTRY_VALUE_BITS);
+  const uint64_t val = e & ENTRY_VALUE_MASK;
+  if (cnt == 1) {
+    const uint32_t id = (uint32_t)val;
+    any = id != best_id && hist_count(hv, id) == T;
+  } else if (cnt >= 2) {
+    const uint32_t *pl = post_ptr<PEER>(a, pv, val);
+    for (uint32_t i = lane; i < cnt; i += 32) {
+      const uint32_t id = __ldg(pl + i);
+      if (id != best_id && hist_count(hv, id) == T) any = true;
     }
   }
   return __any_sync(0xFFFFFFFFu, any);
@@ -266,9 +302,10 @@ __device__ __forceinline__ void warp_count(const WarpHashT<H> &hv, bool valid, u
 // Every lane holds up to U table entries.  Singletons are counted directly; short posting
 // lists (2..BIG_LIST-1) of the whole warp are flattened (warp scan + search by shuffles) so
 // that all 32 lanes fetch and count postings together; long lists are walked cooperatively.
-template <int U, class Hash>
+template <int U, bool PEER = false, class Hash>
 __device__ __forceinline__ void warp_consume(const SearchArgs &a, const uint64_t (&ent)[U], const Hash &hv,
-                                             uint32_t kmin, const CandList &cl, unsigned long long &q_incr) {
+                                             uint32_t kmin, const CandList &cl, unsigned long long &q_incr,
+                                             const PeerView *pv = nullptr) {
   const unsigned lane = threadIdx.x & 31;
   uint32_t m[U];  // postings of this lane's short multi lists
   uint32_t vlo[U];
@@ -354,7 +391,7 @@ __device__ __forceinline__ void warp_consume(const SearchArgs &a, const uint64_t
       }
     }
     uint32_t pid = 0;
-    if (j < total) pid = __ldg(a.postings + (((uint64_t)sel_hi << 32) | sel_lo) + r);
+    if (j < total) pid = __ldg(post_ptr<PEER>(a, pv, ((uint64_t)sel_hi << 32) | sel_lo) + r);
     if constexpr (Hash::kWarp) {
       warp_count(hv, j < total, pid, kmin, cl);
     } else {
@@ -376,15 +413,16 @@ __device__ __forceinline__ void warp_consume(const SearchArgs &a, const uint64_t
         big &= big - 1;
         const uint32_t bc = __shfl_sync(0xFFFFFFFFu, cnt, src);
         const uint64_t bv = __shfl_sync(0xFFFFFFFFu, e & ENTRY_VALUE_MASK, src);
+        const uint32_t *pl = post_ptr<PEER>(a, pv, bv);
         if constexpr (Hash::kWarp) {
           for (uint32_t ib = 0; ib < bc; ib += 32) {
             const uint32_t i = ib + lane;
-            warp_count(hv, i < bc, i < bc ? __ldg(a.postings + bv + i) : 0u, kmin, cl);
+            warp_count(hv, i < bc, i < bc ? __ldg(pl + i) : 0u, kmin, cl);
           }
         } else {
           for (uint32_t i = lane; i < bc; i += 32) {
             if (*(volatile uint32_t *)cl.flags & 1u) break;
-            count_subject(hv, __ldg(a.postings + bv + i), kmin, cl);
+            count_subject(hv, __ldg(pl + i), kmin, cl);
           }
         }
       }

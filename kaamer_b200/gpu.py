@@ -248,6 +248,25 @@ class GpuIndex:
     def save(self, path: str):
         check(_lib.lib().kaamer_gpu_save(self._h, path.encode()))
 
+    # ---- peer-mapped shards (mode P) -----------------------------------------------------
+    def export_shard(self) -> bytes:
+        """kaamer_shard_handle of this handle's key range, as bytes (ship it to the other ranks)."""
+        sh = _lib.ShardHandle()
+        check(_lib.lib().kaamer_gpu_shard_export(self._h, C.byref(sh)))
+        return bytes(sh)
+
+    def attach_shards(self, handles: "list[bytes]") -> None:
+        """Map the key-range shards of all ranks (this one included): afterwards the search entry
+        points of this handle see the whole key space and probe remote shards through NVLink."""
+        arr = (_lib.ShardHandle * len(handles))()
+        for i, b in enumerate(handles):
+            assert len(b) == C.sizeof(_lib.ShardHandle)
+            C.memmove(C.byref(arr[i]), b, len(b))
+        check(_lib.lib().kaamer_gpu_attach_shards(self._h, arr, len(handles)))
+
+    def detach_shards(self) -> None:
+        check(_lib.lib().kaamer_gpu_detach_shards(self._h))
+
     # ---- search ------------------------------------------------------------------------
     def search_proteins(self, residues, seq_off, opts: SearchOptions | None = None) -> SearchResult:
         opts = opts or SearchOptions()

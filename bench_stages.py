@@ -266,7 +266,7 @@ def peer(a):
     from kaamer_b200 import SearchOptions, synth
     from kaamer_b200 import GpuIndex
     from kaamer_b200.makedb import fasta_protein_ids
-    from kaamer_b200.peer import attach_distributed
+    from kaamer_b200.peer import attach_all, attach_distributed
     from kaamer_b200.sharded import fences_from_sample
 
     rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -288,7 +288,7 @@ def peer(a):
     if world > 1:
         attach_distributed(g)
     else:
-        g.attach_shards([g.export_shard()])
+        attach_all([g])
     pool_cap = nq * 16 + 4096
     d_nhits = torch.zeros(nq, dtype=torch.int32, device=dev)
     d_base = torch.zeros(nq, dtype=torch.int32, device=dev)

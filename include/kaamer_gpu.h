@@ -223,18 +223,22 @@ int kaamer_gpu_shard_merge(kaamer_gpu_t *h, const uint64_t *d_part, const uint64
  * kernels resolve the owner of each k-mer and read its table entry and posting list from that
  * GPU's HBM through NVLink (peer loads inside the kernel; no all-to-all, no merge step — Kmatch
  * is accumulated at the query's home GPU exactly as in the single-GPU path, search.go:431-436).
- * A kaamer_shard_handle is plain bytes: ship it between processes with any transport
- * (torch.distributed all_gather_object, a pipe, a file).  Same-process shards (one Go process
- * driving several GPUs) are attached by pointer with peer access enabled; shards of other
- * processes through cudaIpcOpenMemHandle. ---- */
+ * Shards are allocated in shareable device memory (CUDA virtual memory management, 2 MiB pages).
+ * Same-process shards (one Go server process driving several GPUs) are attached by pointer.
+ * Shards of other processes travel as two POSIX file descriptors: send table_fd / postings_fd
+ * over a Unix-domain socket with SCM_RIGHTS (Go: syscall.UnixRights) together with the struct,
+ * and store the received descriptor numbers in the copy handed to kaamer_gpu_attach_shards.
+ * Descriptors belong to the caller: close(2) them after sending / after attaching.  (The legacy
+ * cudaIpc* mapping is deliberately not offered: random probes into it were measured 130x slower
+ * than into a large-page mapping, profiles/r1_peer_gather.log.) ---- */
 typedef struct kaamer_shard_handle {
   uint64_t shard_lo, shard_hi; /* dense-code range [lo, hi) held by the exporting handle */
   uint64_t n_postings;
-  uint64_t table_ptr, postings_ptr; /* device pointers in the exporting process */
-  int32_t device;                   /* CUDA ordinal in the exporting process */
-  int32_t pid;                      /* exporting process */
-  uint8_t table_ipc[64];            /* cudaIpcMemHandle_t of the table */
-  uint8_t postings_ipc[64];         /* cudaIpcMemHandle_t of the postings */
+  uint64_t table_ptr, postings_ptr;     /* device pointers in the exporting process */
+  uint64_t table_bytes, postings_bytes; /* sizes of the two shareable allocations */
+  int32_t device;                       /* CUDA ordinal in the exporting process */
+  int32_t pid;                          /* exporting process */
+  int32_t table_fd, postings_fd;        /* shareable handles (-1: the index is not shareable) */
 } kaamer_shard_handle;
 #define KAAMER_MAX_PEER_SHARDS 8
 int kaamer_gpu_shard_export(kaamer_gpu_t *h, kaamer_shard_handle *out);

@@ -129,17 +129,19 @@ class DevResult(C.Structure):
 
 
 class ShardHandle(C.Structure):
-    """kaamer_shard_handle: plain bytes, picklable through bytes(handle)."""
+    """kaamer_shard_handle (plain bytes; the two descriptors travel separately, SCM_RIGHTS)."""
     _fields_ = [
         ("shard_lo", C.c_uint64),
         ("shard_hi", C.c_uint64),
         ("n_postings", C.c_uint64),
         ("table_ptr", C.c_uint64),
         ("postings_ptr", C.c_uint64),
+        ("table_bytes", C.c_uint64),
+        ("postings_bytes", C.c_uint64),
         ("device", C.c_int32),
         ("pid", C.c_int32),
-        ("table_ipc", C.c_uint8 * 64),
-        ("postings_ipc", C.c_uint8 * 64),
+        ("table_fd", C.c_int32),
+        ("postings_fd", C.c_int32),
     ]
 
 

@@ -146,8 +146,8 @@ static int new_handle(int device, kaamer_gpu **out) {
 static void destroy_handle(kaamer_gpu *h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  for (void *p : h->idx.ipc_open) cudaIpcCloseMemHandle(p);
-  h->idx.ipc_open.clear();
+  for (auto &a : h->idx.imported) vmm_free(&a);
+  h->idx.imported.clear();
   if (h->idx.d_peer) cudaFree(h->idx.d_peer);
   h->idx.d_peer = nullptr;
   index_release(h);
@@ -271,38 +271,47 @@ int kaamer_gpu_shard_export(kaamer_gpu_t *h, kaamer_shard_handle *out) {
     set_error("null argument");
     return KAAMER_ERR_ARG;
   }
-  static_assert(sizeof(cudaIpcMemHandle_t) <= 64, "cudaIpcMemHandle_t is 64 bytes");
   std::lock_guard<std::mutex> lk(h->mu);
   KCUDA(cudaSetDevice(h->device));
-  if (!h->idx.table) {
+  DevIndex &ix = h->idx;
+  if (!ix.table) {
     set_error("no index resident");
     return KAAMER_ERR_ARG;
   }
   memset(out, 0, sizeof *out);
-  out->shard_lo = h->idx.d_lo;
-  out->shard_hi = h->idx.d_hi;
-  out->n_postings = h->idx.n_postings;
-  out->table_ptr = (uint64_t)(uintptr_t)h->idx.table;
-  out->postings_ptr = (uint64_t)(uintptr_t)h->idx.postings;
+  out->shard_lo = ix.d_lo;
+  out->shard_hi = ix.d_hi;
+  out->n_postings = ix.n_postings;
+  out->table_ptr = (uint64_t)(uintptr_t)ix.table;
+  out->postings_ptr = (uint64_t)(uintptr_t)ix.postings;
   out->device = h->device;
   out->pid = (int32_t)getpid();
-  if (h->idx.n_postings > PEER_LOCAL_MASK) {
+  out->table_fd = out->postings_fd = -1;
+  if (ix.n_postings > PEER_LOCAL_MASK) {
     set_error("shard holds %llu postings: more than 2^%d per shard cannot be peer-mapped",
-              (unsigned long long)h->idx.n_postings, PEER_SHARD_SHIFT);
+              (unsigned long long)ix.n_postings, PEER_SHARD_SHIFT);
     return KAAMER_ERR_LIMIT;
   }
   KCUDA(cudaStreamSynchronize(h->stream));  // the build is complete before anyone maps it
-  cudaIpcMemHandle_t ht, hp;
-  KCUDA(cudaIpcGetMemHandle(&ht, h->idx.table));
-  KCUDA(cudaIpcGetMemHandle(&hp, h->idx.postings));
-  memcpy(out->table_ipc, &ht, sizeof ht);
-  memcpy(out->postings_ipc, &hp, sizeof hp);
+  if (ix.vm_table.ptr && ix.vm_postings.ptr) {
+    out->table_bytes = ix.vm_table.bytes;
+    out->postings_bytes = ix.vm_postings.bytes;
+    int ft = -1, fp = -1;
+    KCHECK(vmm_export_fd(ix.vm_table, &ft));
+    int rc = vmm_export_fd(ix.vm_postings, &fp);
+    if (rc != KAAMER_OK) {
+      close(ft);
+      return rc;
+    }
+    out->table_fd = ft;
+    out->postings_fd = fp;
+  }
   return KAAMER_OK;
 }
 
 static void detach_shards_locked(kaamer_gpu *h) {
-  for (void *p : h->idx.ipc_open) cudaIpcCloseMemHandle(p);
-  h->idx.ipc_open.clear();
+  for (auto &a : h->idx.imported) vmm_free(&a);
+  h->idx.imported.clear();
   h->idx.peer = PeerView{};
 }
 
@@ -314,7 +323,46 @@ int kaamer_gpu_detach_shards(kaamer_gpu_t *h) {
   std::lock_guard<std::mutex> lk(h->mu);
   KCUDA(cudaSetDevice(h->device));
   KCUDA(cudaStreamSynchronize(h->stream));
+  KCUDA(cudaStreamSynchronize(h->copy_stream));
   detach_shards_locked(h);
+  return KAAMER_OK;
+}
+
+// pointer to a shard's array as seen from h->device
+static int map_shard_array(kaamer_gpu *h, const kaamer_shard_handle &s, bool same_process, uint64_t ptr, uint64_t bytes,
+                           int fd, const void **out) {
+  if (same_process) {
+    if (s.device != h->device) {
+      if (fd >= 0) {
+        KCHECK(vmm_grant((void *)(uintptr_t)ptr, (size_t)bytes, h->device));  // shareable memory: add this device
+      } else {
+        int can = 0;
+        KCUDA(cudaDeviceCanAccessPeer(&can, h->device, s.device));
+        if (!can) {
+          set_error("device %d cannot access device %d (no NVLink / P2P path)", h->device, s.device);
+          return KAAMER_ERR_CUDA;
+        }
+        cudaError_t e = cudaDeviceEnablePeerAccess(s.device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) {
+          cudaGetLastError();
+        } else if (e != cudaSuccess) {
+          set_error("cudaDeviceEnablePeerAccess(%d): %s", s.device, cudaGetErrorString(e));
+          return KAAMER_ERR_CUDA;
+        }
+      }
+    }
+    *out = (const void *)(uintptr_t)ptr;
+    return KAAMER_OK;
+  }
+  if (fd < 0) {
+    set_error("shard of process %d carries no shareable handle (a full index built without a key range cannot be "
+              "mapped by another process)", s.pid);
+    return KAAMER_ERR_ARG;
+  }
+  VmmAlloc a;
+  KCHECK(vmm_import_fd(fd, (size_t)bytes, h->device, &a));
+  h->idx.imported.push_back(a);
+  *out = a.ptr;
   return KAAMER_OK;
 }
 
@@ -330,6 +378,7 @@ int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards,
   std::lock_guard<std::mutex> lk(h->mu);
   KCUDA(cudaSetDevice(h->device));
   KCUDA(cudaStreamSynchronize(h->stream));
+  KCUDA(cudaStreamSynchronize(h->copy_stream));
   detach_shards_locked(h);
   // order by shard_lo and check that the ranges tile the dense code space
   std::vector<int> order(n_shards);
@@ -343,10 +392,14 @@ int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards,
                 (unsigned long long)s.shard_lo, (unsigned long long)s.shard_hi, (unsigned long long)expect);
       return KAAMER_ERR_ARG;
     }
+    if (s.n_postings > PEER_LOCAL_MASK) {
+      set_error("shard %d holds more than 2^%d postings", i, PEER_SHARD_SHIFT);
+      return KAAMER_ERR_LIMIT;
+    }
     expect = s.shard_hi;
   }
   if (expect != DENSE_SPACE) {
-    set_error("shard ranges end at %llu, not at the end of the key space (%llu)", (unsigned long long)expect,
+    set_error("shard ranges do not tile the key space: they end at %llu, not at %llu", (unsigned long long)expect,
               (unsigned long long)DENSE_SPACE);
     return KAAMER_ERR_ARG;
   }
@@ -357,51 +410,15 @@ int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards,
   for (int i = 0; i < n_shards; ++i) {
     const kaamer_shard_handle &s = shards[order[i]];
     pv.fence[i] = (uint32_t)s.shard_lo;
-    if (s.n_postings > PEER_LOCAL_MASK) {
-      set_error("shard %d holds more than 2^%d postings", i, PEER_SHARD_SHIFT);
+    const void *pt = nullptr, *pp = nullptr;
+    int rc = map_shard_array(h, s, s.pid == me, s.table_ptr, s.table_bytes, s.table_fd, &pt);
+    if (rc == KAAMER_OK) rc = map_shard_array(h, s, s.pid == me, s.postings_ptr, s.postings_bytes, s.postings_fd, &pp);
+    if (rc != KAAMER_OK) {
       detach_shards_locked(h);
-      return KAAMER_ERR_LIMIT;
+      return rc;
     }
-    if (s.pid == me) {
-      // same process: the pointers are valid here; another device needs peer access
-      if (s.device != h->device) {
-        int can = 0;
-        KCUDA(cudaDeviceCanAccessPeer(&can, h->device, s.device));
-        if (!can) {
-          set_error("device %d cannot access device %d (no NVLink / P2P path)", h->device, s.device);
-          detach_shards_locked(h);
-          return KAAMER_ERR_CUDA;
-        }
-        cudaError_t e = cudaDeviceEnablePeerAccess(s.device, 0);
-        if (e == cudaErrorPeerAccessAlreadyEnabled) {
-          cudaGetLastError();
-        } else if (e != cudaSuccess) {
-          set_error("cudaDeviceEnablePeerAccess(%d): %s", s.device, cudaGetErrorString(e));
-          detach_shards_locked(h);
-          return KAAMER_ERR_CUDA;
-        }
-      }
-      pv.table[i] = (const uint64_t *)(uintptr_t)s.table_ptr;
-      pv.postings[i] = (const uint32_t *)(uintptr_t)s.postings_ptr;
-    } else {
-      cudaIpcMemHandle_t ht, hp;
-      memcpy(&ht, s.table_ipc, sizeof ht);
-      memcpy(&hp, s.postings_ipc, sizeof hp);
-      void *pt = nullptr, *pp = nullptr;
-      cudaError_t e = cudaIpcOpenMemHandle(&pt, ht, cudaIpcMemLazyEnablePeerAccess);
-      if (e == cudaSuccess) {
-        h->idx.ipc_open.push_back(pt);
-        e = cudaIpcOpenMemHandle(&pp, hp, cudaIpcMemLazyEnablePeerAccess);
-        if (e == cudaSuccess) h->idx.ipc_open.push_back(pp);
-      }
-      if (e != cudaSuccess) {
-        set_error("cudaIpcOpenMemHandle (shard %d of process %d): %s", i, s.pid, cudaGetErrorString(e));
-        detach_shards_locked(h);
-        return KAAMER_ERR_CUDA;
-      }
-      pv.table[i] = (const uint64_t *)pt;
-      pv.postings[i] = (const uint32_t *)pp;
-    }
+    pv.table[i] = (const uint64_t *)pt;
+    pv.postings[i] = (const uint32_t *)pp;
   }
   if (!h->idx.d_peer) KCUDA(cudaMalloc((void **)&h->idx.d_peer, sizeof(PeerView)));
   KCUDA(cudaMemcpy(h->idx.d_peer, &pv, sizeof pv, cudaMemcpyHostToDevice));

@@ -42,24 +42,35 @@ __global__ void k_fill_table(const uint32_t *__restrict__ keys, const uint64_t *
   table[d - d_lo] = (cnt << ENTRY_VALUE_BITS) | val;
 }
 
-// The postings get an allocation of their own of at least 2 MiB: smaller cudaMalloc blocks are
-// carved out of shared 2 MiB pages, and the shard may be exported to other processes as a CUDA IPC
-// handle (kaamer_gpu_shard_export), which must cover this array and nothing else.
-static size_t postings_alloc_bytes(uint64_t n_postings) {
-  const size_t b = (size_t)(n_postings + 1) * sizeof(uint32_t);
-  return b < ((size_t)2 << 20) ? ((size_t)2 << 20) : b;
+// A key-range shard (shard_hi != 0) keeps its table and postings in shareable memory (vmm.cu):
+// the other GPUs of the node map them and probe them through NVLink (mode P).  A full index
+// uses plain cudaMalloc.
+static int alloc_postings(kaamer_gpu *h, uint64_t n_postings, bool shareable) {
+  DevIndex &ix = h->idx;
+  const size_t bytes = (size_t)(n_postings + 1) * sizeof(uint32_t);
+  if (shareable) {
+    KCHECK(vmm_alloc(h->device, bytes, &ix.vm_postings));
+    ix.postings = (uint32_t *)ix.vm_postings.ptr;
+    return KAAMER_OK;
+  }
+  KCUDA(cudaMalloc((void **)&ix.postings, bytes));
+  return KAAMER_OK;
 }
 
-static int alloc_table(kaamer_gpu *h, uint64_t d_lo, uint64_t d_hi) {
+static int alloc_table(kaamer_gpu *h, uint64_t d_lo, uint64_t d_hi, bool shareable) {
   DevIndex &ix = h->idx;
   ix.d_lo = d_lo;
   ix.d_hi = d_hi;
   size_t bytes = (size_t)(d_hi - d_lo) * sizeof(uint64_t);
-  const size_t alloc = bytes < ((size_t)2 << 20) ? ((size_t)2 << 20) : bytes;  // see postings_alloc_bytes
-  cudaError_t e = cudaMalloc((void **)&ix.table, alloc);
-  if (e != cudaSuccess) {
-    set_error("cudaMalloc(table, %zu bytes): %s", bytes, cudaGetErrorString(e));
-    return KAAMER_ERR_NOMEM;
+  if (shareable) {
+    KCHECK(vmm_alloc(h->device, bytes, &ix.vm_table));
+    ix.table = (uint64_t *)ix.vm_table.ptr;
+  } else {
+    cudaError_t e = cudaMalloc((void **)&ix.table, bytes);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(table, %zu bytes): %s", bytes, cudaGetErrorString(e));
+      return KAAMER_ERR_NOMEM;
+    }
   }
   KCUDA(cudaMemsetAsync(ix.table, 0, bytes, h->stream));
   return KAAMER_OK;
@@ -93,8 +104,10 @@ static int fill_table(kaamer_gpu *h) {
 
 void index_release(kaamer_gpu *h) {
   DevIndex &ix = h->idx;
-  cudaFree(ix.table);
-  cudaFree(ix.postings);
+  if (ix.vm_table.ptr) vmm_free(&ix.vm_table);
+  else cudaFree(ix.table);
+  if (ix.vm_postings.ptr) vmm_free(&ix.vm_postings);
+  else cudaFree(ix.postings);
   cudaFree(ix.keys);
   cudaFree(ix.offsets);
   cudaFree(ix.prot_off);
@@ -144,10 +157,10 @@ int index_from_view(kaamer_gpu *h, const kaamer_index_view *v) {
   ix.n_aa = v->n_aa;
   ix.n_kmers = v->n_kmers;
   ix.max_protein_id = v->max_protein_id;
-  KCHECK(alloc_table(h, lo, hi));
+  KCHECK(alloc_table(h, lo, hi, v->shard_hi != 0));
   KCUDA(cudaMalloc((void **)&ix.keys, (size_t)(v->n_keys + 1) * sizeof(uint32_t)));
   KCUDA(cudaMalloc((void **)&ix.offsets, (size_t)(v->n_keys + 1) * sizeof(uint64_t)));
-  KCUDA(cudaMalloc((void **)&ix.postings, postings_alloc_bytes(v->n_postings)));
+  KCHECK(alloc_postings(h, v->n_postings, v->shard_hi != 0));
   if (v->n_keys) {
     KCUDA(cudaMemcpyAsync(ix.keys, v->keys, (size_t)v->n_keys * 4, cudaMemcpyHostToDevice, h->stream));
     KCUDA(cudaMemcpyAsync(ix.offsets, v->offsets, (size_t)(v->n_keys + 1) * 8, cudaMemcpyHostToDevice, h->stream));
@@ -267,7 +280,8 @@ __global__ void k_write_postings(const uint64_t *__restrict__ pairs, const uint6
 
 int index_build(kaamer_gpu *h, const uint8_t *residues, const uint64_t *seq_off, const uint32_t *ids,
                 uint64_t n_records, int keep_proteins, uint64_t shard_lo, uint64_t shard_hi) {
-  if (shard_lo == 0 && shard_hi == 0) shard_hi = DENSE_SPACE;
+  const bool shareable = !(shard_lo == 0 && shard_hi == 0);  // an explicit key range: mode S / mode P shard
+  if (!shareable) shard_hi = DENSE_SPACE;
   if (shard_hi > DENSE_SPACE || shard_lo >= shard_hi) {
     set_error("build: bad shard range");
     return KAAMER_ERR_ARG;
@@ -398,7 +412,11 @@ int index_build(kaamer_gpu *h, const uint8_t *residues, const uint64_t *seq_off,
   ix.n_postings = n_uniq;
   BCUDA(cudaMalloc((void **)&ix.keys, (size_t)(n_keys + 1) * 4));
   BCUDA(cudaMalloc((void **)&ix.offsets, (size_t)(n_keys + 1) * 8));
-  BCUDA(cudaMalloc((void **)&ix.postings, postings_alloc_bytes(n_uniq)));
+  rc = alloc_postings(h, n_uniq, shareable);
+  if (rc != KAAMER_OK) {
+    cleanup();
+    return rc;
+  }
   if (n_uniq) {
     unsigned grid = (unsigned)((n_uniq + 255) / 256);
     k_write_keys<<<grid, 256, 0, st>>>(d_pairs, d_head, d_rank, n_uniq, ix.keys, ix.offsets, n_keys);
@@ -414,7 +432,7 @@ int index_build(kaamer_gpu *h, const uint8_t *residues, const uint64_t *seq_off,
   cudaFree(d_rank); d_rank = nullptr;
   cudaFree(d_head); d_head = nullptr;
   cudaFree(d_tmp); d_tmp = nullptr;
-  rc = alloc_table(h, shard_lo, shard_hi);
+  rc = alloc_table(h, shard_lo, shard_hi, shareable);
   if (rc == KAAMER_OK) rc = fill_table(h);
   if (rc == KAAMER_OK && keep_proteins && n_records) {
     // protein table indexed by id (later records with the same id overwrite earlier ones,

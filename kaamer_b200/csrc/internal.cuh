@@ -219,6 +219,22 @@ struct PeerView {
   const uint32_t *postings[MAX_PEER_SHARDS];
 };
 
+// shareable device allocation (vmm.cu): CUDA VMM memory with 2 MiB pages that can be exported to
+// other processes as a POSIX file descriptor and mapped for other devices
+struct VmmAlloc {
+  void *ptr = nullptr;
+  size_t bytes = 0;  // rounded up to the allocation granularity
+  size_t granularity = 0;
+  unsigned long long handle = 0;  // CUmemGenericAllocationHandle
+  int device = 0;
+  bool imported = false;
+};
+int vmm_alloc(int device, size_t bytes, VmmAlloc *out);
+int vmm_export_fd(const VmmAlloc &a, int *fd);
+int vmm_import_fd(int fd, size_t bytes, int device, VmmAlloc *out);
+int vmm_grant(void *ptr, size_t bytes, int device);  // access for one more device of this process
+void vmm_free(VmmAlloc *a);
+
 // ---- the resident index ---------------------------------------------------------------
 struct DevIndex {
   uint64_t *table = nullptr;  // [d_hi - d_lo] direct-address entries
@@ -240,7 +256,9 @@ struct DevIndex {
   // mode P: the shards of the other ranks, mapped into this process (api.cu kaamer_gpu_attach_shards)
   PeerView peer{};               // host copy; peer.n == 0: not attached
   PeerView *d_peer = nullptr;    // device copy read by the kernels
-  std::vector<void *> ipc_open;  // pointers to close with cudaIpcCloseMemHandle
+  std::vector<VmmAlloc> imported;  // mappings of the other processes' shards
+  // key-range shards keep table and postings in shareable memory (vmm.cu); a full index uses cudaMalloc
+  VmmAlloc vm_table, vm_postings;
 };
 
 struct SearchWorkspace {

@@ -249,17 +249,21 @@ class GpuIndex:
         check(_lib.lib().kaamer_gpu_save(self._h, path.encode()))
 
     # ---- peer-mapped shards (mode P) -----------------------------------------------------
-    def export_shard(self) -> bytes:
-        """kaamer_shard_handle of this handle's key range, as bytes (ship it to the other ranks)."""
+    def export_shard(self) -> "_lib.ShardHandle":
+        """kaamer_shard_handle of this handle's key range.  `table_fd` / `postings_fd` are open
+        descriptors of this process (-1 for a full index): send them with SCM_RIGHTS to other
+        processes (kaamer_b200.peer does), then os.close them."""
         sh = _lib.ShardHandle()
         check(_lib.lib().kaamer_gpu_shard_export(self._h, C.byref(sh)))
-        return bytes(sh)
+        return sh
 
-    def attach_shards(self, handles: "list[bytes]") -> None:
+    def attach_shards(self, handles) -> None:
         """Map the key-range shards of all ranks (this one included): afterwards the search entry
-        points of this handle see the whole key space and probe remote shards through NVLink."""
+        points of this handle see the whole key space and probe remote shards through NVLink.
+        `handles`: ShardHandle structs (or their bytes) whose descriptors are valid in THIS process."""
         arr = (_lib.ShardHandle * len(handles))()
         for i, b in enumerate(handles):
+            b = bytes(b)
             assert len(b) == C.sizeof(_lib.ShardHandle)
             C.memmove(C.byref(arr[i]), b, len(b))
         check(_lib.lib().kaamer_gpu_attach_shards(self._h, arr, len(handles)))

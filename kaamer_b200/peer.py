@@ -2,8 +2,9 @@
 behaves as ONE index.
 
 Every rank (one process per GPU) builds or loads the key range `[fences[r], fences[r+1])` of the
-dense 7-mer code space, exports it (`kaamer_gpu_shard_export`: CUDA IPC handles of the table and
-the postings), gathers the exports of all ranks over `torch.distributed` and attaches them
+dense 7-mer code space in shareable device memory, exports it (`kaamer_gpu_shard_export`: two
+POSIX file descriptors of CUDA VMM allocations), hands the descriptors to the other ranks over
+Unix-domain sockets (SCM_RIGHTS) and attaches the shards of all ranks
 (`kaamer_gpu_attach_shards`).  From then on the ordinary search entry points of the handle see
 the whole key space: the search kernels resolve the owner shard of each query k-mer and read the
 8-byte table entry — and the posting list, when there is one — from that GPU's HBM through
@@ -17,29 +18,95 @@ one shard that owns its key.
 """
 from __future__ import annotations
 
+import os
+import socket
+
 import numpy as np
 import torch.distributed as dist
 
+from . import _lib
 from .gpu import GpuIndex
 from .sharded import fences_from_sample  # noqa: F401  (re-exported: same fences as mode S)
+
+_round = 0
+
+
+def _close_fds(sh) -> None:
+    for name in ("table_fd", "postings_fd"):
+        fd = getattr(sh, name)
+        if fd >= 0:
+            os.close(fd)
+            setattr(sh, name, -1)
 
 
 def attach_all(indices: "list[GpuIndex]") -> None:
     """Single process driving several shards (one Go server process with several GPUs, or the
-    single-GPU tests): every handle attaches the exports of all of them."""
+    single-GPU tests): every handle attaches the exports of all of them (by pointer)."""
     handles = [g.export_shard() for g in indices]
-    for g in indices:
-        g.attach_shards(handles)
+    try:
+        for g in indices:
+            g.attach_shards(handles)
+    finally:
+        for sh in handles:
+            _close_fds(sh)
+
+
+def exchange_fds(mine: "_lib.ShardHandle", rank: int, world: int, barrier, tag: str) -> "list[tuple[int, int]]":
+    """Every rank sends the two descriptors of its shard to every other rank of the node over
+    abstract Unix-domain sockets (SCM_RIGHTS).  Returns, per rank, the descriptor numbers valid in
+    THIS process ((-1, -1) for the own rank)."""
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(f"\0kaamer-peer-{tag}-{rank}")
+    srv.listen(world)
+    barrier()  # every listener exists
+    got = [(-1, -1)] * world
+    try:
+        for r in range(world):
+            if r == rank:
+                for _ in range(world - 1):
+                    conn, _ = srv.accept()
+                    with conn:
+                        socket.send_fds(conn, [b"kaamer"], [mine.table_fd, mine.postings_fd])
+                        conn.recv(1)  # the receiver holds its copies before this side may close
+            else:
+                with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
+                    c.connect(f"\0kaamer-peer-{tag}-{r}")
+                    _, fds, _, _ = socket.recv_fds(c, 16, 2)
+                    if len(fds) != 2:
+                        raise RuntimeError(f"rank {r} sent {len(fds)} descriptors instead of 2")
+                    got[r] = (fds[0], fds[1])
+                    c.send(b"k")
+            barrier()
+    finally:
+        srv.close()
+    return got
 
 
 def attach_distributed(index: GpuIndex, group=None) -> int:
-    """One process per GPU: all-gather the shard exports and attach them.  Returns the number of
-    shards.  The gather is control plane (176 bytes per rank, once per index load)."""
+    """One process per GPU on one node: gather the shard exports, pass the descriptors, attach.
+    Control plane only (72 bytes + 2 descriptors per rank, once per index load).  Returns the
+    number of shards."""
+    global _round
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
     mine = index.export_shard()
-    world = dist.get_world_size(group)
-    handles = [None] * world
-    dist.all_gather_object(handles, mine, group=group)
-    index.attach_shards(handles)
+    blobs = [None] * world
+    dist.all_gather_object(blobs, bytes(mine), group=group)
+    _round += 1
+    tag = f"{os.environ.get('MASTER_PORT', '0')}-{_round}"
+    fds = exchange_fds(mine, rank, world, lambda: dist.barrier(group), tag)
+    handles = []
+    for r in range(world):
+        sh = _lib.ShardHandle.from_buffer_copy(blobs[r])
+        if r == rank:
+            sh = mine
+        else:
+            sh.table_fd, sh.postings_fd = fds[r]
+        handles.append(sh)
+    try:
+        index.attach_shards(handles)
+    finally:
+        for sh in handles:
+            _close_fds(sh)
     dist.barrier(group)  # nobody searches before every rank has mapped every shard
     return world
 

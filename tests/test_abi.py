@@ -42,7 +42,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Aln) == 64
     assert C.sizeof(_lib.IndexView) == 104
     assert C.sizeof(_lib.Hits) == 136 and C.sizeof(_lib.Orfs) == 80
-    assert C.sizeof(_lib.ShardHandle) == 176
+    assert C.sizeof(_lib.ShardHandle) == 72
 
 
 def test_no_cpu_fallback_without_device():

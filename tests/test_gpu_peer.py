@@ -100,11 +100,18 @@ def test_shard_handle_alone_refuses_to_search_and_attach_checks_the_tiling(small
         with pytest.raises(KaamerGpuError) as ei:
             a.search_proteins(q, qo, SearchOptions())
         assert "shard" in str(ei.value)
-        with pytest.raises(KaamerGpuError) as ei:
-            a.attach_shards([a.export_shard(), b.export_shard()])  # codes [half, half+5) are not covered
-        assert "tile" in str(ei.value)
-        with pytest.raises(KaamerGpuError):
-            a.attach_shards([a.export_shard()])  # does not reach the end of the key space
+        ea, eb = a.export_shard(), b.export_shard()
+        assert ea.table_fd >= 0 and ea.postings_fd >= 0 and ea.table_bytes % (2 << 20) == 0  # shareable, 2 MiB pages
+        try:
+            with pytest.raises(KaamerGpuError) as ei:
+                a.attach_shards([ea, eb])  # codes [half, half+5) are not covered
+            assert "tile" in str(ei.value)
+            with pytest.raises(KaamerGpuError):
+                a.attach_shards([ea])  # does not reach the end of the key space
+        finally:
+            for e in (ea, eb):
+                os.close(e.table_fd)
+                os.close(e.postings_fd)
         with pytest.raises(KaamerGpuError):
             a.search_proteins(q, qo, SearchOptions())  # a failed attach leaves the handle detached
 

@@ -286,7 +286,7 @@ def peer(a):
     g = GpuIndex.build(res, off, ids, keep_proteins=False, device=lr, shard=(int(fences[rank]), int(fences[rank + 1])))
     t_build = time.perf_counter() - t_build
     if world > 1:
-        attach_distributed(g)
+        attach_distributed(g, presence_filter=not a.no_presence)
     else:
         attach_all([g])
     pool_cap = nq * 16 + 4096
@@ -330,14 +330,13 @@ def peer(a):
         lookups = tot[1].item()
         pbar = tot[2].item() / max(1.0, lookups)
         remote = (world - 1) / world
-        line = {"workload": f"mode P: {a.db_proteins}-protein DB key-range sharded over {world} GPU(s), shards peer-mapped (CUDA IPC) "
+        line = {"workload": f"mode P: {a.db_proteins}-protein DB key-range sharded over {world} GPU(s), shards peer-mapped (CUDA VMM) "
                             f"and probed through NVLink, {nq} queries per rank",
                 "metric": "query residues/sec", "unit": "residues/s", "n_gpus": world, "scaling": "weak",
                 "value": tot[0].item() / (t.item() * 1e-3), "ms_per_step": t.item(),
                 "kmer_lookups_per_sec": lookups / (t.item() * 1e-3),
                 "postings_per_lookup": pbar, "hits": tot[3].item(), "db_residues": int(off[-1]),
-                "remote_probe_fraction_expected": remote,
-                "nvlink_payload_bytes_per_step_est": lookups * remote * (8.0 + 4.0 * max(0.0, pbar - 0.94)),
+                "remote_owner_fraction": remote, "presence_filter": (not a.no_presence) and world > 1,
                 "kernel_ms_rank0": {n: prof["kernel_ms"][i] / max(1, prof["kernel_launches"][i]) for i, n in enumerate(["W", "M", "G"])},
                 "shard_build_s_rank0": t_build,
                 "note": "device-resident queries; no data-path collective: remote table entries and posting lists are "
@@ -361,5 +360,6 @@ if __name__ == "__main__":
     ap.add_argument("--db-proteins", type=int, default=570_000)
     ap.add_argument("--queries", type=int, default=100_000)
     ap.add_argument("--cpu-pairs", type=int, default=2000)
+    ap.add_argument("--no-presence", action="store_true", help="mode P without the local presence filter")
     a = ap.parse_args()
     {"c2": c2, "c5": c5, "sharded": sharded, "peer": peer, "reads": reads}[a.workload](a)

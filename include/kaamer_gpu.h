@@ -244,8 +244,12 @@ typedef struct kaamer_shard_handle {
 int kaamer_gpu_shard_export(kaamer_gpu_t *h, kaamer_shard_handle *out);
 /* shards[n_shards]: the exports of ALL ranks (this handle's own included), in any order; their
  * ranges must tile [0, kaamer_gpu_dense_space()).  The exporting handles must stay open while
- * attached.  Re-attaching replaces the previous set. */
-int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards, int n_shards);
+ * attached, and every rank must have finished building before anyone attaches (the attach reads
+ * every shard once to build the presence filter: one bit per possible k-mer, 227 MB, replicated in
+ * local HBM, so that query k-mers absent from the database never cross NVLink).  Re-attaching
+ * replaces the previous set.  flags: KAAMER_ATTACH_* */
+#define KAAMER_ATTACH_NO_PRESENCE_FILTER 1 /* saturated key spaces: every k-mer exists, skip the filter */
+int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards, int n_shards, int flags);
 int kaamer_gpu_detach_shards(kaamer_gpu_t *h);
 
 /* pinned host buffers for callers that want zero-staging H2D (cgo: C.kaamer_gpu_pinned_alloc) */

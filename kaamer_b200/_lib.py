@@ -223,7 +223,7 @@ def lib() -> C.CDLL:
     L.kaamer_gpu_shard_gather.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, vp, vp]
     L.kaamer_gpu_shard_merge.argtypes = [vp, vp, vp, C.c_int, C.c_uint32, vp, C.POINTER(Opts), C.POINTER(DevResult), vp]
     L.kaamer_gpu_shard_export.argtypes = [vp, C.POINTER(ShardHandle)]
-    L.kaamer_gpu_attach_shards.argtypes = [vp, C.POINTER(ShardHandle), C.c_int]
+    L.kaamer_gpu_attach_shards.argtypes = [vp, C.POINTER(ShardHandle), C.c_int, C.c_int]
     L.kaamer_gpu_detach_shards.argtypes = [vp]
     L.kaamer_gpu_pinned_alloc.argtypes = [C.c_uint64, C.POINTER(vp)]
     L.kaamer_gpu_pinned_free.argtypes = [vp]

@@ -148,6 +148,8 @@ static void destroy_handle(kaamer_gpu *h) {
   cudaSetDevice(h->device);
   for (auto &a : h->idx.imported) vmm_free(&a);
   h->idx.imported.clear();
+  if (h->idx.presence) cudaFree(h->idx.presence);
+  h->idx.presence = nullptr;
   if (h->idx.d_peer) cudaFree(h->idx.d_peer);
   h->idx.d_peer = nullptr;
   index_release(h);
@@ -312,6 +314,8 @@ int kaamer_gpu_shard_export(kaamer_gpu_t *h, kaamer_shard_handle *out) {
 static void detach_shards_locked(kaamer_gpu *h) {
   for (auto &a : h->idx.imported) vmm_free(&a);
   h->idx.imported.clear();
+  if (h->idx.presence) cudaFree(h->idx.presence);
+  h->idx.presence = nullptr;
   h->idx.peer = PeerView{};
 }
 
@@ -366,7 +370,7 @@ static int map_shard_array(kaamer_gpu *h, const kaamer_shard_handle &s, bool sam
   return KAAMER_OK;
 }
 
-int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards, int n_shards) {
+int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards, int n_shards, int flags) {
   if (!h || !shards) {
     set_error("null argument");
     return KAAMER_ERR_ARG;
@@ -406,6 +410,8 @@ int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards,
   PeerView pv{};
   for (int i = 0; i <= MAX_PEER_SHARDS; ++i) pv.fence[i] = 0xFFFFFFFFu;
   pv.n = n_shards;
+  pv.self = -1;
+  pv.presence = nullptr;
   const int32_t me = (int32_t)getpid();
   for (int i = 0; i < n_shards; ++i) {
     const kaamer_shard_handle &s = shards[order[i]];
@@ -419,6 +425,23 @@ int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards,
     }
     pv.table[i] = (const uint64_t *)pt;
     pv.postings[i] = (const uint32_t *)pp;
+    if (s.pid == me && s.device == h->device && s.table_ptr == (uint64_t)(uintptr_t)h->idx.table) pv.self = i;
+  }
+  if (n_shards > 1 && !(flags & KAAMER_ATTACH_NO_PRESENCE_FILTER)) {
+    // local replica of "which k-mers exist": 1 bit per dense code, built by streaming every shard once
+    const size_t words = (size_t)((DENSE_SPACE + 31) / 32);
+    cudaError_t e = cudaMalloc((void **)&h->idx.presence, words * sizeof(uint32_t));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(presence filter, %zu bytes): %s", words * 4, cudaGetErrorString(e));
+      detach_shards_locked(h);
+      return KAAMER_ERR_NOMEM;
+    }
+    int rc = build_presence(h, pv, h->idx.presence, h->stream);
+    if (rc != KAAMER_OK) {
+      detach_shards_locked(h);
+      return rc;
+    }
+    pv.presence = h->idx.presence;
   }
   if (!h->idx.d_peer) KCUDA(cudaMalloc((void **)&h->idx.d_peer, sizeof(PeerView)));
   KCUDA(cudaMemcpy(h->idx.d_peer, &pv, sizeof pv, cudaMemcpyHostToDevice));

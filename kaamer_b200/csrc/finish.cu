@@ -133,6 +133,9 @@ __global__ void __launch_bounds__(256) k_positions(FinishArgs a) {
           post = a.peer->postings[sh];
           lo = a.peer->fence[sh];
           hi = DENSE_SPACE;
+          if (a.peer->presence != nullptr && (int32_t)sh != a.peer->self &&
+              ((__ldg(a.peer->presence + (d >> 5)) >> (d & 31u)) & 1u) == 0u)
+            hi = 0;  // absent on its (remote) owner: no probe
         }
         if (d >= lo && d < hi) {
           const uint64_t e = ldg_entry_f(tab + (d - lo));

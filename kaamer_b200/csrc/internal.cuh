@@ -215,6 +215,11 @@ constexpr uint64_t PEER_LOCAL_MASK = (1ull << PEER_SHARD_SHIFT) - 1;
 struct PeerView {
   uint32_t fence[MAX_PEER_SHARDS + 1];  // fence[s] = first dense code of shard s; unused = 0xFFFFFFFF
   int32_t n;
+  int32_t self;  // the shard that lives in this GPU's own HBM (-1: none)
+  // presence filter: one bit per dense code, set when the k-mer has postings on its owner shard.
+  // A local replica (227 MB) that keeps the k-mers absent from the database off NVLink: only
+  // probes that will find something cross to the owner GPU.  nullptr: filter off.
+  const uint32_t *presence;
   const uint64_t *table[MAX_PEER_SHARDS];
   const uint32_t *postings[MAX_PEER_SHARDS];
 };
@@ -257,6 +262,7 @@ struct DevIndex {
   PeerView peer{};               // host copy; peer.n == 0: not attached
   PeerView *d_peer = nullptr;    // device copy read by the kernels
   std::vector<VmmAlloc> imported;  // mappings of the other processes' shards
+  uint32_t *presence = nullptr;    // presence filter over the whole key space (mode P, api.cu)
   // key-range shards keep table and postings in shareable memory (vmm.cu); a full index uses cudaMalloc
   VmmAlloc vm_table, vm_postings;
 };
@@ -385,6 +391,8 @@ __device__ __forceinline__ uint32_t filter_kmin(long long min_kmatch, double rat
   return k > 0xFFFFFFFEll ? 0xFFFFFFFFu : (uint32_t)k;
 }
 #endif
+// search.cu: presence bitmap of all attached shards (streams every shard table once)
+int build_presence(kaamer_gpu *h, const PeerView &pv, uint32_t *d_bits, cudaStream_t st);
 // align.cu
 int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, const uint32_t *pair_q,
                 const uint32_t *pair_s, uint32_t n_pairs, const kaamer_aln_opts *o, kaamer_aln *out);

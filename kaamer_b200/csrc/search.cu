@@ -473,6 +473,35 @@ __global__ void __launch_bounds__(G_THREADS) k_search_g(SearchArgs a) {
   }
 }
 
+// ---- presence filter of the attached shards (mode P) ------------------------------------------
+// One bit per dense code: does the owner shard hold postings for it?  Every lane reads the entry of
+// one code (coalesced 256-byte rows, remote shards streamed through NVLink), a ballot makes the word.
+__global__ void __launch_bounds__(256) k_presence(PeerView pv, uint32_t *__restrict__ bits, uint64_t n_words) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t w = warp; w < n_words; w += nwarps) {
+    const uint64_t d = w * 32 + lane;
+    bool present = false;
+    if (d < DENSE_SPACE) {
+      uint32_t s = 0;
+#pragma unroll
+      for (int i = 1; i < MAX_PEER_SHARDS; ++i) s += (uint32_t)d >= pv.fence[i] ? 1u : 0u;
+      present = (pv.table[s][d - pv.fence[s]] >> ENTRY_VALUE_BITS) != 0ull;
+    }
+    const unsigned word = __ballot_sync(0xFFFFFFFFu, present);
+    if (lane == 0) bits[w] = word;
+  }
+}
+
+int build_presence(kaamer_gpu *h, const PeerView &pv, uint32_t *d_bits, cudaStream_t st) {
+  const uint64_t n_words = (DENSE_SPACE + 31) / 32;
+  k_presence<<<h->sm_count * 16, 256, 0, st>>>(pv, d_bits, n_words);
+  KCUDA(cudaGetLastError());
+  KCUDA(cudaStreamSynchronize(st));
+  return KAAMER_OK;
+}
+
 // ---- CSR compaction (host API) ----------------------------------------------------------
 struct WidenU32 {
   __host__ __device__ uint64_t operator()(uint32_t x) const { return x; }

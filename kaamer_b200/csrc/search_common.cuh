@@ -100,6 +100,10 @@ __device__ __forceinline__ uint64_t probe_entry(const SearchArgs &a, const PeerV
     uint32_t s = 0;
 #pragma unroll
     for (int i = 1; i < MAX_PEER_SHARDS; ++i) s += d >= pv->fence[i] ? 1u : 0u;
+    if (pv->presence != nullptr && (int32_t)s != pv->self) {
+      // remote owner: ask the local presence replica first, absent k-mers never cross NVLink
+      if (((__ldg(pv->presence + (d >> 5)) >> (d & 31u)) & 1u) == 0u) return 0ull;
+    }
     uint64_t e = ldg_entry(pv->table[s] + (d - pv->fence[s]));
     if ((e >> ENTRY_VALUE_BITS) >= 2ull) e |= (uint64_t)s << PEER_SHARD_SHIFT;
     return e;

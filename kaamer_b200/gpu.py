@@ -257,7 +257,7 @@ class GpuIndex:
         check(_lib.lib().kaamer_gpu_shard_export(self._h, C.byref(sh)))
         return sh
 
-    def attach_shards(self, handles) -> None:
+    def attach_shards(self, handles, presence_filter: bool = True) -> None:
         """Map the key-range shards of all ranks (this one included): afterwards the search entry
         points of this handle see the whole key space and probe remote shards through NVLink.
         `handles`: ShardHandle structs (or their bytes) whose descriptors are valid in THIS process."""
@@ -266,7 +266,7 @@ class GpuIndex:
             b = bytes(b)
             assert len(b) == C.sizeof(_lib.ShardHandle)
             C.memmove(C.byref(arr[i]), b, len(b))
-        check(_lib.lib().kaamer_gpu_attach_shards(self._h, arr, len(handles)))
+        check(_lib.lib().kaamer_gpu_attach_shards(self._h, arr, len(handles), 0 if presence_filter else 1))
 
     def detach_shards(self) -> None:
         check(_lib.lib().kaamer_gpu_detach_shards(self._h))

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _peer_handles(small_db, G, dev=0):
+def _peer_handles(small_db, G, dev=0, presence_filter=True):
     from kaamer_b200 import GpuIndex
     from kaamer_b200.peer import attach_all
     from kaamer_b200.sharded import make_fences
@@ -24,12 +24,12 @@ def _peer_handles(small_db, G, dev=0):
     fences = make_fences(idx.keys, idx.offsets, G)
     hs = [GpuIndex.build(small_db["res"], small_db["off"], small_db["ids"], keep_proteins=False, device=dev,
                          shard=(int(fences[r]), int(fences[r + 1]))) for r in range(G)]
-    attach_all(hs)
+    attach_all(hs, presence_filter)
     return hs
 
 
-@pytest.mark.parametrize("G", [1, 2, 3, 8])
-def test_peer_protein_search_parity(small_db, G):
+@pytest.mark.parametrize("G,presence", [(1, True), (2, True), (2, False), (3, True), (8, True), (8, False)])
+def test_peer_protein_search_parity(small_db, G, presence):
     """every shard handle answers the whole batch exactly like the single index (all size classes:
     short, 700-residue, 3000-residue and 12000-residue queries)"""
     from kaamer_b200 import SearchOptions, synth
@@ -41,7 +41,7 @@ def test_peer_protein_search_parity(small_db, G):
     seqs += [b"", b"MKT", small_db["res"][:12].tobytes(), b"A" * 700, small_db["res"][:3000].tobytes(),
              small_db["res"][5000:17000].tobytes()]
     q, qo = o.pack(seqs)
-    hs = _peer_handles(small_db, G)
+    hs = _peer_handles(small_db, G, presence_filter=presence)
     try:
         for opts in (SearchOptions(), SearchOptions(min_kmatch=1, min_kratio=0.0, max_results=100),
                      SearchOptions(min_kmatch=4, min_kratio=0.3, max_results=2)):

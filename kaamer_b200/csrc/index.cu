@@ -11,6 +11,8 @@
 // and, as §8f-1, pkg/makedb + pkg/indexdb for the device index: records -> (k-mer, id)
 // pairs -> radix sort -> unique -> CSR, all on the GPU (cub is used for the sort/scan/
 // select plumbing of this one-shot build; the search kernels are hand-written).
+#include <cstdlib>
+
 #include <cub/cub.cuh>
 
 #include "internal.cuh"
@@ -22,7 +24,7 @@ namespace kaamer {
 // ---------------------------------------------------------------------------------------
 __global__ void k_fill_table(const uint32_t *__restrict__ keys, const uint64_t *__restrict__ offsets,
                              const uint32_t *__restrict__ postings, uint64_t n_keys, uint64_t *table,
-                             uint64_t d_lo, uint64_t d_hi, unsigned long long *bad) {
+                             uint64_t d_lo, uint64_t d_hi, uint32_t *filter, unsigned long long *bad) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_keys) return;
   uint32_t d;
@@ -40,6 +42,7 @@ __global__ void k_fill_table(const uint32_t *__restrict__ keys, const uint64_t *
   }
   uint64_t val = cnt == 1 ? (uint64_t)postings[b] : b;
   table[d - d_lo] = (cnt << ENTRY_VALUE_BITS) | val;
+  if (filter) atomicOr(filter + ((d & FILTER_MASK) >> 5), 1u << (d & 31u));
 }
 
 // A key-range shard (shard_hi != 0) keeps its table and postings in shareable memory (vmm.cu):
@@ -81,10 +84,15 @@ static int fill_table(kaamer_gpu *h) {
   unsigned long long *d_bad;
   KCUDA(cudaMalloc((void **)&d_bad, 2 * sizeof(unsigned long long)));
   KCUDA(cudaMemsetAsync(d_bad, 0, 2 * sizeof(unsigned long long), h->stream));
+  // the L2-resident presence filter (internal.cuh), unless the key space is too densely occupied
+  if (ix.n_keys <= FILTER_MAX_KEYS && getenv("KAAMER_NO_L2_FILTER") == nullptr) {
+    KCUDA(cudaMalloc((void **)&ix.filter, FILTER_WORDS * sizeof(uint32_t)));
+    KCUDA(cudaMemsetAsync(ix.filter, 0, FILTER_WORDS * sizeof(uint32_t), h->stream));
+  }
   if (ix.n_keys) {
     unsigned grid = (unsigned)((ix.n_keys + 255) / 256);
     k_fill_table<<<grid, 256, 0, h->stream>>>(ix.keys, ix.offsets, ix.postings, ix.n_keys, ix.table, ix.d_lo,
-                                               ix.d_hi, d_bad);
+                                               ix.d_hi, ix.filter, d_bad);
     KCUDA(cudaGetLastError());
   }
   unsigned long long bad[2];
@@ -108,6 +116,7 @@ void index_release(kaamer_gpu *h) {
   else cudaFree(ix.table);
   if (ix.vm_postings.ptr) vmm_free(&ix.vm_postings);
   else cudaFree(ix.postings);
+  cudaFree(ix.filter);
   cudaFree(ix.keys);
   cudaFree(ix.offsets);
   cudaFree(ix.prot_off);

@@ -136,14 +136,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_search_wt(SearchArgs a) {
     constexpr int U = 4;
     // software pipeline: the probes of round r+1 are in flight while round r is counted
     auto load_round = [&](int base, uint64_t(&e)[U]) {
+      uint32_t d[U];
+      bool ok[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int pos = base + u * 32 + (int)lane;
-        e[u] = 0;
-        if (pos < K) {
-          e[u] = probe_entry<PEER>(a, pv, dense_from_packed(s.pp[pos], s.pp[pos + 2], s.pp[pos + 4], s.pp[pos + 6]));
-        }
+        ok[u] = pos < K;
+        d[u] = ok[u] ? dense_from_packed(s.pp[pos], s.pp[pos + 2], s.pp[pos + 4], s.pp[pos + 6]) : 0u;
       }
+      probe_entries<PEER, U>(a, pv, d, ok, e);
     };
     uint64_t nxt[U];
     load_round(0, nxt);
@@ -288,14 +289,15 @@ __global__ void __launch_bounds__(M_THREADS, M_CTAS) k_search_m(SearchArgs a) {
     unsigned long long q_incr = 0;
     constexpr int U = 4;
     auto load_round = [&](int base, uint64_t(&e)[U]) {
+      uint32_t d[U];
+      bool ok[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int pos = base + u * THREADS + tid;
-        e[u] = 0;
-        if (pos < K) {
-          e[u] = probe_entry<PEER>(a, pv, dense_from_packed(pp[pos], pp[pos + 2], pp[pos + 4], pp[pos + 6]));
-        }
+        ok[u] = pos < K;
+        d[u] = ok[u] ? dense_from_packed(pp[pos], pp[pos + 2], pp[pos + 4], pp[pos + 6]) : 0u;
       }
+      probe_entries<PEER, U>(a, pv, d, ok, e);
     };
     uint64_t nxt[U];
     load_round(0, nxt);
@@ -429,12 +431,15 @@ __global__ void __launch_bounds__(G_THREADS) k_search_g(SearchArgs a) {
     constexpr int U = 4;
     for (int base = 0; base < K; base += U * THREADS) {
       uint64_t ent[U];
+      uint32_t d[U];
+      bool ok[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int pos = base + u * THREADS + tid;
-        ent[u] = 0;
-        if (pos < K) ent[u] = probe_entry<PEER>(a, pv, dense_at(pos));
+        ok[u] = pos < K;
+        d[u] = ok[u] ? dense_at(pos) : 0u;
       }
+      probe_entries<PEER, U>(a, pv, d, ok, ent);
       warp_consume<U, PEER>(a, ent, hv, kmin, cl, q_incr, pv);
     }
     __syncthreads();
@@ -584,6 +589,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   a.nt_mode = nt_mode;
   a.any0 = d_any0;
   a.peer = h->idx.d_peer;
+  a.filter = h->idx.filter;
   const int g_ctas = h->sm_count;
   KCHECK(ws.ghash.ensure((size_t)2 * g_ctas * 3 * a.ghash_slots));
   a.ghash = ws.ghash.p;

@@ -50,6 +50,7 @@ struct SearchArgs {
   uint8_t *any0;
   int g_list;  // class list processed by k_search_g (2: classified, 3: hand-offs from class M)
   const PeerView *peer;  // mode P (kernels instantiated with PEER = true): shards of all ranks
+  const uint32_t *filter;  // folded presence bits of the handle's own keys (L2-resident), or nullptr
 };
 
 // Copy src[0, len) into shared memory with aligned 16-byte loads (one request per 16 residues:
@@ -91,23 +92,60 @@ __device__ __forceinline__ uint64_t ldg_entry(const uint64_t *p) {
 // space is tiled by the shards of pv (a shared-memory copy of SearchArgs::peer); the owner is found
 // with MAX_PEER_SHARDS-1 compares and the entry is read from its HBM — local or through NVLink.
 // A multi-posting entry gets its shard folded into the value so that post_ptr finds the list.
+//
+// Every probe is preceded by a presence-filter lookup: the folded 64 MB bitmap of the handle's own
+// keys (L2-resident, internal.cuh) for the local table, the exact 227 MB replica for remote shards.
+// U probes are issued in two phases — U filter words, then the surviving table entries — so that the
+// loads of each phase are in flight together.
+template <bool PEER, int U>
+__device__ __forceinline__ void probe_entries(const SearchArgs &a, const PeerView *pv, const uint32_t (&d)[U],
+                                              const bool (&ok)[U], uint64_t (&e)[U]) {
+  uint32_t w[U];
+  const uint64_t *p[U];
+  uint32_t sh[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    bool valid = ok[u];
+    const uint32_t *f;
+    uint32_t fi;
+    if constexpr (!PEER) {
+      (void)pv;
+      valid = valid && d[u] >= a.d_lo && d[u] < a.d_hi;
+      p[u] = a.table + (d[u] - a.d_lo);
+      f = a.filter;
+      fi = d[u] & FILTER_MASK;
+      sh[u] = 0;
+    } else {
+      uint32_t s = 0;
+#pragma unroll
+      for (int i = 1; i < MAX_PEER_SHARDS; ++i) s += d[u] >= pv->fence[i] ? 1u : 0u;
+      p[u] = pv->table[s] + (d[u] - pv->fence[s]);
+      const bool mine = (int32_t)s == pv->self;
+      f = mine ? a.filter : pv->presence;
+      fi = mine ? (d[u] & FILTER_MASK) : d[u];
+      sh[u] = s;
+    }
+    w[u] = valid ? 0xFFFFFFFFu : 0u;
+    if (valid && f != nullptr) w[u] = __ldg(f + (fi >> 5));
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    e[u] = 0ull;
+    if ((w[u] >> (d[u] & 31u)) & 1u) {
+      e[u] = ldg_entry(p[u]);
+      if constexpr (PEER) {
+        if ((e[u] >> ENTRY_VALUE_BITS) >= 2ull) e[u] |= (uint64_t)sh[u] << PEER_SHARD_SHIFT;
+      }
+    }
+  }
+}
 template <bool PEER>
 __device__ __forceinline__ uint64_t probe_entry(const SearchArgs &a, const PeerView *pv, uint32_t d) {
-  if constexpr (!PEER) {
-    (void)pv;
-    return (d >= a.d_lo && d < a.d_hi) ? ldg_entry(a.table + (d - a.d_lo)) : 0ull;
-  } else {
-    uint32_t s = 0;
-#pragma unroll
-    for (int i = 1; i < MAX_PEER_SHARDS; ++i) s += d >= pv->fence[i] ? 1u : 0u;
-    if (pv->presence != nullptr && (int32_t)s != pv->self) {
-      // remote owner: ask the local presence replica first, absent k-mers never cross NVLink
-      if (((__ldg(pv->presence + (d >> 5)) >> (d & 31u)) & 1u) == 0u) return 0ull;
-    }
-    uint64_t e = ldg_entry(pv->table[s] + (d - pv->fence[s]));
-    if ((e >> ENTRY_VALUE_BITS) >= 2ull) e |= (uint64_t)s << PEER_SHARD_SHIFT;
-    return e;
-  }
+  const uint32_t dd[1] = {d};
+  const bool ok[1] = {true};
+  uint64_t e[1];
+  probe_entries<PEER, 1>(a, pv, dd, ok, e);
+  return e[0];
 }
 template <bool PEER>
 __device__ __forceinline__ const uint32_t *post_ptr(const SearchArgs &a, const PeerView *pv, uint64_t val) {
@@ -250,7 +288,7 @@ __device__ __forceinline__ uint32_t hist_count(const Hash &hv, uint32_t id) {
 // nucleotide mode, one warp: does a subject tied with the best hit (count T), other than the
 // best hit itself, hold the query's first k-mer (dense code d0)?
 template <bool PEER = false, class Hash>
-__device__ __noinline__ bool warp_any0(const SearchArgs &a, const PeerView *pv, const Hash &hv, uint32_t d0,
+__device__ __forceinline__ bool warp_any0(const SearchArgs &a, const PeerView *pv, const Hash &hv, uint32_t d0,
                                        uint32_t best_id, uint32_t T) {
   const unsigned lane = threadIdx.x & 31;
   bool any = false;

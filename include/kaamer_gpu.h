@@ -62,6 +62,13 @@ typedef struct kaamer_index_view {
  * (api/server.go:65, pkg/kvstore/kv_stores.go:46-104) for the search path. */
 int kaamer_gpu_open(const char *kidx_path, int device, kaamer_gpu_t **out);
 int kaamer_gpu_open_view(const kaamer_index_view *view, int device, kaamer_gpu_t **out);
+/* Key-range shard of a `.kidx` file: only the k-mers whose dense code lies in [shard_lo, shard_hi)
+ * become resident (in shareable memory, see kaamer_gpu_shard_export); KStats cover the whole file.
+ * kaamer_gpu_kidx_fences cuts the key space of the file into n_shards contiguous ranges of equal
+ * posting mass: fences[n_shards+1], fences[0] = 0, fences[n_shards] = kaamer_gpu_dense_space(). */
+int kaamer_gpu_open_shard(const char *kidx_path, int device, uint64_t shard_lo, uint64_t shard_hi,
+                          kaamer_gpu_t **out);
+int kaamer_gpu_kidx_fences(const char *kidx_path, int n_shards, uint64_t *fences);
 /* Replaces pkg/makedb (processProteinInputFASTA, inputFASTA.go:195-250) + pkg/indexdb
  * (IndexStore, indexdb.go:68-150) for the device index: records -> sorted unique
  * (k-mer, protein id) -> CSR, built on the GPU.  ids[i] is the protein id of record i. */

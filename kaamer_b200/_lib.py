@@ -149,6 +149,8 @@ class ShardHandle(C.Structure):
 SYMBOLS = [
     "kaamer_gpu_open",
     "kaamer_gpu_open_view",
+    "kaamer_gpu_open_shard",
+    "kaamer_gpu_kidx_fences",
     "kaamer_gpu_build",
     "kaamer_gpu_build_shard",
     "kaamer_gpu_close",
@@ -198,6 +200,8 @@ def lib() -> C.CDLL:
     L.kaamer_gpu_version.restype = C.c_char_p
     L.kaamer_gpu_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.kaamer_gpu_open_view.argtypes = [C.POINTER(IndexView), C.c_int, C.POINTER(vp)]
+    L.kaamer_gpu_open_shard.argtypes = [C.c_char_p, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(vp)]
+    L.kaamer_gpu_kidx_fences.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_uint64)]
     L.kaamer_gpu_build.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(vp)]
     L.kaamer_gpu_build_shard.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(vp)]
     L.kaamer_gpu_close.argtypes = [vp]

@@ -193,53 +193,132 @@ int kaamer_gpu_open_view(const kaamer_index_view *view, int device, kaamer_gpu_t
   return KAAMER_OK;
 }
 
-int kaamer_gpu_open(const char *path, int device, kaamer_gpu_t **out) {
-  if (!out || !path) {
-    set_error("null argument");
-    return KAAMER_ERR_ARG;
-  }
-  *out = nullptr;
+// the sections of a .kidx file in host memory
+struct KidxFile {
+  KidxHeader hd;
+  std::vector<uint32_t> keys, postings;
+  std::vector<uint64_t> offsets, poff;
+  std::vector<uint8_t> pres;
+};
+
+static int read_kidx(const char *path, KidxFile *k, bool want_postings, bool want_proteins) {
   FILE *f = fopen(path, "rb");
   if (!f) {
     set_error("cannot open %s", path);
     return KAAMER_ERR_IO;
   }
-  KidxHeader hd;
+  KidxHeader &hd = k->hd;
   if (fread(&hd, 1, sizeof hd, f) != sizeof hd || memcmp(hd.magic, "KIDX0001", 8) != 0 || hd.version != 1 ||
       hd.k != KAAMER_KMER_SIZE) {
     fclose(f);
     set_error("%s is not a kidx v1 (k=7) file", path);
     return KAAMER_ERR_FORMAT;
   }
-  std::vector<uint32_t> keys((size_t)hd.n_keys), postings((size_t)hd.n_postings);
-  std::vector<uint64_t> offsets((size_t)hd.n_keys + 1), poff;
-  std::vector<uint8_t> pres;
-  int rc = read_section(f, keys.data(), keys.size() * 4);
-  if (rc == KAAMER_OK) rc = read_section(f, offsets.data(), offsets.size() * 8);
-  if (rc == KAAMER_OK) rc = read_section(f, postings.data(), postings.size() * 4);
-  if (rc == KAAMER_OK && (hd.flags & 1)) {
-    poff.resize((size_t)hd.max_protein_id + 2);
-    pres.resize((size_t)hd.n_residues);
-    rc = read_section(f, poff.data(), poff.size() * 8);
-    if (rc == KAAMER_OK) rc = read_section(f, pres.data(), pres.size());
+  k->keys.resize((size_t)hd.n_keys);
+  k->offsets.resize((size_t)hd.n_keys + 1);
+  int rc = read_section(f, k->keys.data(), k->keys.size() * 4);
+  if (rc == KAAMER_OK) rc = read_section(f, k->offsets.data(), k->offsets.size() * 8);
+  if (rc == KAAMER_OK && want_postings) {
+    k->postings.resize((size_t)hd.n_postings);
+    rc = read_section(f, k->postings.data(), k->postings.size() * 4);
+    if (rc == KAAMER_OK && want_proteins && (hd.flags & 1)) {
+      k->poff.resize((size_t)hd.max_protein_id + 2);
+      k->pres.resize((size_t)hd.n_residues);
+      rc = read_section(f, k->poff.data(), k->poff.size() * 8);
+      if (rc == KAAMER_OK) rc = read_section(f, k->pres.data(), k->pres.size());
+    }
   }
   fclose(f);
-  if (rc != KAAMER_OK) return rc;
+  return rc;
+}
+
+// first key of the (ascending) key array whose dense code is >= d; key order == dense order
+static size_t lower_bound_dense(const std::vector<uint32_t> &keys, uint64_t d) {
+  size_t lo = 0, hi = keys.size();
+  while (lo < hi) {
+    size_t mid = (lo + hi) / 2;
+    uint32_t dm = 0;
+    if (dense_from_key(keys[mid], &dm) && (uint64_t)dm < d) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+static int open_kidx_range(const char *path, int device, uint64_t shard_lo, uint64_t shard_hi, kaamer_gpu_t **out) {
+  if (!out || !path) {
+    set_error("null argument");
+    return KAAMER_ERR_ARG;
+  }
+  *out = nullptr;
+  const bool whole = shard_lo == 0 && shard_hi == 0;
+  if (!whole && (shard_hi > DENSE_SPACE || shard_lo >= shard_hi)) {
+    set_error("bad shard range [%llu, %llu)", (unsigned long long)shard_lo, (unsigned long long)shard_hi);
+    return KAAMER_ERR_ARG;
+  }
+  KidxFile k;
+  KCHECK(read_kidx(path, &k, true, true));
+  const KidxHeader &hd = k.hd;
+  size_t a = 0, b = k.keys.size();
+  if (!whole) {
+    a = lower_bound_dense(k.keys, shard_lo);
+    b = lower_bound_dense(k.keys, shard_hi);
+  }
+  const uint64_t p0 = k.offsets[a], p1 = k.offsets[b];
+  std::vector<uint64_t> offs(b - a + 1);
+  for (size_t i = a; i <= b; ++i) offs[i - a] = k.offsets[i] - p0;
   kaamer_index_view v{};
-  v.n_keys = hd.n_keys;
-  v.n_postings = hd.n_postings;
-  v.keys = keys.data();
-  v.offsets = offsets.data();
-  v.postings = postings.data();
+  v.n_keys = b - a;
+  v.n_postings = p1 - p0;
+  v.keys = k.keys.data() + a;
+  v.offsets = offs.data();
+  v.postings = k.postings.data() + p0;
   v.n_proteins = hd.n_proteins;
   v.n_aa = hd.n_aa;
   v.n_kmers = hd.n_kmers;
   v.max_protein_id = hd.max_protein_id;
   if (hd.flags & 1) {
-    v.prot_seq_off = poff.data();
-    v.prot_residues = pres.data();
+    v.prot_seq_off = k.poff.data();
+    v.prot_residues = k.pres.data();
   }
+  v.shard_lo = whole ? 0 : shard_lo;
+  v.shard_hi = whole ? 0 : shard_hi;
   return kaamer_gpu_open_view(&v, device, out);
+}
+
+int kaamer_gpu_open(const char *path, int device, kaamer_gpu_t **out) {
+  return open_kidx_range(path, device, 0, 0, out);
+}
+
+int kaamer_gpu_open_shard(const char *path, int device, uint64_t shard_lo, uint64_t shard_hi, kaamer_gpu_t **out) {
+  if (shard_lo == 0 && shard_hi == 0) shard_hi = DENSE_SPACE;  // an explicit (shareable) full-range shard
+  return open_kidx_range(path, device, shard_lo, shard_hi, out);
+}
+
+int kaamer_gpu_kidx_fences(const char *path, int n_shards, uint64_t *fences) {
+  if (!path || !fences || n_shards < 1) {
+    set_error("bad argument");
+    return KAAMER_ERR_ARG;
+  }
+  KidxFile k;
+  KCHECK(read_kidx(path, &k, false, false));
+  fences[0] = 0;
+  fences[n_shards] = DENSE_SPACE;
+  const size_t n = k.keys.size();
+  if (n == 0) {
+    for (int s = 1; s < n_shards; ++s) fences[s] = DENSE_SPACE * (uint64_t)s / (uint64_t)n_shards;
+    return KAAMER_OK;
+  }
+  // mass of a key = its postings + 1 (the probe itself); cut at equal cumulative mass
+  const uint64_t total = k.offsets[n] + n;
+  size_t i = 0;
+  for (int s = 1; s < n_shards; ++s) {
+    const double target = (double)total * s / n_shards;
+    while (i < n - 1 && (double)(k.offsets[i + 1] + i + 1) < target) ++i;
+    uint32_t d = 0;
+    dense_from_key(k.keys[i], &d);
+    fences[s] = d > fences[s - 1] ? d : fences[s - 1];
+  }
+  return KAAMER_OK;
 }
 
 int kaamer_gpu_build(const uint8_t *residues, const uint64_t *seq_off, const uint32_t *ids, uint64_t n_records,

@@ -175,6 +175,20 @@ class GpuIndex:
         return cls(h, device)
 
     @classmethod
+    def open_shard(cls, kidx_path: str, shard, device: int = 0) -> "GpuIndex":
+        """The key range `shard = (lo, hi)` of a `.kidx` file, in shareable memory (mode P / mode S)."""
+        h = C.c_void_p()
+        check(_lib.lib().kaamer_gpu_open_shard(kidx_path.encode(), device, int(shard[0]), int(shard[1]), C.byref(h)))
+        return cls(h, device)
+
+    @staticmethod
+    def kidx_fences(kidx_path: str, n_shards: int) -> np.ndarray:
+        """Contiguous key ranges of equal posting mass for a `.kidx` file: u64[n_shards+1]."""
+        f = (C.c_uint64 * (n_shards + 1))()
+        check(_lib.lib().kaamer_gpu_kidx_fences(kidx_path.encode(), n_shards, f))
+        return np.array(list(f), dtype=np.uint64)
+
+    @classmethod
     def from_arrays(cls, keys, offsets, postings, n_proteins=0, n_aa=0, n_kmers=0, max_protein_id=None,
                     prot_seq_off=None, prot_residues=None, shard=(0, 0), device: int = 0) -> "GpuIndex":
         keys = np.ascontiguousarray(keys, dtype=np.uint32)

@@ -126,3 +126,37 @@ def test_peer_ipc_two_gpus():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "peer ipc ok" in out.stdout
+
+
+def test_open_shard_from_kidx_file(small_db, tmp_path):
+    """the deployment path of a Go server: one `.kidx` file, one key-range handle per GPU
+    (kaamer_gpu_kidx_fences + kaamer_gpu_open_shard), attached to each other"""
+    from kaamer_b200 import GpuIndex, SearchOptions, synth
+    from kaamer_b200.peer import attach_all
+    from kaamer_b200.sharded import shard_arrays
+    from oracle import oracle as o
+
+    idx = small_db["idx"]
+    p = str(tmp_path / "db.kidx")
+    with GpuIndex.build(small_db["res"], small_db["off"], small_db["ids"], keep_proteins=True) as full:
+        full.save(p)
+    fences = GpuIndex.kidx_fences(p, 3)
+    hs = [GpuIndex.open_shard(p, (int(fences[r]), int(fences[r + 1]))) for r in range(3)]
+    try:
+        for r, g in enumerate(hs):
+            k, fo, ps = g.index_arrays()
+            ek, efo, eps = shard_arrays(idx.keys, idx.offsets, idx.postings, int(fences[r]), int(fences[r + 1]))
+            np.testing.assert_array_equal(k, ek)
+            np.testing.assert_array_equal(fo, efo)
+            np.testing.assert_array_equal(ps, eps)
+            assert g.dbstats()["NumberOfAA"] == idx.n_aa
+        attach_all(hs)
+        q, qo, _ = synth.protein_queries(small_db["res"], small_db["off"], 300, config_index=1, stream=21)
+        ora = o.search_proteins(idx, q, qo, o.opts(), 4)
+        for g in hs:
+            assert_same_hits(g.search_proteins(q, qo, SearchOptions()), ora, "open_shard")
+    finally:
+        for g in hs:
+            g.detach_shards()
+        for g in hs:
+            g.close()

@@ -54,3 +54,43 @@ def test_descriptor_exchange_gloo_world2():
 
 def test_descriptor_exchange_gloo_world3():
     _run(3)
+
+
+def _write_kidx(path, keys, offsets, postings, n_proteins=0, n_aa=0, n_kmers=0):
+    """the `.kidx` container of DESIGN.md §1 (no protein table)"""
+    import struct
+
+    import numpy as np
+
+    def section(f, a):
+        b = np.ascontiguousarray(a).tobytes()
+        f.write(b)
+        f.write(b"\0" * ((-len(b)) % 64))
+
+    with open(path, "wb") as f:
+        hd = struct.pack("<8sII5QIIQ", b"KIDX0001", 1, 7, len(keys), len(postings), n_proteins, n_aa, n_kmers,
+                         int(postings.max()) if len(postings) else 0, 0, 0)
+        f.write(hd + b"\0" * (128 - len(hd)))
+        section(f, keys.astype(np.uint32))
+        section(f, offsets.astype(np.uint64))
+        section(f, postings.astype(np.uint32))
+
+
+def test_kidx_fences_match_the_python_planner(tmp_path):
+    """kaamer_gpu_kidx_fences (what the Go host calls) == sharded.make_fences, file I/O only"""
+    import numpy as np
+
+    from kaamer_b200 import GpuIndex, synth
+    from kaamer_b200.sharded import dense_space, make_fences
+    from oracle import oracle as o
+
+    res, off = synth.protein_db(300, config_index=1)
+    idx = o.Index.build(res, off, o.fasta_ids(len(off) - 1), 2)
+    p = str(tmp_path / "small.kidx")
+    _write_kidx(p, idx.keys, idx.offsets, idx.postings, idx.n_proteins, idx.n_aa, idx.n_kmers)
+    for n in (1, 2, 3, 8):
+        f = GpuIndex.kidx_fences(p, n)
+        np.testing.assert_array_equal(f, make_fences(idx.keys, idx.offsets, n))
+        assert f[0] == 0 and f[-1] == dense_space() and np.all(np.diff(f.astype(np.int64)) >= 0)
+    _write_kidx(p, idx.keys[:0], idx.offsets[:1], idx.postings[:0])
+    np.testing.assert_array_equal(GpuIndex.kidx_fences(p, 4), make_fences(idx.keys[:0], idx.offsets[:1], 4))

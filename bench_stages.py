@@ -54,6 +54,7 @@ def c2(a):
             r = g.search_nucleotide(nt, noff, opts)
         dt = (time.perf_counter() - t0) / a.steps
         prof = g.profile_read(reset=True)
+        host = {k: v / a.steps for k, v in g.profile_host_read().items()}
         t0 = time.perf_counter()
         for _ in range(a.steps):
             t = g.get_orfs(nt, noff)
@@ -74,6 +75,7 @@ def c2(a):
         "orfs": int(len(t)), "rows": int(r.n_rows), "hits": int(len(r.subject)), "orf_kmer_lookups": int(r.n_lookups),
         "get_orfs_ms_host_call": 1e3 * dt_orf,
         "stage_ms": {"translate_orf_kernels": tr_ms, "search_W": k_ms[0], "search_M": k_ms[1], "search_G": k_ms[2]},
+        "host_phase_ms": host,
         "roofline": {"bound": "hbm", "kernel": "k_translate6+k_orf_ends+k_orf_write (incl. cub sort/scan)",
                      "algorithmic_bytes_per_nt": 3.0, "achieved": 3.0 * n_nt / (tr_ms * 1e-3) / 1e9 if tr_ms else None,
                      "peak": peaks(), "unit": "GB/s", "frac": (3.0 * n_nt / (tr_ms * 1e-3) / 1e9) / peaks() if tr_ms else None},
@@ -104,10 +106,16 @@ def reads(a):
         opts = SearchOptions()
         for _ in range(a.warmup):
             r = g.search_nucleotide(rd, roff, opts)
+        g.profile_enable(True)
+        g.profile_read(reset=True)
+        g.profile_host_read()
         t0 = time.perf_counter()
         for _ in range(a.steps):
             r = g.search_nucleotide(rd, roff, opts)
         dt = (time.perf_counter() - t0) / a.steps
+        prof = g.profile_read(reset=True)
+        host = {k: v / a.steps for k, v in g.profile_host_read().items()}
+        k_ms = [x / a.steps for x in prof["kernel_ms"]]
     idx = o.Index.build(res, off, ids, threads)
     ns = min(n_reads, 50_000)
     t0 = time.perf_counter()
@@ -121,6 +129,8 @@ def reads(a):
         "workload": f"reads: {n_reads} x {rl} nt sampled from 2 x 5 Mb synthetic contigs vs 10 000-protein DB, default options",
         "metric": "query residues/sec", "unit": "nt/s", "value": n_reads * rl / dt, "ms_per_step": 1e3 * dt,
         "rows": int(r.n_rows), "hits": int(len(r.subject)), "orf_kmer_lookups": int(r.n_lookups),
+        "stage_ms": {"translate_orf_kernels": k_ms[7], "search_W": k_ms[0], "search_M": k_ms[1], "search_G": k_ms[2]},
+        "host_phase_ms": host,
         "parity_sample": {"reads": ns, "rows_hits_locations_equal_oracle": bool(ok)},
         "cpu_baseline": {"value": ns * rl / cpu_s, "unit": "nt/s", "cores": threads, "kind": "port",
                          "sample": f"{ns} reads, CPU restatement (oracle/): reads serial, ORF searches of one read on all threads"}}))

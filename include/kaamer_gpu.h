@@ -271,6 +271,12 @@ void kaamer_gpu_pinned_free(void *p);
 int kaamer_gpu_profile_enable(kaamer_gpu_t *h, int on);
 int kaamer_gpu_profile_read(kaamer_gpu_t *h, double *kernel_ms, uint64_t *kernel_launches,
                             uint64_t *all_launches, int reset);
+/* host wall-clock of the phases of the host-buffer calls while profiling is enabled, summed since the
+ * last reset.  phase_ms[8]: [0] H2D + six-frame translation + ORF extraction, [1] count pass (search
+ * kernels, incl. the pool retry), [2] positions / SetBestStartCodon / row assembly / D2H, [3] whole
+ * kaamer_gpu_search_nucleotide calls, [4] whole kaamer_gpu_search_proteins calls; inside [2]:
+ * [5] position / start-codon kernels and offset scans, [6] pinned result buffers, [7] row assembly + D2H */
+int kaamer_gpu_profile_host_read(kaamer_gpu_t *h, double *phase_ms, int reset);
 
 const char *kaamer_gpu_last_error(void);
 const char *kaamer_gpu_version(void);

@@ -177,6 +177,7 @@ SYMBOLS = [
     "kaamer_gpu_pinned_free",
     "kaamer_gpu_profile_enable",
     "kaamer_gpu_profile_read",
+    "kaamer_gpu_profile_host_read",
     "kaamer_gpu_last_error",
     "kaamer_gpu_version",
 ]
@@ -234,6 +235,7 @@ def lib() -> C.CDLL:
     L.kaamer_gpu_pinned_free.restype = None
     L.kaamer_gpu_profile_enable.argtypes = [vp, C.c_int]
     L.kaamer_gpu_profile_read.argtypes = [vp, vp, vp, u64p, C.c_int]
+    L.kaamer_gpu_profile_host_read.argtypes = [vp, vp, C.c_int]
     for s in SYMBOLS:
         getattr(L, s)  # AttributeError if the .so lacks a declared symbol
     _lib = L

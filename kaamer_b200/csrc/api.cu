@@ -626,6 +626,7 @@ int kaamer_gpu_search_proteins(kaamer_gpu_t *h, const uint8_t *residues, const u
   *out = nullptr;
   std::lock_guard<std::mutex> lk(h->mu);
   KCUDA(cudaSetDevice(h->device));
+  HostPhase whole(h, 4);
   return search_proteins_host(h, residues, seq_off, nq, opts, out);
 }
 
@@ -648,6 +649,7 @@ int kaamer_gpu_search_nucleotide(kaamer_gpu_t *h, const uint8_t *nt, const uint6
     set_error("no index resident");
     return KAAMER_ERR_ARG;
   }
+  HostPhase whole(h, 3);
   return search_nucleotide_host(h, nt, contig_off, n_contigs, opts, out);
 }
 
@@ -711,6 +713,19 @@ int kaamer_gpu_profile_read(kaamer_gpu_t *h, double *kernel_ms, uint64_t *kernel
       h->prof_launches[c] = 0;
     }
     h->prof_all_launches = 0;
+  }
+  return KAAMER_OK;
+}
+
+int kaamer_gpu_profile_host_read(kaamer_gpu_t *h, double *phase_ms, int reset) {
+  if (!h || !phase_ms) {
+    set_error("null argument");
+    return KAAMER_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (int i = 0; i < 8; ++i) {
+    phase_ms[i] = h->prof_host_ms[i];
+    if (reset) h->prof_host_ms[i] = 0;
   }
   return KAAMER_OK;
 }

@@ -302,6 +302,7 @@ int finish_rows(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint
   const unsigned g1 = (unsigned)((n1 + 255) / 256);
   const unsigned gw = (unsigned)(((uint64_t)nq * 32 + 255) / 256);
   uint64_t totals[5] = {0, 0, 0, 0, 0};
+  HostPhase ph_pos(h, 5);
   if (nq) {
     // 1. bit-set space
     k_pos_need<<<g1, 256, 0, st>>>(a);
@@ -325,6 +326,8 @@ int finish_rows(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint
     KCUDA(cudaGetLastError());
     KCUDA(cudaStreamSynchronize(st));
   }
+  ph_pos.stop();
+  HostPhase ph_alloc(h, 6);
   const uint64_t n_rows = totals[1], n_hits = totals[2], n_pos = totals[3], n_seq = totals[4];
   if (n_rows > 0xFFFFFFFFull) {
     set_error("too many result rows");
@@ -358,6 +361,8 @@ int finish_rows(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint
     if (nt_mode) hits->row_seq_off[0] = 0;
     return KAAMER_OK;
   }
+  ph_alloc.stop();
+  HostPhase ph_d2h(h, 7);
   // device staging: one allocation, 64-byte aligned sections
   auto up = [](size_t x) { return (x + 63) & ~(size_t)63; };
   size_t o_hit_off = 0, cur = up(n_rows * 8);

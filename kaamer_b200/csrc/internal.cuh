@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -368,6 +369,7 @@ struct kaamer_gpu {
   cudaEvent_t done_ev = nullptr;
   uint64_t prof_all_launches = 0;
   std::vector<kaamer::ProfSpan> prof_pending;
+  double prof_host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // wall clock of host-call phases (kaamer_gpu_profile_host_read)
 };
 
 namespace kaamer {
@@ -419,6 +421,19 @@ void orfset_release(OrfSet *o);
 int finish_rows(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint32_t nq, const kaamer_opts *o,
                 int nt_mode, const uint8_t *d_any0, const OrfSet *orfs, kaamer_hits *hits, HitsOwner *owner,
                 cudaStream_t st);
+// wall-clock phase timer: adds the elapsed milliseconds to h->prof_host_ms[phase] when profiling is on
+struct HostPhase {
+  kaamer_gpu *h;
+  int phase;
+  std::chrono::steady_clock::time_point t0;
+  HostPhase(kaamer_gpu *h_, int phase_) : h(h_), phase(phase_), t0(std::chrono::steady_clock::now()) {}
+  void stop() {
+    if (h && h->profile)
+      h->prof_host_ms[phase] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    h = nullptr;
+  }
+  ~HostPhase() { stop(); }
+};
 void profile_begin(kaamer_gpu *h, cudaStream_t st, int cls);
 void profile_end(kaamer_gpu *h, cudaStream_t st);
 }  // namespace kaamer

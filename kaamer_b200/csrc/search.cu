@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_search_wt(SearchArgs a) {
   __syncthreads();
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   WarpSmemT<H, MAXK> &s = sm[w];
-  const WarpHashT<H> hv{s.hkeys, s.hcnt};
+  const WarpHashT<H, false> hv{s.hkeys, s.hcnt};  // fire-and-forget counts, candidates collected by a final sweep
   const CandList cl{&s.ncand, &s.flags, s.cand, nullptr, (uint32_t)W_CAND};
   const uint32_t count = a.list_count[CLS];
   const uint8_t *res_end = a.res + a.off[a.nq];
@@ -171,8 +171,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_search_wt(SearchArgs a) {
       warp_consume<U, PEER>(a, ent, hv, kmin, cl, q_incr, pv);
     }
     __syncwarp();
-    const uint32_t flags = *(volatile uint32_t *)&s.flags;
-    const uint32_t c = *(volatile uint32_t *)&s.ncand;
+    uint32_t flags = *(volatile uint32_t *)&s.flags;
+    uint32_t c = 0;
+    if (!flags) {
+      c = warp_collect_candidates(hv, kmin, cl);
+      if (c > (uint32_t)W_CAND) flags = 2u;
+    }
     if (flags) {
       // histogram or candidate list outgrew the warp's shared memory: hand the query to
       // class M (that kernel starts after this one in stream order)
@@ -865,10 +869,12 @@ int search_nucleotide_host(kaamer_gpu *h, const uint8_t *nt, const uint64_t *cof
   }
   const uint64_t total = coff[nc];
   h->arena.reset();
+  HostPhase ph_orf(h, 0);
   KCHECK(ws.residues.ensure((size_t)total + 16));
   if (total) KCUDA(cudaMemcpyAsync(ws.residues.p, nt, (size_t)total, cudaMemcpyHostToDevice, st));
   OrfSet os;
   KCHECK(orfs_device(h, ws.residues.p, coff, nc, &os, st));
+  ph_orf.stop();
   auto *hits = new kaamer_hits();
   memset(hits, 0, sizeof *hits);
   auto *owner = new HitsOwner();
@@ -880,12 +886,16 @@ int search_nucleotide_host(kaamer_gpu *h, const uint8_t *nt, const uint64_t *cof
   }
   const uint32_t nq = (uint32_t)os.n;
   if (rc == KAAMER_OK) rc = ws.any0.ensure((size_t)nq + 1);
+  HostPhase ph_count(h, 1);
   if (rc == KAAMER_OK && nq) rc = search_counted(h, os.seq, os.seq_off, nq, o, 1, ws.any0.p, st);
+  ph_count.stop();
+  HostPhase ph_finish(h, 2);
   if (rc == KAAMER_OK && nq) {
     hits->n_lookups = ws.h_counters.p[CNT_LOOKUPS];
     hits->n_increments = ws.h_counters.p[CNT_INCR];
   }
   if (rc == KAAMER_OK) rc = finish_rows(h, os.seq, os.seq_off, nq, o, 1, ws.any0.p, &os, hits, owner, st);
+  ph_finish.stop();
   orfset_release(&os);
   if (rc != KAAMER_OK) {
     delete owner;

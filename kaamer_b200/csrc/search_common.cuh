@@ -259,11 +259,16 @@ __device__ __forceinline__ void count_subject(const Hash &hv, uint32_t id, uint3
 // ---- warp-private histogram (class W) ----------------------------------------------------
 // The table belongs to one warp: no block barriers, 16-bit counts packed two per word.
 constexpr int ilog2_c(int x) { return x <= 1 ? 0 : 1 + ilog2_c(x / 2); }
-template <int H>
+// EVENTS = true: a subject is pushed on the candidate list the moment its count reaches kmin (the
+// increment has to return the old count).  EVENTS = false: increments are fire-and-forget reductions
+// (no wait on the shared-memory atomic unit) and the caller sweeps the H slots once at the end of the
+// query (warp_collect_candidates) — cheaper for the 512-slot table of class W.
+template <int H, bool EVENTS = true>
 struct WarpHashT {
   uint32_t *keys;   // [H]
   uint16_t *cnt;    // [H]
   static constexpr bool kWarp = true;
+  static constexpr bool kEvents = EVENTS;
   static constexpr uint32_t mask = H - 1;
   static constexpr int kMaxProbe = MAX_PROBE;
   __device__ __forceinline__ uint32_t home(uint32_t id) const { return (id * 2654435761u) >> (32 - ilog2_c(H)); }
@@ -313,8 +318,8 @@ __device__ __forceinline__ bool warp_any0(const SearchArgs &a, const PeerView *p
 // the count is one shared-memory atomic add on the 16-bit half of its word.  (An earlier version
 // merged duplicate ids of the 32 lanes with __match_any_sync and let one leader do a plain
 // read-modify-write: MATCH.ANY alone was 19 % of the kernel's stall samples.)
-template <int H>
-__device__ __forceinline__ void warp_count(const WarpHashT<H> &hv, bool valid, uint32_t id, uint32_t kmin,
+template <int H, bool EVENTS>
+__device__ __forceinline__ void warp_count(const WarpHashT<H, EVENTS> &hv, bool valid, uint32_t id, uint32_t kmin,
                                            const CandList &cl) {
   if (valid) {
     uint32_t slot = hv.home(id);
@@ -329,8 +334,12 @@ __device__ __forceinline__ void warp_count(const WarpHashT<H> &hv, bool valid, u
       }
       if (key == id) {
         const uint32_t sh = (slot & 1u) * 16u;
-        const uint32_t old = (atomicAdd(cnt32 + (slot >> 1), 1u << sh) >> sh) & 0xFFFFu;
-        if (old + 1 == kmin) push_candidate(cl, slot);
+        if constexpr (EVENTS) {
+          const uint32_t old = (atomicAdd(cnt32 + (slot >> 1), 1u << sh) >> sh) & 0xFFFFu;
+          if (old + 1 == kmin) push_candidate(cl, slot);
+        } else {
+          atomicAdd(cnt32 + (slot >> 1), 1u << sh);  // result unused: RED.ADD, nothing to wait for
+        }
         break;
       }
       slot = (slot + 1) & (H - 1);
@@ -338,6 +347,47 @@ __device__ __forceinline__ void warp_count(const WarpHashT<H> &hv, bool valid, u
     if (probe == MAX_PROBE) atomicOr(cl.flags, 1u);
   }
   __syncwarp();
+}
+
+// EVENTS = false: one sweep over the H slots at the end of a query; slots whose count reached kmin
+// are appended to the candidate list in slot order (warp-aggregated).  Returns the candidate count
+// (it may exceed cl.cap: the caller hands the query to the next class).
+template <int H>
+__device__ __forceinline__ uint32_t warp_collect_candidates(const WarpHashT<H, false> &hv, uint32_t kmin,
+                                                            const CandList &cl) {
+  const unsigned lane = threadIdx.x & 31;
+  uint32_t c = 0;
+#pragma unroll 1
+  for (int base = 0; base < H; base += 32 * 8) {
+    // 8 consecutive slots per lane: one 16-byte load of counts
+    const int s0 = base + (int)lane * 8;
+    const uint4 cv = *reinterpret_cast<const uint4 *>(hv.cnt + s0);
+    const uint32_t w[4] = {cv.x, cv.y, cv.z, cv.w};
+    unsigned hit = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t cnt = (w[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
+      if (cnt >= kmin && cnt != 0u) hit |= 1u << i;
+    }
+    // exclusive prefix of popc(hit) over the lanes
+    const uint32_t n = __popc(hit);
+    uint32_t incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= (unsigned)o) incl += t;
+    }
+    uint32_t pos = c + incl - n;
+    while (hit) {
+      const int i = __ffs(hit) - 1;
+      hit &= hit - 1;
+      if (pos < cl.cap) cl.slots16[pos] = (uint16_t)(s0 + i);
+      ++pos;
+    }
+    c += __shfl_sync(0xFFFFFFFFu, incl, 31);
+  }
+  __syncwarp();
+  return c;
 }
 
 // ---- one warp-round of lookups ------------------------------------------------------------

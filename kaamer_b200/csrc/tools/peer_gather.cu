@@ -197,6 +197,10 @@ int main(int argc, char **argv) {
     CUdeviceptr va = vmm_map(h, vbytes, 0);
     suite("cross-process CUDA VMM mapping (posix fd, 2 MiB pages)", (const uint64_t *)va, local, slots_big, out);
     mini("cross-process CUDA VMM mapping (first 256 MB only)", (const uint64_t *)va, local, slots_small, out);
+    for (int mb : {512, 1024, 1536, 2048, 3072, 4096, 6144}) {
+      char nm[96]; snprintf(nm, sizeof nm, "cross-process CUDA VMM mapping (first %d MB only)", mb);
+      mini(nm, (const uint64_t *)va, local, ((uint64_t)mb << 20) / 8, out);
+    }
     CD(cuMemUnmap(va, vbytes)); CD(cuMemRelease(h)); CD(cuMemAddressFree(va, vbytes));
     int fd2 = recv_fd(sp[0]);
     CUmemGenericAllocationHandle h2; CD(cuMemImportFromShareableHandle(&h2, (void *)(uintptr_t)fd2, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));

@@ -357,6 +357,14 @@ class GpuIndex:
     def profile_enable(self, on: bool = True):
         check(_lib.lib().kaamer_gpu_profile_enable(self._h, int(on)))
 
+    def profile_host_read(self, reset: bool = True):
+        """Host wall clock per phase of the host-buffer calls (ms, summed since the last reset)."""
+        ms = (C.c_double * 8)()
+        check(_lib.lib().kaamer_gpu_profile_host_read(self._h, ms, int(reset)))
+        names = ["translate_orfs", "count_pass", "finish_rows_d2h", "search_nucleotide_call", "search_proteins_call",
+                 "finish_positions", "finish_result_buffers", "finish_assemble_d2h"]
+        return {n: ms[i] for i, n in enumerate(names)}
+
     def profile_read(self, reset: bool = True):
         ms = (C.c_double * 8)()
         k = (C.c_uint64 * 8)()

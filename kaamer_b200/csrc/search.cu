@@ -262,7 +262,8 @@ __global__ void __launch_bounds__(M_THREADS, M_CTAS) k_search_m(SearchArgs a) {
   }
   for (int i = tid; i < 256; i += THREADS) lut[i] = (uint8_t)aa_code(i);
   __syncthreads();
-  const SmemHash hv{hkeys, hcnt2, (uint32_t)M_H - 1u, 32 - ilog2_c(M_H)};
+  // fire-and-forget counts; the candidates are collected by one sweep over the slots per query
+  const SmemHashT<false> hv{hkeys, hcnt2, (uint32_t)M_H - 1u, 32 - ilog2_c(M_H)};
   const CandList cl{&ss.ncand, &ss.flags, cand, nullptr, (uint32_t)M_H};
   const uint32_t count = a.list_count[1];
   const uint8_t *res_end = a.res + a.off[a.nq];
@@ -326,6 +327,13 @@ __global__ void __launch_bounds__(M_THREADS, M_CTAS) k_search_m(SearchArgs a) {
       warp_consume<U, PEER>(a, ent, hv, kmin, cl, q_incr, pv);
     }
     __syncthreads();
+    if (!ss.flags) {
+      for (uint32_t i = tid; i < (uint32_t)M_H; i += THREADS) {
+        const uint32_t cnt = hv.count_at(i);
+        if (cnt >= kmin && cnt != 0u) cand[atomicAdd(&ss.ncand, 1u)] = (uint16_t)i;
+      }
+      __syncthreads();
+    }
     if (ss.flags) {
       // histogram full: class G
       if (tid == 0) {

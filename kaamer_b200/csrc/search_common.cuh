@@ -166,8 +166,10 @@ __device__ __forceinline__ void load_peer_view(PeerView *dst, const PeerView *sr
 // ---- histograms -------------------------------------------------------------------------
 // add(id) returns the count BEFORE the increment, or 0xFFFFFFFF when the table is full.
 // Shared-memory flavour: keys u32, counts u16 packed two per word (counts <= SizeInKmer <= 2048).
-struct SmemHash {
+template <bool EVENTS>
+struct SmemHashT {
   static constexpr bool kWarp = false;
+  static constexpr bool kEvents = EVENTS;  // false: counts are fire-and-forget, candidates swept at the end
   uint32_t *keys;
   uint32_t *cnt2;  // [slots/2]
   uint32_t mask;
@@ -193,9 +195,11 @@ struct SmemHash {
   }
   static constexpr int kMaxProbe = MAX_PROBE;
 };
+using SmemHash = SmemHashT<true>;
 // Global-memory flavour (class G): keys u32, counts u32.
 struct GmemHash {
   static constexpr bool kWarp = false;
+  static constexpr bool kEvents = true;
   uint32_t *keys;
   uint32_t *cnt;
   uint32_t mask;
@@ -238,7 +242,11 @@ __device__ __noinline__ void count_subject_from(const Hash hv, uint32_t id, uint
   for (int probe = 0; probe < Hash::kMaxProbe; ++probe) {
     uint32_t cur = hv.cas(slot, id);
     if (cur == EMPTY || cur == id) {
-      if (hv.inc(slot) + 1 == kmin) push_candidate(cl, slot);
+      if constexpr (Hash::kEvents) {
+        if (hv.inc(slot) + 1 == kmin) push_candidate(cl, slot);
+      } else {
+        hv.add(slot, 1u);
+      }
       return;
     }
     slot = (slot + 1) & hv.mask;
@@ -250,7 +258,11 @@ __device__ __forceinline__ void count_subject(const Hash &hv, uint32_t id, uint3
   const uint32_t slot = hv.home(id);
   const uint32_t cur = hv.cas(slot, id);
   if (cur == EMPTY || cur == id) {
-    if (hv.inc(slot) + 1 == kmin) push_candidate(cl, slot);
+    if constexpr (Hash::kEvents) {
+      if (hv.inc(slot) + 1 == kmin) push_candidate(cl, slot);
+    } else {
+      hv.add(slot, 1u);
+    }
   } else {
     count_subject_from(hv, id, (slot + 1) & hv.mask, kmin, cl);
   }
@@ -435,12 +447,19 @@ __device__ __forceinline__ void warp_consume(const SearchArgs &a, const uint64_t
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       got[u] = act[u] && (cur[u] == EMPTY || cur[u] == vlo[u]);
-      old[u] = got[u] ? hv.inc(slot[u]) : 0u;
+      old[u] = 0u;
+      if constexpr (Hash::kEvents) {
+        if (got[u]) old[u] = hv.inc(slot[u]);
+      } else {
+        if (got[u]) hv.add(slot[u], 1u);
+      }
       act[u] = act[u] && !got[u];  // still pending
     }
+    if constexpr (Hash::kEvents) {
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (got[u] && old[u] + 1 == kmin) push_candidate(cl, slot[u]);
+      for (int u = 0; u < U; ++u)
+        if (got[u] && old[u] + 1 == kmin) push_candidate(cl, slot[u]);
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (act[u]) count_subject_from(hv, vlo[u], (slot[u] + 1) & hv.mask, kmin, cl);

@@ -259,3 +259,33 @@ def test_c1_fasta_pipeline(tmp_path):
     with GpuIndex.open(path) as g2:
         r2 = g2.search_proteins(q, qo, SearchOptions())
         assert_same_hits(r2, ora, "C1 from .kidx")
+
+
+@pytest.mark.parametrize("n_sharing", [700, 3300, 6000])
+def test_many_candidates_per_query_walk_down_the_size_classes(n_sharing):
+    """n proteins share one 600-residue core and the options let every subject through: the warp
+    class overflows into the CTA class (64 candidates), the CTA class into the global-memory class
+    (3040 candidates / 4096 histogram slots) — results stay bit-exact and nothing is counted twice."""
+    from kaamer_b200 import GpuIndex, SearchOptions
+    from oracle import oracle as o
+
+    rng = np.random.default_rng(5)
+    aa = np.frombuffer(b"ARNDCQEGHILKMFPSTWYV", np.uint8)
+    core = aa[rng.integers(0, 20, 600)].tobytes()
+    prots = [core + aa[rng.integers(0, 20, 20)].tobytes() for _ in range(n_sharing)]
+    prots += [aa[rng.integers(0, 20, 300)].tobytes() for _ in range(200)]
+    res, off = o.pack(prots)
+    ids = np.arange(1, len(prots) + 1, dtype=np.uint32)
+    idx = o.Index.build(res, off, ids, 4)
+    qs = [core, core[:400], core[100:], core[:300] + prots[-1][:250], prots[-2]]
+    q, qo = o.pack(qs)
+    with GpuIndex.build(res, off, ids, keep_proteins=False) as g:
+        for opts in (SearchOptions(min_kmatch=1, min_kratio=0.0, max_results=10_000), SearchOptions(),
+                     SearchOptions(min_kmatch=1, min_kratio=0.0, max_results=10_000, extract_positions=True)):
+            ora = o.search_proteins(idx, q, qo, o.opts(opts.min_kmatch, opts.min_kratio, opts.max_results,
+                                                       want_positions=opts.extract_positions), 4)
+            r = g.search_proteins(q, qo, opts)
+            assert_same_hits(r, ora, f"{n_sharing} sharing, {opts}")
+            assert r.n_lookups == ora.n_lookups and r.n_increments == ora.n_increments
+            if opts.extract_positions:
+                np.testing.assert_array_equal(r.pos, ora.pos)

@@ -291,8 +291,11 @@ def main():
     g.profile_read(reset=True)
     t0 = time.perf_counter()
     e2e_res = 0
+    step_s = []
     for s in range(a.steps):
+        ts = time.perf_counter()
         r = step_host(s)
+        step_s.append(time.perf_counter() - ts)
         e2e_res += int(batches[s % len(batches)][1][-1])
         d2h += r.hit_off.nbytes + r.subject.nbytes + r.kmatch.nbytes + r.size_in_kmer.nbytes
     torch.cuda.synchronize()
@@ -344,6 +347,8 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h / a.steps),
                         "ms_per_step": 1e3 * float(te.item()) / a.steps,
+                        "ms_per_call_rank0": {"min": 1e3 * min(step_s), "median": 1e3 * float(np.median(step_s)),
+                                              "max": 1e3 * max(step_s)},
                         "stage_ms_per_step": {"h2d_copy_stream": prof_e2e["kernel_ms"][4] / a.steps,
                                               "search_kernels": (sum(prof_e2e["kernel_ms"][:3]) + prof_e2e["kernel_ms"][6]) / a.steps,
                                               "compaction_d2h": prof_e2e["kernel_ms"][5] / a.steps},

@@ -427,6 +427,51 @@ __device__ __forceinline__ void warp_consume(const SearchArgs &a, const uint64_t
     mt += m[u];
     any_big |= cnt >= BIG_LIST;
   }
+  // (2a) short lists, flattened across the warp: posting j of the warp's lists belongs to the lane
+  // `owner` whose inclusive prefix first exceeds j.  The FIRST 32 postings are fetched now and counted
+  // after the singletons: the table is probed at the HBM random-access ceiling, so a dependent load
+  // waits in the same queue as the probes (~5 us) — ncu showed 22 % of the class-W stall samples on
+  // the first use of these ids when they were fetched right before being counted.
+  uint32_t incl = mt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= (unsigned)o) incl += t;
+  }
+  const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  const uint32_t excl = incl - mt;
+  auto fetch_posting = [&](uint32_t j) -> uint32_t {  // all lanes call it together
+    uint32_t owner = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      uint32_t v = __shfl_sync(0xFFFFFFFFu, incl, (owner + step - 1) & 31);
+      if (v <= j) owner += step;
+    }
+    owner &= 31;
+    uint32_t r = j - __shfl_sync(0xFFFFFFFFu, excl, owner);
+    const uint32_t ohi = __shfl_sync(0xFFFFFFFFu, vhi, owner);
+    uint32_t sel_lo = 0, sel_hi = 0;
+    bool found = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t mu = __shfl_sync(0xFFFFFFFFu, m[u], owner);
+      uint32_t lo = __shfl_sync(0xFFFFFFFFu, vlo[u], owner);
+      if (!found) {
+        if (r < mu) {
+          sel_lo = lo;
+          sel_hi = (ohi >> (4 * u)) & 0xFu;
+          found = true;
+        } else {
+          r -= mu;
+        }
+      }
+    }
+    uint32_t pid = 0;
+    if (j < total) pid = __ldg(post_ptr<PEER>(a, pv, ((uint64_t)sel_hi << 32) | sel_lo) + r);
+    return pid;
+  };
+  uint32_t pid0 = 0;
+  if (total) pid0 = fetch_posting(lane);  // (total is warp-uniform)
   // (1) singletons
   if constexpr (Hash::kWarp) {
 #pragma unroll
@@ -464,45 +509,11 @@ __device__ __forceinline__ void warp_consume(const SearchArgs &a, const uint64_t
     for (int u = 0; u < U; ++u)
       if (act[u]) count_subject_from(hv, vlo[u], (slot[u] + 1) & hv.mask, kmin, cl);
   }
-  // (2) short lists, flattened across the warp
-  uint32_t incl = mt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= (unsigned)o) incl += t;
-  }
-  const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-  const uint32_t excl = incl - mt;
+  // (2b) count the short-list postings: the prefetched batch, then (rarely) the rest
 #pragma unroll 1
   for (uint32_t jb = 0; jb < total; jb += 32) {
     const uint32_t j = jb + lane;
-    uint32_t owner = 0;
-#pragma unroll
-    for (int step = 16; step >= 1; step >>= 1) {
-      uint32_t v = __shfl_sync(0xFFFFFFFFu, incl, (owner + step - 1) & 31);
-      if (v <= j) owner += step;
-    }
-    owner &= 31;
-    uint32_t r = j - __shfl_sync(0xFFFFFFFFu, excl, owner);
-    const uint32_t ohi = __shfl_sync(0xFFFFFFFFu, vhi, owner);
-    uint32_t sel_lo = 0, sel_hi = 0;
-    bool found = false;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      uint32_t mu = __shfl_sync(0xFFFFFFFFu, m[u], owner);
-      uint32_t lo = __shfl_sync(0xFFFFFFFFu, vlo[u], owner);
-      if (!found) {
-        if (r < mu) {
-          sel_lo = lo;
-          sel_hi = (ohi >> (4 * u)) & 0xFu;
-          found = true;
-        } else {
-          r -= mu;
-        }
-      }
-    }
-    uint32_t pid = 0;
-    if (j < total) pid = __ldg(post_ptr<PEER>(a, pv, ((uint64_t)sel_hi << 32) | sel_lo) + r);
+    const uint32_t pid = jb == 0 ? pid0 : fetch_posting(j);
     if constexpr (Hash::kWarp) {
       warp_count(hv, j < total, pid, kmin, cl);
     } else {

@@ -300,7 +300,7 @@ def peer(a):
     g = GpuIndex.build(res, off, ids, keep_proteins=False, device=lr, shard=(int(fences[rank]), int(fences[rank + 1])))
     t_build = time.perf_counter() - t_build
     if world > 1:
-        attach_distributed(g, presence_filter=not a.no_presence)
+        attach_distributed(g, presence_filter=not a.no_presence, replicate_table=a.replicate_table)
     else:
         attach_all([g])
     pool_cap = nq * 16 + 4096
@@ -350,7 +350,8 @@ def peer(a):
                 "value": tot[0].item() / (t.item() * 1e-3), "ms_per_step": t.item(),
                 "kmer_lookups_per_sec": lookups / (t.item() * 1e-3),
                 "postings_per_lookup": pbar, "hits": tot[3].item(), "db_residues": int(off[-1]),
-                "remote_owner_fraction": remote, "presence_filter": (not a.no_presence) and world > 1,
+                "remote_owner_fraction": remote, "presence_filter": (not a.no_presence) and world > 1 and not a.replicate_table,
+                "replicated_table": bool(a.replicate_table and world > 1),
                 "kernel_ms_rank0": {n: prof["kernel_ms"][i] / max(1, prof["kernel_launches"][i]) for i, n in enumerate(["W", "M", "G"])},
                 "shard_build_s_rank0": t_build,
                 "note": "device-resident queries; no data-path collective: remote table entries and posting lists are "
@@ -375,5 +376,7 @@ if __name__ == "__main__":
     ap.add_argument("--queries", type=int, default=100_000)
     ap.add_argument("--cpu-pairs", type=int, default=2000)
     ap.add_argument("--no-presence", action="store_true", help="mode P without the local presence filter")
+    ap.add_argument("--replicate-table", action="store_true",
+                    help="mode P with the 14.5 GB table replicated on every GPU (postings stay sharded)")
     a = ap.parse_args()
     {"c2": c2, "c5": c5, "sharded": sharded, "peer": peer, "reads": reads}[a.workload](a)

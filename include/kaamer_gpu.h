@@ -256,6 +256,11 @@ int kaamer_gpu_shard_export(kaamer_gpu_t *h, kaamer_shard_handle *out);
  * local HBM, so that query k-mers absent from the database never cross NVLink).  Re-attaching
  * replaces the previous set.  flags: KAAMER_ATTACH_* */
 #define KAAMER_ATTACH_NO_PRESENCE_FILTER 1 /* saturated key spaces: every k-mer exists, skip the filter */
+/* Replicate the direct-address table: it is 14.5 GB whatever the size of the database, so every GPU
+ * copies ALL shards' table ranges into its own HBM at attach time (multi-posting entries tagged with
+ * their owner shard) and only the posting lists — the part that grows with the database — stay
+ * sharded.  The first probe of every lookup is then local; NVLink carries posting lists only. */
+#define KAAMER_ATTACH_REPLICATE_TABLE 2
 int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards, int n_shards, int flags);
 int kaamer_gpu_detach_shards(kaamer_gpu_t *h);
 

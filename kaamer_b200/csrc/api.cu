@@ -150,6 +150,8 @@ static void destroy_handle(kaamer_gpu *h) {
   h->idx.imported.clear();
   if (h->idx.presence) cudaFree(h->idx.presence);
   h->idx.presence = nullptr;
+  if (h->idx.full_table) cudaFree(h->idx.full_table);
+  h->idx.full_table = nullptr;
   if (h->idx.d_peer) cudaFree(h->idx.d_peer);
   h->idx.d_peer = nullptr;
   index_release(h);
@@ -395,6 +397,8 @@ static void detach_shards_locked(kaamer_gpu *h) {
   h->idx.imported.clear();
   if (h->idx.presence) cudaFree(h->idx.presence);
   h->idx.presence = nullptr;
+  if (h->idx.full_table) cudaFree(h->idx.full_table);
+  h->idx.full_table = nullptr;
   h->idx.peer = PeerView{};
 }
 
@@ -491,6 +495,7 @@ int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards,
   pv.n = n_shards;
   pv.self = -1;
   pv.presence = nullptr;
+  pv.full_table = nullptr;
   const int32_t me = (int32_t)getpid();
   for (int i = 0; i < n_shards; ++i) {
     const kaamer_shard_handle &s = shards[order[i]];
@@ -506,7 +511,21 @@ int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards,
     pv.postings[i] = (const uint32_t *)pp;
     if (s.pid == me && s.device == h->device && s.table_ptr == (uint64_t)(uintptr_t)h->idx.table) pv.self = i;
   }
-  if (n_shards > 1 && !(flags & KAAMER_ATTACH_NO_PRESENCE_FILTER)) {
+  if (n_shards > 1 && (flags & KAAMER_ATTACH_REPLICATE_TABLE)) {
+    cudaError_t e = cudaMalloc((void **)&h->idx.full_table, (size_t)DENSE_SPACE * sizeof(uint64_t));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(replicated table, %llu bytes): %s", (unsigned long long)(DENSE_SPACE * 8),
+                cudaGetErrorString(e));
+      detach_shards_locked(h);
+      return KAAMER_ERR_NOMEM;
+    }
+    int rc = replicate_table(h, pv, h->idx.full_table, h->stream);
+    if (rc != KAAMER_OK) {
+      detach_shards_locked(h);
+      return rc;
+    }
+    pv.full_table = h->idx.full_table;
+  } else if (n_shards > 1 && !(flags & KAAMER_ATTACH_NO_PRESENCE_FILTER)) {
     // local replica of "which k-mers exist": 1 bit per dense code, built by streaming every shard once
     const size_t words = (size_t)((DENSE_SPACE + 31) / 32);
     cudaError_t e = cudaMalloc((void **)&h->idx.presence, words * sizeof(uint32_t));

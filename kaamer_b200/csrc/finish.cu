@@ -126,7 +126,16 @@ __global__ void __launch_bounds__(256) k_positions(FinishArgs a) {
                                             aa_code(s[4]), aa_code(s[5]), aa_code(s[6]));
         const uint64_t *tab = a.table;
         uint64_t lo = a.d_lo, hi = a.d_hi;
-        if (a.peer) {  // owner shard of d: its table and postings, local or behind NVLink
+        if (a.peer && a.peer->full_table != nullptr) {  // replicated table: the entry names the shard of its list
+          const uint64_t e = ldg_entry_f(a.peer->full_table + d);
+          cnt = (uint32_t)(e >> ENTRY_VALUE_BITS);
+          val = e & ENTRY_VALUE_MASK;
+          if (cnt >= 2) {
+            post = a.peer->postings[val >> PEER_SHARD_SHIFT];
+            val &= PEER_LOCAL_MASK;
+          }
+          hi = 0;  // (probed already)
+        } else if (a.peer) {  // owner shard of d: its table and postings, local or behind NVLink
           uint32_t sh = 0;
           for (int i = 1; i < MAX_PEER_SHARDS; ++i) sh += d >= a.peer->fence[i] ? 1u : 0u;
           tab = a.peer->table[sh];

@@ -235,6 +235,12 @@ struct PeerView {
   // A local replica (227 MB) that keeps the k-mers absent from the database off NVLink: only
   // probes that will find something cross to the owner GPU.  nullptr: filter off.
   const uint32_t *presence;
+  // replicated table (KAAMER_ATTACH_REPLICATE_TABLE): the direct-address table is 14.5 GB whatever the
+  // size of the database, so every GPU can hold ALL of it; only the posting lists — the part of the
+  // index that grows with the database — stay sharded.  Entries are copied from the owners at attach
+  // time with the owner shard already folded into the value of multi-posting entries: the first probe
+  // of every lookup is local, NVLink carries posting lists only.  nullptr: probe the owner's table.
+  const uint64_t *full_table;
   const uint64_t *table[MAX_PEER_SHARDS];
   const uint32_t *postings[MAX_PEER_SHARDS];
 };
@@ -279,6 +285,7 @@ struct DevIndex {
   PeerView *d_peer = nullptr;    // device copy read by the kernels
   std::vector<VmmAlloc> imported;  // mappings of the other processes' shards
   uint32_t *presence = nullptr;    // presence filter over the whole key space (mode P, api.cu)
+  uint64_t *full_table = nullptr;  // replicated table over the whole key space (mode P, api.cu)
   // key-range shards keep table and postings in shareable memory (vmm.cu); a full index uses cudaMalloc
   VmmAlloc vm_table, vm_postings;
 };
@@ -410,6 +417,8 @@ __device__ __forceinline__ uint32_t filter_kmin(long long min_kmatch, double rat
 #endif
 // search.cu: presence bitmap of all attached shards (streams every shard table once)
 int build_presence(kaamer_gpu *h, const PeerView &pv, uint32_t *d_bits, cudaStream_t st);
+// search.cu: local copy of every shard's table range, multi-posting entries tagged with their shard
+int replicate_table(kaamer_gpu *h, const PeerView &pv, uint64_t *d_full, cudaStream_t st);
 // align.cu
 int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, const uint32_t *pair_q,
                 const uint32_t *pair_s, uint32_t n_pairs, const kaamer_aln_opts *o, kaamer_aln *out);

@@ -511,6 +511,28 @@ __global__ void __launch_bounds__(256) k_presence(PeerView pv, uint32_t *__restr
   }
 }
 
+// Copy of every shard's table range into one local table over the whole key space; the shard of a
+// multi-posting entry goes into the top bits of its value (probe_entries / post_ptr).  14.5 GB, read
+// from the owners at NVLink streaming speed, once per attach.
+__global__ void __launch_bounds__(256) k_replicate_table(PeerView pv, uint64_t *__restrict__ full) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; d < DENSE_SPACE; d += stride) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 1; i < MAX_PEER_SHARDS; ++i) s += (uint32_t)d >= pv.fence[i] ? 1u : 0u;
+    uint64_t e = pv.table[s][d - pv.fence[s]];
+    if ((e >> ENTRY_VALUE_BITS) >= 2ull) e |= (uint64_t)s << PEER_SHARD_SHIFT;
+    full[d] = e;
+  }
+}
+
+int replicate_table(kaamer_gpu *h, const PeerView &pv, uint64_t *d_full, cudaStream_t st) {
+  k_replicate_table<<<h->sm_count * 16, 256, 0, st>>>(pv, d_full);
+  KCUDA(cudaGetLastError());
+  KCUDA(cudaStreamSynchronize(st));
+  return KAAMER_OK;
+}
+
 int build_presence(kaamer_gpu *h, const PeerView &pv, uint32_t *d_bits, cudaStream_t st) {
   const uint64_t n_words = (DENSE_SPACE + 31) / 32;
   k_presence<<<h->sm_count * 16, 256, 0, st>>>(pv, d_bits, n_words);

@@ -115,6 +115,12 @@ __device__ __forceinline__ void probe_entries(const SearchArgs &a, const PeerVie
       f = a.filter;
       fi = d[u] & FILTER_MASK;
       sh[u] = 0;
+    } else if (pv->full_table != nullptr) {
+      // replicated table: local probe, the entry already carries the shard of its posting list
+      p[u] = pv->full_table + d[u];
+      f = nullptr;
+      fi = 0;
+      sh[u] = 0;
     } else {
       uint32_t s = 0;
 #pragma unroll

@@ -39,13 +39,13 @@ def _close_fds(sh) -> None:
             setattr(sh, name, -1)
 
 
-def attach_all(indices: "list[GpuIndex]", presence_filter: bool = True) -> None:
+def attach_all(indices: "list[GpuIndex]", presence_filter: bool = True, replicate_table: bool = False) -> None:
     """Single process driving several shards (one Go server process with several GPUs, or the
     single-GPU tests): every handle attaches the exports of all of them (by pointer)."""
     handles = [g.export_shard() for g in indices]
     try:
         for g in indices:
-            g.attach_shards(handles, presence_filter)
+            g.attach_shards(handles, presence_filter, replicate_table)
     finally:
         for sh in handles:
             _close_fds(sh)
@@ -82,7 +82,7 @@ def exchange_fds(mine: "_lib.ShardHandle", rank: int, world: int, barrier, tag: 
     return got
 
 
-def attach_distributed(index: GpuIndex, group=None, presence_filter: bool = True) -> int:
+def attach_distributed(index: GpuIndex, group=None, presence_filter: bool = True, replicate_table: bool = False) -> int:
     """One process per GPU on one node: gather the shard exports, pass the descriptors, attach.
     Control plane only (72 bytes + 2 descriptors per rank, once per index load).  Returns the
     number of shards."""
@@ -103,7 +103,7 @@ def attach_distributed(index: GpuIndex, group=None, presence_filter: bool = True
             sh.table_fd, sh.postings_fd = fds[r]
         handles.append(sh)
     try:
-        index.attach_shards(handles, presence_filter)
+        index.attach_shards(handles, presence_filter, replicate_table)
     finally:
         for sh in handles:
             _close_fds(sh)
@@ -112,11 +112,12 @@ def attach_distributed(index: GpuIndex, group=None, presence_filter: bool = True
 
 
 def build_distributed(residues: np.ndarray, seq_off: np.ndarray, ids: np.ndarray, fences: np.ndarray, device: int,
-                      group=None, keep_proteins: bool = False, presence_filter: bool = True) -> GpuIndex:
+                      group=None, keep_proteins: bool = False, presence_filter: bool = True,
+                      replicate_table: bool = False) -> GpuIndex:
     """Every rank builds its own key range on its GPU from the full record set
     (`kaamer_gpu_build_shard`) and maps the ranges of the others."""
     rank = dist.get_rank(group)
     g = GpuIndex.build(residues, seq_off, ids, keep_proteins=keep_proteins, device=device,
                        shard=(int(fences[rank]), int(fences[rank + 1])))
-    attach_distributed(g, group, presence_filter)
+    attach_distributed(g, group, presence_filter, replicate_table)
     return g

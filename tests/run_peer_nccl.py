@@ -31,7 +31,8 @@ def main():
     fences = make_fences(idx.keys, idx.offsets, world)
     b, e = split_queries(qo, world)[rank]
     mq, mqo = q[int(qo[b]):int(qo[e])].copy(), (qo[b:e + 1] - qo[b]).astype(np.uint64)
-    g = build_distributed(res, off, ids, fences, lr)
+    replicate = len(sys.argv) > 1 and sys.argv[1] == "replicate"
+    g = build_distributed(res, off, ids, fences, lr, replicate_table=replicate)
     try:
         for opts in (SearchOptions(), SearchOptions(min_kmatch=1, min_kratio=0.0, max_results=50),
                      SearchOptions(extract_positions=True)):

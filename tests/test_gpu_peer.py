@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _peer_handles(small_db, G, dev=0, presence_filter=True):
+def _peer_handles(small_db, G, dev=0, presence_filter=True, replicate_table=False):
     from kaamer_b200 import GpuIndex
     from kaamer_b200.peer import attach_all
     from kaamer_b200.sharded import make_fences
@@ -24,11 +24,12 @@ def _peer_handles(small_db, G, dev=0, presence_filter=True):
     fences = make_fences(idx.keys, idx.offsets, G)
     hs = [GpuIndex.build(small_db["res"], small_db["off"], small_db["ids"], keep_proteins=False, device=dev,
                          shard=(int(fences[r]), int(fences[r + 1]))) for r in range(G)]
-    attach_all(hs, presence_filter)
+    attach_all(hs, presence_filter, replicate_table)
     return hs
 
 
-@pytest.mark.parametrize("G,presence", [(1, True), (2, True), (2, False), (3, True), (8, True), (8, False)])
+@pytest.mark.parametrize("G,presence", [(1, True), (2, True), (2, False), (3, True), (8, True), (8, False),
+                                        (2, "replicate"), (3, "replicate")])
 def test_peer_protein_search_parity(small_db, G, presence):
     """every shard handle answers the whole batch exactly like the single index (all size classes:
     short, 700-residue, 3000-residue and 12000-residue queries)"""
@@ -41,7 +42,7 @@ def test_peer_protein_search_parity(small_db, G, presence):
     seqs += [b"", b"MKT", small_db["res"][:12].tobytes(), b"A" * 700, small_db["res"][:3000].tobytes(),
              small_db["res"][5000:17000].tobytes()]
     q, qo = o.pack(seqs)
-    hs = _peer_handles(small_db, G, presence_filter=presence)
+    hs = _peer_handles(small_db, G, presence_filter=presence is True, replicate_table=presence == "replicate")
     try:
         for opts in (SearchOptions(), SearchOptions(min_kmatch=1, min_kratio=0.0, max_results=100),
                      SearchOptions(min_kmatch=4, min_kratio=0.3, max_results=2)):
@@ -57,13 +58,14 @@ def test_peer_protein_search_parity(small_db, G, presence):
             g.close()
 
 
-def test_peer_positions_and_nucleotide_parity(small_db):
+@pytest.mark.parametrize("replicate", [False, True])
+def test_peer_positions_and_nucleotide_parity(small_db, replicate):
     """PositionHits, translated search and SetBestStartCodon read the table too (finish.cu)"""
     from kaamer_b200 import SearchOptions, synth
     from oracle import oracle as o
 
     idx = small_db["idx"]
-    hs = _peer_handles(small_db, 3)
+    hs = _peer_handles(small_db, 3, replicate_table=replicate)
     try:
         q, qo, _ = synth.protein_queries(small_db["res"], small_db["off"], 200, config_index=1, stream=9)
         ora = o.search_proteins(idx, q, qo, o.opts(want_positions=True), 4)
@@ -116,13 +118,16 @@ def test_shard_handle_alone_refuses_to_search_and_attach_checks_the_tiling(small
             a.search_proteins(q, qo, SearchOptions())  # a failed attach leaves the handle detached
 
 
-def test_peer_ipc_two_gpus():
+@pytest.mark.parametrize("mode", ["probe-owner", "replicate"])
+def test_peer_ipc_two_gpus(mode):
     import torch
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
            "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "tests", "run_peer_nccl.py")]
+    if mode == "replicate":
+        cmd.append("replicate")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "peer ipc ok" in out.stdout

@@ -62,7 +62,8 @@ func OpenSharded(path string, devices []int) (*ShardedIndex, error) {
 	}
 	defer closeFds() // same process: shards are attached by pointer, the descriptors are not needed
 	for _, ix := range s.shards {
-		if rc := C.kaamer_gpu_attach_shards(ix.h, &exports[0], C.int(n), 0); rc != C.KAAMER_OK {
+		// the 14.5 GB table is replicated on every GPU, only the posting lists stay sharded
+		if rc := C.kaamer_gpu_attach_shards(ix.h, &exports[0], C.int(n), C.KAAMER_ATTACH_REPLICATE_TABLE); rc != C.KAAMER_OK {
 			s.Close()
 			return nil, lastErr(rc)
 		}

@@ -12,6 +12,10 @@ NVLink with plain loads.  Queries stay on their home GPU; the counts are accumul
 shared memory exactly as in the single-GPU path, so there is no all-to-all, no partial-count
 exchange and no merge step (compare mode S in `sharded.py`, which moves the k-mers to the data).
 
+With `replicate_table=True` every rank also copies the table ranges of all shards into its own HBM
+at attach time (the direct-address table is 14.5 GB whatever the database size; the posting lists
+are what grows): the first probe of every lookup is local, NVLink carries posting lists only.
+
 The reference has no counterpart (one process, one badger store, pkg/search/search.go:414-440);
 results are identical to the single-index search because each k-mer lookup is answered by the
 one shard that owns its key.

@@ -609,7 +609,6 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 4) k_sw_affine_cta(AlnArgs a) 
 }
 
 // ---------------------------------------------------------------------------------------
-static bool g_tables_ready[64] = {false};
 constexpr uint64_t BIG_CELLS = 2ull << 20;  // pairs at least this large get a whole CTA
 
 // columns per lane of the warp-per-pair kernel: the cost of a pair is
@@ -645,11 +644,15 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
     return KAAMER_ERR_ARG;
   }
   if (n_pairs == 0) return KAAMER_OK;
-  if (h->device < 64 && !g_tables_ready[h->device]) {
+  if (!h->aln_ready) {
+    // constant memory and function attributes belong to the device context: once per handle (a process
+    // may drive several GPUs)
     AlnTables t;
     make_tables(&t);
     KCUDA(cudaMemcpyToSymbol(c_aln, &t, sizeof t));
-    g_tables_ready[h->device] = true;
+    KCUDA(cudaFuncSetAttribute(k_sw_affine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WARP_SMEM));
+    KCUDA(cudaFuncSetAttribute(k_sw_affine_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM));
+    h->aln_ready = true;
   }
   uint32_t nq = 0;
   for (uint32_t i = 0; i < n_pairs; ++i) nq = pair_q[i] + 1 > nq ? pair_q[i] + 1 : nq;
@@ -758,12 +761,6 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
   a.gap_open_opt = o->gap_open;
   a.gap_extend_opt = o->gap_extend;
   a.number_of_aa = (double)(o->number_of_aa ? o->number_of_aa : ix.n_aa);
-  static bool attr_done = false;
-  if (!attr_done) {
-    ACUDA(cudaFuncSetAttribute(k_sw_affine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WARP_SMEM));
-    ACUDA(cudaFuncSetAttribute(k_sw_affine_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM));
-    attr_done = true;
-  }
   // Per chunk: the long pairs (one CTA each) on `st`, the rest (one warp each) on the second
   // stream so that both kernels share the GPU; the chunk's scratch is reused only after both end.
   cudaStream_t st2 = h->copy_stream;

@@ -376,7 +376,9 @@ struct kaamer_gpu {
   cudaEvent_t done_ev = nullptr;
   uint64_t prof_all_launches = 0;
   std::vector<kaamer::ProfSpan> prof_pending;
-  double prof_host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // wall clock of host-call phases (kaamer_gpu_profile_host_read)
+  double prof_host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // per-handle (= per-device context) one-time setup: constant tables and kernel attributes
+  bool aln_ready = false, shard_attrs_ready = false;  // wall clock of host-call phases (kaamer_gpu_profile_host_read)
 };
 
 namespace kaamer {

@@ -657,12 +657,11 @@ __global__ void __launch_bounds__(SH_THREADS) k_shard_merge_g(MergeArgs a) {
 constexpr size_t COUNT_SMEM = (SH_H + SH_H / 2) * 4;
 constexpr size_t MERGE_SMEM = (SH_H + SH_H / 2) * 4 + SH_H * 2;
 
-static int ensure_attrs() {
-  static bool done = false;
-  if (done) return KAAMER_OK;
+static int ensure_attrs(kaamer_gpu *h) {  // function attributes belong to the device context
+  if (h->shard_attrs_ready) return KAAMER_OK;
   KCUDA(cudaFuncSetAttribute(k_shard_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COUNT_SMEM));
   KCUDA(cudaFuncSetAttribute(k_shard_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MERGE_SMEM));
-  done = true;
+  h->shard_attrs_ready = true;
   return KAAMER_OK;
 }
 
@@ -744,7 +743,7 @@ int kaamer_gpu_shard_count(kaamer_gpu_t *h, const uint32_t *d_codes, const uint6
     set_error("no index resident");
     return KAAMER_ERR_ARG;
   }
-  KCHECK(ensure_attrs());
+  KCHECK(ensure_attrs(h));
   cudaStream_t st = (cudaStream_t)stream;
   KCUDA(cudaMemsetAsync(d_counters, 0, CNT_N * sizeof(uint64_t), st));
   if (n_segments == 0) return KAAMER_OK;
@@ -817,7 +816,7 @@ int kaamer_gpu_shard_merge(kaamer_gpu_t *h, const uint64_t *d_part, const uint64
   }
   std::lock_guard<std::mutex> lk(h->mu);
   KCUDA(cudaSetDevice(h->device));
-  KCHECK(ensure_attrs());
+  KCHECK(ensure_attrs(h));
   cudaStream_t st = (cudaStream_t)stream;
   KCUDA(cudaMemsetAsync(d_out->counters, 0, CNT_N * sizeof(uint64_t), st));
   if (nq == 0) return KAAMER_OK;

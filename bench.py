@@ -284,11 +284,13 @@ def main():
         hq, ho = h_batches[s % len(h_batches)]
         return g.search_proteins_ptr(hq.data_ptr(), ho.data_ptr(), nq, opts)
 
-    for s in range(a.warmup):
-        step_host(s)
+    r = None
+    for s in range(max(a.warmup, len(h_batches) + 1)):
+        # as in the timed loop the previous result is still alive when the next call allocates its own:
+        # the library's pinned-block cache then holds both sets (a cudaHostAlloc costs milliseconds)
+        r = step_host(s)
     barrier()
-    g.profile_enable(True)
-    g.profile_read(reset=True)
+    g.profile_enable(False)  # the timed calls carry no profiling events; the stage times come from extra calls below
     t0 = time.perf_counter()
     e2e_res = 0
     step_s = []
@@ -300,6 +302,11 @@ def main():
         d2h += r.hit_off.nbytes + r.subject.nbytes + r.kmatch.nbytes + r.size_in_kmer.nbytes
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    n_prof = min(a.steps, 4)
+    g.profile_enable(True)
+    g.profile_read(reset=True)
+    for s in range(n_prof):
+        step_host(s)
     prof_e2e = g.profile_read(reset=True)
     g.profile_enable(False)
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -348,10 +355,10 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h / a.steps),
                         "ms_per_step": 1e3 * float(te.item()) / a.steps,
                         "ms_per_call_rank0": {"min": 1e3 * min(step_s), "median": 1e3 * float(np.median(step_s)),
-                                              "max": 1e3 * max(step_s)},
-                        "stage_ms_per_step": {"h2d_copy_stream": prof_e2e["kernel_ms"][4] / a.steps,
-                                              "search_kernels": (sum(prof_e2e["kernel_ms"][:3]) + prof_e2e["kernel_ms"][6]) / a.steps,
-                                              "compaction_d2h": prof_e2e["kernel_ms"][5] / a.steps},
+                                              "max": 1e3 * max(step_s), "argmax": int(np.argmax(step_s))},
+                        "stage_ms_per_step": {"h2d_copy_stream": prof_e2e["kernel_ms"][4] / n_prof,
+                                              "search_kernels": (sum(prof_e2e["kernel_ms"][:3]) + prof_e2e["kernel_ms"][6]) / n_prof,
+                                              "compaction_d2h": prof_e2e["kernel_ms"][5] / n_prof},
                         "note": "kaamer_gpu_search_proteins on pinned host buffers: residues are read in place over PCIe by the search kernels (zero-copy, aligned 16-byte loads), offsets copied H2D, hits compacted and copied D2H"},
                 "gpu_launches": int(prof["all_launches"]),
                 "roofline": roof}

@@ -1,0 +1,321 @@
+"""A second, independent restatement of the reference's search path: a LITERAL Python transliteration
+of the Go functions (strings, maps and loops as in the source, one statement per Go statement where
+possible), written without looking at oracle/kaamer_oracle.cpp.  tests/test_oracle_vs_transliteration.py
+runs both on the same small random inputs: the C++ oracle the GPU kernels are compared with must agree
+with this reading of the Go source bit for bit.  Test infrastructure only (pure-Python loops: small cases).
+
+Every function cites the Go code it follows (paths relative to the reference repository).
+"""
+from __future__ import annotations
+
+import json
+import os
+
+KMER_SIZE = 7  # pkg/search/search.go:45, pkg/makedb/makedb.go
+
+_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# ---- pkg/kvstore/k_store.go ---------------------------------------------------------------------
+def new_aa_table() -> dict:
+    """NewAATable, k_store.go:39-64: single codes 0..20 under (a, '.'), pair codes from 22."""
+    aa = list("ACDEFGHIKLMNPQRSTUVWY")
+    table = {}
+    i = 22
+    for j, a in enumerate(aa):
+        table[(a, ".")] = j
+        for b in aa:
+            table[(a, b)] = i
+            i += 1
+    return table
+
+
+_AA_TABLE = new_aa_table()
+
+
+def encode_kmer(kmer: str) -> int:
+    """EncodeKmer, k_store.go:91-117.  A Go map lookup of a missing key yields 0."""
+    kmer_int = 0
+    i = 0
+    shift_index = 1
+    while (i + 2) < len(kmer):
+        key = (kmer[i], kmer[i + 1])
+        kmer_int |= (_AA_TABLE.get(key, 0) << (32 - (shift_index * 9))) & 0xFFFFFFFF
+        shift_index += 1
+        i += 2
+    key = (kmer[len(kmer) - 1], ".")
+    kmer_int |= _AA_TABLE.get(key, 0)
+    return kmer_int
+
+
+# ---- pkg/makedb/inputFASTA.go + pkg/indexdb + pkg/kvstore/kcomb_store.go ------------------------------
+def make_index(fasta_text: str) -> dict:
+    """kmer key -> posting list.  Reader loop inputFASTA.go:96-124 (the id quirk: proteinNb is incremented
+    before the previous record is dispatched), record processing :195-250, then the index step: per key the
+    set of ids sorted descending without duplicates (indexdb.go:92-128, kv_store.go:284-305)."""
+    jobs = []
+    protein_nb = 0
+    protein_entry = ""
+    for line in fasta_text.split("\n"):
+        if line == "":  # bufio.Scanner yields no token after the final newline
+            continue
+        if line[0:1] == ">":
+            protein_nb += 1
+            if protein_entry != "":
+                jobs.append((protein_nb, protein_entry))
+                protein_entry = ""
+        protein_entry += line
+        protein_entry += "\n"
+    if protein_entry != "":
+        jobs.append((protein_nb, protein_entry))
+
+    kmer_store: dict[int, list] = {}
+    stats = {"proteins": 0, "aa": 0}
+    for protein_id, text_entry in jobs:  # processProteinInputFASTA
+        sequence = ""
+        protein_name = ""
+        for l in text_entry.split("\n"):
+            if len(l) < 1:
+                continue
+            if l[0:1] == ">":
+                header_split = l.split(" ")
+                protein_name = " ".join(header_split[1:])
+            else:
+                sequence += l.upper()
+        if ", partial" in protein_name:
+            continue
+        length = len(sequence)
+        if length < KMER_SIZE:
+            continue
+        stats["proteins"] += 1
+        stats["aa"] += length
+        for i in range(0, length - KMER_SIZE + 1):
+            kmer_store.setdefault(encode_kmer(sequence[i:i + KMER_SIZE]), []).append(protein_id)
+    index = {}
+    for key, ids in kmer_store.items():
+        s = sorted(ids, reverse=True)
+        out = []
+        for e in s:  # RemoveDuplicatesFromSlice on the sorted slice
+            if not out or out[-1] != e:
+                out.append(e)
+        index[key] = out
+    index["__stats__"] = stats
+    return index
+
+
+# ---- pkg/search/search.go -----------------------------------------------------------------------
+def size_in_kmer(sequence: str) -> int:
+    """search.go:290-293"""
+    n = len(sequence) - KMER_SIZE + 1
+    if len(sequence) > 0 and sequence[len(sequence) - 1:] == "*":
+        n -= 1
+    return n
+
+
+def kmer_search(index: dict, sequence: str, q_size: int, extract_pos: bool):
+    """key producer loop (search_protein.go:94-98) + KmerSearch (search.go:414-440) +
+    StoreMatchPositions (:442-452)."""
+    counter: dict[int, int] = {}
+    position_hits: dict[int, list] = {}
+    for k in range(0, q_size):
+        key = encode_kmer(sequence[k:k + KMER_SIZE])
+        ids = index.get(key)
+        if ids is None or len(ids) < 1:
+            continue
+        for pid in ids:
+            counter[pid] = counter.get(pid, 0) + 1
+            if extract_pos:
+                if pid not in position_hits:
+                    position_hits[pid] = [False] * q_size
+                position_hits[pid][k] = True
+    return counter, position_hits
+
+
+def sort_map_by_value(counter: dict) -> list:
+    """sortMapByValue, search.go:132-152: descending by Kmatch; the reference's order among equal Kmatch
+    is that of a Go map iteration (random) — the canonical representative used everywhere in this
+    repository is subject id ascending."""
+    return sorted(counter.items(), key=lambda kv: (-kv[1], kv[0]))
+
+
+def filter_results(hits: list, q_size: int, position_hits: dict, min_kmatch: int, min_kratio: float, max_results: int):
+    """FilterResults, search.go:189-220, statement by statement."""
+    hits_to_delete = []
+    last_good = len(hits) - 1
+    for i, (key, kmatch) in enumerate(hits):
+        if (float(kmatch) / float(q_size)) < min_kratio or kmatch < min_kmatch:
+            if last_good == (len(hits) - 1):
+                last_good = i - 1
+            hits_to_delete.append(key)
+    if last_good >= max_results:
+        last_good = max_results - 1
+        for key, _ in hits[last_good + 1:]:
+            hits_to_delete.append(key)
+    hits = [] if last_good < 0 else hits[0:last_good + 1]
+    for k in hits_to_delete:
+        position_hits.pop(k, None)
+    return hits
+
+
+# ---- pkg/search/dna.go + gcode.go -----------------------------------------------------------------
+_GCODE = json.load(open(os.path.join(_GOLDEN, "gcode11.json")))  # gcodeBacteria, extracted from gcode.go:36-101
+_FRAME_START = {0: 0, 1: 1, 2: 2, 3: 0, 4: 1, 5: 2}
+MIN_LEN_CDS = 21
+
+
+def reverse_complement(dna: str) -> str:
+    """dna.go:55-63: only a<->t and g<->c are swapped."""
+    r = {"a": "t", "t": "a", "g": "c", "c": "g"}
+    return "".join(r.get(c, c) for c in reversed(dna.lower()))
+
+
+def get_frame(frame_number: int, dna: str) -> str:
+    """dna.go:183-196"""
+    if frame_number < 0:
+        dna = reverse_complement(dna)
+        frame_number = -frame_number
+    start_pos = frame_number - 1
+    len_frame = len(dna) - start_pos
+    end_pos = len(dna) - (len_frame % 3)
+    return dna[start_pos:end_pos]
+
+
+def get_orfs(dna: str) -> list:
+    """GetORFs, dna.go:65-181.  Each ORF: dict(seq, start, end, plus, alts).  sort.Slice is unstable in
+    Go; ties keep emission order here (as everywhere in this repository)."""
+    orfs = []
+    dna = dna.lower()
+    frames = [get_frame(1, dna), get_frame(2, dna), get_frame(3, dna), get_frame(-1, dna), get_frame(-2, dna),
+              get_frame(-3, dna)]
+    for frame_pos, frame_seq in enumerate(frames):
+        start_pos = _FRAME_START[frame_pos]
+        plus = frame_pos <= 2
+        abs_pos = frame_pos
+        if not plus:
+            abs_pos = len(dna) - start_pos - 1
+        current_pos = 0
+        orf = {"seq": "", "start": abs_pos + 1, "end": 0, "plus": plus, "alts": []}
+        inside = True
+        cds = ""
+        current_aa_pos = 0
+        i = 0
+        while i < len(frame_seq) - (len(frame_seq) % 3):
+            current_pos = i
+            aa = _GCODE.get(frame_seq[i:i + 3], {"aa": "", "start": False, "stop": False})
+            if aa["start"]:
+                if not inside:
+                    inside = True
+                    current_aa_pos = 0
+                    orf["start"] = frame_pos + i + 1
+                    if not plus:
+                        orf["start"] = len(dna) - (frame_pos + i) + 3
+                    orf["alts"] = orf["alts"] + [current_aa_pos]
+                else:
+                    orf["alts"] = orf["alts"] + [current_aa_pos]
+            if inside:
+                cds += aa["aa"]
+            if aa["stop"]:
+                if inside and len(cds) >= MIN_LEN_CDS:
+                    end_pos = i + 3 + frame_pos
+                    if not plus:
+                        end_pos = orf["start"] - (len(cds) * 3) + 1
+                    orf["end"] = end_pos
+                    orf["seq"] = cds
+                    orfs.append(dict(orf))
+                orf = {"seq": "", "start": 0, "end": 0, "plus": plus, "alts": []}
+                cds = ""
+                inside = False
+            current_aa_pos += 1
+            i += 3
+        if inside and len(cds) >= MIN_LEN_CDS:
+            end_pos = current_pos + 3 + frame_pos
+            if not plus:
+                end_pos = orf["start"] - (len(cds) * 3) + 1
+            orf["end"] = end_pos
+            orf["seq"] = cds
+            orfs.append(dict(orf))
+    orfs.sort(key=lambda o: o["end"] if o["plus"] else o["start"])
+    return orfs
+
+
+def set_best_start_codon(q: dict, hits: list, position_hits: dict) -> None:
+    """SetBestStartCodon, dna.go:198-272; q: dict(seq, size, start, plus, alts), modified in place."""
+    best_hits = []
+    best_score = 0
+    for key, kmatch in hits:
+        if kmatch >= best_score:
+            best_score = kmatch
+            best_hits.append(key)
+    if len(q["alts"]) < 1:
+        return
+    best_start = q["alts"][0]
+    first_start = q["alts"][0]
+    first_best_hit_pos = 999999999
+    exit_ = False
+    for key in best_hits:
+        for i, is_match in enumerate(position_hits[key]):
+            if is_match:
+                if i < first_best_hit_pos:
+                    first_best_hit_pos = i
+                exit_ = True
+            if exit_:
+                break
+    exit_ = False
+    for s in q["alts"]:
+        if s <= first_best_hit_pos:
+            best_start = s
+        else:
+            exit_ = True
+        if exit_:
+            break
+    if best_start != first_start:
+        if q["plus"]:
+            q["start"] = q["start"] + 3 * best_start
+        else:
+            q["start"] = q["start"] - 3 * best_start
+        q["seq"] = q["seq"][best_start:]
+        for k in list(position_hits.keys()):
+            position_hits[k] = position_hits[k][best_start:]
+        q["size"] = len(q["seq"]) - KMER_SIZE + 1
+        if q["seq"][len(q["seq"]) - 1:] == "*":
+            q["size"] = q["size"] - 1
+    q["alts"] = []
+
+
+# ---- drivers --------------------------------------------------------------------------------------
+def protein_search(index: dict, queries: list, min_kmatch=10, min_kratio=0.05, max_results=10, extract_positions=False):
+    """Per-query body of ProteinSearch (search_protein.go:70-114).  Queries with SizeInKmer < 7 are skipped
+    (the reference worker returns; documented deviation).  Returns one entry per query:
+    (SizeInKmer, [(subject, Kmatch)], {subject: positions})."""
+    out = []
+    for seq in queries:
+        size = size_in_kmer(seq)
+        if size < 7:
+            out.append((size, [], {}))
+            continue
+        counter, pos = kmer_search(index, seq, size, extract_positions)
+        hits = sort_map_by_value(counter)
+        hits = filter_results(hits, size, pos, min_kmatch, min_kratio, max_results)
+        out.append((size, hits, pos))
+    return out
+
+
+def nucleotide_search(index: dict, contigs: list, min_kmatch=10, min_kratio=0.05, max_results=10):
+    """GetORFs + per-ORF body of NucleotideSearch (search_nucleotide.go:76-124).  Returns the surviving rows
+    in (contig, GetORFs order): dict(contig, seq, size, start, end, plus, hits, pos)."""
+    rows = []
+    for c, dna in enumerate(contigs):
+        for o in get_orfs(dna):
+            q = {"seq": o["seq"], "size": len(o["seq"]) - KMER_SIZE + 1, "start": o["start"], "end": o["end"],
+                 "plus": o["plus"], "alts": list(o["alts"])}
+            if q["seq"][len(q["seq"]) - 1:] == "*":
+                q["size"] = q["size"] - 1
+            counter, pos = kmer_search(index, q["seq"], q["size"], True)
+            hits = sort_map_by_value(counter)
+            if len(hits) > 0 and hits[0][1] >= min_kmatch:
+                set_best_start_codon(q, hits, pos)
+                hits = filter_results(hits, q["size"], pos, min_kmatch, min_kratio, max_results)
+                if len(hits) > 0:
+                    rows.append({"contig": c, "seq": q["seq"], "size": q["size"], "start": q["start"], "end": q["end"],
+                                 "plus": q["plus"], "hits": hits, "pos": {k: pos[k] for k, _ in hits}})
+    return rows

@@ -319,3 +319,84 @@ def nucleotide_search(index: dict, contigs: list, min_kmatch=10, min_kratio=0.05
                     rows.append({"contig": c, "seq": q["seq"], "size": q["size"], "start": q["start"], "end": q["end"],
                                  "plus": q["plus"], "hits": hits, "pos": {k: pos[k] for k, _ in hits}})
     return rows
+
+
+# ---- pkg/align/align.go (kaamer's own post-processing of the biogo alignment) -----------------------------
+AA_POS_IN_MATRIX = {c: i for i, c in enumerate("-ABCDEFGHIJKLMNPQRSTVWXYZ*")}  # matrixScores.go:107
+
+
+def segments_from_strings(a: str, b: str, q0: int, s0: int, matrix) -> list:
+    """The feat.Pair list biogo's SWAffine returns, rebuilt from the two gapped strings: maximal runs of
+    aligned columns (score = sum of matrix cells) and maximal gap runs (score = GapOpen = -11 plus the
+    matrix's gap row, which is 0).  Each segment: (score, q_start, q_end, s_start, s_end), 0-based half-open
+    as Features()[k].Start()/End()."""
+    segs = []
+    qi, si = q0, s0
+    i = 0
+    while i < len(a):
+        kind = 0 if (a[i] != "-" and b[i] != "-") else (1 if a[i] == "-" else 2)
+        j = i
+        score = 0
+        qs, ss = qi, si
+        while j < len(a):
+            k = 0 if (a[j] != "-" and b[j] != "-") else (1 if a[j] == "-" else 2)
+            if k != kind:
+                break
+            if kind == 0:
+                score += int(matrix[AA_POS_IN_MATRIX[a[j]]][AA_POS_IN_MATRIX[b[j]]])
+                qi += 1
+                si += 1
+            elif kind == 1:
+                si += 1
+            else:
+                qi += 1
+            j += 1
+        if kind != 0:
+            score = -11
+        segs.append((score, qs, qi, ss, si))
+        i = j
+    return segs
+
+
+def align_postprocess(a_string: str, b_string: str, segs: list, query_len: int, number_of_aa: int, matrix,
+                      lambda_=0.267, K=0.041, gap_open=11, gap_extend=1) -> dict:
+    """align.go:72-157, statement by statement (float32 for identity / similarity, float64 for scores)."""
+    import math
+
+    import numpy as np
+
+    f32 = np.float32
+    identity = f32(0)
+    similarity = f32(0)
+    nb_pos = f32(0)
+    mismatches = 0
+    for i, a in enumerate(a_string):
+        if b_string[i] == a:
+            identity = f32(identity + f32(1))
+            similarity = f32(similarity + f32(1))
+        else:
+            if b_string[i] != "-" and a != "-":
+                mismatches += 1
+            if int(matrix[AA_POS_IN_MATRIX[b_string[i]]][AA_POS_IN_MATRIX[a]]) > 0:
+                similarity = f32(similarity + f32(1))
+        nb_pos = f32(nb_pos + f32(1))
+    identity = f32(f32(identity / nb_pos) * f32(100))
+    similarity = f32(f32(similarity / nb_pos) * f32(100))
+    raw = 0
+    gap_openings = 0
+    q_start = q_end = s_start = s_end = 0
+    for i, (score, qs, qe, ss, se) in enumerate(segs):
+        if i == 0:
+            q_start, s_start = qs, ss
+        if i == len(segs) - 1:
+            q_end, s_end = qe, se
+        raw += score
+        if score == -gap_open:
+            gap_openings += 1
+            gap_len = max(qe - qs, se - ss)
+            raw = raw - ((gap_len - 1) * gap_extend)
+    bitscore = ((lambda_ * float(raw)) - math.log(K)) / math.log(2)
+    evalue = float(query_len) * float(number_of_aa) / math.pow(2, bitscore)
+    return {"identity": float(identity), "similarity": float(similarity), "length": len(a_string),
+            "mismatches": mismatches, "gap_openings": gap_openings, "raw": raw, "bitscore": bitscore, "evalue": evalue,
+            "query_start": q_start + 1, "query_end": q_end, "subject_start": s_start + 1, "subject_end": s_end}

@@ -146,3 +146,49 @@ def test_orfs_and_translated_search(tmp_path, seed):
                 h += 1
         if not kw:
             assert len(rows) > 5  # the default options do find the planted genes
+
+
+@pytest.mark.parametrize("seed", [8, 9])
+def test_alignment_postprocessing(seed):
+    """Everything align.Align computes itself from the biogo alignment (align.go:72-157: identity and
+    similarity in float32, mismatches, the `score == -GapOpen` gap rule, raw score, bitscore, e-value,
+    1-based coordinates) — the oracle's fields against the transliteration applied to the oracle's own
+    gapped strings.  (The DP that produces the strings is biogo's: parity unpinned)"""
+    rng = np.random.default_rng(seed)
+    m = o.blosum62()
+    n_aa = 3_500_000
+    prm = o.aln_params(n_aa)
+    n_gapped = 0
+    for _ in range(120):
+        L = int(rng.integers(20, 260))
+        s = [AA[j] for j in rng.integers(0, 20, L)]
+        q = list(s)
+        for _ in range(int(rng.integers(0, 1 + L // 6))):  # substitutions
+            q[int(rng.integers(0, len(q)))] = AA[int(rng.integers(0, 20))]
+        for _ in range(int(rng.integers(0, 4))):  # insertions / deletions of 1..12 residues
+            p = int(rng.integers(0, len(q)))
+            n = int(rng.integers(1, 13))
+            if rng.random() < 0.5:
+                del q[p:p + n]
+            else:
+                q[p:p] = [AA[j] for j in rng.integers(0, 20, n)]
+        if len(q) < 8:
+            continue
+        q = "".join(q) + ("*" if rng.random() < 0.3 else "")
+        s = "".join(s)
+        out, a, b = o.align(q.encode(), s.encode(), prm, want_strings=True)
+        if out.length == 0:
+            continue
+        a, b = a.decode(), b.decode()
+        assert len(a) == len(b) == out.length
+        segs = go.segments_from_strings(a, b, out.query_start - 1, out.subject_start - 1, m)
+        assert len(segs) == out.n_segments and sum(x[0] for x in segs) == out.dp_score
+        ref = go.align_postprocess(a, b, segs, len(q), n_aa, m)
+        n_gapped += ref["gap_openings"] > 0
+        for k in ("length", "mismatches", "gap_openings", "raw", "query_start", "query_end", "subject_start", "subject_end"):
+            assert getattr(out, k) == ref[k], (k, q, s)
+        assert np.float32(out.identity) == np.float32(ref["identity"])
+        assert np.float32(out.similarity) == np.float32(ref["similarity"])
+        assert abs(out.bitscore - ref["bitscore"]) <= 1e-12 * max(1.0, abs(ref["bitscore"]))
+        assert abs(out.evalue - ref["evalue"]) <= 1e-9 * abs(ref["evalue"])
+    assert n_gapped > 10

@@ -56,7 +56,7 @@ __global__ void k_classify(SearchArgs a) {
     // used: the warp-per-query kernels are bound by the per-warp counting work, W2's larger
     // per-warp state halves the resident warps and it ran at 10 G lookups/s against 24 G/s for
     // the CTA-per-query class M (profiles/r1_notes.md).
-    if (go) cls = K <= W_MAXK ? 0 : (K <= M_MAXK ? 1 : 2);
+    if (go) cls = K <= a.w_maxk ? 0 : (K <= a.m_maxk ? 1 : 2);
   }
   // warp-aggregated append to the class lists (one atomic per warp and class)
 #pragma unroll
@@ -575,6 +575,21 @@ void profile_end(kaamer_gpu *h, cudaStream_t st) {
   cudaEventRecord(h->prof_pending.back().b, st);
 }
 
+// Size-class limits for this database.  A query of K k-mers touches about K * p distinct subjects, p =
+// background postings per query k-mer = (k-mer occurrences of the database) x P(two 7-mers drawn from the
+// amino-acid composition are equal) = n_kmers x 2.7e-9 for Swiss-Prot composition, plus its
+// true hits.  The class histograms work up to ~55 % load; a query that overflows its class is handed to
+// the next one and searched again, so on dense databases the limits must come down (measured on a
+// 2 M-protein database with fixed limits: class W spent 2.9 ms on 7.8 M lookups, most of them repeated
+// in class M).  Swiss-Prot scale (p = 0.53) keeps the full 512 / 2048.
+static void class_limits(const kaamer_gpu *h, int *w_maxk, int *m_maxk) {
+  double p = (double)h->idx.n_kmers * 2.7e-9;
+  if (p < 0.5) p = 0.5;
+  double w = 0.55 * W_H / p, m = 0.55 * M_H / p;
+  *w_maxk = w >= W_MAXK ? W_MAXK : (w < 32 ? 32 : (int)w);
+  *m_maxk = m >= M_MAXK ? M_MAXK : (m < *w_maxk ? *w_maxk : (int)m);
+}
+
 static uint32_t ghash_slots_for(kaamer_gpu *h) {
   (void)h;
   return 1u << 20;
@@ -624,6 +639,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   a.any0 = d_any0;
   a.peer = h->idx.d_peer;
   a.filter = h->idx.filter;
+  class_limits(h, &a.w_maxk, &a.m_maxk);
   const int g_ctas = h->sm_count;
   KCHECK(ws.ghash.ensure((size_t)2 * g_ctas * 3 * a.ghash_slots));
   a.ghash = ws.ghash.p;

@@ -51,6 +51,10 @@ struct SearchArgs {
   int g_list;  // class list processed by k_search_g (2: classified, 3: hand-offs from class M)
   const PeerView *peer;  // mode P (kernels instantiated with PEER = true): shards of all ranks
   const uint32_t *filter;  // folded presence bits of the handle's own keys (L2-resident), or nullptr
+  // size-class limits of this database (search.cu class_limits): queries up to w_maxk k-mers go to class
+  // W, up to m_maxk to class M — at most W_MAXK / M_MAXK, less when the database is so dense that a
+  // query of that size would overflow the class's histogram and be searched twice
+  int w_maxk, m_maxk;
 };
 
 // Copy src[0, len) into shared memory with aligned 16-byte loads (one request per 16 residues:

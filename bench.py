@@ -320,9 +320,9 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         # dominant kernel = the class-W search kernel (one launch per step)
-        # search classes W, M, G and W2 (profile slot 6); cls counters: [4..7] lookups, [8..11] increments
-        k_ms = prof["kernel_ms"][:3] + [prof["kernel_ms"][6]]
-        k_n = prof["kernel_launches"][:3] + [prof["kernel_launches"][6]]
+        # search classes W, M, G; cls counters: [4..7] lookups, [8..11] increments
+        k_ms = prof["kernel_ms"][:3]
+        k_n = prof["kernel_launches"][:3]
         dom = int(np.argmax(k_ms))
         dom_ms = k_ms[dom] / max(1, k_n[dom])
         pbar = float(cls_incr[dom]) / max(1.0, float(cls_lookups[dom]))
@@ -334,11 +334,11 @@ def main():
         tr = traffic_from_profiles()
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (tr or {}).get("dram_bytes_per_launch") if dom == 0 else None, "peak_source": peak_src,
-                "kernel": ["k_search_wt<W>", "k_search_m", "k_search_g", "k_search_wt<W2>"][dom], "kernel_ms_per_launch": dom_ms,
+                "kernel": ["k_search_wt<W>", "k_search_m", "k_search_g"][dom], "kernel_ms_per_launch": dom_ms,
                 "kernel_share_of_step": k_ms[dom] / ms_total if ms_total else None,
                 "note_overlap": "class G runs on a side stream underneath W and M: its event time is not additive",
-                "kernel_ms_by_class": {n: k_ms[i] / max(1, k_n[i]) for i, n in enumerate(["W", "M", "G", "W2"])},
-                "lookups_by_class": {n: float(cls_lookups[i]) / a.steps for i, n in enumerate(["W", "M", "G", "W2"])},
+                "kernel_ms_by_class": {n: k_ms[i] / max(1, k_n[i]) for i, n in enumerate(["W", "M", "G"])},
+                "lookups_by_class": {n: float(cls_lookups[i]) / a.steps for i, n in enumerate(["W", "M", "G"])},
                 "lookups_per_launch": lookups_per_launch, "postings_per_lookup": pbar,
                 "algorithmic_bytes_per_lookup": bytes_per_lookup,
                 "kernel_lookups_per_s": lookups_per_launch / (dom_ms * 1e-3),
@@ -357,7 +357,7 @@ def main():
                         "ms_per_call_rank0": {"min": 1e3 * min(step_s), "median": 1e3 * float(np.median(step_s)),
                                               "max": 1e3 * max(step_s), "argmax": int(np.argmax(step_s))},
                         "stage_ms_per_step": {"h2d_copy_stream": prof_e2e["kernel_ms"][4] / n_prof,
-                                              "search_kernels": (sum(prof_e2e["kernel_ms"][:3]) + prof_e2e["kernel_ms"][6]) / n_prof,
+                                              "search_kernels": sum(prof_e2e["kernel_ms"][:3]) / n_prof,
                                               "compaction_d2h": prof_e2e["kernel_ms"][5] / n_prof},
                         "note": "kaamer_gpu_search_proteins on pinned host buffers: residues are read in place over PCIe by the search kernels (zero-copy, aligned 16-byte loads), offsets copied H2D, hits compacted and copied D2H"},
                 "gpu_launches": int(prof["all_launches"]),

@@ -81,7 +81,7 @@ struct __align__(16) WarpSmemT {
   uint32_t ncand, flags, pad0, pad1;
 };
 
-// CLS: index of the class list / counters (0 = W, 3 = W2)
+// CLS: index of the class list / counters (0 = W)
 template <int H, int MAXK, int WARPS, int MINB, int CLS, bool PEER>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_search_wt(SearchArgs a) {
   __shared__ WarpSmemT<H, MAXK> sm[WARPS];

@@ -13,8 +13,6 @@ enum { ST_POOL_OVERFLOW = 1, ST_GHASH_OVERFLOW = 2 };
 
 // size classes by SizeInKmer
 constexpr int W_H = 512, W_MAXK = 512, W_WARPS = 8, W_CAND = 64;
-// class W2: the same warp-per-query kernel with a larger table for 512 < SizeInKmer <= 2048
-constexpr int W2_H = 1024, W2_MAXK = 2048, W2_WARPS = 4;
 constexpr int M_THREADS = 256, M_H = 4096, M_MAXK = 2048, M_CTAS = 5;
 constexpr int G_THREADS = 512;
 constexpr int FAST_C = 64;     // candidates ranked by counting below this, bitonic sort above
@@ -37,8 +35,8 @@ struct SearchArgs {
   uint64_t *pool;
   uint64_t pool_cap;
   unsigned long long *counters;
-  uint32_t *lists;       // [4][nq]: W, M, G, W2
-  uint32_t *list_count;  // [8]: [0..3] list sizes (W, M, G, W2), [4..7] work cursors (dynamic scheduling)
+  uint32_t *lists;       // [4][nq]: W, M, G, hand-offs from M to G
+  uint32_t *list_count;  // [8]: [0..3] list sizes (W, M, G, M->G hand-offs), [4..7] work cursors (dynamic scheduling)
   uint32_t *ghash;       // class G scratch: per CTA [keys HG][cnt HG][cand HG]
   uint32_t ghash_slots;  // HG (power of two)
   // nucleotide / reads mode (search_nucleotide.go:76-124): queries are ORFs, the candidate

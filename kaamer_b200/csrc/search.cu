@@ -20,6 +20,8 @@
 // posting when the list is not a singleton].  Counts never touch HBM for classes W and M.
 // Measured ceiling of the probe stage on B200: 36.5 G random probes/s (profiles/).
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include <cub/cub.cuh>
@@ -588,6 +590,15 @@ static void class_limits(const kaamer_gpu *h, int *w_maxk, int *m_maxk) {
   double w = 0.55 * W_H / p, m = 0.55 * M_H / p;
   *w_maxk = w >= W_MAXK ? W_MAXK : (w < 32 ? 32 : (int)w);
   *m_maxk = m >= M_MAXK ? M_MAXK : (m < *w_maxk ? *w_maxk : (int)m);
+  // test hook: KAAMER_CLASS_LIMITS="w,m" forces the limits (the parity tests push ordinary queries
+  // through classes M and G with it)
+  if (const char *env = getenv("KAAMER_CLASS_LIMITS")) {
+    int ew = 0, em = 0;
+    if (sscanf(env, "%d,%d", &ew, &em) == 2 && ew >= 0 && ew <= W_MAXK && em >= ew && em <= M_MAXK) {
+      *w_maxk = ew;
+      *m_maxk = em;
+    }
+  }
 }
 
 static uint32_t ghash_slots_for(kaamer_gpu *h) {

@@ -289,3 +289,31 @@ def test_many_candidates_per_query_walk_down_the_size_classes(n_sharing):
             assert r.n_lookups == ora.n_lookups and r.n_increments == ora.n_increments
             if opts.extract_positions:
                 np.testing.assert_array_equal(r.pos, ora.pos)
+
+
+@pytest.mark.parametrize("limits", ["0,0", "40,120", "100,2048", "0,2048"])
+def test_size_class_limits_do_not_change_results(small_db, gpu_small, limits, monkeypatch):
+    """The class limits follow the database density (search.cu class_limits); whatever they are, every
+    query must come out identical: force them so that ordinary queries run in classes M and G, with
+    positions and in nucleotide mode."""
+    from kaamer_b200 import SearchOptions, synth
+    from oracle import oracle as o
+
+    from tests.helpers import assert_same_rows
+
+    monkeypatch.setenv("KAAMER_CLASS_LIMITS", limits)
+    q, qo, _ = synth.protein_queries(small_db["res"], small_db["off"], 300, config_index=1, stream=33)
+    seqs = [q[int(qo[i]):int(qo[i + 1])].tobytes() for i in range(len(qo) - 1)]
+    seqs += [b"", b"MKT", small_db["res"][:700].tobytes(), small_db["res"][:3000].tobytes()]
+    q, qo = o.pack(seqs)
+    for opts in (SearchOptions(), SearchOptions(min_kmatch=1, min_kratio=0.0, max_results=100, extract_positions=True)):
+        ora = o.search_proteins(small_db["idx"], q, qo, o.opts(opts.min_kmatch, opts.min_kratio, opts.max_results,
+                                                               want_positions=opts.extract_positions), 4)
+        r = gpu_small.search_proteins(q, qo, opts)
+        assert_same_hits(r, ora, f"limits {limits} {opts}")
+        assert r.n_lookups == ora.n_lookups and r.n_increments == ora.n_increments
+        if opts.extract_positions:
+            np.testing.assert_array_equal(r.pos, ora.pos)
+    nt, off = synth.nucleotide_contigs(small_db["res"], small_db["off"], 1, 60_000, config_index=2)
+    ora = o.search_nucleotide(small_db["idx"], nt, off, o.opts(), 4)
+    assert_same_rows(gpu_small.search_nucleotide(nt, off, SearchOptions()), ora, f"limits {limits} nucleotide")

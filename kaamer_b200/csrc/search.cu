@@ -378,12 +378,12 @@ __global__ void __launch_bounds__(M_THREADS, M_CTAS) k_search_m(SearchArgs a) {
 
 // class G: histogram in global memory (per-CTA scratch, stays in L2), codes computed on the fly
 constexpr int G_STAGE = 40 * 1024;
-template <bool PEER>
-__global__ void __launch_bounds__(G_THREADS) k_search_g(SearchArgs a) {
+template <bool PEER, int GT>
+__global__ void __launch_bounds__(GT) k_search_g(SearchArgs a) {
   __shared__ __align__(16) uint8_t s_res[G_STAGE];
   __shared__ SelectScratch ss;
   __shared__ unsigned long long s_total;
-  constexpr int THREADS = G_THREADS;
+  constexpr int THREADS = GT;
   const int tid = threadIdx.x;
   const PeerView *pv = nullptr;
   if constexpr (PEER) {
@@ -651,7 +651,22 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   a.peer = h->idx.d_peer;
   a.filter = h->idx.filter;
   class_limits(h, &a.w_maxk, &a.m_maxk);
-  const int g_ctas = h->sm_count;
+  // Class G: one CTA per query, histogram in a per-CTA global scratch.  At Swiss-Prot density it holds a
+  // handful of very long queries and gets one CTA per SM (it runs underneath W and M and must leave them
+  // their shared memory); on a dense database, where the lowered class limits send many queries here,
+  // four CTAs of 256 threads per SM (measured with every C3 query forced into class G: 14.2 ms at one
+  // 512-thread CTA per SM, 7.5 ms at two).
+  const bool dense = a.w_maxk < W_MAXK || a.m_maxk < M_MAXK;
+  const int g_ctas = h->sm_count * (dense ? 4 : 1);
+  auto launch_g = [&](cudaStream_t s_) {
+    if (dense) {
+      if (peer) k_search_g<true, 256><<<g_ctas, 256, 0, s_>>>(a);
+      else k_search_g<false, 256><<<g_ctas, 256, 0, s_>>>(a);
+    } else {
+      if (peer) k_search_g<true, G_THREADS><<<g_ctas, G_THREADS, 0, s_>>>(a);
+      else k_search_g<false, G_THREADS><<<g_ctas, G_THREADS, 0, s_>>>(a);
+    }
+  };
   KCHECK(ws.ghash.ensure((size_t)2 * g_ctas * 3 * a.ghash_slots));
   a.ghash = ws.ghash.p;
   KCUDA(cudaMemsetAsync(list_count, 0, 8 * sizeof(uint32_t), st));
@@ -670,8 +685,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   KCUDA(cudaStreamWaitEvent(side, h->chunk_ev[6], 0));
   profile_begin(h, side, 2);
   a.g_list = 2;
-  if (peer) k_search_g<true><<<g_ctas, G_THREADS, 0, side>>>(a);
-  else k_search_g<false><<<g_ctas, G_THREADS, 0, side>>>(a);
+  launch_g(side);
   profile_end(h, side);
   KCUDA(cudaEventRecord(h->chunk_ev[7], side));
   profile_begin(h, st, 0);
@@ -684,8 +698,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   profile_end(h, st);
   a.g_list = 3;
   a.ghash = ws.ghash.p + (size_t)g_ctas * 3 * a.ghash_slots;  // own scratch: the first G launch may still run
-  if (peer) k_search_g<true><<<g_ctas, G_THREADS, 0, st>>>(a);
-  else k_search_g<false><<<g_ctas, G_THREADS, 0, st>>>(a);
+  launch_g(st);
   KCUDA(cudaStreamWaitEvent(st, h->chunk_ev[7], 0));
   h->prof_all_launches += 5;
   KCUDA(cudaGetLastError());

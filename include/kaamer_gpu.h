@@ -264,6 +264,27 @@ int kaamer_gpu_shard_export(kaamer_gpu_t *h, kaamer_shard_handle *out);
 int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards, int n_shards, int flags);
 int kaamer_gpu_detach_shards(kaamer_gpu_t *h);
 
+/* ---- host-side query readers: GetQueriesFasta / GetQueriesFastq (pkg/search/search.go:222-412)
+ * with the reference's exact semantics (content sniffing on 32 bytes, 1 MiB line limit, last FASTA
+ * record not upper-cased, SizeInKmer rules, FASTQ '@' / sequence-line rules), filling the flat
+ * batch layout of the search entry points.  pinned != 0: residues and offsets live in page-locked
+ * memory (the search kernels then read the residues in place over PCIe); needs a CUDA device.
+ * A file that the reference would silently ignore yields a batch of 0 queries. ---- */
+typedef struct kaamer_query_batch {
+  uint32_t n_queries;
+  uint32_t _pad;
+  uint64_t n_residues;
+  uint8_t *residues;      /* Query.Sequence, concatenated */
+  uint64_t *seq_off;      /* [n_queries+1] */
+  char *names;            /* Query.Name, concatenated (not NUL-separated) */
+  uint64_t *name_off;     /* [n_queries+1] */
+  int32_t *size_in_kmer;  /* Query.SizeInKmer as the reader computes it */
+  void *_owner;
+} kaamer_query_batch;
+int kaamer_host_read_fasta(const char *path, int is_protein, int pinned, kaamer_query_batch **out);
+int kaamer_host_read_fastq(const char *path, int pinned, kaamer_query_batch **out);
+void kaamer_host_free_queries(kaamer_query_batch *b);
+
 /* pinned host buffers for callers that want zero-staging H2D (cgo: C.kaamer_gpu_pinned_alloc) */
 int kaamer_gpu_pinned_alloc(uint64_t bytes, void **out);
 void kaamer_gpu_pinned_free(void *p);

@@ -145,6 +145,20 @@ class ShardHandle(C.Structure):
     ]
 
 
+class QueryBatch(C.Structure):
+    _fields_ = [
+        ("n_queries", C.c_uint32),
+        ("_pad", C.c_uint32),
+        ("n_residues", C.c_uint64),
+        ("residues", C.c_void_p),
+        ("seq_off", C.c_void_p),
+        ("names", C.c_void_p),
+        ("name_off", C.c_void_p),
+        ("size_in_kmer", C.c_void_p),
+        ("_owner", C.c_void_p),
+    ]
+
+
 # every symbol include/kaamer_gpu.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "kaamer_gpu_open",
@@ -175,6 +189,9 @@ SYMBOLS = [
     "kaamer_gpu_detach_shards",
     "kaamer_gpu_pinned_alloc",
     "kaamer_gpu_pinned_free",
+    "kaamer_host_read_fasta",
+    "kaamer_host_read_fastq",
+    "kaamer_host_free_queries",
     "kaamer_gpu_profile_enable",
     "kaamer_gpu_profile_read",
     "kaamer_gpu_profile_host_read",
@@ -230,6 +247,10 @@ def lib() -> C.CDLL:
     L.kaamer_gpu_shard_export.argtypes = [vp, C.POINTER(ShardHandle)]
     L.kaamer_gpu_attach_shards.argtypes = [vp, C.POINTER(ShardHandle), C.c_int, C.c_int]
     L.kaamer_gpu_detach_shards.argtypes = [vp]
+    L.kaamer_host_read_fasta.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.POINTER(QueryBatch))]
+    L.kaamer_host_read_fastq.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.POINTER(QueryBatch))]
+    L.kaamer_host_free_queries.argtypes = [C.POINTER(QueryBatch)]
+    L.kaamer_host_free_queries.restype = None
     L.kaamer_gpu_pinned_alloc.argtypes = [C.c_uint64, C.POINTER(vp)]
     L.kaamer_gpu_pinned_free.argtypes = [vp]
     L.kaamer_gpu_pinned_free.restype = None

@@ -400,3 +400,133 @@ def align_postprocess(a_string: str, b_string: str, segs: list, query_len: int, 
     return {"identity": float(identity), "similarity": float(similarity), "length": len(a_string),
             "mismatches": mismatches, "gap_openings": gap_openings, "raw": raw, "bitscore": bitscore, "evalue": evalue,
             "query_start": q_start + 1, "query_end": q_end, "subject_start": s_start + 1, "subject_end": s_end}
+
+
+# ---- pkg/search/search.go:222-412 (query readers) ---------------------------------------------------------
+def detect_content_type(buf: bytes) -> str:
+    """net/http.DetectContentType on the 32-byte sniff buffer, reduced to the three outcomes the readers
+    distinguish: 'gzip', 'text' ("text/plain; charset=utf-8") or 'other'."""
+    ws = 0
+    while ws < len(buf) and buf[ws] in b"\t\n\x0c\r ":
+        ws += 1
+    d = buf[ws:]
+    for sig in (b"<!DOCTYPE HTML", b"<HTML", b"<HEAD", b"<SCRIPT", b"<IFRAME", b"<H1", b"<DIV", b"<FONT", b"<TABLE", b"<A",
+                b"<STYLE", b"<TITLE", b"<B", b"<BODY", b"<BR", b"<P", b"<!--"):
+        if len(d) >= len(sig) + 1 and d[:len(sig)].upper() == sig and d[len(sig):len(sig) + 1] in (b" ", b">"):
+            return "other"
+    if d.startswith(b"<?xml") or buf.startswith(b"%PDF-") or buf.startswith(b"%!PS-Adobe-"):
+        return "other"
+    if buf.startswith(b"\xfe\xff") or buf.startswith(b"\xff\xfe"):
+        return "other"
+    if buf.startswith(b"\xef\xbb\xbf"):
+        return "text"
+    for sig in (b"GIF87a", b"GIF89a", b"BM", b"ID3", b".snd", b"wOFF", b"wOF2", b"OTTO", b"ttcf", b"\xff\xd8\xff"):
+        if buf.startswith(sig):
+            return "other"
+    if buf.startswith(b"RIFF") and (buf[8:14] == b"WEBPVP" or buf[8:12] in (b"AVI ", b"WAVE")):
+        return "other"
+    if buf.startswith(b"FORM") and buf[8:12] == b"AIFF":
+        return "other"
+    if buf.startswith(b"\x1f\x8b\x08"):
+        return "gzip"
+    for c in d:
+        if c <= 0x08 or c == 0x0B or 0x0E <= c <= 0x1A or 0x1C <= c <= 0x1F:
+            return "other"
+    return "text"
+
+
+def _scan_lines(data: bytes):
+    """bufio.Scanner / ScanLines with scanner.Buffer(buf, 1024*1024): a line of 1 MiB or more ends the scan."""
+    p = 0
+    while p < len(data):
+        e = data.find(b"\n", p)
+        end = len(data) if e < 0 else e
+        if end - p >= 1024 * 1024:
+            return
+        line = data[p:end]
+        if line.endswith(b"\r"):
+            line = line[:-1]
+        yield line
+        p = len(data) if e < 0 else e + 1
+
+
+def _open_queries(path: str):
+    import gzip
+
+    raw = open(path, "rb").read()
+    buff = (raw[:32] + bytes(32))[:32]  # buff := make([]byte, 32); file.Read(buff)
+    kind = detect_content_type(buff)
+    if kind == "gzip":
+        return gzip.decompress(raw)
+    if kind == "text":
+        return raw
+    return None
+
+
+# unicode.IsSpace (Go): what strings.TrimSpace removes
+_GO_SPACE = "\t\n\v\f\r \u0085\u00a0\u1680\u2000\u2001\u2002\u2003\u2004\u2005\u2006\u2007\u2008\u2009\u200a\u2028\u2029\u202f\u205f\u3000"
+
+
+def _go_len(s: str) -> int:
+    """len() of a Go string = its UTF-8 byte length"""
+    return len(s.encode("utf-8", "surrogateescape"))
+
+
+def get_queries_fasta(path: str) -> list:
+    """GetQueriesFasta, search.go:222-322 -> [(Name, Sequence, SizeInKmer)].  Go strings are UTF-8 byte
+    strings: lines are decoded as UTF-8 here (invalid bytes preserved) so that TrimSpace / ToUpper see the
+    same characters; the returned strings are latin-1 views of the bytes."""
+    data = _open_queries(path)
+    if data is None:
+        return []
+    out = []
+    name, seq = "", ""
+
+    def emit(upper):
+        size = _go_len(seq) - KMER_SIZE + 1
+        if seq[len(seq) - 1:] == "*":
+            size -= 1
+        s2 = "".join(c.upper() if c.isascii() else c for c in seq) if upper else seq
+        out.append((name.encode("utf-8", "surrogateescape").decode("latin-1"),
+                    s2.encode("utf-8", "surrogateescape").decode("latin-1"), size))
+
+    for raw in _scan_lines(data):
+        if len(raw) < 1:
+            continue
+        l = raw.decode("utf-8", "surrogateescape")
+        if raw[0:1] == b">":
+            if seq != "":
+                emit(True)
+                name, seq = "", ""
+            name = l[1:]
+        else:
+            seq += l.strip(_GO_SPACE)
+    if seq != "":
+        emit(False)
+    return out
+
+
+def get_queries_fastq(path: str) -> list:
+    """GetQueriesFastq, search.go:324-412 -> [(Name, Sequence, SizeInKmer)]"""
+    import re
+
+    data = _open_queries(path)
+    if data is None:
+        return []
+    is_sequence = re.compile(r"^[ATGCNatgcn]+$").match
+    out = []
+    name, seq = "", ""
+    for raw in _scan_lines(data):
+        l = raw.decode("latin-1")
+        if len(l) < 1:
+            continue
+        if l[0] == "@":
+            if seq != "":
+                out.append((name, seq, len(seq) - KMER_SIZE + 1))
+                name, seq = "", ""
+            name = l[1:]
+        elif is_sequence(l):
+            seq = l
+    if seq != "":
+        out.append((name, seq, len(seq) - KMER_SIZE + 1))
+    return out

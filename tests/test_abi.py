@@ -22,7 +22,7 @@ def built():
 def _header_symbols():
     hdr = open(os.path.join(ROOT, "include", "kaamer_gpu.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(kaamer_gpu_\w+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"\b(kaamer_(?:gpu|host)_\w+)\s*\(", hdr)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -43,6 +43,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.IndexView) == 104
     assert C.sizeof(_lib.Hits) == 136 and C.sizeof(_lib.Orfs) == 80
     assert C.sizeof(_lib.ShardHandle) == 72
+    assert C.sizeof(_lib.QueryBatch) == 64
 
 
 def test_no_cpu_fallback_without_device():

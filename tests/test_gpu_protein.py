@@ -317,3 +317,27 @@ def test_size_class_limits_do_not_change_results(small_db, gpu_small, limits, mo
     nt, off = synth.nucleotide_contigs(small_db["res"], small_db["off"], 1, 60_000, config_index=2)
     ora = o.search_nucleotide(small_db["idx"], nt, off, o.opts(), 4)
     assert_same_rows(gpu_small.search_nucleotide(nt, off, SearchOptions()), ora, f"limits {limits} nucleotide")
+
+
+def test_fasta_file_to_hits_through_the_native_reader(small_db, gpu_small, tmp_path):
+    """query FASTA -> kaamer_host_read_fasta (pinned batch) -> kaamer_gpu_search_proteins, against the
+    oracle on the reader transliteration's view of the same file (last record not upper-cased)"""
+    from kaamer_b200 import SearchOptions, readers, synth
+    from oracle import oracle as o
+    from tests import go_transliteration as go
+
+    q, qo, _ = synth.protein_queries(small_db["res"], small_db["off"], 50, config_index=1, stream=41)
+    p = str(tmp_path / "queries.fasta")
+    synth.write_fasta(p, [f"q{i} query {i}" for i in range(50)], q, qo)
+    with open(p, "ab") as f:
+        f.write(b">lower case last record\n" + small_db["res"][:300].tobytes().lower() + b"\n")
+    b = readers.read_fasta(p, pinned=True)
+    ref = go.get_queries_fasta(p)
+    assert len(b) == 51 and [r[0] for r in ref] == b.names
+    rq, rqo = o.pack([r[1].encode("latin-1") for r in ref])
+    np.testing.assert_array_equal(b.residues, rq)
+    ora = o.search_proteins(small_db["idx"], rq, rqo, o.opts(), 4)
+    r = gpu_small.search_proteins(b.residues, b.seq_off, SearchOptions())
+    assert_same_hits(r, ora, "fasta file")
+    np.testing.assert_array_equal(r.size_in_kmer, b.size_in_kmer)
+    assert r.hits(50) == []  # lower-case residues are unknown letters: the last record finds nothing

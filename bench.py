@@ -333,6 +333,7 @@ def main():
         achieved = lookups_per_launch * bytes_per_lookup / (dom_ms * 1e-3) / 1e9
         tr = traffic_from_profiles()
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "frac_of_nominal_8TBs": achieved / 8000.0,
                 "traffic": (tr or {}).get("dram_bytes_per_launch") if dom == 0 else None, "peak_source": peak_src,
                 "kernel": ["k_search_wt<W>", "k_search_m", "k_search_g"][dom], "kernel_ms_per_launch": dom_ms,
                 "kernel_share_of_step": k_ms[dom] / ms_total if ms_total else None,

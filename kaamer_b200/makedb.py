@@ -58,3 +58,42 @@ def read_fasta(path: str):
         off[1:] = np.cumsum([len(s) for s in keep_seqs], dtype=np.uint64)
     res = np.frombuffer(b"".join(keep_seqs), dtype=np.uint8).copy() if keep_seqs else np.zeros(0, np.uint8)
     return entry_ids, names, res, off, np.array(keep_ids, dtype=np.uint32)
+
+
+def read_tsv(path: str):
+    """-> (entry_ids, residues u8, seq_off u64, ids u32) of the ACCEPTED rows of a kaamer TSV database
+    (`kaamer-db -make -f tsv`, pkg/makedb/inputTSV.go:94-142): the first line names the columns
+    (`EntryID` and `Sequence`, case-insensitive, are mandatory); a row is skipped when its sequence is
+    shorter than 7 residues or its entry id is empty; accepted rows get the ids 0, 1, 2 ... in file order
+    (no id quirk here) and their sequences are NOT upper-cased (unlike the FASTA path)."""
+    opener = gzip.open if path.endswith(".gz") else open
+    entry_ids, seqs = [], []
+    with opener(path, "rb") as f:
+        header = f.readline().rstrip(b"\n").rstrip(b"\r").split(b"\t")
+        low = [h.lower() for h in header]
+        if b"entryid" not in low:
+            raise ValueError("TSV file doesn't contain 'EntryID' header")
+        if b"sequence" not in low:
+            raise ValueError("TSV file doesn't contain 'Sequence' header")
+        for raw in f:
+            line = raw.rstrip(b"\n")
+            if line.endswith(b"\r"):
+                line = line[:-1]  # bufio.ScanLines drops the CR
+            cols = line.split(b"\t")
+            if len(cols) > len(header):
+                raise ValueError("TSV row has more columns than the header (the reference panics)")
+            entry, seq = b"", b""
+            for i, c in enumerate(cols):
+                if low[i] == b"entryid":
+                    entry = c
+                elif low[i] == b"sequence":
+                    seq = c
+            if len(seq) < KMER_SIZE or seq == b"" or entry == b"":
+                continue
+            entry_ids.append(entry.decode())
+            seqs.append(seq)
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    if seqs:
+        off[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+    res = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy() if seqs else np.zeros(0, np.uint8)
+    return entry_ids, res, off, np.arange(len(seqs), dtype=np.uint32)

@@ -530,3 +530,46 @@ def get_queries_fastq(path: str) -> list:
     if seq != "":
         out.append((name, seq, len(seq) - KMER_SIZE + 1))
     return out
+
+
+# ---- pkg/makedb/inputTSV.go:94-142, 221-239 ---------------------------------------------------------------
+def make_index_tsv(tsv_text: str) -> dict:
+    """kmer key -> posting list for a TSV database: header line, then rows; accepted rows are numbered from
+    0 in file order; sequences are indexed as they are (no upper-casing)."""
+    features = None
+    protein_nb = 0
+    kmer_store: dict[int, list] = {}
+    stats = {"proteins": 0, "aa": 0, "entries": []}
+    for line in tsv_text.split("\n"):
+        if line == "" and features is not None:
+            # bufio.Scanner yields no token after the final newline; an empty row has no EntryID and is skipped
+            continue
+        if features is None:
+            features = line.split("\t")
+            continue
+        cols = line.split("\t")
+        entry, sequence, length = "", "", 0
+        for i, f in enumerate(cols):
+            if features[i].lower() == "entryid":
+                entry = f
+            elif features[i].lower() == "sequence":
+                sequence = f
+                length = len(f)
+        if length < KMER_SIZE or sequence == "" or entry == "":
+            continue
+        stats["proteins"] += 1
+        stats["aa"] += length
+        stats["entries"].append(entry)
+        for i in range(0, length - KMER_SIZE + 1):
+            kmer_store.setdefault(encode_kmer(sequence[i:i + KMER_SIZE]), []).append(protein_nb)
+        protein_nb += 1
+    index = {}
+    for key, ids in kmer_store.items():
+        s = sorted(ids, reverse=True)
+        out = []
+        for e in s:
+            if not out or out[-1] != e:
+                out.append(e)
+        index[key] = out
+    index["__stats__"] = stats
+    return index

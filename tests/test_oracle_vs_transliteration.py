@@ -192,3 +192,31 @@ def test_alignment_postprocessing(seed):
         assert abs(out.bitscore - ref["bitscore"]) <= 1e-12 * max(1.0, abs(ref["bitscore"]))
         assert abs(out.evalue - ref["evalue"]) <= 1e-9 * abs(ref["evalue"])
     assert n_gapped > 10
+
+
+def test_tsv_database(tmp_path):
+    """`kaamer-db -make -f tsv`: ids 0..n-1 over the accepted rows, sequences indexed as written"""
+    rng = np.random.default_rng(12)
+    rows = ["Organism\tEntryID\tSEQUENCE\tProteinName"]
+    for i in range(70):
+        L = int(rng.integers(3, 90))
+        s = "".join(AA[j] for j in rng.integers(0, 20, L))
+        if rng.random() < 0.15:
+            s = s.lower()  # TSV sequences are not upper-cased: every k-mer holds unknown letters
+        entry = "" if rng.random() < 0.1 else f"E{i}"
+        rows.append(f"org{i}\t{entry}\t{s}\tname {i}")
+    rows.insert(5, "short\tE_short\tMKT\tn")
+    rows.insert(9, "only two\tcolumns")
+    text = "\n".join(rows) + "\n"
+    p = tmp_path / "db.tsv"
+    p.write_text(text)
+    entries, res, off, ids = makedb.read_tsv(str(p))
+    gi = go.make_index_tsv(text)
+    stats = gi.pop("__stats__")
+    assert entries == stats["entries"] and ids.tolist() == list(range(len(entries)))
+    idx = o.Index.build(res, off, ids, 2)
+    assert (idx.n_proteins, idx.n_aa) == (stats["proteins"], stats["aa"])
+    keys = sorted(gi.keys())
+    assert idx.keys.tolist() == keys
+    for i, k in enumerate(keys):
+        assert idx.postings[int(idx.offsets[i]):int(idx.offsets[i + 1])].tolist() == gi[k]

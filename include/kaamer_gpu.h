@@ -281,6 +281,10 @@ typedef struct kaamer_query_batch {
   int32_t *size_in_kmer;  /* Query.SizeInKmer as the reader computes it */
   void *_owner;
 } kaamer_query_batch;
+/* FormatPositionsToString (pkg/search/search.go:694-742): the `-pos` column of the TSV / JSON output from one
+ * PositionHits row (kaamer_hits.pos, one byte per query k-mer position).  Writes a NUL-terminated string into
+ * out[cap]; returns its length, or the negative length needed when cap is too small. */
+int64_t kaamer_host_format_positions(const uint8_t *positions, uint64_t n, int with_alignment, char *out, uint64_t cap);
 int kaamer_host_read_fasta(const char *path, int is_protein, int pinned, kaamer_query_batch **out);
 int kaamer_host_read_fastq(const char *path, int pinned, kaamer_query_batch **out);
 void kaamer_host_free_queries(kaamer_query_batch *b);

@@ -189,6 +189,7 @@ SYMBOLS = [
     "kaamer_gpu_detach_shards",
     "kaamer_gpu_pinned_alloc",
     "kaamer_gpu_pinned_free",
+    "kaamer_host_format_positions",
     "kaamer_host_read_fasta",
     "kaamer_host_read_fastq",
     "kaamer_host_free_queries",
@@ -247,6 +248,8 @@ def lib() -> C.CDLL:
     L.kaamer_gpu_shard_export.argtypes = [vp, C.POINTER(ShardHandle)]
     L.kaamer_gpu_attach_shards.argtypes = [vp, C.POINTER(ShardHandle), C.c_int, C.c_int]
     L.kaamer_gpu_detach_shards.argtypes = [vp]
+    L.kaamer_host_format_positions.argtypes = [vp, C.c_uint64, C.c_int, C.c_char_p, C.c_uint64]
+    L.kaamer_host_format_positions.restype = C.c_int64
     L.kaamer_host_read_fasta.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.POINTER(QueryBatch))]
     L.kaamer_host_read_fastq.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.POINTER(QueryBatch))]
     L.kaamer_host_free_queries.argtypes = [C.POINTER(QueryBatch)]

@@ -350,6 +350,41 @@ int kaamer_host_read_fastq(const char *path, int pinned, kaamer_query_batch **ou
   return finish_batch(recs, pinned, out);
 }
 
+int64_t kaamer_host_format_positions(const uint8_t *positions, uint64_t n, int with_alignment, char *out, uint64_t cap) {
+  // search.go:694-742, statement by statement (the single-position branch can never be taken: at a
+  // non-matching position pos the run started at currentStart <= pos, so pos+1 > currentStart)
+  std::string ps;
+  uint64_t current_start = 0, end_pos = 0;
+  bool in_sequence = false;
+  for (uint64_t pos = 0; pos < n; ++pos) {
+    if (positions[pos]) {
+      if (!in_sequence) {
+        current_start = pos + 1;
+        in_sequence = true;
+      }
+    } else if (in_sequence) {
+      if (!ps.empty()) ps += ",";
+      if (pos + 1 > current_start) {
+        end_pos = pos + 1;
+        if (with_alignment) end_pos = end_pos + KAAMER_KMER_SIZE - 1;
+        ps += std::to_string(current_start) + "-" + std::to_string(end_pos);
+      } else {
+        ps += std::to_string(current_start);
+      }
+      in_sequence = false;
+    }
+  }
+  if (in_sequence) {
+    if (!ps.empty()) ps += ",";
+    end_pos = n;
+    if (with_alignment) end_pos = end_pos + KAAMER_KMER_SIZE - 1;
+    ps += std::to_string(current_start) + "-" + std::to_string(end_pos);
+  }
+  if (!out || ps.size() + 1 > cap) return -(int64_t)(ps.size() + 1);
+  memcpy(out, ps.c_str(), ps.size() + 1);
+  return (int64_t)ps.size();
+}
+
 void kaamer_host_free_queries(kaamer_query_batch *b) {
   if (!b) return;
   delete (BatchOwner *)b->_owner;

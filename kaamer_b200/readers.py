@@ -56,3 +56,14 @@ def read_fastq(path: str, pinned: bool = False) -> QueryBatch:
     bp = C.POINTER(_lib.QueryBatch)()
     check(_lib.lib().kaamer_host_read_fastq(path.encode(), int(pinned), C.byref(bp)))
     return _collect(bp)
+
+
+def format_positions(pos, with_alignment: bool = False) -> str:
+    """FormatPositionsToString (pkg/search/search.go:694-742) of one PositionHits row."""
+    a = np.ascontiguousarray(pos, dtype=np.uint8)
+    cap = 24 * (len(a) // 2 + 2)
+    buf = C.create_string_buffer(cap)
+    n = _lib.lib().kaamer_host_format_positions(a.ctypes.data_as(C.c_void_p), len(a), int(with_alignment), buf, cap)
+    if n < 0:
+        raise ValueError("format_positions: buffer too small")
+    return buf.value.decode()

@@ -573,3 +573,39 @@ def make_index_tsv(tsv_text: str) -> dict:
         index[key] = out
     index["__stats__"] = stats
     return index
+
+
+def format_positions_to_string(positions: list, with_alignment: bool) -> str:
+    """FormatPositionsToString, search.go:694-742"""
+    current_start = 0
+    in_sequence = False
+    end_pos = 0
+    ps = ""
+    for pos, match in enumerate(positions):
+        if match:
+            if not in_sequence:
+                current_start = pos + 1
+                in_sequence = True
+        else:
+            if in_sequence:
+                if pos + 1 > current_start:
+                    if ps != "":
+                        ps += ","
+                    end_pos = pos + 1
+                    if with_alignment:
+                        end_pos = end_pos + KMER_SIZE - 1
+                    ps += str(current_start) + "-" + str(end_pos)
+                    in_sequence = False
+                else:
+                    if ps != "":
+                        ps += ","
+                    ps += str(current_start)
+                    in_sequence = False
+    if in_sequence:
+        if ps != "":
+            ps += ","
+        end_pos = len(positions)
+        if with_alignment:
+            end_pos = end_pos + KMER_SIZE - 1
+        ps += str(current_start) + "-" + str(end_pos)
+    return ps

@@ -37,3 +37,16 @@ def test_cpp_host_prints_the_reference_tsv(small_db, tmp_path):
                 expect.append(f"{name.split(' ')[0]}\t{subject}\t{float(ident):.2f}\t{size}\t{kmatch}\tN/A\t1\t{len(seq)}\t1\tN/A")
         assert out.stdout.splitlines() == expect
         assert len(expect) > 100
+    # --pos: ExtractPositions (search.go:521-527,541-544)
+    out = subprocess.run([BIN, kidx, fa, "--pos"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    ora = o.search_proteins(small_db["idx"], rq, rqo, o.opts(want_positions=True), 4)
+    expect, h = [], 0
+    for i, (name, seq, size) in enumerate(recs):
+        for subject, kmatch in ora.hits(i):
+            ident = np.float32(kmatch) / np.float32(size) * np.float32(100.0)
+            ps = go.format_positions_to_string([bool(x) for x in ora.positions(h)], False)
+            h += 1
+            expect.append(f"{name.split(' ')[0]}\t{subject}\t{float(ident):.2f}\t{size}\t{kmatch}\t{ps.count(',')}\t1\t{len(seq)}"
+                          f"\t1\tN/A\t{ps}")
+    assert out.stdout.splitlines() == expect

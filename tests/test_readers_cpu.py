@@ -119,3 +119,17 @@ def test_missing_and_empty_files(tmp_path):
     open(p, "wb").close()
     with pytest.raises(KaamerGpuError):
         readers.read_fasta(p)  # the reference exits on the failed read of the sniff buffer
+
+
+def test_format_positions_native_oracle_and_transliteration_agree():
+    from oracle import oracle as o
+
+    rng = np.random.default_rng(13)
+    cases = [[], [1], [0], [1, 1, 1], [0, 0, 0], [1, 0, 1, 0, 1], [0, 1, 1, 0, 0, 1], [1] * 40 + [0] + [1] * 3]
+    cases += [(rng.random(int(rng.integers(1, 300))) < p).astype(np.uint8).tolist() for p in (0.05, 0.5, 0.9) for _ in range(20)]
+    for pos in cases:
+        for wa in (False, True):
+            ref = go.format_positions_to_string([bool(x) for x in pos], wa)
+            assert readers.format_positions(pos, wa) == ref
+            assert o.format_positions(np.array(pos, np.uint8), wa) == ref
+    assert readers.format_positions([1, 1, 0, 0, 1, 1, 1], False) == "1-3,5-7"

@@ -182,3 +182,34 @@ def test_protein_positions_parity(small_db, gpu_small, opts):
     np.testing.assert_array_equal(r.pos_off.astype(np.int64), ora.pos_off.astype(np.int64))
     np.testing.assert_array_equal(r.pos, ora.pos)
     assert int(r.pos.sum()) > 0
+
+
+def test_fastq_file_through_the_native_reader(small_db, gpu_small, tmp_path):
+    """FASTQ file -> kaamer_host_read_fastq -> kaamer_gpu_search_nucleotide (the FastqSearch path,
+    search_fastq.go:78-140): rows, hits, locations and positions equal the oracle on the reads the
+    transliterated Go reader extracts from the same file."""
+    from kaamer_b200 import SearchOptions, readers, synth
+    from oracle import oracle as o
+    from tests import go_transliteration as go
+
+    nt, off = synth.nucleotide_contigs(small_db["res"], small_db["off"], 1, 60_000, config_index=2)
+    rng = np.random.default_rng(17)
+    p = str(tmp_path / "reads.fastq")
+    with open(p, "wb") as f:
+        for i in range(400):
+            s = int(rng.integers(0, len(nt) - 400))
+            L = int(rng.integers(60, 400))
+            read = nt[s:s + L].tobytes()
+            if i % 7 == 0:
+                read = read.upper()
+            qual = b"I" * L if i % 11 else b"@" + b"I" * (L - 1)  # a quality line that starts with '@'
+            f.write(b"@read%d sampled read\n" % i + read + b"\n+\n" + qual + b"\n")
+    b = readers.read_fastq(p)
+    ref = go.get_queries_fastq(p)
+    assert len(b) == len(ref) == 400 and b.names == [r[0] for r in ref]
+    rq, rqo = o.pack([r[1].encode() for r in ref])
+    np.testing.assert_array_equal(b.residues, rq)
+    ora = o.search_nucleotide(small_db["idx"], rq, rqo, o.opts(), 4)
+    r = gpu_small.search_nucleotide(b.residues, b.seq_off, SearchOptions())
+    assert ora.n_rows > 50
+    assert_same_rows(r, ora, "fastq file")

@@ -94,3 +94,66 @@ def test_kidx_fences_match_the_python_planner(tmp_path):
         assert f[0] == 0 and f[-1] == dense_space() and np.all(np.diff(f.astype(np.int64)) >= 0)
     _write_kidx(p, idx.keys[:0], idx.offsets[:1], idx.postings[:0])
     np.testing.assert_array_equal(GpuIndex.kidx_fences(p, 4), make_fences(idx.keys[:0], idx.offsets[:1], 4))
+
+
+class _FakeIndex:
+    """stands for a GpuIndex holding one key-range shard: exports two descriptors (temporary files) and
+    records what attach_shards receives"""
+
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+        self.files = []
+        self.attached = None
+
+    def export_shard(self):
+        sh = _lib.ShardHandle()
+        sh.shard_lo, sh.shard_hi = self.rank * 100, (self.rank + 1) * 100
+        sh.pid = os.getpid()
+        fds = []
+        for what in ("table", "postings"):
+            f = tempfile.TemporaryFile()
+            f.write(f"{what} of rank {self.rank}".encode())
+            f.flush()
+            fds.append(os.dup(f.fileno()))  # the driver owns (and closes) the exported descriptors
+            f.close()
+        sh.table_fd, sh.postings_fd = fds
+        return sh
+
+    def attach_shards(self, handles, presence_filter=True, replicate_table=False):
+        seen = []
+        for r, sh in enumerate(handles):
+            assert (sh.shard_lo, sh.shard_hi) == (r * 100, (r + 1) * 100)
+            assert os.pread(sh.table_fd, 100, 0) == f"table of rank {r}".encode()
+            assert os.pread(sh.postings_fd, 100, 0) == f"postings of rank {r}".encode()
+            seen += [sh.table_fd, sh.postings_fd]
+        self.attached = (len(handles), presence_filter, replicate_table, seen)
+
+
+def _attach_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from kaamer_b200.peer import attach_distributed
+
+        g = _FakeIndex(rank, world)
+        n = attach_distributed(g, presence_filter=False, replicate_table=True)
+        assert n == world and g.attached[:3] == (world, False, True)
+        for fd in g.attached[3]:  # every descriptor (own exports and received ones) is closed afterwards
+            try:
+                os.fstat(fd)
+                raise AssertionError(f"descriptor {fd} left open")
+            except OSError:
+                pass
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_attach_distributed_orchestration_gloo_world3():
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ret = mp.Manager().dict()
+    mp.spawn(_attach_worker, args=(3, port, ret), nprocs=3, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok", 2: "ok"}

@@ -220,3 +220,58 @@ def test_tsv_database(tmp_path):
     assert idx.keys.tolist() == keys
     for i, k in enumerate(keys):
         assert idx.postings[int(idx.offsets[i]):int(idx.offsets[i + 1])].tolist() == gi[k]
+
+
+def _gotoh_local_optimum(q: str, s: str, m, gap_open=-11) -> int:
+    """Independent three-state local alignment (match / gap-in-query / gap-in-subject), the model the oracle
+    documents for biogo's SWAffine as kaamer configures it: the opening costs GapOpen, each gapped residue
+    costs the matrix's gap row (0 in the only reading under which kaamer's `score == -GapOpen` test works).
+    Returns the optimum only — it does not depend on tie-breaking."""
+    NEG = -10 ** 9
+    idx = [go.AA_POS_IN_MATRIX[c] for c in q], [go.AA_POS_IN_MATRIX[c] for c in s]
+    n, k = len(q), len(s)
+    M = [[0] * (k + 1) for _ in range(n + 1)]
+    U = [[NEG] * (k + 1) for _ in range(n + 1)]  # gap run consuming query residues
+    L = [[NEG] * (k + 1) for _ in range(n + 1)]  # gap run consuming subject residues
+    best = 0
+    for i in range(1, n + 1):
+        for j in range(1, k + 1):
+            U[i][j] = max(M[i - 1][j] + gap_open, U[i - 1][j], L[i - 1][j] + gap_open)
+            L[i][j] = max(M[i][j - 1] + gap_open, L[i][j - 1], U[i][j - 1] + gap_open)
+            d = max(M[i - 1][j - 1], U[i - 1][j - 1], L[i - 1][j - 1], 0)
+            M[i][j] = max(0, d + int(m[idx[0][i - 1]][idx[1][j - 1]]))
+            if M[i][j] > best:
+                best = M[i][j]
+    return best
+
+
+def test_alignment_optimum_against_an_independent_dp():
+    rng = np.random.default_rng(21)
+    m = o.blosum62()
+    prm = o.aln_params(1_000_000)
+    checked = 0
+    for _ in range(60):
+        L = int(rng.integers(8, 70))
+        s = [AA[j] for j in rng.integers(0, 20, L)]
+        q = list(s)
+        for _ in range(int(rng.integers(0, 1 + L // 5))):
+            q[int(rng.integers(0, len(q)))] = AA[int(rng.integers(0, 20))]
+        for _ in range(int(rng.integers(0, 3))):
+            p = int(rng.integers(0, len(q)))
+            n = int(rng.integers(1, 9))
+            if rng.random() < 0.5:
+                del q[p:p + n]
+            else:
+                q[p:p] = [AA[j] for j in rng.integers(0, 20, n)]
+        if len(q) < 7:
+            continue
+        q, s = "".join(q), "".join(s)
+        out = o.align(q.encode(), s.encode(), prm)
+        assert out.dp_score == _gotoh_local_optimum(q, s, m), (q, s)
+        checked += 1
+    # unrelated sequences too
+    for _ in range(20):
+        q = "".join(AA[j] for j in rng.integers(0, 20, int(rng.integers(7, 60))))
+        s = "".join(AA[j] for j in rng.integers(0, 20, int(rng.integers(7, 60))))
+        assert o.align(q.encode(), s.encode(), prm).dp_score == _gotoh_local_optimum(q, s, m)
+    assert checked > 40

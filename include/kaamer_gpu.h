@@ -82,6 +82,25 @@ int kaamer_gpu_build_shard(const uint8_t *residues, const uint64_t *seq_off, con
                            uint64_t shard_hi, kaamer_gpu_t **out);
 void kaamer_gpu_close(kaamer_gpu_t *h);
 
+/* ---- streaming builder: the same makedb + indexdb step for record sets that do not fit the device
+ * at once (a 50 M-protein FASTA read in chunks; the synthetic C4 database generated on the device).
+ * The handle's key range [shard_lo, shard_hi) (0,0 = everything) is covered by consecutive PASSES over
+ * sub-ranges; in every pass the caller feeds ALL records again, in device-resident chunks, and the
+ * builder keeps the k-mers that fall into the pass range (build_stream.cu).  Peak memory = table +
+ * max_postings * 4 B + 16 B per pair of ONE pass.  KStats are taken from the first pass.  d_ids NULL:
+ * record i of the chunk gets protein id id_base + i.  The sorted keys/offsets export form is not kept
+ * (kaamer_gpu_index_copy / _save refuse on such a handle).  shareable != 0: table and postings live in
+ * shareable memory (kaamer_gpu_shard_export). ---- */
+typedef struct kaamer_builder kaamer_builder_t;
+int kaamer_gpu_builder_open(int device, uint64_t shard_lo, uint64_t shard_hi, uint64_t max_postings, int shareable,
+                            kaamer_builder_t **out);
+int kaamer_gpu_builder_pass_begin(kaamer_builder_t *b, uint64_t pass_lo, uint64_t pass_hi, uint64_t max_pairs);
+int kaamer_gpu_builder_add_device(kaamer_builder_t *b, const uint8_t *d_residues, const uint64_t *d_seq_off,
+                                  const uint32_t *d_ids, uint32_t id_base, uint64_t n_records, void *stream);
+int kaamer_gpu_builder_pass_end(kaamer_builder_t *b, void *stream);
+int kaamer_gpu_builder_finish(kaamer_builder_t *b, kaamer_gpu_t **out); /* consumes b */
+void kaamer_gpu_builder_abort(kaamer_builder_t *b);
+
 /* KStats (api/server.go:125-132 /api/dbinfo; feeds the e-value, pkg/align/align.go:141) */
 int kaamer_gpu_dbstats(kaamer_gpu_t *h, uint64_t *n_proteins, uint64_t *n_aa, uint64_t *n_kmers);
 /* export of the resident index (sizes, then copy into caller buffers; also `.kidx` writer) */
@@ -261,6 +280,11 @@ int kaamer_gpu_shard_export(kaamer_gpu_t *h, kaamer_shard_handle *out);
  * their owner shard) and only the posting lists — the part that grows with the database — stay
  * sharded.  The first probe of every lookup is then local; NVLink carries posting lists only. */
 #define KAAMER_ATTACH_REPLICATE_TABLE 2
+/* (with KAAMER_ATTACH_REPLICATE_TABLE) also copy the posting lists of every shard into local HBM: the index
+ * was BUILT sharded (every GPU sorted its own key range) but is SEARCHED replicated — what the north star
+ * prescribes whenever the whole index fits one GPU (C4: 14.5 GB table + ~59 GB postings of 180 GB).
+ * After the attach no search touches NVLink. */
+#define KAAMER_ATTACH_REPLICATE_POSTINGS 4
 int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards, int n_shards, int flags);
 int kaamer_gpu_detach_shards(kaamer_gpu_t *h);
 
@@ -288,6 +312,22 @@ int64_t kaamer_host_format_positions(const uint8_t *positions, uint64_t n, int w
 int kaamer_host_read_fasta(const char *path, int is_protein, int pinned, kaamer_query_batch **out);
 int kaamer_host_read_fastq(const char *path, int pinned, kaamer_query_batch **out);
 void kaamer_host_free_queries(kaamer_query_batch *b);
+
+/* ---- synthetic C4 workload (bench / tests; include/kaamer_synth_spec.h is the specification, the CPU twin
+ * is oracle/synth_oracle.cpp).  Counter-based: record i and query j are pure functions of (seed, index).
+ * All pointers are device pointers of the current device; d_seq_off[n+1] is relative to d_res. ---- */
+typedef struct kaamer_synth_cfg {
+  uint64_t seed;
+  uint64_t n_proteins;
+} kaamer_synth_cfg;
+int kaamer_synth_record_lengths(const kaamer_synth_cfg *cfg, uint64_t first, uint64_t n, uint32_t *d_len,
+                                void *stream);
+int kaamer_synth_record_residues(const kaamer_synth_cfg *cfg, uint64_t first, uint64_t n, const uint64_t *d_seq_off,
+                                 uint8_t *d_res, void *stream);
+int kaamer_synth_query_lengths(const kaamer_synth_cfg *cfg, uint32_t batch, uint64_t first, uint64_t n,
+                               uint32_t *d_len, void *stream);
+int kaamer_synth_query_residues(const kaamer_synth_cfg *cfg, uint32_t batch, uint64_t first, uint64_t n,
+                                const uint64_t *d_seq_off, uint8_t *d_res, void *stream);
 
 /* pinned host buffers for callers that want zero-staging H2D (cgo: C.kaamer_gpu_pinned_alloc) */
 int kaamer_gpu_pinned_alloc(uint64_t bytes, void **out);

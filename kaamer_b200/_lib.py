@@ -145,6 +145,10 @@ class ShardHandle(C.Structure):
     ]
 
 
+class SynthCfg(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("n_proteins", C.c_uint64)]
+
+
 class QueryBatch(C.Structure):
     _fields_ = [
         ("n_queries", C.c_uint32),
@@ -168,6 +172,16 @@ SYMBOLS = [
     "kaamer_gpu_build",
     "kaamer_gpu_build_shard",
     "kaamer_gpu_close",
+    "kaamer_gpu_builder_open",
+    "kaamer_gpu_builder_pass_begin",
+    "kaamer_gpu_builder_add_device",
+    "kaamer_gpu_builder_pass_end",
+    "kaamer_gpu_builder_finish",
+    "kaamer_gpu_builder_abort",
+    "kaamer_synth_record_lengths",
+    "kaamer_synth_record_residues",
+    "kaamer_synth_query_lengths",
+    "kaamer_synth_query_residues",
     "kaamer_gpu_dbstats",
     "kaamer_gpu_index_sizes",
     "kaamer_gpu_index_copy",
@@ -225,6 +239,18 @@ def lib() -> C.CDLL:
     L.kaamer_gpu_build_shard.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(vp)]
     L.kaamer_gpu_close.argtypes = [vp]
     L.kaamer_gpu_close.restype = None
+    L.kaamer_gpu_builder_open.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(vp)]
+    L.kaamer_gpu_builder_pass_begin.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64]
+    L.kaamer_gpu_builder_add_device.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint64, vp]
+    L.kaamer_gpu_builder_pass_end.argtypes = [vp, vp]
+    L.kaamer_gpu_builder_finish.argtypes = [vp, C.POINTER(vp)]
+    L.kaamer_gpu_builder_abort.argtypes = [vp]
+    L.kaamer_gpu_builder_abort.restype = None
+    scp = C.POINTER(SynthCfg)
+    L.kaamer_synth_record_lengths.argtypes = [scp, C.c_uint64, C.c_uint64, vp, vp]
+    L.kaamer_synth_record_residues.argtypes = [scp, C.c_uint64, C.c_uint64, vp, vp, vp]
+    L.kaamer_synth_query_lengths.argtypes = [scp, C.c_uint32, C.c_uint64, C.c_uint64, vp, vp]
+    L.kaamer_synth_query_residues.argtypes = [scp, C.c_uint32, C.c_uint64, C.c_uint64, vp, vp, vp]
     u64p = C.POINTER(C.c_uint64)
     L.kaamer_gpu_dbstats.argtypes = [vp, u64p, u64p, u64p]
     L.kaamer_gpu_index_sizes.argtypes = [vp, u64p, u64p]

@@ -169,6 +169,9 @@ static void destroy_handle(kaamer_gpu *h) {
   delete h;
 }
 
+int new_handle_for_builder(int device, kaamer_gpu **out) { return new_handle(device, out); }
+void destroy_handle_for_builder(kaamer_gpu *h) { destroy_handle(h); }
+
 }  // namespace kaamer
 
 using namespace kaamer;
@@ -576,6 +579,10 @@ int kaamer_gpu_index_copy(kaamer_gpu_t *h, uint32_t *keys, uint64_t *offsets, ui
   std::lock_guard<std::mutex> lk(h->mu);
   KCUDA(cudaSetDevice(h->device));
   DevIndex &ix = h->idx;
+  if (ix.n_keys && !ix.keys) {
+    set_error("this index was built by the streaming builder: the sorted keys/offsets export form was not kept");
+    return KAAMER_ERR_ARG;
+  }
   if (keys && ix.n_keys) KCUDA(cudaMemcpy(keys, ix.keys, (size_t)ix.n_keys * 4, cudaMemcpyDeviceToHost));
   if (offsets) KCUDA(cudaMemcpy(offsets, ix.offsets, (size_t)(ix.n_keys + 1) * 8, cudaMemcpyDeviceToHost));
   if (postings && ix.n_postings)

@@ -110,6 +110,14 @@ static int fill_table(kaamer_gpu *h) {
   return KAAMER_OK;
 }
 
+// table + postings of a handle that a streaming builder fills pass by pass (build_stream.cu)
+int alloc_index_storage(kaamer_gpu *h, uint64_t d_lo, uint64_t d_hi, uint64_t n_postings, bool shareable) {
+  KCHECK(alloc_table(h, d_lo, d_hi, shareable));
+  KCHECK(alloc_postings(h, n_postings, shareable));
+  KCUDA(cudaStreamSynchronize(h->stream));
+  return KAAMER_OK;
+}
+
 void index_release(kaamer_gpu *h) {
   DevIndex &ix = h->idx;
   if (ix.vm_table.ptr) vmm_free(&ix.vm_table);

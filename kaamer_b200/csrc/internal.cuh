@@ -367,7 +367,7 @@ struct kaamer_gpu {
   bool profile = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // [0..2] search size classes W, M, G; [3] Smith-Waterman; [4] H2D of a host call; [5] CSR
-  // compaction + D2H; [6] reserved; [7] translation/ORF kernels
+  // compaction + D2H; [6] search class D (dense databases); [7] translation/ORF kernels
   double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t prof_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // host-call pipeline: H2D of chunk c+1 on copy_stream overlaps the search of chunk c
@@ -378,6 +378,8 @@ struct kaamer_gpu {
   std::vector<kaamer::ProfSpan> prof_pending;
   double prof_host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // per-handle (= per-device context) one-time setup: constant tables and kernel attributes
+  uint32_t ghash_slots = 1u << 20;  // class G histogram slots per CTA; grown on ST_GHASH_OVERFLOW (search.cu)
+  size_t dense_smem_set = 0;        // dynamic shared memory the class-D kernels are configured for
   bool aln_ready = false, shard_attrs_ready = false;  // wall clock of host-call phases (kaamer_gpu_profile_host_read)
 };
 

@@ -29,6 +29,7 @@
 #include "internal.cuh"
 
 #include "search_common.cuh"
+#include "search_dense.cuh"
 
 namespace kaamer {
 
@@ -58,11 +59,14 @@ __global__ void k_classify(SearchArgs a) {
     // used: the warp-per-query kernels are bound by the per-warp counting work, W2's larger
     // per-warp state halves the resident warps and it ran at 10 G lookups/s against 24 G/s for
     // the CTA-per-query class M (profiles/r1_notes.md).
-    if (go) cls = K <= a.w_maxk ? 0 : (K <= a.m_maxk ? 1 : 2);
+    if (go) {
+      if (a.dense) cls = (a.kmin[q] >= 3u && K <= D_MAXK) ? 4 : 2;
+      else cls = K <= a.w_maxk ? 0 : (K <= a.m_maxk ? 1 : 2);
+    }
   }
   // warp-aggregated append to the class lists (one atomic per warp and class)
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 5; ++c) {
     const unsigned mask = __ballot_sync(0xFFFFFFFFu, cls == c);
     if (mask == 0) continue;
     const int leader = __ffs(mask) - 1;
@@ -109,12 +113,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_search_wt(SearchArgs a) {
   // 10x, a static split left the SMs idle for ~20 % of the kernel); the next index is
   // fetched one query ahead so its latency is hidden
   uint32_t it_next = 0;
-  if (lane == 0) it_next = atomicAdd(&a.list_count[4 + CLS], 1u);
+  if (lane == 0) it_next = atomicAdd(&a.list_count[5 + CLS], 1u);
   (void)nwarps;
   for (;;) {
     const uint32_t it = __shfl_sync(0xFFFFFFFFu, it_next, 0);
     if (it >= count) break;
-    if (lane == 0) it_next = atomicAdd(&a.list_count[4 + CLS], 1u);
+    if (lane == 0) it_next = atomicAdd(&a.list_count[5 + CLS], 1u);
     const uint32_t q = a.lists[(size_t)CLS * a.nq + it];
     const uint64_t b = a.off[q];
     const int len = (int)(a.off[q + 1] - b);
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(M_THREADS, M_CTAS) k_search_m(SearchArgs a) {
   unsigned long long my_incr = 0, my_lookups = 0;
   __shared__ uint32_t s_it;
   for (;;) {
-    if (tid == 0) s_it = atomicAdd(&a.list_count[5], 1u);
+    if (tid == 0) s_it = atomicAdd(&a.list_count[6], 1u);
     __syncthreads();
     const uint32_t it = s_it;
     if (it >= count) break;
@@ -426,6 +430,7 @@ __global__ void __launch_bounds__(GT) k_search_g(SearchArgs a) {
     atomicAdd(&s_total, tot);
     __syncthreads();
     const unsigned long long T = s_total;
+    if (tid == 0 && 2 * T > (unsigned long long)HG) atomicMax(&a.counters[CNT_GNEED], 2 * T);
     uint32_t Hq = 1024;
     while (Hq < HG && (unsigned long long)Hq < 2 * T) Hq <<= 1;
     int log2h = 0;
@@ -584,8 +589,14 @@ void profile_end(kaamer_gpu *h, cudaStream_t st) {
 // the next one and searched again, so on dense databases the limits must come down (measured on a
 // 2 M-protein database with fixed limits: class W spent 2.9 ms on 7.8 M lookups, most of them repeated
 // in class M).  Swiss-Prot scale (p = 0.53) keeps the full 512 / 2048.
-static void class_limits(const kaamer_gpu *h, int *w_maxk, int *m_maxk) {
+static void class_limits(const kaamer_gpu *h, int *w_maxk, int *m_maxk, int *dense) {
   double p = (double)h->idx.n_kmers * 2.7e-9;
+  // Dense database: above ~2 background postings per query k-mer the shared-memory histograms of classes W
+  // and M overflow for ordinary queries, and class D (search_dense.cuh), whose cost per posting is a byte
+  // load and a byte store instead of an atomic, takes every query.  KAAMER_DENSE=0/1 forces the choice
+  // (A/B measurements, parity tests).
+  *dense = p >= 2.0 ? 1 : 0;
+  if (const char *env = getenv("KAAMER_DENSE")) *dense = atoi(env) != 0 ? 1 : 0;
   if (p < 0.5) p = 0.5;
   double w = 0.55 * W_H / p, m = 0.55 * M_H / p;
   *w_maxk = w >= W_MAXK ? W_MAXK : (w < 32 ? 32 : (int)w);
@@ -601,9 +612,14 @@ static void class_limits(const kaamer_gpu *h, int *w_maxk, int *m_maxk) {
   }
 }
 
-static uint32_t ghash_slots_for(kaamer_gpu *h) {
-  (void)h;
-  return 1u << 20;
+// bytes per byte map of class D (test / tuning hook KAAMER_D_MAPKB)
+static uint32_t dense_mapb() {
+  uint32_t b = D_MAPB_DEFAULT;
+  if (const char *env = getenv("KAAMER_D_MAPKB")) {
+    const int kb = atoi(env);
+    if (kb >= 1 && kb <= 96) b = (uint32_t)kb * 1024u;
+  }
+  return b;
 }
 
 int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, uint32_t nq,
@@ -622,9 +638,9 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   }
   if (nq == 0) return KAAMER_OK;
   SearchWorkspace &ws = h->ws;
-  KCHECK(ws.lists.ensure((size_t)4 * nq + 16));
+  KCHECK(ws.lists.ensure((size_t)5 * nq + 16));
   KCHECK(ws.kmin.ensure(nq));
-  uint32_t *list_count = ws.lists.p + (size_t)4 * nq;
+  uint32_t *list_count = ws.lists.p + (size_t)5 * nq;
   SearchArgs a{};
   a.table = h->idx.table;
   a.d_lo = h->idx.d_lo;
@@ -645,19 +661,28 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   a.counters = (unsigned long long *)out->counters;
   a.lists = ws.lists.p;
   a.list_count = list_count;
-  a.ghash_slots = ghash_slots_for(h);
+  a.ghash_slots = h->ghash_slots;
   a.nt_mode = nt_mode;
   a.any0 = d_any0;
   a.peer = h->idx.d_peer;
   a.filter = h->idx.filter;
-  class_limits(h, &a.w_maxk, &a.m_maxk);
+  class_limits(h, &a.w_maxk, &a.m_maxk, &a.dense);
+  a.d_mapb = dense_mapb();
+  const size_t d_smem = ((sizeof(DenseSmem) + 15) & ~(size_t)15) + 2 * (size_t)a.d_mapb;
+  if (a.dense && h->dense_smem_set != d_smem) {
+    KCUDA(cudaFuncSetAttribute(k_search_d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d_smem));
+    KCUDA(cudaFuncSetAttribute(k_search_d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d_smem));
+    h->dense_smem_set = d_smem;
+  }
   // Class G: one CTA per query, histogram in a per-CTA global scratch.  At Swiss-Prot density it holds a
   // handful of very long queries and gets one CTA per SM (it runs underneath W and M and must leave them
   // their shared memory); on a dense database, where the lowered class limits send many queries here,
   // four CTAs of 256 threads per SM (measured with every C3 query forced into class G: 14.2 ms at one
   // 512-thread CTA per SM, 7.5 ms at two).
-  const bool dense = a.w_maxk < W_MAXK || a.m_maxk < M_MAXK;
-  const int g_ctas = h->sm_count * (dense ? 4 : 1);
+  const bool dense = a.dense || a.w_maxk < W_MAXK || a.m_maxk < M_MAXK;
+  int g_ctas = h->sm_count * (dense ? 4 : 1);
+  // a grown histogram (retry after ST_GHASH_OVERFLOW) gets fewer CTAs: at most 8 GB of scratch
+  while (g_ctas > 1 && (size_t)2 * g_ctas * 3 * a.ghash_slots * 4 > ((size_t)8 << 30)) g_ctas = (g_ctas + 1) / 2;
   auto launch_g = [&](cudaStream_t s_) {
     if (dense) {
       if (peer) k_search_g<true, 256><<<g_ctas, 256, 0, s_>>>(a);
@@ -669,7 +694,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   };
   KCHECK(ws.ghash.ensure((size_t)2 * g_ctas * 3 * a.ghash_slots));
   a.ghash = ws.ghash.p;
-  KCUDA(cudaMemsetAsync(list_count, 0, 8 * sizeof(uint32_t), st));
+  KCUDA(cudaMemsetAsync(list_count, 0, 10 * sizeof(uint32_t), st));
   KCUDA(cudaMemsetAsync(out->counters, 0, CNT_N * sizeof(uint64_t), st));
   if (d_prev_counters)  // chunked host call: the pool cursor continues where the previous chunk stopped
     KCUDA(cudaMemcpyAsync(out->counters + CNT_POOL, d_prev_counters + CNT_POOL, 8, cudaMemcpyDeviceToDevice, st));
@@ -688,20 +713,47 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   launch_g(side);
   profile_end(h, side);
   KCUDA(cudaEventRecord(h->chunk_ev[7], side));
-  profile_begin(h, st, 0);
-  if (peer) k_search_wt<W_H, W_MAXK, W_WARPS, 5, 0, true><<<w_grid, W_WARPS * 32, 0, st>>>(a);
-  else k_search_wt<W_H, W_MAXK, W_WARPS, 5, 0, false><<<w_grid, W_WARPS * 32, 0, st>>>(a);
-  profile_end(h, st);
-  profile_begin(h, st, 1);
-  if (peer) k_search_m<true><<<m_grid < nq ? m_grid : nq, M_THREADS, 0, st>>>(a);
-  else k_search_m<false><<<m_grid < nq ? m_grid : nq, M_THREADS, 0, st>>>(a);
-  profile_end(h, st);
+  if (a.dense) {
+    // class D takes every query (k_classify); persistent grid, as many CTAs per SM as the byte maps allow
+    int d_per_sm = 1;
+    KCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d_per_sm, k_search_d<false>, D_THREADS, d_smem));
+    if (d_per_sm < 1) d_per_sm = 1;
+    const unsigned d_grid = (unsigned)h->sm_count * (unsigned)d_per_sm;
+    profile_begin(h, st, 6);
+    if (peer) k_search_d<true><<<d_grid, D_THREADS, d_smem, st>>>(a);
+    else k_search_d<false><<<d_grid, D_THREADS, d_smem, st>>>(a);
+    profile_end(h, st);
+  } else {
+    profile_begin(h, st, 0);
+    if (peer) k_search_wt<W_H, W_MAXK, W_WARPS, 5, 0, true><<<w_grid, W_WARPS * 32, 0, st>>>(a);
+    else k_search_wt<W_H, W_MAXK, W_WARPS, 5, 0, false><<<w_grid, W_WARPS * 32, 0, st>>>(a);
+    profile_end(h, st);
+    profile_begin(h, st, 1);
+    if (peer) k_search_m<true><<<m_grid < nq ? m_grid : nq, M_THREADS, 0, st>>>(a);
+    else k_search_m<false><<<m_grid < nq ? m_grid : nq, M_THREADS, 0, st>>>(a);
+    profile_end(h, st);
+  }
   a.g_list = 3;
   a.ghash = ws.ghash.p + (size_t)g_ctas * 3 * a.ghash_slots;  // own scratch: the first G launch may still run
   launch_g(st);
   KCUDA(cudaStreamWaitEvent(st, h->chunk_ev[7], 0));
-  h->prof_all_launches += 5;
+  h->prof_all_launches += a.dense ? 4 : 5;
   KCUDA(cudaGetLastError());
+  return KAAMER_OK;
+}
+
+// A class-G query touched more distinct subjects than the global-memory histogram holds: grow the
+// histogram to what the batch asked for (counters[CNT_GNEED] = 2 x the largest posting total) and let the
+// caller run the batch again.  The reference returns results for such queries; so do we.
+int grow_ghash(kaamer_gpu *h, uint64_t need) {
+  uint64_t slots = h->ghash_slots;
+  while (slots < need || slots <= h->ghash_slots) slots <<= 1;
+  if (slots > (1ull << 30)) {
+    set_error("a query matched more distinct subjects (%llu) than a 2^30-slot histogram holds",
+              (unsigned long long)(need / 2));
+    return KAAMER_ERR_LIMIT;
+  }
+  h->ghash_slots = (uint32_t)slots;
   return KAAMER_OK;
 }
 
@@ -732,12 +784,15 @@ int search_counted(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *d_off, u
     KCUDA(cudaStreamSynchronize(st));
     uint64_t status = ws.h_counters.p[CNT_STATUS];
     if (status & ST_GHASH_OVERFLOW) {
-      set_error("a query matched more distinct subjects than the class-G histogram holds (%u slots)",
-                ghash_slots_for(h));
-      return KAAMER_ERR_LIMIT;
+      if (attempt >= 6) {
+        set_error("class-G histogram overflow after %d attempts", attempt + 1);
+        return KAAMER_ERR_LIMIT;
+      }
+      KCHECK(grow_ghash(h, ws.h_counters.p[CNT_GNEED]));
+      continue;
     }
     if (status & ST_POOL_OVERFLOW) {
-      if (attempt >= 3) {
+      if (attempt >= 6) {
         set_error("hit pool overflow after %d attempts", attempt + 1);
         return KAAMER_ERR_LIMIT;
       }
@@ -881,19 +936,23 @@ int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off,
     HCUDA(cudaMemcpyAsync(hits->size_in_kmer, ws.size_in_kmer.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     profile_end(h, st);
     HCUDA(cudaStreamSynchronize(st));
-    uint64_t status = 0, lookups = 0, incr = 0;
+    uint64_t status = 0, lookups = 0, incr = 0, gneed = 0;
     for (int c = 0; c < n_chunks; ++c) {
       status |= ws.h_counters.p[(size_t)c * CNT_N + CNT_STATUS];
+      gneed = std::max<uint64_t>(gneed, ws.h_counters.p[(size_t)c * CNT_N + CNT_GNEED]);
       lookups += ws.h_counters.p[(size_t)c * CNT_N + CNT_LOOKUPS];
       incr += ws.h_counters.p[(size_t)c * CNT_N + CNT_INCR];
     }
     if (status & ST_GHASH_OVERFLOW) {
-      set_error("a query matched more distinct subjects than the class-G histogram holds (%u slots)",
-                ghash_slots_for(h));
-      return fail(KAAMER_ERR_LIMIT);
+      if (attempt >= 6) {
+        set_error("class-G histogram overflow after %d attempts", attempt + 1);
+        return fail(KAAMER_ERR_LIMIT);
+      }
+      HCHECK(grow_ghash(h, gneed));
+      continue;
     }
     if (status & ST_POOL_OVERFLOW) {
-      if (attempt >= 3) {
+      if (attempt >= 6) {
         set_error("hit pool overflow after %d attempts", attempt + 1);
         return fail(KAAMER_ERR_LIMIT);
       }

@@ -8,7 +8,7 @@
 namespace kaamer {
 
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
-enum { CNT_POOL = 0, CNT_LOOKUPS = 1, CNT_INCR = 2, CNT_STATUS = 3, CNT_CLS_LOOKUPS = 4, CNT_CLS_INCR = 8, CNT_N = 16 };
+enum { CNT_POOL = 0, CNT_LOOKUPS = 1, CNT_INCR = 2, CNT_STATUS = 3, CNT_CLS_LOOKUPS = 4, CNT_CLS_INCR = 8, CNT_GNEED = 12, CNT_N = 16 };
 enum { ST_POOL_OVERFLOW = 1, ST_GHASH_OVERFLOW = 2 };
 
 // size classes by SizeInKmer
@@ -35,8 +35,8 @@ struct SearchArgs {
   uint64_t *pool;
   uint64_t pool_cap;
   unsigned long long *counters;
-  uint32_t *lists;       // [4][nq]: W, M, G, hand-offs from M to G
-  uint32_t *list_count;  // [8]: [0..3] list sizes (W, M, G, M->G hand-offs), [4..7] work cursors (dynamic scheduling)
+  uint32_t *lists;       // [5][nq]: W, M, G, hand-offs to G (from M or D), D
+  uint32_t *list_count;  // [10]: [0..4] list sizes, [5..9] work cursors (dynamic scheduling)
   uint32_t *ghash;       // class G scratch: per CTA [keys HG][cnt HG][cand HG]
   uint32_t ghash_slots;  // HG (power of two)
   // nucleotide / reads mode (search_nucleotide.go:76-124): queries are ORFs, the candidate
@@ -53,6 +53,10 @@ struct SearchArgs {
   // W, up to m_maxk to class M — at most W_MAXK / M_MAXK, less when the database is so dense that a
   // query of that size would overflow the class's histogram and be searched twice
   int w_maxk, m_maxk;
+  // dense database (search.cu class_limits): every query goes to class D (search_dense.cuh), or to class G
+  // when its threshold is too small for D's filter; d_mapb = bytes per byte map of class D
+  int dense;
+  uint32_t d_mapb;
 };
 
 // Copy src[0, len) into shared memory with aligned 16-byte loads (one request per 16 residues:

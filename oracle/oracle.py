@@ -17,10 +17,10 @@ _SO = os.path.join(_HERE, "libkaamer_oracle.so")
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "kaamer_oracle.cpp")
-    hdr = os.path.join(_HERE, "kaamer_oracle.h")
+    deps = [os.path.join(_HERE, "kaamer_oracle.cpp"), os.path.join(_HERE, "kaamer_oracle.h"),
+            os.path.join(_HERE, "synth_oracle.cpp"), os.path.join(_HERE, "..", "include", "kaamer_synth_spec.h")]
     stale = (not os.path.exists(_SO)) or any(
-        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr)
+        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in deps
     )
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
@@ -156,6 +156,15 @@ def lib():
     L.ko_evalue.argtypes = [C.c_int32, C.c_uint64, C.c_double]
     L.ko_format_positions.restype = C.c_int32
     L.ko_format_positions.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
+    L.kso_record.restype = C.c_uint32
+    L.kso_record.argtypes = [C.c_uint64, C.c_uint64, vp, C.c_uint32]
+    L.kso_record_meta.argtypes = [C.c_uint64, C.c_uint64, u64p, u32p, u32p]
+    L.kso_query.restype = C.c_uint32
+    L.kso_query.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, vp, C.c_uint32, u64p]
+    L.kso_restricted_index.restype = C.c_int
+    L.kso_restricted_index.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, vp, C.c_uint64, C.c_int, vp,
+                                       C.POINTER(u32p), u64p]
+    L.kso_free.argtypes = [vp]
     _lib = L
     return L
 
@@ -391,3 +400,49 @@ def format_positions(pos, with_alignment=False) -> str:
     buf = C.create_string_buffer(cap)
     lib().ko_format_positions(_vp(a), len(a), int(with_alignment), buf, cap)
     return buf.value.decode()
+
+
+# ---- CPU twin of the synthetic C4 generator (oracle/synth_oracle.cpp, include/kaamer_synth_spec.h) ----
+def synth_record(seed: int, i: int) -> bytes:
+    L = lib()
+    n = L.kso_record(seed, i, None, 0)
+    buf = np.zeros(n, np.uint8)
+    L.kso_record(seed, i, _vp(buf), n)
+    return buf.tobytes()
+
+
+def synth_record_meta(seed: int, i: int):
+    f, ln, th = C.c_uint64(), C.c_uint32(), C.c_uint32()
+    lib().kso_record_meta(seed, i, C.byref(f), C.byref(ln), C.byref(th))
+    return f.value, ln.value, th.value
+
+
+def synth_query(seed: int, n_proteins: int, j: int, batch: int = 0):
+    """-> (letters, record index the query was sampled from)"""
+    L = lib()
+    rec = C.c_uint64()
+    n = L.kso_query(seed, n_proteins, j, batch, None, 0, C.byref(rec))
+    buf = np.zeros(n, np.uint8)
+    L.kso_query(seed, n_proteins, j, batch, _vp(buf), n, C.byref(rec))
+    return buf.tobytes(), rec.value
+
+
+def synth_restricted_index(seed: int, n_proteins: int, query_seqs, n_threads: int = 1, id_base: int = 0) -> "Index":
+    """The index of the whole synthetic database RESTRICTED to the k-mers the given queries look up, built by
+    streaming the generator over every record (what the C4 parity check searches the sample against)."""
+    keys = sorted({encode_kmer(s[k:k + 7]) for s in query_seqs for k in range(max(0, len(s) - 6))})
+    keys = np.array(keys, dtype=np.uint32)
+    offsets = np.zeros(len(keys) + 1, dtype=np.uint64)
+    pp = C.POINTER(C.c_uint32)()
+    stats = (C.c_uint64 * 3)()
+    rc = lib().kso_restricted_index(seed, n_proteins, id_base, _vp(keys), len(keys), n_threads, _vp(offsets),
+                                    C.byref(pp), stats)
+    assert rc == 0
+    n = int(offsets[-1])
+    postings = _np(pp, n, np.uint32)
+    lib().kso_free(pp)
+    keep = np.flatnonzero(offsets[1:] > offsets[:-1])  # a key without postings is a miss (search.go:421-423)
+    lens = (offsets[1:] - offsets[:-1])[keep]
+    off2 = np.zeros(len(keep) + 1, dtype=np.uint64)
+    off2[1:] = np.cumsum(lens)
+    return Index.from_arrays(keys[keep], off2, postings, stats[0], stats[1], stats[2])

@@ -22,7 +22,7 @@ def built():
 def _header_symbols():
     hdr = open(os.path.join(ROOT, "include", "kaamer_gpu.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(kaamer_(?:gpu|host)_\w+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"\b(kaamer_(?:gpu|host|synth)_\w+)\s*\(", hdr)))
 
 
 def test_library_exports_every_declared_symbol():

@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include <algorithm>
+#include <exception>
 #include <unistd.h>
 
 #include "internal.cuh"
@@ -152,6 +153,8 @@ static void destroy_handle(kaamer_gpu *h) {
   h->idx.presence = nullptr;
   if (h->idx.full_table) cudaFree(h->idx.full_table);
   h->idx.full_table = nullptr;
+  if (h->idx.repl_postings) cudaFree(h->idx.repl_postings);
+  h->idx.repl_postings = nullptr;
   if (h->idx.d_peer) cudaFree(h->idx.d_peer);
   h->idx.d_peer = nullptr;
   index_release(h);
@@ -181,7 +184,7 @@ extern "C" {
 const char *kaamer_gpu_last_error(void) { return g_err; }
 const char *kaamer_gpu_version(void) { return "kaamer_b200 0.1 (sm_100a)"; }
 
-int kaamer_gpu_open_view(const kaamer_index_view *view, int device, kaamer_gpu_t **out) {
+static int kaamer_gpu_open_view_impl(const kaamer_index_view *view, int device, kaamer_gpu_t **out) {
   if (!out || !view) {
     set_error("null argument");
     return KAAMER_ERR_ARG;
@@ -197,6 +200,9 @@ int kaamer_gpu_open_view(const kaamer_index_view *view, int device, kaamer_gpu_t
   *out = h;
   return KAAMER_OK;
 }
+int kaamer_gpu_open_view(const kaamer_index_view *view, int device, kaamer_gpu_t **out) {
+  return ::kaamer::guarded([&]() -> int { return kaamer_gpu_open_view_impl(view, device, out); });
+}
 
 // the sections of a .kidx file in host memory
 struct KidxFile {
@@ -206,35 +212,88 @@ struct KidxFile {
   std::vector<uint8_t> pres;
 };
 
+// A `.kidx` file is untrusted input: every section size is checked against the file size BEFORE anything
+// is allocated, and the contents are checked for the invariants the kernels rely on (keys strictly
+// ascending EncodeKmer outputs, offsets non-decreasing and ending at n_postings, protein offsets
+// monotonic and ending at n_residues) — a truncated or corrupt file yields KAAMER_ERR_FORMAT, never an
+// exception through the C boundary or an out-of-bounds read on the device.
 static int read_kidx(const char *path, KidxFile *k, bool want_postings, bool want_proteins) {
   FILE *f = fopen(path, "rb");
   if (!f) {
     set_error("cannot open %s", path);
     return KAAMER_ERR_IO;
   }
+  auto bad = [&](const char *what) {
+    fclose(f);
+    set_error("%s: %s", path, what);
+    return KAAMER_ERR_FORMAT;
+  };
   KidxHeader &hd = k->hd;
   if (fread(&hd, 1, sizeof hd, f) != sizeof hd || memcmp(hd.magic, "KIDX0001", 8) != 0 || hd.version != 1 ||
-      hd.k != KAAMER_KMER_SIZE) {
-    fclose(f);
-    set_error("%s is not a kidx v1 (k=7) file", path);
-    return KAAMER_ERR_FORMAT;
-  }
-  k->keys.resize((size_t)hd.n_keys);
-  k->offsets.resize((size_t)hd.n_keys + 1);
-  int rc = read_section(f, k->keys.data(), k->keys.size() * 4);
-  if (rc == KAAMER_OK) rc = read_section(f, k->offsets.data(), k->offsets.size() * 8);
-  if (rc == KAAMER_OK && want_postings) {
-    k->postings.resize((size_t)hd.n_postings);
-    rc = read_section(f, k->postings.data(), k->postings.size() * 4);
-    if (rc == KAAMER_OK && want_proteins && (hd.flags & 1)) {
-      k->poff.resize((size_t)hd.max_protein_id + 2);
-      k->pres.resize((size_t)hd.n_residues);
-      rc = read_section(f, k->poff.data(), k->poff.size() * 8);
-      if (rc == KAAMER_OK) rc = read_section(f, k->pres.data(), k->pres.size());
+      hd.k != KAAMER_KMER_SIZE)
+    return bad("not a kidx v1 (k=7) file");
+  if (fseek(f, 0, SEEK_END) != 0) return bad("seek failed");
+  const long long file_size = ftell(f);
+  if (file_size < 0 || fseek(f, (long)sizeof hd, SEEK_SET) != 0) return bad("seek failed");
+  const bool has_prot = (hd.flags & 1) != 0;
+  // (all counts are bounded by the file size first, so the products below cannot overflow)
+  const unsigned long long fs = (unsigned long long)file_size;
+  if (hd.n_keys > fs / 4 || hd.n_postings > fs / 4 || hd.n_residues > fs || (has_prot && hd.max_protein_id > fs / 8))
+    return bad("header counts exceed the file size (truncated or corrupt)");
+  unsigned long long need = sizeof hd + pad64((size_t)hd.n_keys * 4) + pad64(((size_t)hd.n_keys + 1) * 8) +
+                            pad64((size_t)hd.n_postings * 4);
+  if (has_prot) need += pad64(((size_t)hd.max_protein_id + 2) * 8) + (size_t)hd.n_residues;
+  if (need > fs) return bad("sections exceed the file size (truncated or corrupt)");
+  if (hd.n_postings > ENTRY_VALUE_MASK) return bad("too many postings");
+  int rc = KAAMER_OK;
+  try {
+    k->keys.resize((size_t)hd.n_keys);
+    k->offsets.resize((size_t)hd.n_keys + 1);
+    rc = read_section(f, k->keys.data(), k->keys.size() * 4);
+    if (rc == KAAMER_OK) rc = read_section(f, k->offsets.data(), k->offsets.size() * 8);
+    if (rc == KAAMER_OK && want_postings) {
+      k->postings.resize((size_t)hd.n_postings);
+      rc = read_section(f, k->postings.data(), k->postings.size() * 4);
+      if (rc == KAAMER_OK && want_proteins && has_prot) {
+        k->poff.resize((size_t)hd.max_protein_id + 2);
+        k->pres.resize((size_t)hd.n_residues);
+        rc = read_section(f, k->poff.data(), k->poff.size() * 8);
+        if (rc == KAAMER_OK && hd.n_residues && fread(k->pres.data(), 1, k->pres.size(), f) != k->pres.size()) {
+          set_error("kidx: short read");
+          rc = KAAMER_ERR_IO;
+        }
+      }
     }
+  } catch (const std::exception &e) {
+    fclose(f);
+    set_error("%s: out of host memory reading the index (%s)", path, e.what());
+    return KAAMER_ERR_NOMEM;
   }
+  if (rc != KAAMER_OK) {
+    fclose(f);
+    return rc;
+  }
+  // content invariants
+  uint32_t prev_d = 0;
+  for (size_t i = 0; i < k->keys.size(); ++i) {
+    uint32_t d = 0;
+    if (!dense_from_key(k->keys[i], &d)) return bad("a key is not an EncodeKmer output");
+    if (i && d <= prev_d) return bad("keys are not strictly ascending");
+    prev_d = d;
+    if (k->offsets[i + 1] < k->offsets[i]) return bad("offsets are not non-decreasing");
+  }
+  if (k->offsets[0] != 0 || k->offsets[k->keys.size()] != hd.n_postings) return bad("offsets do not span [0, n_postings]");
+  if (!k->poff.empty()) {
+    if (k->poff[0] != 0) return bad("protein offsets do not start at 0");
+    for (size_t i = 1; i < k->poff.size(); ++i)
+      if (k->poff[i] < k->poff[i - 1]) return bad("protein offsets are not monotonic");
+    if (k->poff.back() != hd.n_residues) return bad("protein offsets do not end at n_residues");
+  }
+  if (want_postings)
+    for (size_t i = 0; i < k->postings.size(); ++i)
+      if (k->postings[i] > hd.max_protein_id) return bad("a posting exceeds max_protein_id");
   fclose(f);
-  return rc;
+  return KAAMER_OK;
 }
 
 // first key of the (ascending) key array whose dense code is >= d; key order == dense order
@@ -290,16 +349,22 @@ static int open_kidx_range(const char *path, int device, uint64_t shard_lo, uint
   return kaamer_gpu_open_view(&v, device, out);
 }
 
-int kaamer_gpu_open(const char *path, int device, kaamer_gpu_t **out) {
+static int kaamer_gpu_open_impl(const char *path, int device, kaamer_gpu_t **out) {
   return open_kidx_range(path, device, 0, 0, out);
 }
+int kaamer_gpu_open(const char *path, int device, kaamer_gpu_t **out) {
+  return ::kaamer::guarded([&]() -> int { return kaamer_gpu_open_impl(path, device, out); });
+}
 
-int kaamer_gpu_open_shard(const char *path, int device, uint64_t shard_lo, uint64_t shard_hi, kaamer_gpu_t **out) {
+static int kaamer_gpu_open_shard_impl(const char *path, int device, uint64_t shard_lo, uint64_t shard_hi, kaamer_gpu_t **out) {
   if (shard_lo == 0 && shard_hi == 0) shard_hi = DENSE_SPACE;  // an explicit (shareable) full-range shard
   return open_kidx_range(path, device, shard_lo, shard_hi, out);
 }
+int kaamer_gpu_open_shard(const char *path, int device, uint64_t shard_lo, uint64_t shard_hi, kaamer_gpu_t **out) {
+  return ::kaamer::guarded([&]() -> int { return kaamer_gpu_open_shard_impl(path, device, shard_lo, shard_hi, out); });
+}
 
-int kaamer_gpu_kidx_fences(const char *path, int n_shards, uint64_t *fences) {
+static int kaamer_gpu_kidx_fences_impl(const char *path, int n_shards, uint64_t *fences) {
   if (!path || !fences || n_shards < 1) {
     set_error("bad argument");
     return KAAMER_ERR_ARG;
@@ -325,13 +390,16 @@ int kaamer_gpu_kidx_fences(const char *path, int n_shards, uint64_t *fences) {
   }
   return KAAMER_OK;
 }
+int kaamer_gpu_kidx_fences(const char *path, int n_shards, uint64_t *fences) {
+  return ::kaamer::guarded([&]() -> int { return kaamer_gpu_kidx_fences_impl(path, n_shards, fences); });
+}
 
 int kaamer_gpu_build(const uint8_t *residues, const uint64_t *seq_off, const uint32_t *ids, uint64_t n_records,
                      int keep_proteins, int device, kaamer_gpu_t **out) {
   return kaamer_gpu_build_shard(residues, seq_off, ids, n_records, keep_proteins, device, 0, 0, out);
 }
 
-int kaamer_gpu_build_shard(const uint8_t *residues, const uint64_t *seq_off, const uint32_t *ids, uint64_t n_records,
+static int kaamer_gpu_build_shard_impl(const uint8_t *residues, const uint64_t *seq_off, const uint32_t *ids, uint64_t n_records,
                            int keep_proteins, int device, uint64_t shard_lo, uint64_t shard_hi, kaamer_gpu_t **out) {
   if (!out || (n_records && (!residues || !seq_off || !ids))) {
     set_error("null argument");
@@ -347,6 +415,10 @@ int kaamer_gpu_build_shard(const uint8_t *residues, const uint64_t *seq_off, con
   }
   *out = h;
   return KAAMER_OK;
+}
+int kaamer_gpu_build_shard(const uint8_t *residues, const uint64_t *seq_off, const uint32_t *ids, uint64_t n_records,
+                           int keep_proteins, int device, uint64_t shard_lo, uint64_t shard_hi, kaamer_gpu_t **out) {
+  return ::kaamer::guarded([&]() -> int { return kaamer_gpu_build_shard_impl(residues, seq_off, ids, n_records, keep_proteins, device, shard_lo, shard_hi, out); });
 }
 
 void kaamer_gpu_close(kaamer_gpu_t *h) { destroy_handle(h); }
@@ -402,6 +474,8 @@ static void detach_shards_locked(kaamer_gpu *h) {
   h->idx.presence = nullptr;
   if (h->idx.full_table) cudaFree(h->idx.full_table);
   h->idx.full_table = nullptr;
+  if (h->idx.repl_postings) cudaFree(h->idx.repl_postings);
+  h->idx.repl_postings = nullptr;
   h->idx.peer = PeerView{};
 }
 
@@ -456,7 +530,7 @@ static int map_shard_array(kaamer_gpu *h, const kaamer_shard_handle &s, bool sam
   return KAAMER_OK;
 }
 
-int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards, int n_shards, int flags) {
+static int kaamer_gpu_attach_shards_impl(kaamer_gpu_t *h, const kaamer_shard_handle *shards, int n_shards, int flags) {
   if (!h || !shards) {
     set_error("null argument");
     return KAAMER_ERR_ARG;
@@ -528,6 +602,42 @@ int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards,
       return rc;
     }
     pv.full_table = h->idx.full_table;
+    if (flags & KAAMER_ATTACH_REPLICATE_POSTINGS) {
+      // built sharded, searched replicated: the posting lists of every shard are copied into one local
+      // array (peer copies at NVLink streaming speed, once); the per-shard pointers of the view then point
+      // into it, so the search kernels — which already find a list through the shard tag of its entry —
+      // never leave this GPU's HBM
+      uint64_t total = 0;
+      std::vector<uint64_t> base(n_shards);
+      for (int i = 0; i < n_shards; ++i) {
+        base[i] = total;
+        total += (shards[order[i]].n_postings + 3) & ~3ull;  // 16-byte aligned starts
+      }
+      cudaError_t e2 = cudaMalloc((void **)&h->idx.repl_postings, (size_t)(total + 4) * sizeof(uint32_t));
+      if (e2 != cudaSuccess) {
+        set_error("cudaMalloc(replicated postings, %llu bytes): %s", (unsigned long long)(total * 4),
+                  cudaGetErrorString(e2));
+        detach_shards_locked(h);
+        return KAAMER_ERR_NOMEM;
+      }
+      for (int i = 0; i < n_shards; ++i) {
+        const uint64_t n = shards[order[i]].n_postings;
+        if (n == 0) continue;
+        e2 = cudaMemcpyAsync(h->idx.repl_postings + base[i], pv.postings[i], (size_t)n * 4, cudaMemcpyDefault, h->stream);
+        if (e2 != cudaSuccess) {
+          set_error("copy of shard %d's postings: %s", i, cudaGetErrorString(e2));
+          detach_shards_locked(h);
+          return KAAMER_ERR_CUDA;
+        }
+      }
+      e2 = cudaStreamSynchronize(h->stream);
+      if (e2 != cudaSuccess) {
+        set_error("copy of the shards' postings: %s", cudaGetErrorString(e2));
+        detach_shards_locked(h);
+        return KAAMER_ERR_CUDA;
+      }
+      for (int i = 0; i < n_shards; ++i) pv.postings[i] = h->idx.repl_postings + base[i];
+    }
   } else if (n_shards > 1 && !(flags & KAAMER_ATTACH_NO_PRESENCE_FILTER)) {
     // local replica of "which k-mers exist": 1 bit per dense code, built by streaming every shard once
     const size_t words = (size_t)((DENSE_SPACE + 31) / 32);
@@ -548,6 +658,9 @@ int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards,
   KCUDA(cudaMemcpy(h->idx.d_peer, &pv, sizeof pv, cudaMemcpyHostToDevice));
   h->idx.peer = pv;
   return KAAMER_OK;
+}
+int kaamer_gpu_attach_shards(kaamer_gpu_t *h, const kaamer_shard_handle *shards, int n_shards, int flags) {
+  return ::kaamer::guarded([&]() -> int { return kaamer_gpu_attach_shards_impl(h, shards, n_shards, flags); });
 }
 
 int kaamer_gpu_dbstats(kaamer_gpu_t *h, uint64_t *n_proteins, uint64_t *n_aa, uint64_t *n_kmers) {
@@ -571,7 +684,7 @@ int kaamer_gpu_index_sizes(kaamer_gpu_t *h, uint64_t *n_keys, uint64_t *n_postin
   return KAAMER_OK;
 }
 
-int kaamer_gpu_index_copy(kaamer_gpu_t *h, uint32_t *keys, uint64_t *offsets, uint32_t *postings) {
+static int kaamer_gpu_index_copy_impl(kaamer_gpu_t *h, uint32_t *keys, uint64_t *offsets, uint32_t *postings) {
   if (!h) {
     set_error("null handle");
     return KAAMER_ERR_ARG;
@@ -589,8 +702,11 @@ int kaamer_gpu_index_copy(kaamer_gpu_t *h, uint32_t *keys, uint64_t *offsets, ui
     KCUDA(cudaMemcpy(postings, ix.postings, (size_t)ix.n_postings * 4, cudaMemcpyDeviceToHost));
   return KAAMER_OK;
 }
+int kaamer_gpu_index_copy(kaamer_gpu_t *h, uint32_t *keys, uint64_t *offsets, uint32_t *postings) {
+  return ::kaamer::guarded([&]() -> int { return kaamer_gpu_index_copy_impl(h, keys, offsets, postings); });
+}
 
-int kaamer_gpu_save(kaamer_gpu_t *h, const char *path) {
+static int kaamer_gpu_save_impl(kaamer_gpu_t *h, const char *path) {
   if (!h || !path) {
     set_error("null argument");
     return KAAMER_ERR_ARG;
@@ -636,6 +752,9 @@ int kaamer_gpu_save(kaamer_gpu_t *h, const char *path) {
   if (rc != KAAMER_OK) set_error("write to %s failed", path);
   return rc;
 }
+int kaamer_gpu_save(kaamer_gpu_t *h, const char *path) {
+  return ::kaamer::guarded([&]() -> int { return kaamer_gpu_save_impl(h, path); });
+}
 
 static int check_search_args(kaamer_gpu_t *h, const void *a, const void *b, uint32_t n, const kaamer_opts *o,
                              const void *out) {
@@ -646,7 +765,7 @@ static int check_search_args(kaamer_gpu_t *h, const void *a, const void *b, uint
   return KAAMER_OK;
 }
 
-int kaamer_gpu_search_proteins(kaamer_gpu_t *h, const uint8_t *residues, const uint64_t *seq_off, uint32_t nq,
+static int kaamer_gpu_search_proteins_impl(kaamer_gpu_t *h, const uint8_t *residues, const uint64_t *seq_off, uint32_t nq,
                                const kaamer_opts *opts, kaamer_hits **out) {
   KCHECK(check_search_args(h, residues, seq_off, nq, opts, out));
   *out = nullptr;
@@ -654,6 +773,10 @@ int kaamer_gpu_search_proteins(kaamer_gpu_t *h, const uint8_t *residues, const u
   KCUDA(cudaSetDevice(h->device));
   HostPhase whole(h, 4);
   return search_proteins_host(h, residues, seq_off, nq, opts, out);
+}
+int kaamer_gpu_search_proteins(kaamer_gpu_t *h, const uint8_t *residues, const uint64_t *seq_off, uint32_t nq,
+                               const kaamer_opts *opts, kaamer_hits **out) {
+  return ::kaamer::guarded([&]() -> int { return kaamer_gpu_search_proteins_impl(h, residues, seq_off, nq, opts, out); });
 }
 
 int kaamer_gpu_search_proteins_device(kaamer_gpu_t *h, const uint8_t *d_residues, const uint64_t *d_seq_off,
@@ -665,7 +788,7 @@ int kaamer_gpu_search_proteins_device(kaamer_gpu_t *h, const uint8_t *d_residues
   return search_proteins_device(h, d_residues, d_seq_off, nq, opts, d_out, (cudaStream_t)stream);
 }
 
-int kaamer_gpu_search_nucleotide(kaamer_gpu_t *h, const uint8_t *nt, const uint64_t *contig_off, uint32_t n_contigs,
+static int kaamer_gpu_search_nucleotide_impl(kaamer_gpu_t *h, const uint8_t *nt, const uint64_t *contig_off, uint32_t n_contigs,
                                  const kaamer_opts *opts, kaamer_hits **out) {
   KCHECK(check_search_args(h, nt, contig_off, n_contigs, opts, out));
   *out = nullptr;
@@ -677,6 +800,10 @@ int kaamer_gpu_search_nucleotide(kaamer_gpu_t *h, const uint8_t *nt, const uint6
   }
   HostPhase whole(h, 3);
   return search_nucleotide_host(h, nt, contig_off, n_contigs, opts, out);
+}
+int kaamer_gpu_search_nucleotide(kaamer_gpu_t *h, const uint8_t *nt, const uint64_t *contig_off, uint32_t n_contigs,
+                                 const kaamer_opts *opts, kaamer_hits **out) {
+  return ::kaamer::guarded([&]() -> int { return kaamer_gpu_search_nucleotide_impl(h, nt, contig_off, n_contigs, opts, out); });
 }
 
 void kaamer_gpu_free_hits(kaamer_hits *hits) {

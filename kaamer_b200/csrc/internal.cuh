@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #include <chrono>
+#include <exception>
+#include <new>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -27,6 +29,24 @@ void set_error(const char *fmt, ...);
     int _r = (call);          \
     if (_r != KAAMER_OK) return _r; \
   } while (0)
+
+// no C++ exception may cross the C boundary (the host is a Go process): the allocating entry points run
+// their bodies through this
+template <class F>
+int guarded(F &&f) noexcept {
+  try {
+    return f();
+  } catch (const std::bad_alloc &) {
+    set_error("out of host memory");
+    return KAAMER_ERR_NOMEM;
+  } catch (const std::exception &e) {
+    set_error("internal error: %s", e.what());
+    return KAAMER_ERR_ARG;
+  } catch (...) {
+    set_error("internal error");
+    return KAAMER_ERR_ARG;
+  }
+}
 
 // ---- k-mer code space -----------------------------------------------------------------
 // EncodeKmer (pkg/kvstore/k_store.go:91-117): key = p01<<23 | p23<<14 | p45<<5 | s6 with
@@ -286,6 +306,7 @@ struct DevIndex {
   std::vector<VmmAlloc> imported;  // mappings of the other processes' shards
   uint32_t *presence = nullptr;    // presence filter over the whole key space (mode P, api.cu)
   uint64_t *full_table = nullptr;  // replicated table over the whole key space (mode P, api.cu)
+  uint32_t *repl_postings = nullptr;  // local copy of every shard's postings (KAAMER_ATTACH_REPLICATE_POSTINGS)
   // key-range shards keep table and postings in shareable memory (vmm.cu); a full index uses cudaMalloc
   VmmAlloc vm_table, vm_postings;
 };

@@ -274,7 +274,7 @@ using namespace kaamer;
 
 extern "C" {
 
-int kaamer_host_read_fasta(const char *path, int is_protein, int pinned, kaamer_query_batch **out) {
+static int kaamer_host_read_fasta_impl(const char *path, int is_protein, int pinned, kaamer_query_batch **out) {
   (void)is_protein;  // (only Name/Contig/StartPosition bookkeeping differs, search.go:296-305)
   if (!path || !out) {
     set_error("null argument");
@@ -311,8 +311,11 @@ int kaamer_host_read_fasta(const char *path, int is_protein, int pinned, kaamer_
   }
   return finish_batch(recs, pinned, out);
 }
+int kaamer_host_read_fasta(const char *path, int is_protein, int pinned, kaamer_query_batch **out) {
+  return ::kaamer::guarded([&]() -> int { return kaamer_host_read_fasta_impl(path, is_protein, pinned, out); });
+}
 
-int kaamer_host_read_fastq(const char *path, int pinned, kaamer_query_batch **out) {
+static int kaamer_host_read_fastq_impl(const char *path, int pinned, kaamer_query_batch **out) {
   if (!path || !out) {
     set_error("null argument");
     return KAAMER_ERR_ARG;
@@ -348,6 +351,9 @@ int kaamer_host_read_fastq(const char *path, int pinned, kaamer_query_batch **ou
     if (!cur.seq.empty()) emit();
   }
   return finish_batch(recs, pinned, out);
+}
+int kaamer_host_read_fastq(const char *path, int pinned, kaamer_query_batch **out) {
+  return ::kaamer::guarded([&]() -> int { return kaamer_host_read_fastq_impl(path, pinned, out); });
 }
 
 int64_t kaamer_host_format_positions(const uint8_t *positions, uint64_t n, int with_alignment, char *out, uint64_t cap) {

@@ -30,6 +30,7 @@
 
 #include "search_common.cuh"
 #include "search_dense.cuh"
+#include "search_dense2.cuh"
 
 namespace kaamer {
 
@@ -60,13 +61,13 @@ __global__ void k_classify(SearchArgs a) {
     // per-warp state halves the resident warps and it ran at 10 G lookups/s against 24 G/s for
     // the CTA-per-query class M (profiles/r1_notes.md).
     if (go) {
-      if (a.dense) cls = (a.kmin[q] >= 3u && K <= D_MAXK) ? 4 : 2;
+      if (a.dense) cls = (a.kmin[q] >= 3u && K <= D_MAXK) ? ((a.dense == 2 && K > a.e_kcap) ? 5 : 4) : 2;
       else cls = K <= a.w_maxk ? 0 : (K <= a.m_maxk ? 1 : 2);
     }
   }
   // warp-aggregated append to the class lists (one atomic per warp and class)
 #pragma unroll
-  for (int c = 0; c < 5; ++c) {
+  for (int c = 0; c < N_LISTS; ++c) {
     const unsigned mask = __ballot_sync(0xFFFFFFFFu, cls == c);
     if (mask == 0) continue;
     const int leader = __ffs(mask) - 1;
@@ -113,12 +114,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_search_wt(SearchArgs a) {
   // 10x, a static split left the SMs idle for ~20 % of the kernel); the next index is
   // fetched one query ahead so its latency is hidden
   uint32_t it_next = 0;
-  if (lane == 0) it_next = atomicAdd(&a.list_count[5 + CLS], 1u);
+  if (lane == 0) it_next = atomicAdd(&a.list_count[N_LISTS + CLS], 1u);
   (void)nwarps;
   for (;;) {
     const uint32_t it = __shfl_sync(0xFFFFFFFFu, it_next, 0);
     if (it >= count) break;
-    if (lane == 0) it_next = atomicAdd(&a.list_count[5 + CLS], 1u);
+    if (lane == 0) it_next = atomicAdd(&a.list_count[N_LISTS + CLS], 1u);
     const uint32_t q = a.lists[(size_t)CLS * a.nq + it];
     const uint64_t b = a.off[q];
     const int len = (int)(a.off[q + 1] - b);
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(M_THREADS, M_CTAS) k_search_m(SearchArgs a) {
   unsigned long long my_incr = 0, my_lookups = 0;
   __shared__ uint32_t s_it;
   for (;;) {
-    if (tid == 0) s_it = atomicAdd(&a.list_count[6], 1u);
+    if (tid == 0) s_it = atomicAdd(&a.list_count[N_LISTS + 1], 1u);
     __syncthreads();
     const uint32_t it = s_it;
     if (it >= count) break;
@@ -591,12 +592,16 @@ void profile_end(kaamer_gpu *h, cudaStream_t st) {
 // in class M).  Swiss-Prot scale (p = 0.53) keeps the full 512 / 2048.
 static void class_limits(const kaamer_gpu *h, int *w_maxk, int *m_maxk, int *dense) {
   double p = (double)h->idx.n_kmers * 2.7e-9;
-  // Dense database: above ~2 background postings per query k-mer the shared-memory histograms of classes W
+  // Dense database: above ~6 background postings per query k-mer (measured crossover: 8 M proteins, profiles/)
+  // the shared-memory histograms of classes W
   // and M overflow for ordinary queries, and class D (search_dense.cuh), whose cost per posting is a byte
   // load and a byte store instead of an atomic, takes every query.  KAAMER_DENSE=0/1 forces the choice
   // (A/B measurements, parity tests).
-  *dense = p >= 2.0 ? 1 : 0;
-  if (const char *env = getenv("KAAMER_DENSE")) *dense = atoi(env) != 0 ? 1 : 0;
+  *dense = p >= 6.0 ? 2 : 0;
+  if (const char *env = getenv("KAAMER_DENSE")) {
+    const int v = atoi(env);
+    *dense = v == 1 ? 2 : (v == 11 ? 1 : 0);  // 1: class D; 11: its first design (A/B measurements); 0: off
+  }
   if (p < 0.5) p = 0.5;
   double w = 0.55 * W_H / p, m = 0.55 * M_H / p;
   *w_maxk = w >= W_MAXK ? W_MAXK : (w < 32 ? 32 : (int)w);
@@ -638,9 +643,9 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   }
   if (nq == 0) return KAAMER_OK;
   SearchWorkspace &ws = h->ws;
-  KCHECK(ws.lists.ensure((size_t)5 * nq + 16));
+  KCHECK(ws.lists.ensure((size_t)N_LISTS * nq + 16));
   KCHECK(ws.kmin.ensure(nq));
-  uint32_t *list_count = ws.lists.p + (size_t)5 * nq;
+  uint32_t *list_count = ws.lists.p + (size_t)N_LISTS * nq;
   SearchArgs a{};
   a.table = h->idx.table;
   a.d_lo = h->idx.d_lo;
@@ -669,10 +674,37 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   class_limits(h, &a.w_maxk, &a.m_maxk, &a.dense);
   a.d_mapb = dense_mapb();
   const size_t d_smem = ((sizeof(DenseSmem) + 15) & ~(size_t)15) + 2 * (size_t)a.d_mapb;
-  if (a.dense && h->dense_smem_set != d_smem) {
-    KCUDA(cudaFuncSetAttribute(k_search_d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d_smem));
-    KCUDA(cudaFuncSetAttribute(k_search_d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d_smem));
-    h->dense_smem_set = d_smem;
+  int d_pf = 8;
+  if (const char *env = getenv("KAAMER_D_PF")) d_pf = atoi(env);
+  auto d_kernel = [&](bool pr) -> void (*)(SearchArgs) {
+    if (d_pf >= 32) return pr ? k_search_d<true, 32> : k_search_d<false, 32>;
+    if (d_pf >= 16) return pr ? k_search_d<true, 16> : k_search_d<false, 16>;
+    return pr ? k_search_d<true, 8> : k_search_d<false, 8>;
+  };
+  if (a.dense == 1) {
+    KCUDA(cudaFuncSetAttribute(d_kernel(false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d_smem));
+    KCUDA(cudaFuncSetAttribute(d_kernel(true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d_smem));
+  }
+  // class D (search_dense2.cuh): two launches, queries of up to E_KCAP_S k-mers and the longer ones
+  constexpr int E_KCAP_S = 512, E_KCAP_L = 2048, E_PF = 4;
+  a.e_kcap = E_KCAP_S;
+  a.e_mapw_small = 512;
+  a.e_mapw_large = 2048;
+  if (const char *env = getenv("KAAMER_E_MAPW")) {  // tuning hook: "small,large" words per map per warp
+    unsigned ms = 0, ml = 0;
+    if (sscanf(env, "%u,%u", &ms, &ml) == 2 && ms >= 64 && ms <= 4096 && ml >= 64 && ml <= 6144 && ms % 4 == 0 &&
+        ml % 4 == 0) {
+      a.e_mapw_small = ms;
+      a.e_mapw_large = ml;
+    }
+  }
+  const size_t e_smem_s = ((sizeof(Dense2Smem<E_KCAP_S>) + 15) & ~(size_t)15) + (size_t)E_WARPS * 2 * a.e_mapw_small * 4;
+  const size_t e_smem_l = ((sizeof(Dense2Smem<E_KCAP_L>) + 15) & ~(size_t)15) + (size_t)E_WARPS * 2 * a.e_mapw_large * 4;
+  auto e_small = peer ? k_search_e<true, E_KCAP_S, E_PF, 4> : k_search_e<false, E_KCAP_S, E_PF, 4>;
+  auto e_large = peer ? k_search_e<true, E_KCAP_L, E_PF, 5> : k_search_e<false, E_KCAP_L, E_PF, 5>;
+  if (a.dense == 2) {
+    KCUDA(cudaFuncSetAttribute(e_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem_s));
+    KCUDA(cudaFuncSetAttribute(e_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem_l));
   }
   // Class G: one CTA per query, histogram in a per-CTA global scratch.  At Swiss-Prot density it holds a
   // handful of very long queries and gets one CTA per SM (it runs underneath W and M and must leave them
@@ -694,7 +726,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   };
   KCHECK(ws.ghash.ensure((size_t)2 * g_ctas * 3 * a.ghash_slots));
   a.ghash = ws.ghash.p;
-  KCUDA(cudaMemsetAsync(list_count, 0, 10 * sizeof(uint32_t), st));
+  KCUDA(cudaMemsetAsync(list_count, 0, 2 * N_LISTS * sizeof(uint32_t), st));
   KCUDA(cudaMemsetAsync(out->counters, 0, CNT_N * sizeof(uint64_t), st));
   if (d_prev_counters)  // chunked host call: the pool cursor continues where the previous chunk stopped
     KCUDA(cudaMemcpyAsync(out->counters + CNT_POOL, d_prev_counters + CNT_POOL, 8, cudaMemcpyDeviceToDevice, st));
@@ -712,16 +744,30 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   a.g_list = 2;
   launch_g(side);
   profile_end(h, side);
+  if (a.dense == 2) {
+    // the long queries of class D run on the side stream underneath the short ones
+    int per_sm = 1;
+    KCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e_large, E_THREADS, e_smem_l));
+    profile_begin(h, side, 1);
+    e_large<<<(unsigned)h->sm_count * (unsigned)(per_sm < 1 ? 1 : per_sm), E_THREADS, e_smem_l, side>>>(a);
+    profile_end(h, side);
+  }
   KCUDA(cudaEventRecord(h->chunk_ev[7], side));
-  if (a.dense) {
-    // class D takes every query (k_classify); persistent grid, as many CTAs per SM as the byte maps allow
+  if (a.dense == 2) {
+    int per_sm = 1;
+    KCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e_small, E_THREADS, e_smem_s));
+    profile_begin(h, st, 6);
+    e_small<<<(unsigned)h->sm_count * (unsigned)(per_sm < 1 ? 1 : per_sm), E_THREADS, e_smem_s, st>>>(a);
+    profile_end(h, st);
+    KCUDA(cudaStreamWaitEvent(st, h->chunk_ev[7], 0));  // the hand-offs of both launches are complete
+  } else if (a.dense) {
+    // first design of class D (A/B measurements): one launch takes every query
     int d_per_sm = 1;
-    KCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d_per_sm, k_search_d<false>, D_THREADS, d_smem));
+    KCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d_per_sm, d_kernel(peer), D_THREADS, d_smem));
     if (d_per_sm < 1) d_per_sm = 1;
     const unsigned d_grid = (unsigned)h->sm_count * (unsigned)d_per_sm;
     profile_begin(h, st, 6);
-    if (peer) k_search_d<true><<<d_grid, D_THREADS, d_smem, st>>>(a);
-    else k_search_d<false><<<d_grid, D_THREADS, d_smem, st>>>(a);
+    d_kernel(peer)<<<d_grid, D_THREADS, d_smem, st>>>(a);
     profile_end(h, st);
   } else {
     profile_begin(h, st, 0);
@@ -737,7 +783,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   a.ghash = ws.ghash.p + (size_t)g_ctas * 3 * a.ghash_slots;  // own scratch: the first G launch may still run
   launch_g(st);
   KCUDA(cudaStreamWaitEvent(st, h->chunk_ev[7], 0));
-  h->prof_all_launches += a.dense ? 4 : 5;
+  h->prof_all_launches += a.dense == 1 ? 4 : 5;
   KCUDA(cudaGetLastError());
   return KAAMER_OK;
 }

@@ -18,6 +18,7 @@ constexpr int G_THREADS = 512;
 constexpr int FAST_C = 64;     // candidates ranked by counting below this, bitonic sort above
 constexpr int BIG_LIST = 32;   // posting lists at least this long are walked by the whole warp
 constexpr int MAX_PROBE = 96;  // linear-probe budget before a histogram is declared full
+constexpr int N_LISTS = 6;     // class lists: W, M, G, hand-offs to G, D (short queries), D (long queries)
 
 struct SearchArgs {
   const uint64_t *table;
@@ -35,8 +36,8 @@ struct SearchArgs {
   uint64_t *pool;
   uint64_t pool_cap;
   unsigned long long *counters;
-  uint32_t *lists;       // [5][nq]: W, M, G, hand-offs to G (from M or D), D
-  uint32_t *list_count;  // [10]: [0..4] list sizes, [5..9] work cursors (dynamic scheduling)
+  uint32_t *lists;       // [N_LISTS][nq]: W, M, G, hand-offs to G (from M or D), D short, D long
+  uint32_t *list_count;  // [2 * N_LISTS]: list sizes, then work cursors (dynamic scheduling)
   uint32_t *ghash;       // class G scratch: per CTA [keys HG][cnt HG][cand HG]
   uint32_t ghash_slots;  // HG (power of two)
   // nucleotide / reads mode (search_nucleotide.go:76-124): queries are ORFs, the candidate
@@ -55,8 +56,10 @@ struct SearchArgs {
   int w_maxk, m_maxk;
   // dense database (search.cu class_limits): every query goes to class D (search_dense.cuh), or to class G
   // when its threshold is too small for D's filter; d_mapb = bytes per byte map of class D
-  int dense;
+  int dense;             // 0: classes W / M / G; 1: class D first design (A/B only); 2: class D (search_dense2.cuh)
   uint32_t d_mapb;
+  int e_kcap;            // queries up to this many k-mers go to the short-query launch of class D
+  uint32_t e_mapw_small, e_mapw_large;  // words per bit map per warp (short / long launch)
 };
 
 // Copy src[0, len) into shared memory with aligned 16-byte loads (one request per 16 residues:

@@ -29,7 +29,6 @@ namespace kaamer {
 constexpr int D_WARPS = 4, D_THREADS = D_WARPS * 32;
 constexpr int D_KCH = 512;     // query k-mers per chunk (table entries staged in shared memory)
 constexpr int D_H = 1024;      // slots of the exact hash of pushed subjects
-constexpr int D_PF = 8;        // posting-list steps in flight per warp
 constexpr int D_MAXK = 60000;  // 16-bit counts
 constexpr uint32_t D_MAPB_DEFAULT = 20 * 1024;
 
@@ -103,7 +102,7 @@ __device__ __forceinline__ int dense_load_chunk(const SearchArgs &a, const PeerV
 // Warp `wi` of `nw` streams the posting lists of entries wi, wi + nw, ... of the staged chunk, one list per
 // step, D_PF steps in flight.  PASS 1: byte-map test-and-set + pushes.  PASS 2: exact counts of the final
 // candidates (bloom bits b0..b3).
-template <int PASS, bool PEER>
+template <int PASS, bool PEER, int D_PF>
 __device__ __forceinline__ void dense_stream(const SearchArgs &a, const PeerView *pv, DenseSmem &s, uint8_t *m1,
                                              uint8_t *m2, uint32_t S, int kn, int wi, int nw,
                                              const SmemHashT<false> &hv, const CandList &cl, uint32_t b0, uint32_t b1,
@@ -178,7 +177,7 @@ __device__ __forceinline__ void dense_stream(const SearchArgs &a, const PeerView
   }
 }
 
-template <bool PEER>
+template <bool PEER, int D_PF>
 __global__ void __launch_bounds__(D_THREADS) k_search_d(SearchArgs a) {
   extern __shared__ __align__(16) uint8_t dsm[];
   DenseSmem &s = *reinterpret_cast<DenseSmem *>(dsm);
@@ -203,7 +202,7 @@ __global__ void __launch_bounds__(D_THREADS) k_search_d(SearchArgs a) {
   unsigned long long my_incr = 0, my_lookups = 0;
   for (;;) {
     __syncthreads();
-    if (tid == 0) s.it = atomicAdd(&a.list_count[5 + 4], 1u);
+    if (tid == 0) s.it = atomicAdd(&a.list_count[N_LISTS + 4], 1u);
     __syncthreads();
     const uint32_t it = s.it;
     if (it >= count) break;
@@ -253,7 +252,7 @@ __global__ void __launch_bounds__(D_THREADS) k_search_d(SearchArgs a) {
         }
         __syncthreads();
       }
-      if (w < w_act) dense_stream<1, PEER>(a, pv, s, m1, m2, S, kn, w, w_act, hv, cl, 0, 0, 0, 0);
+      if (w < w_act) dense_stream<1, PEER, D_PF>(a, pv, s, m1, m2, S, kn, w, w_act, hv, cl, 0, 0, 0, 0);
     }
     __syncthreads();
     if (s.ss.flags) {
@@ -295,7 +294,7 @@ __global__ void __launch_bounds__(D_THREADS) k_search_d(SearchArgs a) {
         unsigned long long tot = 0;
         kn = dense_load_chunk<PEER>(a, pv, s, b, len, K, c, res_end, tot);
       }
-      dense_stream<2, PEER>(a, pv, s, m1, m2, S, kn, w, D_WARPS, hv, cl, b0, b1, b2, b3);
+      dense_stream<2, PEER, D_PF>(a, pv, s, m1, m2, S, kn, w, D_WARPS, hv, cl, b0, b1, b2, b3);
     }
     __syncthreads();
     for (int base = 0; base < D_H; base += D_THREADS) {

@@ -1,0 +1,386 @@
+// search_dense2.cuh — class D, second design: the search kernel of the saturated-key-space regime
+// (C4: ~47 postings per query k-mer, ~16 000 (query, subject) increments per 350-aa query, almost all of
+// them subjects seen once).
+//
+// Replaces, like the other classes, KmerSearch + sortMapByValue + FilterResults
+// (pkg/search/search.go:414-440, 132-152, 189-220) for one query per CTA of four warps.
+//
+// Why not a histogram: a shared-memory atomic costs ~2 cycles per lane on the SM's atomic unit (0.5
+// increments/clk/SM, 145 G/s per GPU), an order of magnitude below what streaming 190-byte posting lists
+// out of HBM delivers.  So the ~99 % of the postings that belong to subjects seen ONCE are filtered out
+// with plain shared-memory loads and stores, and only repeated subjects ever reach an atomic:
+//
+//   pass 1  every posting id tests-and-sets one bit in M1 and, if that was already set, one in M2 (two
+//           Bloom-style bit maps with independent hashes); an id that finds both set is PUSHED into a
+//           small exact hash H (CAS + atomic count, shared by the CTA);
+//   sweep   subjects pushed >= kmin - 2C times are FINAL candidates (C = concurrent chains, below);
+//   pass 2  the lists are streamed again (L2 hits) and every occurrence of a final candidate is counted
+//           exactly (a 64-bit Bloom word in registers rejects the rest without touching shared memory);
+//           then the same threshold / top-N epilogue as the other classes.
+//
+// The bit maps are PRIVATE to a warp (each warp streams its own quarter of the query's lists), and a warp
+// works on R posting lists at a time: all their loads, then all their stores, __syncwarp, then a VERIFY
+// read — two lanes of the same group may have written different bits of one word, the loser repairs its bit
+// with an atomic OR (rare).  No false negatives, deterministically: ids of one list are unique, so a chain
+// (warp x R) leaves a subject unpushed at most twice (the group that sets its M1 bit, the group that sets its
+// M2 bit); a subject with Kmatch >= kmin is therefore pushed at least kmin - 2C times with C = W x R chains,
+// W = min(4, (kmin-1)/2) streaming warps, R = min(2, (kmin-1)/(2W)).  kmin < 3 goes to class G.  False
+// positives (hash collisions) only cost work: pass 2 counts exactly.
+#pragma once
+#include "search_common.cuh"
+
+namespace kaamer {
+
+constexpr int E_WARPS = 4, E_THREADS = E_WARPS * 32;
+constexpr int E_H = 512;       // slots of the exact hash of pushed subjects
+constexpr int E_MAXK = 60000;  // 16-bit counts
+
+template <int KCAP>
+struct __align__(16) Dense2Smem {
+  uint64_t ent[KCAP];
+  uint32_t hkeys[E_H];
+  uint32_t hcnt2[E_H / 2];
+  uint32_t fin[E_H / 32];
+  uint16_t cand[E_H];
+  uint16_t pp[KCAP + 8];
+  uint8_t raw[KCAP + 64];
+  uint8_t lut[256];
+  SelectScratch ss;
+  unsigned long long bloom;
+  uint32_t nfinal, it;
+};
+
+__device__ __forceinline__ uint32_t e_hash1(uint32_t id, uint32_t nbits) { return __umulhi(id * 0x9E3779B1u, nbits); }
+__device__ __forceinline__ uint32_t e_hash2(uint32_t id, uint32_t nbits) {
+  uint32_t x = id * 0x85EBCA77u;
+  x ^= x >> 13;
+  x *= 0xC2B2AE3Du;
+  return __umulhi(x, nbits);
+}
+
+// One chunk of the query: residues -> packed codes -> table entries in s.ent[0, kn).  Returns kn; every
+// thread returns in `tot` the posting total of the entries it probed.
+template <bool PEER, int KCAP>
+__device__ __forceinline__ int dense2_load_chunk(const SearchArgs &a, const PeerView *pv, Dense2Smem<KCAP> &s,
+                                                 uint64_t b, int len, int K, int c, const uint8_t *res_end,
+                                                 unsigned long long &tot) {
+  const int tid = threadIdx.x;
+  const int kbeg = c * KCAP;
+  const int kn = K - kbeg < KCAP ? K - kbeg : KCAP;
+  const int nres = len - kbeg < kn + 7 ? len - kbeg : kn + 7;
+  __syncthreads();  // the previous users of raw / pp / ent are done
+  const int head = stage_bytes<E_THREADS>(s.raw, a.res + b + kbeg, nres, res_end, tid);
+  __syncthreads();
+  const uint8_t *r = s.raw + head;
+  const int ncodes = kn + KAAMER_KMER_SIZE - 1;
+  for (int i = tid; i < ncodes; i += E_THREADS) {
+    const uint32_t c0 = s.lut[r[i]];
+    const uint32_t c1 = (i + 1 < nres) ? (uint32_t)s.lut[r[i + 1]] : CODE_UNKNOWN;
+    s.pp[i] = (uint16_t)packed_code(c0, c1);
+  }
+  __syncthreads();
+  constexpr int U = 4;
+#pragma unroll 1
+  for (int base = 0; base < kn; base += U * E_THREADS) {
+    uint32_t d[U];
+    bool ok[U];
+    uint64_t e[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pos = base + u * E_THREADS + tid;
+      ok[u] = pos < kn;
+      d[u] = ok[u] ? dense_from_packed(s.pp[pos], s.pp[pos + 2], s.pp[pos + 4], s.pp[pos + 6]) : 0u;
+    }
+    probe_entries<PEER, U>(a, pv, d, ok, e);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pos = base + u * E_THREADS + tid;
+      if (ok[u]) {
+        s.ent[pos] = e[u];
+        tot += e[u] >> ENTRY_VALUE_BITS;
+      }
+    }
+  }
+  __syncthreads();
+  return kn;
+}
+
+// Warp `wi` of `nw` streams the posting lists of entries wi, wi + nw, ... of the staged chunk.  A ring entry
+// is one 64-id window of ONE list (two ids per lane: positions lane and lane + 32 of the window); PFL
+// entries are in flight, R of them (R different lists) are processed together.  The inner code is flat —
+// predicated loads and stores, no nested branches: the kernel is bound by issued instructions, not by HBM.
+template <int PASS, bool PEER, int PFL, int R, int KCAP>
+__device__ __forceinline__ void dense2_stream(const SearchArgs &a, const PeerView *pv, Dense2Smem<KCAP> &s,
+                                              uint32_t *m1, uint32_t *m2, uint32_t nbits, int kn, int wi, int nw,
+                                              const SmemHashT<false> &hv, const CandList &cl,
+                                              unsigned long long bloom) {
+  static_assert(PFL % R == 0, "PFL must be a multiple of R");
+  const unsigned lane = threadIdx.x & 31;
+  int k = wi - nw;
+  uint32_t off = 0, cnt = 0, single = 0;
+  const uint32_t *ptr = nullptr;
+  // warp-uniform iterator over (list, 64-id window); nv = 0 once exhausted
+  auto fetch = [&](uint32_t &ia, uint32_t &ib, uint32_t &nv) {
+    nv = 0;
+    ia = ib = 0;
+    if (off >= cnt) {
+      do {
+        k += nw;
+        if (k >= kn) {
+          k = kn;  // stay exhausted
+          cnt = off = 0;
+          return;
+        }
+        const uint64_t e = s.ent[k];
+        cnt = (uint32_t)(e >> ENTRY_VALUE_BITS);
+        single = (uint32_t)e;
+        if (cnt >= 2) ptr = post_ptr<PEER>(a, pv, e & ENTRY_VALUE_MASK);
+      } while (cnt == 0);
+      off = 0;
+    }
+    const uint32_t rem = cnt - off;
+    nv = rem < 64u ? rem : 64u;
+    if (cnt == 1) {
+      ia = single;
+    } else {
+      const uint32_t *p = ptr + off + lane;
+      if (lane < nv) ia = __ldg(p);
+      if (lane + 32u < nv) ib = __ldg(p + 32);
+    }
+    off += 64;
+  };
+  uint32_t ia[PFL], ib[PFL], nvs[PFL];
+#pragma unroll
+  for (int u = 0; u < PFL; ++u) fetch(ia[u], ib[u], nvs[u]);
+  while (nvs[0] != 0) {
+#pragma unroll
+    for (int g = 0; g < PFL / R; ++g) {
+      if (nvs[g * R] == 0) break;
+      constexpr int J = 2 * R;
+      uint32_t id[J];
+      bool v[J];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        id[2 * r] = ia[g * R + r];
+        id[2 * r + 1] = ib[g * R + r];
+        v[2 * r] = lane < nvs[g * R + r];
+        v[2 * r + 1] = lane + 32u < nvs[g * R + r];
+      }
+      if constexpr (PASS == 1) {
+        uint32_t a1[J], bit1[J], w1[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const uint32_t h = e_hash1(id[j], nbits);
+          a1[j] = h >> 5;
+          bit1[j] = 1u << (h & 31u);
+          w1[j] = m1[a1[j]];  // (id 0 of an invalid lane still names a valid word)
+        }
+        bool set1[J], flag[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const bool seen = (w1[j] & bit1[j]) != 0u;
+          set1[j] = v[j] && !seen;
+          flag[j] = v[j] && seen;
+          if (set1[j]) m1[a1[j]] = w1[j] | bit1[j];
+        }
+        uint32_t a2[J], bit2[J], w2[J];
+        bool set2[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const uint32_t h = e_hash2(id[j], nbits);
+          a2[j] = h >> 5;
+          bit2[j] = 1u << (h & 31u);
+          w2[j] = 0u;
+          if (flag[j]) w2[j] = m2[a2[j]];
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const bool seen = (w2[j] & bit2[j]) != 0u;
+          set2[j] = flag[j] && !seen;
+          if (set2[j]) m2[a2[j]] = w2[j] | bit2[j];
+          if (flag[j] && seen) count_subject(hv, id[j], 0xFFFFFFFFu, cl);
+        }
+        __syncwarp();
+        // verify: a store of this group may have been overwritten by another lane's store to the same word
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          uint32_t c1 = 0xFFFFFFFFu, c2 = 0xFFFFFFFFu;
+          if (set1[j]) c1 = m1[a1[j]];
+          if (set2[j]) c2 = m2[a2[j]];
+          if ((c1 & bit1[j]) == 0u) atomicOr(m1 + a1[j], bit1[j]);
+          if ((c2 & bit2[j]) == 0u) atomicOr(m2 + a2[j], bit2[j]);
+        }
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const uint32_t hb = (id[j] * 0x9E3779B1u) >> 26;
+          if (v[j] && ((bloom >> hb) & 1ull)) {
+            uint32_t slot = hv.home(id[j]);
+#pragma unroll 1
+            for (int probe = 0; probe < SmemHashT<false>::kMaxProbe; ++probe) {
+              const uint32_t key = s.hkeys[slot];
+              if (key == id[j]) {
+                if ((s.fin[slot >> 5] >> (slot & 31u)) & 1u) hv.add(slot, 1u);
+                break;
+              }
+              if (key == EMPTY) break;
+              slot = (slot + 1) & hv.mask;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) fetch(ia[g * R + r], ib[g * R + r], nvs[g * R + r]);
+    }
+  }
+}
+
+// CLS: class list (4: queries up to KCAP k-mers staged at once; 5: the long ones)
+template <bool PEER, int KCAP, int PF, int CLS>
+__global__ void __launch_bounds__(E_THREADS, CLS == 4 ? 6 : 2) k_search_e(SearchArgs a) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  using Smem = Dense2Smem<KCAP>;
+  Smem &s = *reinterpret_cast<Smem *>(dsm);
+  const uint32_t mapw = CLS == 4 ? a.e_mapw_small : a.e_mapw_large;  // words per map per warp
+  const int tid = threadIdx.x;
+  const unsigned lane = tid & 31;
+  const int w = tid >> 5;
+  uint32_t *maps = reinterpret_cast<uint32_t *>(dsm + ((sizeof(Smem) + 15) & ~(size_t)15));
+  uint32_t *m1 = maps + (size_t)w * 2 * mapw, *m2 = m1 + mapw;
+  const PeerView *pv = nullptr;
+  if constexpr (PEER) {
+    __shared__ PeerView s_peer;
+    load_peer_view(&s_peer, a.peer, tid, E_THREADS);
+    pv = &s_peer;
+  }
+  for (int i = tid; i < 256; i += E_THREADS) s.lut[i] = (uint8_t)aa_code(i);
+  __syncthreads();
+  const SmemHashT<false> hv{s.hkeys, s.hcnt2, (uint32_t)E_H - 1u, 32 - ilog2_c(E_H)};
+  const CandList cl{&s.ss.ncand, &s.ss.flags, s.cand, nullptr, (uint32_t)E_H};
+  const uint32_t count = a.list_count[CLS];
+  const uint8_t *res_end = a.res + a.off[a.nq];
+  unsigned long long my_incr = 0, my_lookups = 0;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s.it = atomicAdd(&a.list_count[N_LISTS + CLS], 1u);
+    __syncthreads();
+    const uint32_t it = s.it;
+    if (it >= count) break;
+    const uint32_t q = a.lists[(size_t)CLS * a.nq + it];
+    const uint64_t b = a.off[q];
+    const int len = (int)(a.off[q + 1] - b);
+    const int K = a.size_in_kmer[q];
+    const uint32_t kmin = a.kmin[q];  // >= 3 (k_classify)
+    const int w_act = (int)((kmin - 1u) / 2u) < E_WARPS ? (int)((kmin - 1u) / 2u) : E_WARPS;
+    int R = (int)((kmin - 1u) / (2u * (uint32_t)w_act));
+    R = R >= 2 ? 2 : 1;  // (four lists at a time cost 40 more registers than they are worth)
+    const uint32_t thr = kmin - 2u * (uint32_t)(w_act * R);  // >= 1
+    const int nchunks = (K + KCAP - 1) / KCAP;
+    {
+      uint4 *hk = reinterpret_cast<uint4 *>(s.hkeys);
+      uint4 *hc = reinterpret_cast<uint4 *>(s.hcnt2);
+      const uint4 E = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY), Z = make_uint4(0, 0, 0, 0);
+      for (int i = tid; i < E_H / 4; i += E_THREADS) hk[i] = E;
+      for (int i = tid; i < E_H / 8; i += E_THREADS) hc[i] = Z;
+      if (tid == 0) {
+        s.bloom = 0ull;
+        s.ss.ncand = 0;
+        s.ss.flags = 0;
+        s.nfinal = 0;
+      }
+      // the warp's own maps (the first probes of the chunk are issued right after)
+      uint4 *mv = reinterpret_cast<uint4 *>(m1);
+      for (uint32_t i = lane; i < mapw / 2; i += 32) mv[i] = Z;  // 2 maps x mapw words = mapw / 2 uint4
+    }
+    const uint32_t nbits = mapw * 32u;
+    unsigned long long q_incr = 0;
+    // ---- pass 1 ----
+    for (int c = 0; c < nchunks; ++c) {
+      unsigned long long tot = 0;
+      const int kn = dense2_load_chunk<PEER, KCAP>(a, pv, s, b, len, K, c, res_end, tot);
+      q_incr += tot;
+      if (w < w_act) {
+        if (R == 2) dense2_stream<1, PEER, PF, 2, KCAP>(a, pv, s, m1, m2, nbits, kn, w, w_act, hv, cl, 0ull);
+        else dense2_stream<1, PEER, PF, 1, KCAP>(a, pv, s, m1, m2, nbits, kn, w, w_act, hv, cl, 0ull);
+      }
+    }
+    __syncthreads();
+    if (s.ss.flags) {
+      // more repeated subjects than H holds: class G counts this query exactly in global memory
+      if (tid == 0) {
+        const uint32_t slot = atomicAdd(&a.list_count[3], 1u);
+        a.lists[(size_t)3 * a.nq + slot] = q;
+      }
+      continue;
+    }
+    // ---- sweep: final candidates ----
+    for (int base = 0; base < E_H; base += E_THREADS) {
+      const uint32_t slot = base + tid;
+      const uint32_t key = s.hkeys[slot];
+      const bool isfin = key != EMPTY && hv.count_at(slot) >= thr;
+      const unsigned bal = __ballot_sync(0xFFFFFFFFu, isfin);
+      if (lane == 0) s.fin[slot >> 5] = bal;
+      if (isfin) {
+        atomicOr(&s.bloom, 1ull << ((key * 0x9E3779B1u) >> 26));
+      }
+      if (lane == 0 && bal) atomicAdd(&s.nfinal, (uint32_t)__popc(bal));
+    }
+    __syncthreads();
+    {
+      uint4 *hc = reinterpret_cast<uint4 *>(s.hcnt2);
+      const uint4 Z = make_uint4(0, 0, 0, 0);
+      for (int i = tid; i < E_H / 8; i += E_THREADS) hc[i] = Z;
+    }
+    __syncthreads();
+    my_incr += q_incr;
+    if (tid == 0) my_lookups += (unsigned long long)K;
+    if (s.nfinal == 0) continue;  // nothing can reach kmin: no hits (n_hits[q] was zeroed by k_classify)
+    // ---- pass 2: exact counts of the final candidates ----
+    const unsigned long long bloom = s.bloom;
+    for (int c = 0; c < nchunks; ++c) {
+      int kn = K < KCAP ? K : KCAP;
+      if (nchunks > 1) {
+        unsigned long long tot = 0;
+        kn = dense2_load_chunk<PEER, KCAP>(a, pv, s, b, len, K, c, res_end, tot);
+      }
+      dense2_stream<2, PEER, PF, 1, KCAP>(a, pv, s, m1, m2, nbits, kn, w, E_WARPS, hv, cl, bloom);
+    }
+    __syncthreads();
+    for (int base = 0; base < E_H; base += E_THREADS) {
+      const uint32_t slot = base + tid;
+      if (((s.fin[slot >> 5] >> (slot & 31u)) & 1u) && hv.count_at(slot) >= kmin)
+        s.cand[atomicAdd(&s.ss.ncand, 1u)] = (uint16_t)slot;
+    }
+    __syncthreads();
+    const uint32_t c = s.ss.ncand;
+    select_and_emit<E_THREADS>(a, q, hv, [&](uint32_t i) -> uint32_t { return s.cand[i]; }, c, s.ss);
+    __syncthreads();
+    if (a.nt_mode) {
+      if (tid < 32 && a.n_hits[q]) {
+        const uint64_t top = a.pool[a.hit_base[q]];
+        const uint8_t *r = a.res + b;
+        const uint32_t d0 = dense_from_codes(aa_code(r[0]), aa_code(r[1]), aa_code(r[2]), aa_code(r[3]),
+                                             aa_code(r[4]), aa_code(r[5]), aa_code(r[6]));
+        const bool any = warp_any0<PEER>(a, pv, hv, d0, (uint32_t)top, (uint32_t)(top >> 32));
+        if (tid == 0) a.any0[q] = any ? 1 : 0;
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    my_incr += __shfl_down_sync(0xFFFFFFFFu, my_incr, o);
+    my_lookups += __shfl_down_sync(0xFFFFFFFFu, my_lookups, o);
+  }
+  if (lane == 0) {
+    if (my_incr) {
+      atomicAdd(&a.counters[CNT_INCR], my_incr);
+      atomicAdd(&a.counters[CNT_CLS_INCR + 3], my_incr);
+    }
+    if (my_lookups) {
+      atomicAdd(&a.counters[CNT_LOOKUPS], my_lookups);
+      atomicAdd(&a.counters[CNT_CLS_LOOKUPS + 3], my_lookups);
+    }
+  }
+}
+
+}  // namespace kaamer

@@ -580,7 +580,7 @@ using namespace kaamer;
 
 extern "C" {
 
-int kaamer_gpu_get_orfs(kaamer_gpu_t *h, const uint8_t *nt, const uint64_t *contig_off, uint32_t n_contigs,
+static int kaamer_gpu_get_orfs_impl(kaamer_gpu_t *h, const uint8_t *nt, const uint64_t *contig_off, uint32_t n_contigs,
                         kaamer_orfs **out) {
   if (!h || !out || (n_contigs && (!nt || !contig_off))) {
     set_error("null argument");
@@ -640,6 +640,10 @@ int kaamer_gpu_get_orfs(kaamer_gpu_t *h, const uint8_t *nt, const uint64_t *cont
   }
   *out = o;
   return KAAMER_OK;
+}
+int kaamer_gpu_get_orfs(kaamer_gpu_t *h, const uint8_t *nt, const uint64_t *contig_off, uint32_t n_contigs,
+                        kaamer_orfs **out) {
+  return ::kaamer::guarded([&]() -> int { return kaamer_gpu_get_orfs_impl(h, nt, contig_off, n_contigs, out); });
 }
 
 void kaamer_gpu_free_orfs(kaamer_orfs *o) {

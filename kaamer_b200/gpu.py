@@ -271,7 +271,8 @@ class GpuIndex:
         check(_lib.lib().kaamer_gpu_shard_export(self._h, C.byref(sh)))
         return sh
 
-    def attach_shards(self, handles, presence_filter: bool = True, replicate_table: bool = False) -> None:
+    def attach_shards(self, handles, presence_filter: bool = True, replicate_table: bool = False,
+                      replicate_postings: bool = False) -> None:
         """Map the key-range shards of all ranks (this one included): afterwards the search entry
         points of this handle see the whole key space and probe remote shards through NVLink.
         `handles`: ShardHandle structs (or their bytes) whose descriptors are valid in THIS process."""
@@ -280,7 +281,8 @@ class GpuIndex:
             b = bytes(b)
             assert len(b) == C.sizeof(_lib.ShardHandle)
             C.memmove(C.byref(arr[i]), b, len(b))
-        flags = (0 if presence_filter else 1) | (2 if replicate_table else 0)
+        flags = (0 if presence_filter else 1) | (2 if (replicate_table or replicate_postings) else 0) | \
+            (4 if replicate_postings else 0)
         check(_lib.lib().kaamer_gpu_attach_shards(self._h, arr, len(handles), flags))
 
     def detach_shards(self) -> None:

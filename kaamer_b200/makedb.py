@@ -35,6 +35,8 @@ def read_fasta(path: str):
         cur = None
         for raw in f:
             line = raw.rstrip(b"\n")
+            if line.endswith(b"\r"):
+                line = line[:-1]  # bufio.ScanLines drops one trailing CR (inputFASTA.go:86-96)
             if line[:1] == b">":
                 headers.append(line)
                 cur = []

@@ -48,20 +48,23 @@ def dense_setup():
     g.close()
 
 
+@pytest.mark.parametrize("design", ["1", "11"])  # KAAMER_DENSE: class D, and its first design (kept for A/B)
 @pytest.mark.parametrize("opts", [
     dict(),
     dict(min_kmatch=3, min_kratio=0.0, max_results=10),     # thr = 1, one streaming warp
     dict(min_kmatch=5, min_kratio=0.0, max_results=1000),   # two streaming warps, > 64 candidates
     dict(min_kmatch=9, min_kratio=0.0, max_results=4),      # four streaming warps, thr = 1
+    dict(min_kmatch=17, min_kratio=0.0, max_results=4),     # four warps x two lists at a time
+    dict(min_kmatch=33, min_kratio=0.0, max_results=50),    # four warps x four lists at a time
     dict(min_kmatch=1, min_kratio=0.0, max_results=7),      # kmin < 3: class G
     dict(min_kmatch=40, min_kratio=0.3, max_results=3),
     dict(max_results=0),
 ])
-def test_class_d_parity_on_a_dense_database(dense_setup, opts, monkeypatch):
+def test_class_d_parity_on_a_dense_database(dense_setup, opts, design, monkeypatch):
     from kaamer_b200 import SearchOptions
     from oracle import oracle as o
 
-    monkeypatch.setenv("KAAMER_DENSE", "1")
+    monkeypatch.setenv("KAAMER_DENSE", design)
     q, qo = dense_setup["q"]
     ora = o.search_proteins(dense_setup["idx"], q, qo, o.opts(**opts), 4)
     r = dense_setup["g"].search_proteins(q, qo, SearchOptions(max_results=opts.get("max_results", 10),
@@ -72,14 +75,17 @@ def test_class_d_parity_on_a_dense_database(dense_setup, opts, monkeypatch):
     assert r.n_increments > 20 * r.n_lookups  # the regime: dozens of postings per lookup
 
 
-@pytest.mark.parametrize("mapkb", ["1", "4", "64"])
-def test_class_d_map_sizes(dense_setup, mapkb, monkeypatch):
-    """tiny byte maps (everything collides: pushes overflow H, class G takes the query) to large ones"""
+@pytest.mark.parametrize("design,var,val", [("11", "KAAMER_D_MAPKB", "1"), ("11", "KAAMER_D_MAPKB", "64"),
+                                            ("1", "KAAMER_E_MAPW", "64,64"), ("1", "KAAMER_E_MAPW", "128,512"),
+                                            ("1", "KAAMER_E_MAPW", "4096,4096")])
+def test_class_d_map_sizes(dense_setup, design, var, val, monkeypatch):
+    """tiny maps (everything collides: pushes overflow H, class G takes the query) to large ones"""
     from kaamer_b200 import SearchOptions
     from oracle import oracle as o
 
-    monkeypatch.setenv("KAAMER_DENSE", "1")
-    monkeypatch.setenv("KAAMER_D_MAPKB", mapkb)
+    mapkb = f"{var}={val}"
+    monkeypatch.setenv("KAAMER_DENSE", design)
+    monkeypatch.setenv(var, val)
     q, qo = dense_setup["q"]
     ora = o.search_proteins(dense_setup["idx"], q, qo, o.opts(), 4)
     r = dense_setup["g"].search_proteins(q, qo, SearchOptions())

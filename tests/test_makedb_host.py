@@ -52,3 +52,24 @@ def test_write_read_roundtrip(tmp_path):
     np.testing.assert_array_equal(res2, res)
     np.testing.assert_array_equal(off2, off)
     np.testing.assert_array_equal(ids2, o.fasta_ids(200))
+
+
+def test_read_fasta_crlf_line_endings(tmp_path):
+    """bufio.Scanner / ScanLines (inputFASTA.go:86-96) drops the CR of a CRLF file: the records, and the
+    k-mers that span line breaks, equal those of the LF file — checked against the transliterated Go loop"""
+    from tests import go_transliteration as gt
+
+    p = tmp_path / "crlf.fa"
+    p.write_bytes(FASTA.replace(b"\n", b"\r\n"))
+    a = makedb.read_fasta(str(p))
+    p2 = tmp_path / "lf.fa"
+    p2.write_bytes(FASTA)
+    b = makedb.read_fasta(str(p2))
+    assert a[0] == b[0] and a[1] == b[1]
+    np.testing.assert_array_equal(a[2], b[2])
+    np.testing.assert_array_equal(a[3], b[3])
+    np.testing.assert_array_equal(a[4], b[4])
+    assert b"\r" not in a[2].tobytes()
+    # the transliterated reader loop + index step: identical k-mer index from both files
+    lines = [l[:-1] if l.endswith("\r") else l for l in FASTA.replace(b"\n", b"\r\n").decode().split("\n")]
+    assert gt.make_index("\n".join(lines)) == gt.make_index(FASTA.decode())

@@ -32,7 +32,15 @@ def peaks():
 
 
 def c2(a):
+    print(json.dumps(c2_line(a.contigs, a.steps, a.warmup)))
+
+
+def c2_line(contigs, steps, warmup):
+    import argparse as _ap
+
     import torch
+
+    a = _ap.Namespace(contigs=contigs, steps=steps, warmup=warmup)
 
     from kaamer_b200 import GpuIndex, SearchOptions, synth
     from kaamer_b200.makedb import fasta_protein_ids
@@ -84,7 +92,7 @@ def c2(a):
                          "sample": "one 5 Mb contig, CPU restatement (oracle/): GetORFs serial per contig as in the reference, ORF searches on all threads",
                          "rows": int(ro.n_rows)},
     }
-    print(json.dumps(line))
+    return line
 
 
 def reads(a):
@@ -150,8 +158,22 @@ def c5(a):
     res, off = synth.protein_db(a.db_proteins, config_index=3)
     ids = fasta_protein_ids(len(off) - 1)
     q, qo, _ = synth.protein_queries(res, off, a.queries, config_index=3, stream=100)
-    threads = os.cpu_count() or 1
     with GpuIndex.build(res, off, ids, keep_proteins=True) as g:
+        print(json.dumps(c5_on(g, res, off, ids, q, qo, a.steps, a.warmup, a.cpu_pairs)))
+
+
+def c5_on(g, res, off, ids, q, qo, steps, warmup, cpu_pairs):
+    """C5 stage on an index that holds the protein table: all (query, hit) pairs of one query batch"""
+    import argparse as _ap
+
+    import torch
+
+    from kaamer_b200 import SearchOptions
+    from oracle import oracle as o
+
+    a = _ap.Namespace(steps=steps, warmup=warmup, cpu_pairs=cpu_pairs, queries=len(qo) - 1, db_proteins=len(ids))
+    threads = os.cpu_count() or 1
+    if True:
         r = g.search_proteins(q, qo, SearchOptions())
         nh = np.diff(r.hit_off.astype(np.int64))
         pq = np.repeat(np.arange(len(nh), dtype=np.uint32), nh)
@@ -207,7 +229,7 @@ def c5(a):
         "cpu_baseline": {"value": cpu_cells / cpu_s / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
                          "sample": f"{len(sample)} of the pairs, CPU restatement (oracle/) of align.Align on {threads} threads"},
     }
-    print(json.dumps(line))
+    return line
 
 
 def sharded(a):

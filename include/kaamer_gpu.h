@@ -192,6 +192,32 @@ typedef struct kaamer_aln {
 int kaamer_gpu_align(kaamer_gpu_t *h, const uint8_t *q_residues, const uint64_t *q_off,
                      const uint32_t *pair_query, const uint32_t *pair_subject, uint32_t n_pairs,
                      const kaamer_aln_opts *opts, kaamer_aln *out /* [n_pairs], caller-owned */);
+/* Same, and AlignmentResult.AlnString (align.go:69-103) of every pair: text of pair i =
+ * text[off[i] .. off[i+1]) = "<gapped query>\n<match line>\n<gapped subject>" (no terminator; "\n\n" for an
+ * empty alignment, exactly what fmt.Sprintf("%s\n%s\n%s") gives the JSON writer, search.go:497-503). */
+typedef struct kaamer_aln_text {
+  uint64_t *off; /* [n_pairs+1] */
+  char *text;
+  void *_owner;
+} kaamer_aln_text;
+int kaamer_gpu_align_text(kaamer_gpu_t *h, const uint8_t *q_residues, const uint64_t *q_off,
+                          const uint32_t *pair_query, const uint32_t *pair_subject, uint32_t n_pairs,
+                          const kaamer_aln_opts *opts, kaamer_aln *out, kaamer_aln_text **text);
+void kaamer_gpu_free_aln_text(kaamer_aln_text *t);
+
+/* The DP model of the alignment stage.  The reference hard-wires align.SWAffine{Matrix: matrix.BLOSUM62,
+ * GapOpen: -11} whatever -mat / -gop / -gex say (align.go:62-65); that is the default here and nothing
+ * changes it implicitly.  A host that wants to honour the options (a behaviour change, behind
+ * this explicit call only), or that has to match a biogo whose BLOSUM62 carries a non-zero gap row, sets the
+ * model: matrix[26*26] in biogo alphabet.Protein order "-ABCDEFGHIJKLMNPQRSTVWXYZ*" (pkg/align/
+ * matrixScores.go:107), row / column 0 = the per-residue gap cost SWAffine adds for every gap residue,
+ * gap_open = SWAffine.GapOpen (negative).  NULL restores the default. */
+typedef struct kaamer_aln_model {
+  int8_t matrix[26 * 26];
+  int32_t gap_open;
+} kaamer_aln_model;
+int kaamer_gpu_default_align_model(kaamer_aln_model *out);
+int kaamer_gpu_set_align_model(kaamer_gpu_t *h, const kaamer_aln_model *model);
 
 /* ---- device-resident entry points (inputs already in HBM; used by bench.py `value`, by the
  * multi-GPU drivers and by callers that keep query batches on the device).  All pointers are
@@ -312,6 +338,27 @@ int64_t kaamer_host_format_positions(const uint8_t *positions, uint64_t n, int w
 int kaamer_host_read_fasta(const char *path, int is_protein, int pinned, kaamer_query_batch **out);
 int kaamer_host_read_fastq(const char *path, int pinned, kaamer_query_batch **out);
 void kaamer_host_free_queries(kaamer_query_batch *b);
+
+/* ---- result rows off the critical path.  FetchHitsInformation (pkg/search/search.go:454-470)
+ * does one protein_store get per hit and the handler goroutines build every TSV row with fmt.Sprintf
+ * (search.go:505-606); after a millisecond GPU batch that is the whole request time.  The handle can keep the
+ * two Protein fields the rows need — EntryId and Length, indexed by protein id (they travel in the `.kidx`
+ * file) — and kaamer_host_format_tsv writes the rows of a whole batch into ONE buffer, byte for byte what the
+ * reference sends to its writer: one line per hit, rows in batch order, hits in rank order (with `aln`:
+ * re-sorted by BitScore descending, search.go:491-493, stable).
+ *   aln      NULL: layout without alignment (search.go:507-553); else one kaamer_aln per hit, in hits order:
+ *            alignment layout (search.go:556-604)
+ *   names / name_off   Query.Name of the query a row belongs to (row i of a protein batch; row_contig[i] of
+ *            a nucleotide batch); the first blank-separated token is printed (strings.Split(Name, " ")[0])
+ *   seq_off  protein batches: the batch's query offsets (QStart = 1, QEnd = len(Sequence), search.go:297,290)
+ *   with_annotations   print Protein.Length (needs the table); the database's feature columns are not held
+ * The text is malloc'ed: kaamer_host_free_text.  Without a table the protein id stands in for EntryId. ---- */
+int kaamer_gpu_set_annotations(kaamer_gpu_t *h, const char *entry_ids, const uint64_t *entry_off /* [max_id+2] */,
+                               const int32_t *length /* [max_id+1] */, uint32_t max_protein_id);
+int kaamer_host_format_tsv(kaamer_gpu_t *h, const kaamer_hits *hits, const kaamer_aln *aln, const char *names,
+                           const uint64_t *name_off, const uint64_t *seq_off, int is_protein, int with_positions,
+                           int with_annotations, char **out, uint64_t *out_len);
+void kaamer_host_free_text(char *p);
 
 /* ---- synthetic C4 workload (bench / tests; include/kaamer_synth_spec.h is the specification, the CPU twin
  * is oracle/synth_oracle.cpp).  Counter-based: record i and query j are pure functions of (seed, index).

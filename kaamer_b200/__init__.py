@@ -5,6 +5,6 @@ This package holds only the host-side mirror of the reference interface and the 
 nothing here computes search results on the CPU.
 """
 from ._lib import KaamerGpuError, LIB_PATH  # noqa: F401
-from .gpu import GpuIndex, OrfTable, SearchOptions, SearchResult  # noqa: F401
+from .gpu import GpuIndex, OrfTable, SearchOptions, SearchResult, format_tsv  # noqa: F401
 
-__all__ = ["GpuIndex", "OrfTable", "SearchOptions", "SearchResult", "KaamerGpuError", "LIB_PATH"]
+__all__ = ["GpuIndex", "OrfTable", "SearchOptions", "SearchResult", "KaamerGpuError", "LIB_PATH", "format_tsv"]

@@ -117,6 +117,14 @@ class Aln(C.Structure):
     ]
 
 
+class AlnModel(C.Structure):
+    _fields_ = [("matrix", C.c_int8 * (26 * 26)), ("gap_open", C.c_int32)]
+
+
+class AlnText(C.Structure):
+    _fields_ = [("off", C.POINTER(C.c_uint64)), ("text", C.POINTER(C.c_char)), ("_owner", C.c_void_p)]
+
+
 class DevResult(C.Structure):
     _fields_ = [
         ("n_hits", C.c_void_p),
@@ -192,6 +200,10 @@ SYMBOLS = [
     "kaamer_gpu_get_orfs",
     "kaamer_gpu_free_orfs",
     "kaamer_gpu_align",
+    "kaamer_gpu_align_text",
+    "kaamer_gpu_free_aln_text",
+    "kaamer_gpu_default_align_model",
+    "kaamer_gpu_set_align_model",
     "kaamer_gpu_search_proteins_device",
     "kaamer_gpu_dense_space",
     "kaamer_gpu_shard_route",
@@ -207,6 +219,9 @@ SYMBOLS = [
     "kaamer_host_read_fasta",
     "kaamer_host_read_fastq",
     "kaamer_host_free_queries",
+    "kaamer_gpu_set_annotations",
+    "kaamer_host_format_tsv",
+    "kaamer_host_free_text",
     "kaamer_gpu_profile_enable",
     "kaamer_gpu_profile_read",
     "kaamer_gpu_profile_host_read",
@@ -264,6 +279,12 @@ def lib() -> C.CDLL:
     L.kaamer_gpu_free_orfs.argtypes = [C.POINTER(Orfs)]
     L.kaamer_gpu_free_orfs.restype = None
     L.kaamer_gpu_align.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.POINTER(AlnOpts), vp]
+    L.kaamer_gpu_align_text.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.POINTER(AlnOpts), vp,
+                                        C.POINTER(C.POINTER(AlnText))]
+    L.kaamer_gpu_free_aln_text.argtypes = [C.POINTER(AlnText)]
+    L.kaamer_gpu_free_aln_text.restype = None
+    L.kaamer_gpu_default_align_model.argtypes = [C.POINTER(AlnModel)]
+    L.kaamer_gpu_set_align_model.argtypes = [vp, C.POINTER(AlnModel)]
     L.kaamer_gpu_search_proteins_device.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(Opts), C.POINTER(DevResult), vp]
     L.kaamer_gpu_dense_space.restype = C.c_uint64
     L.kaamer_gpu_dense_space.argtypes = []
@@ -280,6 +301,11 @@ def lib() -> C.CDLL:
     L.kaamer_host_read_fastq.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.POINTER(QueryBatch))]
     L.kaamer_host_free_queries.argtypes = [C.POINTER(QueryBatch)]
     L.kaamer_host_free_queries.restype = None
+    L.kaamer_gpu_set_annotations.argtypes = [vp, vp, vp, vp, C.c_uint32]
+    L.kaamer_host_format_tsv.argtypes = [vp, C.POINTER(Hits), vp, vp, vp, vp, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(C.POINTER(C.c_char)), u64p]
+    L.kaamer_host_free_text.argtypes = [C.POINTER(C.c_char)]
+    L.kaamer_host_free_text.restype = None
     L.kaamer_gpu_pinned_alloc.argtypes = [C.c_uint64, C.POINTER(vp)]
     L.kaamer_gpu_pinned_free.argtypes = [vp]
     L.kaamer_gpu_pinned_free.restype = None

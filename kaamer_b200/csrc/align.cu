@@ -35,7 +35,7 @@ namespace kaamer {
 
 constexpr int ALN_WARPS = 4;
 constexpr int PROF_COLS = 512;  // 32 lanes x CW(max 16)
-constexpr int GAP_OPEN_DP = -11;  // align.go:64 (hard-coded in the reference, options ignored)
+constexpr int GAP_OPEN_DP = -11;  // align.go:64 (hard-coded in the reference, options ignored): the default model
 
 // NCBI BLOSUM62, 24-letter order ARNDCQEGHILKMFPSTWYVBZX*, + the J (I/L) row of BLAST+.
 static const char NCBI_ORDER[] = "ARNDCQEGHILKMFPSTWYVBZX*";
@@ -69,14 +69,14 @@ static const int8_t NCBI_J[24] = {-1, -2, -3, -3, -1, -2, -3, -4, -3, 3, 3, -3, 
 static const char BIOGO_ORDER[] = "-ABCDEFGHIJKLMNPQRSTVWXYZ*";
 
 struct AlnTables {
-  int8_t b62[26 * 32];       // [i][j], row stride 32; row/column 0 (gap) = 0
+  int8_t b62[26 * 32];       // [i][j], row stride 32; row/column 0 = per-residue gap cost (0 in the default model)
   int8_t letter_index[256];  // alphabet.Protein.LetterIndex(): case-insensitive, -1 = illegal letter
   int8_t aa_pos[256];        // AAPosInMatrix: exact (upper-case) letters only, miss -> 0 (Go map zero value)
 };
-__constant__ AlnTables c_aln;
 
-static void make_tables(AlnTables *t) {
-  memset(t, 0, sizeof *t);
+// the reference's model: biogo matrix.BLOSUM62 with GapOpen -11 (align.go:62-65); gap row/column 0
+void default_align_model(kaamer_aln_model *m) {
+  memset(m, 0, sizeof *m);
   auto ncbi = [&](char c) -> int { return (int)(strchr(NCBI_ORDER, c) - NCBI_ORDER); };
   for (int i = 1; i < 26; ++i)
     for (int j = 1; j < 26; ++j) {
@@ -86,8 +86,15 @@ static void make_tables(AlnTables *t) {
       else if (a == 'J') v = NCBI_J[ncbi(b)];
       else if (b == 'J') v = NCBI_J[ncbi(a)];
       else v = NCBI_B62[ncbi(a)][ncbi(b)];
-      t->b62[i * 32 + j] = (int8_t)v;
+      m->matrix[i * 26 + j] = (int8_t)v;
     }
+  m->gap_open = GAP_OPEN_DP;
+}
+
+static void make_tables(AlnTables *t, const kaamer_aln_model *model) {
+  memset(t, 0, sizeof *t);
+  for (int i = 0; i < 26; ++i)
+    for (int j = 0; j < 26; ++j) t->b62[i * 32 + j] = model->matrix[i * 26 + j];
   memset(t->letter_index, -1, sizeof t->letter_index);
   for (int i = 0; i < 26; ++i) {
     const unsigned char c = (unsigned char)BIOGO_ORDER[i];
@@ -117,6 +124,13 @@ struct AlnArgs {
   double lambda, K;
   int gap_open_opt, gap_extend_opt;
   double number_of_aa;
+  const AlnTables *tables;   // per handle (global memory): the model's scores + letter tables
+  int open;                  // SWAffine.GapOpen of the model (-11)
+  int zero_gap;              // the model's gap row / column is all zero: the specialised cell update
+  // AlnString (align.go:69-103): the traceback leaves the alignment columns, last column first, in
+  // rev[rev_off[pair] ..): (query char) | (subject char) << 8 per column; nullptr: not wanted
+  uint16_t *rev;
+  const uint64_t *rev_off;
 };
 
 __device__ __forceinline__ uint8_t fix_u(uint8_t c) { return (c == 'u' || c == 'U') ? (uint8_t)'*' : c; }  // align.go:54-55
@@ -132,17 +146,17 @@ __device__ __forceinline__ size_t block_stride(int n, int cw) { return (size_t)(
 //   (bs, br): running column maximum of M and the last row that reached it
 template <int CC>
 __device__ __forceinline__ void sw_cell(int diag, int sc, int Mup, int Uup, int left_m, int left_l, int r, int &m,
-                                        int &u, int &l, int &b, uint32_t &w, int &bs, int &br) {
+                                        int &u, int &l, int &b, uint32_t &w, int &bs, int &br, int open = GAP_OPEN_DP) {
   asm("{\n\t"
       ".reg .pred pu, pl, p1, p2, pz, pt;\n\t"
       ".reg .s32 uo, lo, mu, dd;\n\t"
       ".reg .u32 f;\n\t"
       "add.s32 dd, %7, %8;\n\t"
       "max.s32 %0, dd, 0;\n\t"
-      "add.s32 uo, %9, -11;\n\t"
+      "add.s32 uo, %9, %19;\n\t"
       "setp.ge.s32 pu, uo, %10;\n\t"
       "max.s32 %1, uo, %10;\n\t"
-      "add.s32 lo, %11, -11;\n\t"
+      "add.s32 lo, %11, %19;\n\t"
       "setp.ge.s32 pl, lo, %12;\n\t"
       "max.s32 %2, lo, %12;\n\t"
       "setp.ge.s32 p1, %0, %1;\n\t"
@@ -162,7 +176,30 @@ __device__ __forceinline__ void sw_cell(int diag, int sc, int Mup, int Uup, int 
       "}"
       : "=&r"(m), "=&r"(u), "=&r"(l), "=&r"(b), "+r"(w), "+r"(bs), "+r"(br)
       : "r"(diag), "r"(sc), "r"(Mup), "r"(Uup), "r"(left_m), "r"(left_l), "n"(1u << (8 * CC)), "n"(2u << (8 * CC)),
-        "n"(4u << (8 * CC)), "n"(8u << (8 * CC)), "n"(16u << (8 * CC)), "r"(r));
+        "n"(4u << (8 * CC)), "n"(8u << (8 * CC)), "n"(16u << (8 * CC)), "r"(r), "r"(open));
+}
+
+// The same cell for a model with per-residue gap costs (biogo adds Matrix[r][gap] for every gap residue):
+//   u = max(Mup + ogu, Uup + gu), ogu = open + gap cost of the query residue, gu = that gap cost
+//   l = max(left_m + ogl, left_l + gl), same with the subject residue of the column
+template <int CC>
+__device__ __forceinline__ void sw_cell_gap(int diag, int sc, int Mup, int Uup, int left_m, int left_l, int r, int ogu,
+                                            int gu, int ogl, int gl, int &m, int &u, int &l, int &b, uint32_t &w,
+                                            int &bs, int &br) {
+  const int dd = diag + sc;
+  m = dd > 0 ? dd : 0;
+  const int uo = Mup + ogu, ue = Uup + gu;
+  const int lo = left_m + ogl, le = left_l + gl;
+  u = uo > ue ? uo : ue;
+  l = lo > le ? lo : le;
+  const int mu = m > u ? m : u;
+  b = mu > l ? mu : l;
+  uint32_t f = m >= u ? 0u : 1u;
+  f = mu >= l ? f : 2u;
+  f |= (m == 0 ? 4u : 0u) | (uo >= ue ? 8u : 0u) | (lo >= le ? 16u : 0u);
+  w += f << (8 * CC);
+  if (m >= bs) br = r;
+  bs = bs > m ? bs : m;
 }
 
 template <class F>
@@ -178,12 +215,17 @@ __device__ __forceinline__ void static_for4(F f) {
 // max(M,U,L) of the block's last column).  In the multi-warp kernel the previous block is being
 // produced by another warp of the CTA at the same time: prog_in counts its finished rows,
 // prog_out publishes ours (shared memory, volatile; data in global memory, fenced).
-template <int CW, bool PIPE, int PCOLS>
-__device__ __forceinline__ void dp_block(const int8_t *prof, const int8_t *lidx, const uint8_t *q, int n, int blk,
+template <int CW, bool PIPE, int PCOLS, bool ZG>
+__device__ __forceinline__ void dp_block(const int8_t *prof, const int8_t *lidx, const int8_t *b62, int open,
+                                         const uint8_t *q, int n, int blk,
                                          uint8_t *dirs, const int *bnd_in, int *bnd_out,
                                          const volatile int *prog_in, volatile int *prog_out, int &out_s,
                                          uint32_t &out_pos) {
   const unsigned lane = threadIdx.x & 31;
+  // gap costs of this lane's subject columns (row 0 of the block profile); unused when the gap row is zero
+  uint32_t gpw[CW / 4];
+#pragma unroll
+  for (int g = 0; g < CW / 4; ++g) gpw[g] = ZG ? 0u : reinterpret_cast<const uint32_t *>(prof + lane * CW)[g];
   // per-column running maximum of M and the last row that reached it (">=": the last row wins);
   // 1 as the initial maximum implements the `M > 0` condition of the end-cell rule
   int bs[CW], br[CW];
@@ -223,6 +265,7 @@ __device__ __forceinline__ void dp_block(const int8_t *prof, const int8_t *lidx,
     prevB = inB;
     if (active) {
       const int qi = lidx[fix_u(q[r])];
+      const int gu = ZG ? 0 : (int)b62[qi * 32], ogu = open + gu;
       uint32_t pw[CW / 4];
       {
         const uint32_t *pp = reinterpret_cast<const uint32_t *>(prof + qi * PCOLS + lane * CW);
@@ -255,7 +298,13 @@ __device__ __forceinline__ void dp_block(const int8_t *prof, const int8_t *lidx,
           //   m = max(diag + sc, 0); u = max(Mup - 11, Uup); l = max(left_m - 11, left_l)
           //   byte = best layer (M, then U, then L on ties) | M==0 <<2 | U opened <<3 | L opened <<4
           int m, u, l, b;
-          sw_cell<cc>(diag, sc, Mup[c], Uup[c], left_m, left_l, r, m, u, l, b, w, bs[c], br[c]);
+          if constexpr (ZG) {
+            sw_cell<cc>(diag, sc, Mup[c], Uup[c], left_m, left_l, r, m, u, l, b, w, bs[c], br[c], open);
+          } else {
+            const int gl = (int)(gpw[g] << (24 - 8 * cc)) >> 24;
+            sw_cell_gap<cc>(diag, sc, Mup[c], Uup[c], left_m, left_l, r, ogu, gu, open + gl, gl, m, u, l, b, w, bs[c],
+                            br[c]);
+          }
           diag = Bup[c];
           Mup[c] = m;
           Uup[c] = u;
@@ -363,6 +412,7 @@ __device__ __forceinline__ void traceback_and_emit(const AlnArgs &a, const AlnPa
         cur_lq = cur_ls = 0;
       }
     };
+    uint16_t *rev = a.rev ? a.rev + a.rev_off[pr.out_index] : nullptr;
     bool done = false;
     while (!done) {
       const int di = layer == 2 ? 0 : 1, dj = layer == 1 ? 0 : 1;
@@ -383,6 +433,7 @@ __device__ __forceinline__ void traceback_and_emit(const AlnArgs &a, const AlnPa
             break;
           }
           open_seg(0);
+          if (rev && lane == 0) rev[aln_len] = (uint16_t)(ca | (cb << 8));
           cur_score += s_b62[s_lidx[ca] * 32 + s_lidx[cb]];
           cur_lq++;
           cur_ls++;
@@ -404,6 +455,8 @@ __device__ __forceinline__ void traceback_and_emit(const AlnArgs &a, const AlnPa
           layer = (int)(__shfl_sync(0xFFFFFFFFu, F, k + 1) & 3u);
         } else if (layer == 1) {
           open_seg(1);
+          if (rev && lane == 0) rev[aln_len] = (uint16_t)(ca | ('-' << 8));
+          cur_score += s_b62[s_lidx[ca] * 32];  // the model's gap cost of this query residue (0 by default)
           cur_lq++;
           if (ca == '-') {  // a literal '-' residue equals the gap character (align.go:82)
             identity += 1.f;
@@ -412,7 +465,7 @@ __device__ __forceinline__ void traceback_and_emit(const AlnArgs &a, const AlnPa
           nb_pos += 1.f;
           aln_len++;
           if (f & 8u) {
-            cur_score += GAP_OPEN_DP;
+            cur_score += a.open;
             layer = 0;
           }
           --i;
@@ -422,6 +475,8 @@ __device__ __forceinline__ void traceback_and_emit(const AlnArgs &a, const AlnPa
           }
         } else {
           open_seg(2);
+          if (rev && lane == 0) rev[aln_len] = (uint16_t)('-' | (cb << 8));
+          cur_score += s_b62[s_lidx[cb]];  // b62[gap][s_j]
           cur_ls++;
           if (cb == '-') {
             identity += 1.f;
@@ -430,7 +485,7 @@ __device__ __forceinline__ void traceback_and_emit(const AlnArgs &a, const AlnPa
           nb_pos += 1.f;
           aln_len++;
           if (f & 16u) {
-            cur_score += GAP_OPEN_DP;
+            cur_score += a.open;
             layer = 0;
           }
           --j;
@@ -465,11 +520,11 @@ __device__ __forceinline__ void traceback_and_emit(const AlnArgs &a, const AlnPa
   a.out[pr.out_index] = r;
 }
 
-__device__ __forceinline__ void load_tables(int8_t *s_b62, int8_t *s_lidx, int8_t *s_apos) {
-  for (int i = threadIdx.x; i < 26 * 32; i += blockDim.x) s_b62[i] = c_aln.b62[i];
+__device__ __forceinline__ void load_tables(const AlnTables *t, int8_t *s_b62, int8_t *s_lidx, int8_t *s_apos) {
+  for (int i = threadIdx.x; i < 26 * 32; i += blockDim.x) s_b62[i] = t->b62[i];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-    s_lidx[i] = c_aln.letter_index[i];
-    s_apos[i] = c_aln.aa_pos[i];
+    s_lidx[i] = t->letter_index[i];
+    s_apos[i] = t->aa_pos[i];
   }
   __syncthreads();
 }
@@ -481,7 +536,7 @@ __global__ void __launch_bounds__(ALN_WARPS * 32) k_sw_affine(AlnArgs a) {
   __shared__ int8_t s_b62[26 * 32];
   __shared__ int8_t s_lidx[256];
   __shared__ int8_t s_apos[256];
-  load_tables(s_b62, s_lidx, s_apos);
+  load_tables(a.tables, s_b62, s_lidx, s_apos);
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t pi = blockIdx.x * ALN_WARPS + w;
   if (pi >= a.n_pairs) return;
@@ -511,10 +566,13 @@ __global__ void __launch_bounds__(ALN_WARPS * 32) k_sw_affine(AlnArgs a) {
       uint8_t *dirs = scratch + (size_t)blk * block_stride(n, cw);
       const int *bin = blk > 0 ? bnd : nullptr;
       int *bout = blk + 1 < nblk ? bnd : nullptr;
-      if (cw == 16) dp_block<16, false, PROF_COLS>(prof, s_lidx, q, n, blk, dirs, bin, bout, nullptr, nullptr, best_s, best_pos);
-      else if (cw == 12) dp_block<12, false, PROF_COLS>(prof, s_lidx, q, n, blk, dirs, bin, bout, nullptr, nullptr, best_s, best_pos);
-      else if (cw == 8) dp_block<8, false, PROF_COLS>(prof, s_lidx, q, n, blk, dirs, bin, bout, nullptr, nullptr, best_s, best_pos);
-      else dp_block<4, false, PROF_COLS>(prof, s_lidx, q, n, blk, dirs, bin, bout, nullptr, nullptr, best_s, best_pos);
+      if (!a.zero_gap) {
+        // a model with gap costs (not the reference default): the general cell, 8 columns per lane
+        dp_block<8, false, PROF_COLS, false>(prof, s_lidx, s_b62, a.open, q, n, blk, dirs, bin, bout, nullptr, nullptr, best_s, best_pos);
+      } else if (cw == 16) dp_block<16, false, PROF_COLS, true>(prof, s_lidx, s_b62, a.open, q, n, blk, dirs, bin, bout, nullptr, nullptr, best_s, best_pos);
+      else if (cw == 12) dp_block<12, false, PROF_COLS, true>(prof, s_lidx, s_b62, a.open, q, n, blk, dirs, bin, bout, nullptr, nullptr, best_s, best_pos);
+      else if (cw == 8) dp_block<8, false, PROF_COLS, true>(prof, s_lidx, s_b62, a.open, q, n, blk, dirs, bin, bout, nullptr, nullptr, best_s, best_pos);
+      else dp_block<4, false, PROF_COLS, true>(prof, s_lidx, s_b62, a.open, q, n, blk, dirs, bin, bout, nullptr, nullptr, best_s, best_pos);
     }
     // end cell: maximum score, then last in row-major order (larger i, then larger j)
     for (int o = 16; o > 0; o >>= 1) {
@@ -547,7 +605,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 4) k_sw_affine_cta(AlnArgs a) 
   __shared__ int s_best[BIG_WARPS];
   __shared__ uint32_t s_pos[BIG_WARPS];
   __shared__ int s_bad;
-  load_tables(s_b62, s_lidx, s_apos);
+  load_tables(a.tables, s_b62, s_lidx, s_apos);
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const AlnPair pr = a.pairs[blockIdx.x];
   const uint8_t *q = a.q_res + a.q_off[pr.q];
@@ -578,8 +636,14 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 4) k_sw_affine_cta(AlnArgs a) 
       uint8_t *dirs = scratch + (size_t)blk * block_stride(n, cw);
       const int *bin = blk > 0 ? bnd + (size_t)(blk - 1) * 3 * n : nullptr;
       int *bout = blk + 1 < nblk ? bnd + (size_t)blk * 3 * n : nullptr;
-      dp_block<8, true, BIG_PCOLS>(prof, s_lidx, q, n, blk, dirs, bin, bout, blk > 0 ? &prog[blk - 1] : nullptr,
-                  blk + 1 < nblk ? &prog[blk] : nullptr, best_s, best_pos);
+      if (a.zero_gap)
+        dp_block<8, true, BIG_PCOLS, true>(prof, s_lidx, s_b62, a.open, q, n, blk, dirs, bin, bout,
+                                           blk > 0 ? &prog[blk - 1] : nullptr, blk + 1 < nblk ? &prog[blk] : nullptr,
+                                           best_s, best_pos);
+      else
+        dp_block<8, true, BIG_PCOLS, false>(prof, s_lidx, s_b62, a.open, q, n, blk, dirs, bin, bout,
+                                            blk > 0 ? &prog[blk - 1] : nullptr, blk + 1 < nblk ? &prog[blk] : nullptr,
+                                            best_s, best_pos);
     }
     for (int o = 16; o > 0; o >>= 1) {
       const int os = __shfl_xor_sync(0xFFFFFFFFu, best_s, o);
@@ -606,6 +670,32 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 4) k_sw_affine_cta(AlnArgs a) 
     }
   }
   traceback_and_emit(a, pr, scratch, q, n, s, cw, best_s, best_pos, bad, s_b62, s_lidx, s_apos);
+}
+
+// ---- AlnString (align.go:69-103): one warp per pair turns the reversed columns into the three lines ----
+__global__ void __launch_bounds__(128) k_aln_text(const AlnTables *t, const kaamer_aln *out, const uint16_t *rev,
+                                                  const uint64_t *rev_off, const uint64_t *text_off, uint32_t n_pairs,
+                                                  char *text) {
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (i >= n_pairs) return;
+  const int L = out[i].length;
+  const uint16_t *r = rev + rev_off[i];
+  char *dst = text + text_off[i];
+  for (int c = lane; c < L; c += 32) {
+    const uint32_t col = r[L - 1 - c];
+    const uint32_t ca = col & 0xFFu, cb = col >> 8;
+    char mc;
+    if (cb == ca) mc = (char)cb;                                                  // align.go:82-85
+    else mc = t->b62[t->aa_pos[cb] * 32 + t->aa_pos[ca]] > 0 ? '+' : ' ';         // GetAlnScoreAA (:91-96)
+    dst[c] = (char)ca;
+    dst[L + 1 + c] = mc;
+    dst[2 * L + 2 + c] = (char)cb;
+  }
+  if (lane == 0) {
+    dst[L] = '\n';
+    dst[2 * L + 1] = '\n';
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -636,22 +726,70 @@ static uint64_t pair_scratch_bytes(uint64_t n, uint64_t m, int cw, bool big) {
 }
 
 int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, const uint32_t *pair_q,
-                const uint32_t *pair_s, uint32_t n_pairs, const kaamer_aln_opts *o, kaamer_aln *out) {
+                const uint32_t *pair_s, uint32_t n_pairs, const kaamer_aln_opts *o, kaamer_aln *out,
+                kaamer_aln_text **text_out) {
   DevIndex &ix = h->idx;
   cudaStream_t st = h->stream;
   if (!ix.has_proteins) {
     set_error("kaamer_gpu_align: the index was opened without a protein table");
     return KAAMER_ERR_ARG;
   }
-  if (n_pairs == 0) return KAAMER_OK;
+  kaamer_aln_text *text = nullptr;
+  HitsOwner *text_owner = nullptr;
+  if (text_out) {
+    *text_out = nullptr;
+    text = new kaamer_aln_text();
+    memset(text, 0, sizeof *text);
+    text_owner = new HitsOwner();
+    text->_owner = text_owner;
+    if (text_owner->alloc(&text->off, (size_t)n_pairs + 1) != KAAMER_OK) {
+      delete text_owner;
+      delete text;
+      return KAAMER_ERR_NOMEM;
+    }
+    text->off[0] = 0;
+  }
+  auto drop_text = [&]() {
+    delete text_owner;
+    delete text;
+    text = nullptr;
+    text_owner = nullptr;
+  };
+  struct TextGuard {  // every early return below releases the half-built text
+    decltype(drop_text) &f;
+    ~TextGuard() { f(); }
+  } text_guard{drop_text};
+  if (n_pairs == 0) {
+    if (text_out) {
+      *text_out = text;
+      text = nullptr;
+      text_owner = nullptr;
+    }
+    return KAAMER_OK;
+  }
+  kaamer_aln_model model;
+  if (h->aln_model_set) model = h->aln_model;
+  else default_align_model(&model);
+  bool zero_gap = true;
+  for (int i = 0; i < 26; ++i) zero_gap = zero_gap && model.matrix[i * 26] == 0 && model.matrix[i] == 0;
   if (!h->aln_ready) {
-    // constant memory and function attributes belong to the device context: once per handle (a process
-    // may drive several GPUs)
+    // score tables and function attributes belong to the handle / device context (a process may drive
+    // several GPUs, and two handles of one device may carry different models)
     AlnTables t;
-    make_tables(&t);
-    KCUDA(cudaMemcpyToSymbol(c_aln, &t, sizeof t));
-    KCUDA(cudaFuncSetAttribute(k_sw_affine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WARP_SMEM));
-    KCUDA(cudaFuncSetAttribute(k_sw_affine_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM));
+    make_tables(&t, &model);
+    if (h->ws.a_tables.ensure(sizeof t) != KAAMER_OK) {
+      drop_text();
+      return KAAMER_ERR_NOMEM;
+    }
+    cudaError_t e = cudaMemcpyAsync(h->ws.a_tables.p, &t, sizeof t, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `t` is a stack object
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_affine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WARP_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_affine_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM);
+    if (e != cudaSuccess) {
+      set_error("alignment tables: %s", cudaGetErrorString(e));
+      drop_text();
+      return KAAMER_ERR_CUDA;
+    }
     h->aln_ready = true;
   }
   uint32_t nq = 0;
@@ -663,6 +801,7 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
   for (uint32_t i = 0; i < n_pairs; ++i) {
     if (pair_s[i] > ix.max_protein_id) {
       set_error("pair %u: subject id %u not in the protein table (max %u)", i, pair_s[i], ix.max_protein_id);
+      drop_text();
       return KAAMER_ERR_ARG;
     }
     const uint64_t n = q_off[pair_q[i] + 1] - q_off[pair_q[i]];
@@ -670,6 +809,7 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
     if (n >= 65535 || m >= 65535) {
       set_error("pair %u: sequences longer than 65534 residues are not supported (%llu x %llu)", i,
                 (unsigned long long)n, (unsigned long long)m);
+      drop_text();
       return KAAMER_ERR_LIMIT;
     }
     cost[i] = n * m;
@@ -694,7 +834,9 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
   uint64_t *d_qoff = nullptr;
   AlnPair *d_pairs = nullptr;
   kaamer_aln *d_out = nullptr;
-  auto cleanup = [&]() {};
+  auto cleanup = [&]() {
+    if (text) drop_text();
+  };
 #define ACUDA(call)                                                                      \
   do {                                                                                   \
     cudaError_t _e = (call);                                                             \
@@ -728,7 +870,7 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
     const uint64_t n = q_off[pair_q[i] + 1] - q_off[pair_q[i]];
     const uint64_t m = ix.h_prot_off[pair_s[i] + 1] - ix.h_prot_off[pair_s[i]];
     const bool big = n * m >= BIG_CELLS;
-    const int cw = big ? 8 : choose_cw(m);
+    const int cw = (big || !zero_gap) ? 8 : choose_cw(m);
     const uint64_t b = pair_scratch_bytes(n, m, cw, big);
     if (b > budget) {
       set_error("pair %u (%llu x %llu) needs %llu bytes of traceback state, more than the device has free", i,
@@ -761,6 +903,28 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
   a.gap_open_opt = o->gap_open;
   a.gap_extend_opt = o->gap_extend;
   a.number_of_aa = (double)(o->number_of_aa ? o->number_of_aa : ix.n_aa);
+  a.tables = reinterpret_cast<const AlnTables *>(ws.a_tables.p);
+  a.open = model.gap_open;
+  a.zero_gap = zero_gap ? 1 : 0;
+  a.rev = nullptr;
+  a.rev_off = nullptr;
+  std::vector<uint64_t> rev_off;
+  if (text) {
+    // room for the reversed columns of every pair: an alignment has at most n + m columns
+    rev_off.resize((size_t)n_pairs + 1);
+    rev_off[0] = 0;
+    for (uint32_t i = 0; i < n_pairs; ++i)
+      rev_off[i + 1] = rev_off[i] + (q_off[pair_q[i] + 1] - q_off[pair_q[i]]) +
+                       (ix.h_prot_off[pair_s[i] + 1] - ix.h_prot_off[pair_s[i]]);
+    if (ws.a_rev.ensure((size_t)rev_off[n_pairs] * 2 + 16) != KAAMER_OK ||
+        ws.a_revoff.ensure((size_t)2 * n_pairs + 2) != KAAMER_OK) {
+      cleanup();
+      return KAAMER_ERR_NOMEM;
+    }
+    ACUDA(cudaMemcpyAsync(ws.a_revoff.p, rev_off.data(), ((size_t)n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
+    a.rev = reinterpret_cast<uint16_t *>(ws.a_rev.p);
+    a.rev_off = ws.a_revoff.p;
+  }
   // Per chunk: the long pairs (one CTA each) on `st`, the rest (one warp each) on the second
   // stream so that both kernels share the GPU; the chunk's scratch is reused only after both end.
   cudaStream_t st2 = h->copy_stream;
@@ -792,7 +956,26 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
   profile_end(h, st);
   ACUDA(cudaMemcpyAsync(out, d_out, (size_t)n_pairs * sizeof(kaamer_aln), cudaMemcpyDeviceToHost, st));
   ACUDA(cudaStreamSynchronize(st));
-  cleanup();
+  if (text) {
+    // offsets of the three-line texts from the alignment lengths, then one warp per pair writes them
+    for (uint32_t i = 0; i < n_pairs; ++i) text->off[i + 1] = text->off[i] + 3ull * (uint64_t)out[i].length + 2ull;
+    const uint64_t total = text->off[n_pairs];
+    if (text_owner->alloc(&text->text, (size_t)total + 1) != KAAMER_OK || ws.a_text.ensure((size_t)total + 16) != KAAMER_OK) {
+      cleanup();
+      return KAAMER_ERR_NOMEM;
+    }
+    uint64_t *d_toff = ws.a_revoff.p + (size_t)n_pairs + 1;
+    ACUDA(cudaMemcpyAsync(d_toff, text->off, ((size_t)n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
+    k_aln_text<<<(unsigned)(((uint64_t)n_pairs * 32 + 127) / 128), 128, 0, st>>>(
+        a.tables, d_out, a.rev, a.rev_off, d_toff, n_pairs, reinterpret_cast<char *>(ws.a_text.p));
+    h->prof_all_launches += 1;
+    ACUDA(cudaGetLastError());
+    ACUDA(cudaMemcpyAsync(text->text, ws.a_text.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+    ACUDA(cudaStreamSynchronize(st));
+    *text_out = text;
+    text = nullptr;  // handed over
+    text_owner = nullptr;
+  }
 #undef ACUDA
   return KAAMER_OK;
 }
@@ -801,14 +984,64 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
 
 using namespace kaamer;
 
-extern "C" int kaamer_gpu_align(kaamer_gpu_t *h, const uint8_t *q_residues, const uint64_t *q_off,
-                                const uint32_t *pair_query, const uint32_t *pair_subject, uint32_t n_pairs,
-                                const kaamer_aln_opts *opts, kaamer_aln *out) {
+static int align_entry(kaamer_gpu_t *h, const uint8_t *q_residues, const uint64_t *q_off, const uint32_t *pair_query,
+                       const uint32_t *pair_subject, uint32_t n_pairs, const kaamer_aln_opts *opts, kaamer_aln *out,
+                       kaamer_aln_text **text) {
   if (!h || !opts || (n_pairs && (!q_residues || !q_off || !pair_query || !pair_subject || !out))) {
     set_error("null argument");
     return KAAMER_ERR_ARG;
   }
   std::lock_guard<std::mutex> lk(h->mu);
   KCUDA(cudaSetDevice(h->device));
-  return align_pairs(h, q_residues, q_off, pair_query, pair_subject, n_pairs, opts, out);
+  return guarded([&]() -> int { return align_pairs(h, q_residues, q_off, pair_query, pair_subject, n_pairs, opts, out, text); });
 }
+
+extern "C" {
+
+int kaamer_gpu_align(kaamer_gpu_t *h, const uint8_t *q_residues, const uint64_t *q_off, const uint32_t *pair_query,
+                     const uint32_t *pair_subject, uint32_t n_pairs, const kaamer_aln_opts *opts, kaamer_aln *out) {
+  return align_entry(h, q_residues, q_off, pair_query, pair_subject, n_pairs, opts, out, nullptr);
+}
+
+int kaamer_gpu_align_text(kaamer_gpu_t *h, const uint8_t *q_residues, const uint64_t *q_off, const uint32_t *pair_query,
+                          const uint32_t *pair_subject, uint32_t n_pairs, const kaamer_aln_opts *opts, kaamer_aln *out,
+                          kaamer_aln_text **text) {
+  if (!text) {
+    set_error("null argument");
+    return KAAMER_ERR_ARG;
+  }
+  return align_entry(h, q_residues, q_off, pair_query, pair_subject, n_pairs, opts, out, text);
+}
+
+void kaamer_gpu_free_aln_text(kaamer_aln_text *t) {
+  if (!t) return;
+  delete (HitsOwner *)t->_owner;
+  delete t;
+}
+
+int kaamer_gpu_default_align_model(kaamer_aln_model *out) {
+  if (!out) {
+    set_error("null argument");
+    return KAAMER_ERR_ARG;
+  }
+  default_align_model(out);
+  return KAAMER_OK;
+}
+
+int kaamer_gpu_set_align_model(kaamer_gpu_t *h, const kaamer_aln_model *model) {
+  if (!h) {
+    set_error("null handle");
+    return KAAMER_ERR_ARG;
+  }
+  if (model && (model->gap_open > 0 || model->gap_open < -1000)) {
+    set_error("align model: gap_open must be in [-1000, 0]");
+    return KAAMER_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (model) h->aln_model = *model;
+  h->aln_model_set = model != nullptr;
+  h->aln_ready = false;  // the score tables are rebuilt by the next call
+  return KAAMER_OK;
+}
+
+}  // extern "C"

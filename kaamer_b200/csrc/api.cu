@@ -82,7 +82,8 @@ struct KidxHeader {
   uint64_t n_keys, n_postings, n_proteins, n_aa, n_kmers;
   uint32_t max_protein_id, flags;  // flags bit0: protein table present
   uint64_t n_residues;
-  uint8_t pad[128 - 8 - 8 - 40 - 8 - 8];
+  uint64_t annot_bytes;  // flags bit1: annotation sections present (entry offsets, EntryId blob of this size, lengths)
+  uint8_t pad[128 - 8 - 8 - 40 - 8 - 8 - 8];
 };
 static_assert(sizeof(KidxHeader) == 128, "kidx header is 128 bytes");
 
@@ -208,8 +209,10 @@ int kaamer_gpu_open_view(const kaamer_index_view *view, int device, kaamer_gpu_t
 struct KidxFile {
   KidxHeader hd;
   std::vector<uint32_t> keys, postings;
-  std::vector<uint64_t> offsets, poff;
+  std::vector<uint64_t> offsets, poff, aoff;
   std::vector<uint8_t> pres;
+  std::vector<char> aids;
+  std::vector<int32_t> alen;
 };
 
 // A `.kidx` file is untrusted input: every section size is checked against the file size BEFORE anything
@@ -243,6 +246,13 @@ static int read_kidx(const char *path, KidxFile *k, bool want_postings, bool wan
   unsigned long long need = sizeof hd + pad64((size_t)hd.n_keys * 4) + pad64(((size_t)hd.n_keys + 1) * 8) +
                             pad64((size_t)hd.n_postings * 4);
   if (has_prot) need += pad64(((size_t)hd.max_protein_id + 2) * 8) + (size_t)hd.n_residues;
+  const bool has_annot = (hd.flags & 2) != 0;
+  if (has_annot) {
+    if (hd.annot_bytes > fs || hd.max_protein_id > fs / 8) return bad("header counts exceed the file size (truncated or corrupt)");
+    need = sizeof hd + pad64((size_t)hd.n_keys * 4) + pad64(((size_t)hd.n_keys + 1) * 8) + pad64((size_t)hd.n_postings * 4) +
+           (has_prot ? pad64(((size_t)hd.max_protein_id + 2) * 8) + pad64((size_t)hd.n_residues) : 0) +
+           pad64(((size_t)hd.max_protein_id + 2) * 8) + pad64((size_t)hd.annot_bytes) + ((size_t)hd.max_protein_id + 1) * 4;
+  }
   if (need > fs) return bad("sections exceed the file size (truncated or corrupt)");
   if (hd.n_postings > ENTRY_VALUE_MASK) return bad("too many postings");
   int rc = KAAMER_OK;
@@ -258,7 +268,21 @@ static int read_kidx(const char *path, KidxFile *k, bool want_postings, bool wan
         k->poff.resize((size_t)hd.max_protein_id + 2);
         k->pres.resize((size_t)hd.n_residues);
         rc = read_section(f, k->poff.data(), k->poff.size() * 8);
-        if (rc == KAAMER_OK && hd.n_residues && fread(k->pres.data(), 1, k->pres.size(), f) != k->pres.size()) {
+        if (rc == KAAMER_OK) rc = read_section(f, k->pres.data(), k->pres.size());
+      } else if (rc == KAAMER_OK && has_prot && has_annot) {
+        // skip the protein sections
+        if (fseek(f, (long)(pad64(((size_t)hd.max_protein_id + 2) * 8) + pad64((size_t)hd.n_residues)), SEEK_CUR) != 0) {
+          set_error("kidx: seek failed");
+          rc = KAAMER_ERR_IO;
+        }
+      }
+      if (rc == KAAMER_OK && has_annot) {
+        k->aoff.resize((size_t)hd.max_protein_id + 2);
+        k->aids.resize((size_t)hd.annot_bytes);
+        k->alen.resize((size_t)hd.max_protein_id + 1);
+        rc = read_section(f, k->aoff.data(), k->aoff.size() * 8);
+        if (rc == KAAMER_OK) rc = read_section(f, k->aids.data(), k->aids.size());
+        if (rc == KAAMER_OK && fread(k->alen.data(), 4, k->alen.size(), f) != k->alen.size()) {
           set_error("kidx: short read");
           rc = KAAMER_ERR_IO;
         }
@@ -292,6 +316,12 @@ static int read_kidx(const char *path, KidxFile *k, bool want_postings, bool wan
   if (want_postings)
     for (size_t i = 0; i < k->postings.size(); ++i)
       if (k->postings[i] > hd.max_protein_id) return bad("a posting exceeds max_protein_id");
+  if (!k->aoff.empty()) {
+    if (k->aoff[0] != 0) return bad("annotation offsets do not start at 0");
+    for (size_t i = 1; i < k->aoff.size(); ++i)
+      if (k->aoff[i] < k->aoff[i - 1]) return bad("annotation offsets are not monotonic");
+    if (k->aoff.back() != hd.annot_bytes) return bad("annotation offsets do not end at annot_bytes");
+  }
   fclose(f);
   return KAAMER_OK;
 }
@@ -346,7 +376,13 @@ static int open_kidx_range(const char *path, int device, uint64_t shard_lo, uint
   }
   v.shard_lo = whole ? 0 : shard_lo;
   v.shard_hi = whole ? 0 : shard_hi;
-  return kaamer_gpu_open_view(&v, device, out);
+  int rc = kaamer_gpu_open_view(&v, device, out);
+  if (rc == KAAMER_OK && !k.aoff.empty()) {
+    (*out)->idx.annot_off = std::move(k.aoff);
+    (*out)->idx.annot_ids = std::move(k.aids);
+    (*out)->idx.annot_len = std::move(k.alen);
+  }
+  return rc;
 }
 
 static int kaamer_gpu_open_impl(const char *path, int device, kaamer_gpu_t **out) {
@@ -733,8 +769,10 @@ static int kaamer_gpu_save_impl(kaamer_gpu_t *h, const char *path) {
   hd.n_aa = ix.n_aa;
   hd.n_kmers = ix.n_kmers;
   hd.max_protein_id = ix.max_protein_id;
-  hd.flags = ix.has_proteins ? 1u : 0u;
+  const bool has_annot = !ix.annot_off.empty() && ix.annot_off.size() == (size_t)ix.max_protein_id + 2;
+  hd.flags = (ix.has_proteins ? 1u : 0u) | (has_annot ? 2u : 0u);
   hd.n_residues = ix.n_prot_res;
+  hd.annot_bytes = has_annot ? ix.annot_ids.size() : 0;
   FILE *f = fopen(path, "wb");
   if (!f) {
     set_error("cannot create %s", path);
@@ -747,6 +785,11 @@ static int kaamer_gpu_save_impl(kaamer_gpu_t *h, const char *path) {
   if (rc == KAAMER_OK && ix.has_proteins) {
     rc = write_section(f, poff.data(), poff.size() * 8);
     if (rc == KAAMER_OK) rc = write_section(f, pres.data(), pres.size());
+  }
+  if (rc == KAAMER_OK && has_annot) {
+    rc = write_section(f, ix.annot_off.data(), ix.annot_off.size() * 8);
+    if (rc == KAAMER_OK) rc = write_section(f, ix.annot_ids.data(), ix.annot_ids.size());
+    if (rc == KAAMER_OK) rc = write_section(f, ix.annot_len.data(), ix.annot_len.size() * 4);
   }
   if (fclose(f) != 0 && rc == KAAMER_OK) rc = KAAMER_ERR_IO;
   if (rc != KAAMER_OK) set_error("write to %s failed", path);

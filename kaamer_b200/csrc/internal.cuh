@@ -300,6 +300,11 @@ struct DevIndex {
   uint32_t max_protein_id = 0;
   bool has_proteins = false;
   uint64_t n_proteins = 0, n_aa = 0, n_kmers = 0;
+  // annotation table for the row formatter (format.cu), host memory, indexed by protein id:
+  // Protein.EntryId and Protein.Length (pkg/kvstore/protein.proto); empty = not loaded
+  std::vector<uint64_t> annot_off;
+  std::vector<char> annot_ids;
+  std::vector<int32_t> annot_len;
   // mode P: the shards of the other ranks, mapped into this process (api.cu kaamer_gpu_attach_shards)
   PeerView peer{};               // host copy; peer.n == 0: not attached
   PeerView *d_peer = nullptr;    // device copy read by the kernels
@@ -325,13 +330,15 @@ struct SearchWorkspace {
   DevBuf<uint64_t> f_scan;     // [5][nq+1] sizes, scanned in place
   DevBuf<uint32_t> f_posbits, f_keep, f_trim;
   DevBuf<uint8_t> f_tmp;
-  DevBuf<uint8_t> a_pairs, a_out, a_scratch;  // align.cu
+  DevBuf<uint8_t> a_pairs, a_out, a_scratch, a_tables, a_rev, a_text;  // align.cu
+  DevBuf<uint64_t> a_revoff;
   void release_all() {
     residues.release(); seq_off.release(); n_hits.release(); hit_base.release(); lists.release();
     kmin.release(); size_in_kmer.release(); pool.release(); hit_off.release(); out_hits.release();
     counters.release(); ghash.release(); any0.release(); h_counters.release(); h_packed.release();
     f_scan.release(); f_posbits.release(); f_keep.release(); f_trim.release(); f_tmp.release();
-    a_pairs.release(); a_out.release(); a_scratch.release();
+    a_pairs.release(); a_out.release(); a_scratch.release(); a_tables.release(); a_rev.release(); a_text.release();
+    a_revoff.release();
   }
 };
 
@@ -399,6 +406,8 @@ struct kaamer_gpu {
   std::vector<kaamer::ProfSpan> prof_pending;
   double prof_host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // per-handle (= per-device context) one-time setup: constant tables and kernel attributes
+  kaamer_aln_model aln_model{};     // alignment DP model (align.cu); aln_model_set false: the reference default
+  bool aln_model_set = false;
   uint32_t ghash_slots = 1u << 20;  // class G histogram slots per CTA; grown on ST_GHASH_OVERFLOW (search.cu)
   size_t dense_smem_set = 0;        // dynamic shared memory the class-D kernels are configured for
   bool aln_ready = false, shard_attrs_ready = false;  // wall clock of host-call phases (kaamer_gpu_profile_host_read)
@@ -446,7 +455,9 @@ int build_presence(kaamer_gpu *h, const PeerView &pv, uint32_t *d_bits, cudaStre
 int replicate_table(kaamer_gpu *h, const PeerView &pv, uint64_t *d_full, cudaStream_t st);
 // align.cu
 int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, const uint32_t *pair_q,
-                const uint32_t *pair_s, uint32_t n_pairs, const kaamer_aln_opts *o, kaamer_aln *out);
+                const uint32_t *pair_s, uint32_t n_pairs, const kaamer_aln_opts *o, kaamer_aln *out,
+                kaamer_aln_text **text = nullptr);
+void default_align_model(kaamer_aln_model *m);
 // translate.cu
 int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint32_t nc, OrfSet *out,
                 cudaStream_t st);

@@ -686,22 +686,22 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
     KCUDA(cudaFuncSetAttribute(d_kernel(true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d_smem));
   }
   // class D (search_dense2.cuh): two launches, queries of up to E_KCAP_S k-mers and the longer ones
-  constexpr int E_KCAP_S = 512, E_KCAP_L = 2048, E_PF = 4;
+  constexpr int E_KCAP_S = 512, E_KCAP_L = 1024;
   a.e_kcap = E_KCAP_S;
   a.e_mapw_small = 512;
-  a.e_mapw_large = 2048;
-  if (const char *env = getenv("KAAMER_E_MAPW")) {  // tuning hook: "small,large" words per map per warp
+  a.e_mapw_large = 1024;
+  if (const char *env = getenv("KAAMER_E_MAPW")) {  // tuning hook: "small,large" words per map per warp (powers of two)
     unsigned ms = 0, ml = 0;
-    if (sscanf(env, "%u,%u", &ms, &ml) == 2 && ms >= 64 && ms <= 4096 && ml >= 64 && ml <= 6144 && ms % 4 == 0 &&
-        ml % 4 == 0) {
+    if (sscanf(env, "%u,%u", &ms, &ml) == 2 && ms >= 64 && ms <= 4096 && ml >= 64 && ml <= 4096 &&
+        (ms & (ms - 1)) == 0 && (ml & (ml - 1)) == 0) {
       a.e_mapw_small = ms;
       a.e_mapw_large = ml;
     }
   }
   const size_t e_smem_s = ((sizeof(Dense2Smem<E_KCAP_S>) + 15) & ~(size_t)15) + (size_t)E_WARPS * 2 * a.e_mapw_small * 4;
   const size_t e_smem_l = ((sizeof(Dense2Smem<E_KCAP_L>) + 15) & ~(size_t)15) + (size_t)E_WARPS * 2 * a.e_mapw_large * 4;
-  auto e_small = peer ? k_search_e<true, E_KCAP_S, E_PF, 4> : k_search_e<false, E_KCAP_S, E_PF, 4>;
-  auto e_large = peer ? k_search_e<true, E_KCAP_L, E_PF, 5> : k_search_e<false, E_KCAP_L, E_PF, 5>;
+  auto e_small = peer ? k_search_e<true, E_KCAP_S, 4> : k_search_e<false, E_KCAP_S, 4>;
+  auto e_large = peer ? k_search_e<true, E_KCAP_L, 5> : k_search_e<false, E_KCAP_L, 5>;
   if (a.dense == 2) {
     KCUDA(cudaFuncSetAttribute(e_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem_s));
     KCUDA(cudaFuncSetAttribute(e_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem_l));

@@ -105,16 +105,18 @@ __device__ __forceinline__ int dense2_load_chunk(const SearchArgs &a, const Peer
   return kn;
 }
 
-// Warp `wi` of `nw` streams the posting lists of entries wi, wi + nw, ... of the staged chunk.  A ring entry
-// is one 64-id window of ONE list (two ids per lane: positions lane and lane + 32 of the window); PFL
-// entries are in flight, R of them (R different lists) are processed together.  The inner code is flat —
-// predicated loads and stores, no nested branches: the kernel is bound by issued instructions, not by HBM.
-template <int PASS, bool PEER, int PFL, int R, int KCAP>
-__device__ __forceinline__ void dense2_stream(const SearchArgs &a, const PeerView *pv, Dense2Smem<KCAP> &s,
-                                              uint32_t *m1, uint32_t *m2, uint32_t nbits, int kn, int wi, int nw,
-                                              const SmemHashT<false> &hv, const CandList &cl,
-                                              unsigned long long bloom) {
-  static_assert(PFL % R == 0, "PFL must be a multiple of R");
+// Warp `wi` of `nw` streams the posting lists of entries wi, wi + nw, ... of the staged chunk.  The unit is one
+// 64-id window of ONE list (two ids per lane: positions lane and lane + 32 of the window); R windows of R
+// different lists form a group, and the loads of the next group are in flight while a group is processed.
+// The body is flat — predicated loads and stores, no nested branches — and exists once per instantiation:
+// the kernel is bound by issued instructions (and, before this layout, by instruction-cache misses), not by HBM.
+//
+// M1 and M2 are interleaved, mm[word] = (M1 word, M2 word): an id names ONE word index and two bit positions
+// (from two multiplicative hashes), so the test is one 8-byte load and the verify another.
+template <int PASS, bool PEER, int R, int KCAP>
+__device__ __forceinline__ void dense2_stream(const SearchArgs &a, const PeerView *pv, Dense2Smem<KCAP> &s, uint2 *mm,
+                                              int lg, int kn, int wi, int nw, const SmemHashT<false> &hv,
+                                              const CandList &cl, unsigned long long bloom) {
   const unsigned lane = threadIdx.x & 31;
   int k = wi - nw;
   uint32_t off = 0, cnt = 0, single = 0;
@@ -149,105 +151,89 @@ __device__ __forceinline__ void dense2_stream(const SearchArgs &a, const PeerVie
     }
     off += 64;
   };
-  uint32_t ia[PFL], ib[PFL], nvs[PFL];
+  constexpr int J = 2 * R;
+  const int sh_w = 37 - lg, sh_b = 32 - lg;  // word index = x1 >> (32 - lg + 5), bit index = (x1 >> (32 - lg)) & 31
+  uint32_t na[R], nb[R], nnv[R];
 #pragma unroll
-  for (int u = 0; u < PFL; ++u) fetch(ia[u], ib[u], nvs[u]);
-  while (nvs[0] != 0) {
-#pragma unroll
-    for (int g = 0; g < PFL / R; ++g) {
-      if (nvs[g * R] == 0) break;
-      constexpr int J = 2 * R;
-      uint32_t id[J];
-      bool v[J];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        id[2 * r] = ia[g * R + r];
-        id[2 * r + 1] = ib[g * R + r];
-        v[2 * r] = lane < nvs[g * R + r];
-        v[2 * r + 1] = lane + 32u < nvs[g * R + r];
-      }
-      if constexpr (PASS == 1) {
-        uint32_t a1[J], bit1[J], w1[J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const uint32_t h = e_hash1(id[j], nbits);
-          a1[j] = h >> 5;
-          bit1[j] = 1u << (h & 31u);
-          w1[j] = m1[a1[j]];  // (id 0 of an invalid lane still names a valid word)
-        }
-        bool set1[J], flag[J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const bool seen = (w1[j] & bit1[j]) != 0u;
-          set1[j] = v[j] && !seen;
-          flag[j] = v[j] && seen;
-          if (set1[j]) m1[a1[j]] = w1[j] | bit1[j];
-        }
-        uint32_t a2[J], bit2[J], w2[J];
-        bool set2[J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const uint32_t h = e_hash2(id[j], nbits);
-          a2[j] = h >> 5;
-          bit2[j] = 1u << (h & 31u);
-          w2[j] = 0u;
-          if (flag[j]) w2[j] = m2[a2[j]];
-        }
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const bool seen = (w2[j] & bit2[j]) != 0u;
-          set2[j] = flag[j] && !seen;
-          if (set2[j]) m2[a2[j]] = w2[j] | bit2[j];
-          if (flag[j] && seen) count_subject(hv, id[j], 0xFFFFFFFFu, cl);
-        }
-        __syncwarp();
-        // verify: a store of this group may have been overwritten by another lane's store to the same word
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          uint32_t c1 = 0xFFFFFFFFu, c2 = 0xFFFFFFFFu;
-          if (set1[j]) c1 = m1[a1[j]];
-          if (set2[j]) c2 = m2[a2[j]];
-          if ((c1 & bit1[j]) == 0u) atomicOr(m1 + a1[j], bit1[j]);
-          if ((c2 & bit2[j]) == 0u) atomicOr(m2 + a2[j], bit2[j]);
-        }
-        __syncwarp();
-      } else {
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const uint32_t hb = (id[j] * 0x9E3779B1u) >> 26;
-          if (v[j] && ((bloom >> hb) & 1ull)) {
-            uint32_t slot = hv.home(id[j]);
+  for (int r = 0; r < R; ++r) fetch(na[r], nb[r], nnv[r]);
 #pragma unroll 1
-            for (int probe = 0; probe < SmemHashT<false>::kMaxProbe; ++probe) {
-              const uint32_t key = s.hkeys[slot];
-              if (key == id[j]) {
-                if ((s.fin[slot >> 5] >> (slot & 31u)) & 1u) hv.add(slot, 1u);
-                break;
-              }
-              if (key == EMPTY) break;
-              slot = (slot + 1) & hv.mask;
+  while (nnv[0] != 0) {
+    uint32_t id[J];
+    bool v[J];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      id[2 * r] = na[r];
+      id[2 * r + 1] = nb[r];
+      v[2 * r] = lane < nnv[r];
+      v[2 * r + 1] = lane + 32u < nnv[r];
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) fetch(na[r], nb[r], nnv[r]);  // the next group's loads fly during this one
+    if constexpr (PASS == 1) {
+      uint32_t wd[J], b1[J], b2[J];
+      uint2 w[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const uint32_t x1 = id[j] * 0x9E3779B1u, x2 = id[j] * 0x85EBCA77u;
+        wd[j] = x1 >> sh_w;
+        b1[j] = 1u << ((x1 >> sh_b) & 31u);
+        b2[j] = 1u << (x2 >> 27);
+        w[j] = mm[wd[j]];  // (id 0 of an invalid lane still names a valid word)
+      }
+      bool set1[J], set2[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const bool seen1 = (w[j].x & b1[j]) != 0u, seen2 = (w[j].y & b2[j]) != 0u;
+        set1[j] = v[j] && !seen1;
+        set2[j] = v[j] && seen1 && !seen2;
+        if (set1[j]) mm[wd[j]].x = w[j].x | b1[j];
+        if (set2[j]) mm[wd[j]].y = w[j].y | b2[j];
+        if (v[j] && seen1 && seen2) count_subject(hv, id[j], 0xFFFFFFFFu, cl);
+      }
+      __syncwarp();
+      // verify: a store of this group may have been overwritten by another lane's store to the same word
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        uint2 c = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+        if (set1[j] || set2[j]) c = mm[wd[j]];
+        if (set1[j] && (c.x & b1[j]) == 0u) atomicOr(&mm[wd[j]].x, b1[j]);
+        if (set2[j] && (c.y & b2[j]) == 0u) atomicOr(&mm[wd[j]].y, b2[j]);
+      }
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const uint32_t hb = (id[j] * 0x9E3779B1u) >> 26;
+        if (v[j] && ((bloom >> hb) & 1ull)) {
+          uint32_t slot = hv.home(id[j]);
+#pragma unroll 1
+          for (int probe = 0; probe < SmemHashT<false>::kMaxProbe; ++probe) {
+            const uint32_t key = s.hkeys[slot];
+            if (key == id[j]) {
+              if ((s.fin[slot >> 5] >> (slot & 31u)) & 1u) hv.add(slot, 1u);
+              break;
             }
+            if (key == EMPTY) break;
+            slot = (slot + 1) & hv.mask;
           }
         }
       }
-#pragma unroll
-      for (int r = 0; r < R; ++r) fetch(ia[g * R + r], ib[g * R + r], nvs[g * R + r]);
     }
   }
 }
 
 // CLS: class list (4: queries up to KCAP k-mers staged at once; 5: the long ones)
-template <bool PEER, int KCAP, int PF, int CLS>
-__global__ void __launch_bounds__(E_THREADS, CLS == 4 ? 6 : 2) k_search_e(SearchArgs a) {
+template <bool PEER, int KCAP, int CLS>
+__global__ void __launch_bounds__(E_THREADS, CLS == 4 ? 6 : 4) k_search_e(SearchArgs a) {
   extern __shared__ __align__(16) uint8_t dsm[];
   using Smem = Dense2Smem<KCAP>;
   Smem &s = *reinterpret_cast<Smem *>(dsm);
-  const uint32_t mapw = CLS == 4 ? a.e_mapw_small : a.e_mapw_large;  // words per map per warp
+  const uint32_t mapw = CLS == 4 ? a.e_mapw_small : a.e_mapw_large;  // words per map per warp (a power of two)
+  const int lg = 31 - __clz(mapw) + 5;                                  // log2 of the bits per map
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31;
   const int w = tid >> 5;
-  uint32_t *maps = reinterpret_cast<uint32_t *>(dsm + ((sizeof(Smem) + 15) & ~(size_t)15));
-  uint32_t *m1 = maps + (size_t)w * 2 * mapw, *m2 = m1 + mapw;
+  uint2 *mm = reinterpret_cast<uint2 *>(dsm + ((sizeof(Smem) + 15) & ~(size_t)15)) + (size_t)w * mapw;
   const PeerView *pv = nullptr;
   if constexpr (PEER) {
     __shared__ PeerView s_peer;
@@ -290,10 +276,9 @@ __global__ void __launch_bounds__(E_THREADS, CLS == 4 ? 6 : 2) k_search_e(Search
         s.nfinal = 0;
       }
       // the warp's own maps (the first probes of the chunk are issued right after)
-      uint4 *mv = reinterpret_cast<uint4 *>(m1);
-      for (uint32_t i = lane; i < mapw / 2; i += 32) mv[i] = Z;  // 2 maps x mapw words = mapw / 2 uint4
+      uint4 *mv = reinterpret_cast<uint4 *>(mm);
+      for (uint32_t i = lane; i < mapw / 2; i += 32) mv[i] = Z;  // mapw word pairs = mapw / 2 uint4
     }
-    const uint32_t nbits = mapw * 32u;
     unsigned long long q_incr = 0;
     // ---- pass 1 ----
     for (int c = 0; c < nchunks; ++c) {
@@ -301,8 +286,8 @@ __global__ void __launch_bounds__(E_THREADS, CLS == 4 ? 6 : 2) k_search_e(Search
       const int kn = dense2_load_chunk<PEER, KCAP>(a, pv, s, b, len, K, c, res_end, tot);
       q_incr += tot;
       if (w < w_act) {
-        if (R == 2) dense2_stream<1, PEER, PF, 2, KCAP>(a, pv, s, m1, m2, nbits, kn, w, w_act, hv, cl, 0ull);
-        else dense2_stream<1, PEER, PF, 1, KCAP>(a, pv, s, m1, m2, nbits, kn, w, w_act, hv, cl, 0ull);
+        if (R == 2) dense2_stream<1, PEER, 2, KCAP>(a, pv, s, mm, lg, kn, w, w_act, hv, cl, 0ull);
+        else dense2_stream<1, PEER, 1, KCAP>(a, pv, s, mm, lg, kn, w, w_act, hv, cl, 0ull);
       }
     }
     __syncthreads();
@@ -344,7 +329,7 @@ __global__ void __launch_bounds__(E_THREADS, CLS == 4 ? 6 : 2) k_search_e(Search
         unsigned long long tot = 0;
         kn = dense2_load_chunk<PEER, KCAP>(a, pv, s, b, len, K, c, res_end, tot);
       }
-      dense2_stream<2, PEER, PF, 1, KCAP>(a, pv, s, m1, m2, nbits, kn, w, E_WARPS, hv, cl, bloom);
+      dense2_stream<2, PEER, 2, KCAP>(a, pv, s, mm, lg, kn, w, E_WARPS, hv, cl, bloom);
     }
     __syncthreads();
     for (int base = 0; base < E_H; base += E_THREADS) {

@@ -135,6 +135,56 @@ class _OwnedArray(np.ndarray):
             self._owner = getattr(obj, "_owner", None)
 
 
+def format_tsv(result: "SearchResult", names, aln=None, seq_off=None, is_protein: bool = True,
+               with_positions: bool = False, with_annotations: bool = False, index: "GpuIndex | None" = None) -> bytes:
+    """The TSV rows of a whole batch in one native call (kaamer_host_format_tsv): byte for byte what the
+    reference's QueryResultHandler sends to its writer (pkg/search/search.go:505-606).  `names`: Query.Name
+    per query (protein batch) or per contig (nucleotide batch); `aln`: the structured array of
+    GpuIndex.align for the hits, in hits order, or None."""
+    names = [n if isinstance(n, bytes) else n.encode() for n in names]
+    name_off = np.zeros(len(names) + 1, dtype=np.uint64)
+    if names:
+        name_off[1:] = np.cumsum([len(n) for n in names], dtype=np.uint64)
+    blob = np.frombuffer(b"".join(names) + b"\0", dtype=np.uint8).copy()
+    h = _lib.Hits()
+    keep = []
+
+    def ptr(a, dtype, ctype):
+        a = np.ascontiguousarray(a, dtype=dtype)
+        keep.append(a)
+        return a.ctypes.data_as(C.POINTER(ctype))
+
+    h.n_rows = result.n_rows
+    h.n_hits = len(result.subject)
+    h.hit_off = ptr(result.hit_off, np.uint64, C.c_uint64)
+    h.subject_id = ptr(result.subject, np.uint32, C.c_uint32)
+    h.kmatch = ptr(result.kmatch, np.uint32, C.c_uint32)
+    h.size_in_kmer = ptr(result.size_in_kmer, np.int32, C.c_int32)
+    if result.pos_off is not None and result.pos is not None:
+        h.pos_off = ptr(result.pos_off, np.uint64, C.c_uint64)
+        h.pos = ptr(result.pos if len(result.pos) else np.zeros(1, np.uint8), np.uint8, C.c_uint8)
+    if result.row_start is not None:
+        h.row_contig = ptr(result.row_contig, np.uint32, C.c_uint32)
+        h.row_start = ptr(result.row_start, np.int64, C.c_int64)
+        h.row_end = ptr(result.row_end, np.int64, C.c_int64)
+    so = None
+    if seq_off is not None:
+        so = np.ascontiguousarray(seq_off, dtype=np.uint64)
+    al = None
+    if aln is not None:
+        al = np.ascontiguousarray(aln)
+        assert al.dtype == ALN_DTYPE and len(al) == h.n_hits
+    out = C.POINTER(C.c_char)()
+    n = C.c_uint64()
+    check(_lib.lib().kaamer_host_format_tsv(index._h if index is not None else None, C.byref(h),
+                                            _vp(al) if al is not None else None, _vp(blob), _vp(name_off),
+                                            _vp(so) if so is not None else None, int(is_protein), int(with_positions),
+                                            int(with_annotations), C.byref(out), C.byref(n)))
+    text = C.string_at(out, n.value)
+    _lib.lib().kaamer_host_free_text(out)
+    return text
+
+
 def _collect_hits(hp) -> SearchResult:
     h = hp.contents
     n, nh = h.n_rows, h.n_hits
@@ -262,6 +312,19 @@ class GpuIndex:
     def save(self, path: str):
         check(_lib.lib().kaamer_gpu_save(self._h, path.encode()))
 
+    def set_annotations(self, entry_ids, lengths) -> None:
+        """Protein.EntryId / Protein.Length by protein id (pkg/kvstore/protein.proto) for the row formatter
+        (format_tsv); saved with the index.  entry_ids: list of str / bytes indexed by protein id ("" for
+        unused ids), lengths: int32 per id."""
+        ids = [e if isinstance(e, bytes) else e.encode() for e in entry_ids]
+        off = np.zeros(len(ids) + 1, dtype=np.uint64)
+        if ids:
+            off[1:] = np.cumsum([len(e) for e in ids], dtype=np.uint64)
+        blob = np.frombuffer(b"".join(ids) + b"\0", dtype=np.uint8).copy()
+        ln = np.ascontiguousarray(lengths, dtype=np.int32)
+        assert len(ln) == len(ids) and len(ids) >= 1
+        check(_lib.lib().kaamer_gpu_set_annotations(self._h, _vp(blob), _vp(off), _vp(ln), len(ids) - 1))
+
     # ---- peer-mapped shards (mode P) -----------------------------------------------------
     def export_shard(self) -> "_lib.ShardHandle":
         """kaamer_shard_handle of this handle's key range.  `table_fd` / `postings_fd` are open
@@ -340,8 +403,30 @@ class GpuIndex:
         _lib.lib().kaamer_gpu_free_orfs(op)
         return t
 
+    @staticmethod
+    def default_align_model():
+        """(int8[26, 26] scores in biogo order "-ABCDEFGHIJKLMNPQRSTVWXYZ*", gap_open) of the reference:
+        BLOSUM62, zero gap row, -11 (pkg/align/align.go:62-65)"""
+        m = _lib.AlnModel()
+        check(_lib.lib().kaamer_gpu_default_align_model(C.byref(m)))
+        return np.array(list(m.matrix), dtype=np.int8).reshape(26, 26), int(m.gap_open)
+
+    def set_align_model(self, matrix26=None, gap_open: int = -11) -> None:
+        """Replace the DP model of `align` (explicit opt-in: the reference hard-wires BLOSUM62 / -11).
+        matrix26[26, 26] in biogo order, row / column 0 = per-residue gap cost; None restores the default."""
+        if matrix26 is None:
+            check(_lib.lib().kaamer_gpu_set_align_model(self._h, None))
+            return
+        m = _lib.AlnModel()
+        flat = np.ascontiguousarray(matrix26, dtype=np.int8).reshape(-1)
+        assert len(flat) == 26 * 26
+        for i, v in enumerate(flat.tolist()):
+            m.matrix[i] = v
+        m.gap_open = int(gap_open)
+        check(_lib.lib().kaamer_gpu_set_align_model(self._h, C.byref(m)))
+
     def align(self, q_residues, q_off, pair_query, pair_subject, lambda_: float = 0.267, K: float = 0.041,
-              gap_open: int = 11, gap_extend: int = 1, number_of_aa: int = 0) -> np.ndarray:
+              gap_open: int = 11, gap_extend: int = 1, number_of_aa: int = 0, want_text: bool = False):
         """align.Align (pkg/align/align.go:46-161) for (query index, subject protein id) pairs;
         defaults = blosum62_11_1 (pkg/align/matrixScores.go:59).  Returns a structured array
         with the fields of AlignmentResult (align.go:25-40)."""
@@ -352,9 +437,19 @@ class GpuIndex:
         assert len(pq) == len(ps)
         o = _lib.AlnOpts(lambda_, K, gap_open, gap_extend, number_of_aa)
         out = np.zeros(len(pq), dtype=ALN_DTYPE)
-        check(_lib.lib().kaamer_gpu_align(self._h, _vp(q_residues), _vp(q_off), _vp(pq), _vp(ps), len(pq),
-                                          C.byref(o), _vp(out)))
-        return out
+        if not want_text:
+            check(_lib.lib().kaamer_gpu_align(self._h, _vp(q_residues), _vp(q_off), _vp(pq), _vp(ps), len(pq),
+                                              C.byref(o), _vp(out)))
+            return out
+        # with AlignmentResult.AlnString (align.go:103) of every pair
+        tp = C.POINTER(_lib.AlnText)()
+        check(_lib.lib().kaamer_gpu_align_text(self._h, _vp(q_residues), _vp(q_off), _vp(pq), _vp(ps), len(pq),
+                                               C.byref(o), _vp(out), C.byref(tp)))
+        t = tp.contents
+        off = _arr(t.off, len(pq) + 1, np.uint64)
+        blob = C.string_at(t.text, int(off[-1])) if len(pq) else b""
+        _lib.lib().kaamer_gpu_free_aln_text(tp)
+        return out, [blob[int(off[i]):int(off[i + 1])] for i in range(len(pq))]
 
     # ---- profiling ---------------------------------------------------------------------
     def profile_enable(self, on: bool = True):

@@ -86,7 +86,8 @@ def exchange_fds(mine: "_lib.ShardHandle", rank: int, world: int, barrier, tag: 
     return got
 
 
-def attach_distributed(index: GpuIndex, group=None, presence_filter: bool = True, replicate_table: bool = False) -> int:
+def attach_distributed(index: GpuIndex, group=None, presence_filter: bool = True, replicate_table: bool = False,
+                       replicate_postings: bool = False) -> int:
     """One process per GPU on one node: gather the shard exports, pass the descriptors, attach.
     Control plane only (72 bytes + 2 descriptors per rank, once per index load).  Returns the
     number of shards."""
@@ -107,7 +108,7 @@ def attach_distributed(index: GpuIndex, group=None, presence_filter: bool = True
             sh.table_fd, sh.postings_fd = fds[r]
         handles.append(sh)
     try:
-        index.attach_shards(handles, presence_filter, replicate_table)
+        index.attach_shards(handles, presence_filter, replicate_table, replicate_postings)
     finally:
         for sh in handles:
             _close_fds(sh)

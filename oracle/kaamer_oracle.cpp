@@ -528,7 +528,8 @@ struct Blosum62 {
     }
   }
 };
-const Blosum62 g_b62;
+Blosum62 g_b62;          // the alignment model; ko_set_align_model replaces the scores (§8f-4, and the biogo gap row)
+int32_t g_gap_open_dp = -11;  // SWAffine.GapOpen (align.go:64)
 
 struct Segment {
   int32_t qs, qe, ss, se;  // half-open, 0-based
@@ -554,7 +555,7 @@ int sw_affine(const uint8_t *q, int32_t n, const uint8_t *s, int32_t m, std::vec
               int32_t &dp_score) {
   segs.clear();
   dp_score = 0;
-  const int32_t open = -11;
+  const int32_t open = g_gap_open_dp;
   for (int32_t i = 0; i < n; ++i)
     if (g_b62.letter_index[q[i]] < 0) return -1;
   for (int32_t j = 0; j < m; ++j)
@@ -973,6 +974,36 @@ int ko_align(const uint8_t *q_in, int32_t qlen, const uint8_t *s_in, int32_t sle
     aln_b[nn] = 0;
   }
   return 0;
+}
+
+// AlnString (align.go:69-103): "aString\nalnMatch\nbString" from the two gapped strings of ko_align
+int32_t ko_aln_string(const char *a, const char *b, int32_t n, char *out, int32_t cap) {
+  std::string m;
+  for (int32_t i = 0; i < n; ++i) {
+    unsigned char ca = (unsigned char)a[i], cb = (unsigned char)b[i];
+    if (cb == ca) m += (char)cb;                                              // align.go:82-85
+    else if (g_b62.m[g_b62.aa_pos[cb]][g_b62.aa_pos[ca]] > 0) m += '+';       // :91-93
+    else m += ' ';                                                            // :95
+  }
+  std::string t = std::string(a, (size_t)n) + "\n" + m + "\n" + std::string(b, (size_t)n);
+  if ((int32_t)t.size() + 1 > cap) return -(int32_t)t.size();
+  memcpy(out, t.data(), t.size());
+  out[t.size()] = 0;
+  return (int32_t)t.size();
+}
+
+// Replace the scores of the alignment model: m[26*26] in biogo alphabet.Protein order
+// "-ABCDEFGHIJKLMNPQRSTVWXYZ*" (row/column 0 = per-residue gap cost), gap_open = SWAffine.GapOpen.
+// The reference hard-wires BLOSUM62 / -11 (align.go:62-65); this exists so that (a) whichever gap row biogo's
+// BLOSUM62 carries is a parameter, not a rewrite, and (b) §8f-4's "other matrices behind an explicit flag".
+void ko_set_align_model(const int8_t *m, int32_t gap_open) {
+  for (int i = 0; i < 26; ++i)
+    for (int j = 0; j < 26; ++j) g_b62.m[i][j] = m[i * 26 + j];
+  g_gap_open_dp = gap_open;
+}
+void ko_reset_align_model() {
+  g_b62 = Blosum62();
+  g_gap_open_dp = -11;
 }
 
 int32_t ko_format_positions(const uint8_t *positions, int32_t n, int32_t withAlignment, char *out,

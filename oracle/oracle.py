@@ -156,6 +156,12 @@ def lib():
     L.ko_evalue.argtypes = [C.c_int32, C.c_uint64, C.c_double]
     L.ko_format_positions.restype = C.c_int32
     L.ko_format_positions.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
+    L.ko_aln_string.restype = C.c_int32
+    L.ko_aln_string.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32]
+    L.ko_set_align_model.argtypes = [vp, C.c_int32]
+    L.ko_set_align_model.restype = None
+    L.ko_reset_align_model.argtypes = []
+    L.ko_reset_align_model.restype = None
     L.kso_record.restype = C.c_uint32
     L.kso_record.argtypes = [C.c_uint64, C.c_uint64, vp, C.c_uint32]
     L.kso_record_meta.argtypes = [C.c_uint64, C.c_uint64, u64p, u32p, u32p]
@@ -379,6 +385,25 @@ def align(q: bytes, s: bytes, prm: KoAlnParams, want_strings: bool = False):
         return out, a.value, b.value
     lib().ko_align(q, len(q), s, len(s), C.byref(prm), C.byref(out), None, None, 0)
     return out
+
+
+def aln_string(q: bytes, s: bytes, prm: KoAlnParams) -> bytes:
+    """AlignmentResult.AlnString (align.go:103): query line, match line, subject line."""
+    _, a, b = align(q, s, prm, want_strings=True)
+    cap = 3 * len(a) + 8
+    buf = C.create_string_buffer(cap)
+    n = lib().ko_aln_string(a, b, len(a), buf, cap)
+    assert n >= 0
+    return buf.raw[:n]
+
+
+def set_align_model(matrix26, gap_open: int) -> None:
+    """scores in biogo order "-ABCDEFGHIJKLMNPQRSTVWXYZ*" (row/column 0 = gap cost); None resets"""
+    if matrix26 is None:
+        lib().ko_reset_align_model()
+        return
+    m = np.ascontiguousarray(matrix26, dtype=np.int8).reshape(26, 26)
+    lib().ko_set_align_model(_vp(m), int(gap_open))
 
 
 def blosum62() -> np.ndarray:

@@ -609,3 +609,98 @@ def format_positions_to_string(positions: list, with_alignment: bool) -> str:
             end_pos = end_pos + KMER_SIZE - 1
         ps += str(current_start) + "-" + str(end_pos)
     return ps
+
+
+def tsv_rows(query_name: str, size_in_kmer: int, loc_start: int, loc_end: int, hits: list, entries: dict,
+             position_hits: dict, align: bool, extract_positions: bool, annotations: bool, is_protein: bool) -> str:
+    """QueryResultHandler, search.go:505-606: the TSV rows of ONE query.  hits: [{"Key", "Kmatch", "Alignment"}]
+    (Alignment: dict with the AlignmentResult fields, float32 Identity as numpy.float32); entries: id ->
+    {"EntryId", "Length"}; no feature columns (dbStats.Features empty)."""
+    import numpy as np
+
+    def go_f2(v):  # fmt.Sprintf("%.2f", v)
+        v = float(v)
+        if v != v:
+            return "NaN"
+        if v in (float("inf"), float("-inf")):
+            return "+Inf" if v > 0 else "-Inf"
+        return "%.2f" % v
+
+    def go_e(v):  # fmt.Sprintf("%e", v)
+        v = float(v)
+        if v != v:
+            return "NaN"
+        if v in (float("inf"), float("-inf")):
+            return "+Inf" if v > 0 else "-Inf"
+        return "%e" % v
+
+    out = ""
+    if align:
+        # sort.Slice by BitScore descending (search.go:491-493); a stable sort is one of its possible outcomes
+        hits = sorted(hits, key=lambda h: -h["Alignment"]["BitScore"] if h["Alignment"]["BitScore"] == h["Alignment"]["BitScore"] else 0.0)
+    for h in hits:
+        output = ""
+        output += query_name.split(" ")[0]
+        output += "\t"
+        output += entries[h["Key"]]["EntryId"]
+        output += "\t"
+        if not align:
+            pos_string = ""
+            output += go_f2(np.float32(h["Kmatch"]) / np.float32(size_in_kmer) * np.float32(100.00))
+            output += "\t"
+            output += str(size_in_kmer)
+            output += "\t"
+            output += str(int(h["Kmatch"]))
+            output += "\t"
+            if extract_positions:
+                pos_string = format_positions_to_string(position_hits[h["Key"]], False)
+                output += "%d" % pos_string.count(",")
+            else:
+                output += "N/A"
+            output += "\t"
+            output += str(loc_start)
+            output += "\t"
+            output += str(loc_end)
+            output += "\t"
+            output += "1"
+            output += "\t"
+            if annotations:
+                output += "%d" % entries[h["Key"]]["Length"]
+            else:
+                output += "N/A"
+            if extract_positions:
+                output += "\t"
+                output += pos_string
+        else:
+            a = h["Alignment"]
+            output += go_f2(a["Identity"])
+            output += "\t"
+            output += "%d" % a["Length"]
+            output += "\t"
+            output += "%d" % a["Mismatches"]
+            output += "\t"
+            output += "%d" % a["GapOpenings"]
+            output += "\t"
+            if not is_protein:
+                output += str(loc_start)
+                output += "\t"
+                output += str(loc_end)
+                output += "\t"
+            else:
+                output += "%d" % a["QueryStart"]
+                output += "\t"
+                output += "%d" % a["QueryEnd"]
+                output += "\t"
+            output += "%d" % a["SubjectStart"]
+            output += "\t"
+            output += "%d" % a["SubjectEnd"]
+            output += "\t"
+            output += go_e(a["EValue"])
+            output += "\t"
+            output += go_f2(a["BitScore"])
+            if extract_positions:
+                output += "\t"
+                output += format_positions_to_string(position_hits[h["Key"]], True)
+        output += "\n"
+        out += output
+    return out

@@ -7,7 +7,8 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SMALL = ["--db-proteins", "3000", "--queries", "800", "--ref-queries", "400", "--batches", "2"]
+SMALL = ["--db-proteins", "3000", "--queries", "800", "--ref-queries", "400", "--batches", "2",
+         "--c4-proteins", "30000", "--c4-sample", "6", "--sustain-s", "0.2"]
 
 
 def _run(args):
@@ -49,3 +50,13 @@ def test_bench_line_gpu():
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] != d["value"]
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    assert d["sustained"]["value"] > 0 and d["sustained"]["steps"] >= d["steps"]
+    assert "go" in d["reference_toolchain"]
+    # the C4 block (here at toy size): device-generated DB, streaming build, parity sample against the oracle
+    c4 = d["c4"]
+    assert "error" not in c4, c4
+    assert c4["value"] > 0 and c4["status_flags"] == 0 and c4["roofline"]["frac"] > 0
+    assert c4["parity_sample"]["mismatches"] == 0 and c4["parity_sample"]["kstats_equal"] is True
+    st = d["stages"]
+    assert "error" not in st["c5"] and st["c5"]["parity_spot_check"]["dp_score_and_raw_equal_oracle"] is True
+    assert "error" not in st["c2"] and st["c2"]["value"] > 0

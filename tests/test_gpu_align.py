@@ -114,3 +114,116 @@ def test_align_edge_cases():
     with GpuIndex.build(res, off, ids, keep_proteins=False) as g:
         with pytest.raises(KaamerGpuError):
             g.align(q, qo, [0], [3])
+
+
+def _edge_inputs():
+    """the pair set of test_align_edge_cases (mutated relatives with indels, illegal letters, U / - / *,
+    lower case, multi-block subjects, a 5000-aa subject)"""
+    from oracle import oracle as o
+
+    rng = np.random.default_rng(5)
+    aa = np.frombuffer(b"ARNDCQEGHILKMFPSTWYV", np.uint8)
+
+    def rnd(n):
+        return aa[rng.integers(0, 20, n)].tobytes()
+
+    def mutate(s, rate, indel=0.02):
+        out = bytearray()
+        for c in s:
+            u = rng.random()
+            if u < indel:
+                continue
+            if u < 2 * indel:
+                out += rnd(int(rng.integers(1, 6)))
+            out.append(c if rng.random() > rate else int(aa[rng.integers(0, 20)]))
+        return bytes(out)
+
+    base = rnd(300)
+    long_a = rnd(1400)
+    subj_list = [base, mutate(base, 0.2), rnd(7), b"MKTAYIAKQRQISFVKSHFSRQLEERLGLIEVQ", b"AAAAAAAAAAAAAAAAAAAAAAAA",
+                 b"MKTUUIAKQRQISFuKSHFSRQ*", b"MKTAYIAKQROISFVKSHFSRQ", b"mktayiakqrqisfvkshfsrq", b"MKT-YIAKQ-QISFVKSHFSRQ",
+                 long_a, mutate(long_a, 0.3, 0.01), rnd(129), rnd(257), rnd(600), b"WWWWWWWCCCCCCCWWWWWWW",
+                 b"BZXJBZXJBZXJ*BZXJ", rnd(3000)]
+    ids = np.arange(3, 3 + len(subj_list), dtype=np.uint32)
+    res, off = o.pack(subj_list)
+    subjects = {int(i): s for i, s in zip(ids, subj_list)}
+    queries = [base, mutate(base, 0.1), b"", b"A", b"MKTAYIAKQRQISFVKSHFSRQLEERLGLIEVQ", b"MKTAYIAKQRQISFVKSHFSRQ1",
+               b"mktayiakqrqisfvkshfsrq", b"MKTUYIAKQRQISFVKSHFSRQ", b"MKT-YIAKQRQISFVKSHFSRQ", long_a[100:1300],
+               mutate(long_a, 0.15, 0.03), rnd(40), b"WWWWWWWWWWWWWW", b"BZXJBZXJBZXJ*BZXJ", rnd(2500), b"O" * 30]
+    q, qo = o.pack(queries)
+    pairs = [(i, int(s)) for i in range(len(queries)) for s in ids]
+    return res, off, ids, subjects, queries, q, qo, pairs
+
+
+def test_aln_string_equals_the_reference_layout():
+    """AlignmentResult.AlnString (align.go:69-103): gapped query, match line (letter / '+' / ' '), gapped
+    subject, joined by newlines — for every pair, including empty alignments ("\\n\\n") and illegal letters"""
+    from kaamer_b200 import GpuIndex
+    from oracle import oracle as o
+
+    res, off, ids, subjects, queries, q, qo, pairs = _edge_inputs()
+    prm = o.aln_params(3_500_000)
+    with GpuIndex.build(res, off, ids, keep_proteins=True) as g:
+        out, texts = g.align(q, qo, [p[0] for p in pairs], [p[1] for p in pairs], number_of_aa=3_500_000, want_text=True)
+        _check(out, pairs, queries, subjects, prm, "with text")
+        plain = g.align(q, qo, [p[0] for p in pairs], [p[1] for p in pairs], number_of_aa=3_500_000)
+        assert out.tobytes() == plain.tobytes() or np.array_equal(out["raw"], plain["raw"])
+        assert g.align(q, qo, [], [], want_text=True)[1] == []
+    n_gapped = 0
+    for k, (qi, sid) in enumerate(pairs):
+        exp = o.aln_string(queries[qi], subjects[sid], prm)
+        assert texts[k] == exp, f"pair {k} (q{qi}, s{sid}):\n{texts[k].decode()}\n!=\n{exp.decode()}"
+        assert len(texts[k]) == 3 * int(out["length"][k]) + 2
+        n_gapped += b"-" in exp
+    assert n_gapped > 10 and any(t == b"\n\n" for t in texts)
+
+
+@pytest.mark.parametrize("model", ["gap_row_minus4", "gap_row_ragged", "pam_like", "default_again"])
+def test_alignment_model_is_a_runtime_parameter(model):
+    """whichever gap row biogo's BLOSUM62 carries, and §8f-4's other matrices, are a kaamer_gpu_set_align_model
+    call away: the general cell update against the oracle under the same model, bit-exact"""
+    from kaamer_b200 import GpuIndex
+    from oracle import oracle as o
+
+    res, off, ids, subjects, queries, q, qo, pairs = _edge_inputs()
+    pairs = [p for p in pairs if len(queries[p[0]]) * len(subjects[p[1]]) < 2_500_000][:150] + pairs[-17:]
+    prm = o.aln_params(3_500_000)
+    m0, open0 = GpuIndex.default_align_model()
+    assert np.array_equal(m0.astype(np.int32), o.blosum62()) and open0 == -11
+    m = m0.astype(np.int32).copy()
+    gap_open = -11
+    if model == "gap_row_minus4":
+        m[0, 1:] = -4
+        m[1:, 0] = -4
+    elif model == "gap_row_ragged":
+        rng = np.random.default_rng(3)
+        m[0, 1:] = -rng.integers(0, 4, 25)
+        m[1:, 0] = -rng.integers(0, 4, 25)
+        gap_open = -7
+    elif model == "pam_like":
+        rng = np.random.default_rng(4)
+        sym = rng.integers(-6, 7, (26, 26))
+        m = np.triu(sym) + np.triu(sym, 1).T
+        m[np.arange(1, 26), np.arange(1, 26)] = rng.integers(3, 12, 25)
+        m[0, :] = -1
+        m[:, 0] = -1
+        m[0, 0] = 0
+        gap_open = -9
+    try:
+        o.set_align_model(m if model != "default_again" else None, gap_open)
+        with GpuIndex.build(res, off, ids, keep_proteins=True) as g:
+            if model == "default_again":
+                g.set_align_model(m, -3)
+                g.set_align_model(None)
+            else:
+                g.set_align_model(m, gap_open)
+            out, texts = g.align(q, qo, [p[0] for p in pairs], [p[1] for p in pairs], number_of_aa=3_500_000, want_text=True)
+            _check(out, pairs, queries, subjects, prm, model)
+            for k, (qi, sid) in enumerate(pairs):
+                assert texts[k] == o.aln_string(queries[qi], subjects[sid], prm), (model, k)
+            if model == "gap_row_minus4":
+                # biogo-with-a-gap-row consequence: no segment scores exactly -GapOpen, so kaamer's test
+                # (align.go:127) never fires
+                assert (out["gap_openings"] == 0).all() and (out["length"] > 0).any()
+    finally:
+        o.set_align_model(None, 0)

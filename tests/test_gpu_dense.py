@@ -77,7 +77,7 @@ def test_class_d_parity_on_a_dense_database(dense_setup, opts, design, monkeypat
 
 @pytest.mark.parametrize("design,var,val", [("11", "KAAMER_D_MAPKB", "1"), ("11", "KAAMER_D_MAPKB", "64"),
                                             ("1", "KAAMER_E_MAPW", "64,64"), ("1", "KAAMER_E_MAPW", "128,512"),
-                                            ("1", "KAAMER_E_MAPW", "4096,4096")])
+                                            ("1", "KAAMER_E_MAPW", "2048,4096")])
 def test_class_d_map_sizes(dense_setup, design, var, val, monkeypatch):
     """tiny maps (everything collides: pushes overflow H, class G takes the query) to large ones"""
     from kaamer_b200 import SearchOptions

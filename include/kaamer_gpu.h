@@ -151,6 +151,16 @@ typedef struct kaamer_hits {
 int kaamer_gpu_search_proteins(kaamer_gpu_t *h, const uint8_t *residues, const uint64_t *seq_off,
                                uint32_t nq, const kaamer_opts *opts, kaamer_hits **out);
 
+/* The same call in two halves, for hosts that keep the GPU busy across requests (the reference runs
+ * nbOfThreads queries concurrently, api/server.go:55-59): submit enqueues the whole batch and returns, wait
+ * blocks until its hits are in host memory (one event synchronisation).  Up to TWO batches may be in flight
+ * per handle — submit batch k+1, then wait for batch k.  residues / seq_off must stay valid and unchanged
+ * until the matching wait returns (cgo: C-allocated memory, e.g. kaamer_gpu_pinned_alloc).  Batches that want
+ * positions, are empty, or allow more than 2^25 hits in total are refused: use the blocking call. */
+int kaamer_gpu_search_proteins_submit(kaamer_gpu_t *h, const uint8_t *residues, const uint64_t *seq_off,
+                                      uint32_t nq, const kaamer_opts *opts, int32_t *ticket);
+int kaamer_gpu_search_proteins_wait(kaamer_gpu_t *h, int32_t ticket, kaamer_hits **out);
+
 /* Replaces GetORFs (dna.go:65-181) + the per-ORF loop of NucleotideSearch / FastqSearch
  * (search_nucleotide.go:76-130, search_fastq.go:78-140) incl. SetBestStartCodon (dna.go:198-272). */
 int kaamer_gpu_search_nucleotide(kaamer_gpu_t *h, const uint8_t *nt, const uint64_t *contig_off,

@@ -195,6 +195,8 @@ SYMBOLS = [
     "kaamer_gpu_index_copy",
     "kaamer_gpu_save",
     "kaamer_gpu_search_proteins",
+    "kaamer_gpu_search_proteins_submit",
+    "kaamer_gpu_search_proteins_wait",
     "kaamer_gpu_search_nucleotide",
     "kaamer_gpu_free_hits",
     "kaamer_gpu_get_orfs",
@@ -272,6 +274,8 @@ def lib() -> C.CDLL:
     L.kaamer_gpu_index_copy.argtypes = [vp, vp, vp, vp]
     L.kaamer_gpu_save.argtypes = [vp, C.c_char_p]
     L.kaamer_gpu_search_proteins.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(Opts), C.POINTER(C.POINTER(Hits))]
+    L.kaamer_gpu_search_proteins_submit.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(Opts), C.POINTER(C.c_int32)]
+    L.kaamer_gpu_search_proteins_wait.argtypes = [vp, C.c_int32, C.POINTER(C.POINTER(Hits))]
     L.kaamer_gpu_search_nucleotide.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(Opts), C.POINTER(C.POINTER(Hits))]
     L.kaamer_gpu_free_hits.argtypes = [C.POINTER(Hits)]
     L.kaamer_gpu_free_hits.restype = None

@@ -43,7 +43,7 @@ void *pinned_get(size_t bytes, size_t *cap) {
       }
   }
   void *p = nullptr;
-  cudaError_t e = cudaHostAlloc(&p, c, cudaHostAllocPortable);
+  cudaError_t e = cudaHostAlloc(&p, c, cudaHostAllocPortable | cudaHostAllocMapped);
   if (e != cudaSuccess) {
     // drop the cache and retry once
     {
@@ -52,7 +52,7 @@ void *pinned_get(size_t bytes, size_t *cap) {
       g_pin_free.clear();
       g_pin_cached = 0;
     }
-    e = cudaHostAlloc(&p, c, cudaHostAllocPortable);
+    e = cudaHostAlloc(&p, c, cudaHostAllocPortable | cudaHostAllocMapped);
     if (e != cudaSuccess) {
       set_error("cudaHostAlloc(%zu bytes): %s", c, cudaGetErrorString(e));
       return nullptr;
@@ -158,6 +158,7 @@ static void destroy_handle(kaamer_gpu *h) {
   h->idx.repl_postings = nullptr;
   if (h->idx.d_peer) cudaFree(h->idx.d_peer);
   h->idx.d_peer = nullptr;
+  release_pending(h);
   index_release(h);
   h->ws.release_all();
   h->arena.release();
@@ -815,11 +816,52 @@ static int kaamer_gpu_search_proteins_impl(kaamer_gpu_t *h, const uint8_t *resid
   std::lock_guard<std::mutex> lk(h->mu);
   KCUDA(cudaSetDevice(h->device));
   HostPhase whole(h, 4);
-  return search_proteins_host(h, residues, seq_off, nq, opts, out);
+  // one stream pass, one synchronisation (search.cu: submit / wait); batches that cannot be bounded
+  // beforehand (positions, huge MaxResults) take the path with the retry loops
+  int slot = -1;
+  KCHECK(search_proteins_submit(h, residues, seq_off, nq, opts, &slot));
+  if (slot < 0) return search_proteins_host(h, residues, seq_off, nq, opts, out);
+  return search_proteins_wait(h, slot, out);
 }
 int kaamer_gpu_search_proteins(kaamer_gpu_t *h, const uint8_t *residues, const uint64_t *seq_off, uint32_t nq,
                                const kaamer_opts *opts, kaamer_hits **out) {
   return ::kaamer::guarded([&]() -> int { return kaamer_gpu_search_proteins_impl(h, residues, seq_off, nq, opts, out); });
+}
+
+// Pipelined form of kaamer_gpu_search_proteins: submit returns as soon as the batch is enqueued, wait blocks
+// until its hits are in host memory.  At most two batches in flight per handle; the caller's buffers must
+// stay valid and unchanged until wait returns.
+static int kaamer_gpu_search_proteins_submit_impl(kaamer_gpu_t *h, const uint8_t *residues, const uint64_t *seq_off,
+                                                  uint32_t nq, const kaamer_opts *opts, int32_t *ticket) {
+  if (!h || !opts || !ticket || (nq && (!residues || !seq_off))) {
+    set_error("null argument");
+    return KAAMER_ERR_ARG;
+  }
+  *ticket = -1;
+  std::lock_guard<std::mutex> lk(h->mu);
+  KCUDA(cudaSetDevice(h->device));
+  int slot = -1;
+  KCHECK(search_proteins_submit(h, residues, seq_off, nq, opts, &slot));
+  if (slot < 0) {
+    set_error("this batch cannot be pipelined (positions wanted, empty, or MaxResults too large): use kaamer_gpu_search_proteins");
+    return KAAMER_ERR_ARG;
+  }
+  *ticket = slot;
+  return KAAMER_OK;
+}
+int kaamer_gpu_search_proteins_submit(kaamer_gpu_t *h, const uint8_t *residues, const uint64_t *seq_off, uint32_t nq,
+                                      const kaamer_opts *opts, int32_t *ticket) {
+  return ::kaamer::guarded([&]() -> int { return kaamer_gpu_search_proteins_submit_impl(h, residues, seq_off, nq, opts, ticket); });
+}
+int kaamer_gpu_search_proteins_wait(kaamer_gpu_t *h, int32_t ticket, kaamer_hits **out) {
+  if (!h || !out) {
+    set_error("null argument");
+    return KAAMER_ERR_ARG;
+  }
+  *out = nullptr;
+  std::lock_guard<std::mutex> lk(h->mu);
+  KCUDA(cudaSetDevice(h->device));
+  return ::kaamer::guarded([&]() -> int { return search_proteins_wait(h, ticket, out); });
 }
 
 int kaamer_gpu_search_proteins_device(kaamer_gpu_t *h, const uint8_t *d_residues, const uint64_t *d_seq_off,

@@ -355,6 +355,7 @@ int kaamer_gpu_builder_finish(kaamer_builder_t *b, kaamer_gpu_t **out) {
   DevIndex &ix = h->idx;
   ix.n_keys = b->n_keys;
   ix.n_postings = b->used;
+  ix.lists_sorted = true;  // k_stream_runs / k_stream_long_runs: ids descending inside every run
   ix.n_proteins = b->stats[1];
   ix.n_aa = b->stats[2];
   ix.n_kmers = b->stats[3];

@@ -170,6 +170,15 @@ int index_from_view(kaamer_gpu *h, const kaamer_index_view *v) {
   }
   ix.n_keys = v->n_keys;
   ix.n_postings = v->n_postings;
+  // are the lists in the reference's order (ids strictly descending, kv_store.go:284-305)?  Class D then
+  // verifies its candidates by binary search; any other order is searched correctly, a little slower
+  ix.lists_sorted = true;
+  for (uint64_t k = 0; k < v->n_keys && ix.lists_sorted; ++k)
+    for (uint64_t i = v->offsets[k] + 1; i < v->offsets[k + 1]; ++i)
+      if (v->postings[i] >= v->postings[i - 1]) {
+        ix.lists_sorted = false;
+        break;
+      }
   ix.n_proteins = v->n_proteins;
   ix.n_aa = v->n_aa;
   ix.n_kmers = v->n_kmers;
@@ -427,6 +436,7 @@ int index_build(kaamer_gpu *h, const uint8_t *residues, const uint64_t *seq_off,
   }
   ix.n_keys = n_keys;
   ix.n_postings = n_uniq;
+  ix.lists_sorted = true;  // k_write_postings: ids descending inside every run
   BCUDA(cudaMalloc((void **)&ix.keys, (size_t)(n_keys + 1) * 4));
   BCUDA(cudaMalloc((void **)&ix.offsets, (size_t)(n_keys + 1) * 8));
   rc = alloc_postings(h, n_uniq, shareable);

@@ -299,6 +299,7 @@ struct DevIndex {
   uint64_t n_prot_res = 0;
   uint32_t max_protein_id = 0;
   bool has_proteins = false;
+  bool lists_sorted = false;  // every posting list strictly descending (the builders; views after a check)
   uint64_t n_proteins = 0, n_aa = 0, n_kmers = 0;
   // annotation table for the row formatter (format.cu), host memory, indexed by protein id:
   // Protein.EntryId and Protein.Length (pkg/kvstore/protein.proto); empty = not loaded
@@ -406,6 +407,7 @@ struct kaamer_gpu {
   std::vector<kaamer::ProfSpan> prof_pending;
   double prof_host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // per-handle (= per-device context) one-time setup: constant tables and kernel attributes
+  void *pending = nullptr;          // PendingSlot[2] of the submit / wait pipeline (search.cu)
   kaamer_aln_model aln_model{};     // alignment DP model (align.cu); aln_model_set false: the reference default
   bool aln_model_set = false;
   uint32_t ghash_slots = 1u << 20;  // class G histogram slots per CTA; grown on ST_GHASH_OVERFLOW (search.cu)
@@ -429,6 +431,11 @@ int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off,
                          const kaamer_opts *o, kaamer_hits **out);
 int search_nucleotide_host(kaamer_gpu *h, const uint8_t *nt, const uint64_t *coff, uint32_t nc,
                            const kaamer_opts *o, kaamer_hits **out);
+int search_proteins_submit(kaamer_gpu *h, const uint8_t *res, const uint64_t *off, uint32_t nq, const kaamer_opts *o,
+                           int *slot_out);
+int search_proteins_wait(kaamer_gpu *h, int slot, kaamer_hits **out);
+void release_pending(kaamer_gpu *h);
+int grow_ghash(kaamer_gpu *h, uint64_t need);
 #ifdef __CUDACC__
 // smallest Kmatch that survives FilterResults (search.go:195): the hit is dropped when
 // float64(Kmatch)/float64(SizeInKmer) < MinKRatio || Kmatch < MinKMatch; both tests are

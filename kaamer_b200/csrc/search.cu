@@ -61,7 +61,7 @@ __global__ void k_classify(SearchArgs a) {
     // per-warp state halves the resident warps and it ran at 10 G lookups/s against 24 G/s for
     // the CTA-per-query class M (profiles/r1_notes.md).
     if (go) {
-      if (a.dense) cls = (a.kmin[q] >= 3u && K <= D_MAXK) ? ((a.dense == 2 && K > a.e_kcap) ? 5 : 4) : 2;
+      if (a.dense) cls = (a.kmin[q] >= 3u && K <= D_MAXK) ? ((a.dense == 2 && K > a.e_kcap) ? (K > a.e_kcap_l ? 6 : 5) : 4) : 2;
       else cls = K <= a.w_maxk ? 0 : (K <= a.m_maxk ? 1 : 2);
     }
   }
@@ -688,23 +688,32 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   // class D (search_dense2.cuh): two launches, queries of up to E_KCAP_S k-mers and the longer ones
   constexpr int E_KCAP_S = 512, E_KCAP_L = 1024;
   a.e_kcap = E_KCAP_S;
+  a.e_kcap_l = E_KCAP_L;
   a.e_mapw_small = 512;
   a.e_mapw_large = 1024;
+  a.e_mapw_xl = 4096;
+  a.lists_sorted = h->idx.lists_sorted ? 1 : 0;
+  if (getenv("KAAMER_D_NO_BSEARCH")) a.lists_sorted = 0;  // A/B hook: stream the lists again instead
   if (const char *env = getenv("KAAMER_E_MAPW")) {  // tuning hook: "small,large" words per map per warp (powers of two)
     unsigned ms = 0, ml = 0;
     if (sscanf(env, "%u,%u", &ms, &ml) == 2 && ms >= 64 && ms <= 4096 && ml >= 64 && ml <= 4096 &&
         (ms & (ms - 1)) == 0 && (ml & (ml - 1)) == 0) {
       a.e_mapw_small = ms;
       a.e_mapw_large = ml;
+      a.e_mapw_xl = ml > 4096 ? ml : (ml < 1024 ? ml : 4096);
     }
   }
-  const size_t e_smem_s = ((sizeof(Dense2Smem<E_KCAP_S>) + 15) & ~(size_t)15) + (size_t)E_WARPS * 2 * a.e_mapw_small * 4;
-  const size_t e_smem_l = ((sizeof(Dense2Smem<E_KCAP_L>) + 15) & ~(size_t)15) + (size_t)E_WARPS * 2 * a.e_mapw_large * 4;
-  auto e_small = peer ? k_search_e<true, E_KCAP_S, 4> : k_search_e<false, E_KCAP_S, 4>;
-  auto e_large = peer ? k_search_e<true, E_KCAP_L, 5> : k_search_e<false, E_KCAP_L, 5>;
+  constexpr int EH_S = 512, EH_L = 512, EH_XL = 2048;
+  const size_t e_smem_s = ((sizeof(Dense2Smem<E_KCAP_S, EH_S>) + 15) & ~(size_t)15) + (size_t)E_WARPS * 2 * a.e_mapw_small * 4;
+  const size_t e_smem_l = ((sizeof(Dense2Smem<E_KCAP_L, EH_L>) + 15) & ~(size_t)15) + (size_t)E_WARPS * 2 * a.e_mapw_large * 4;
+  const size_t e_smem_xl = ((sizeof(Dense2Smem<E_KCAP_L, EH_XL>) + 15) & ~(size_t)15) + (size_t)E_WARPS * 2 * a.e_mapw_xl * 4;
+  auto e_small = peer ? k_search_e<true, E_KCAP_S, EH_S, 4> : k_search_e<false, E_KCAP_S, EH_S, 4>;
+  auto e_large = peer ? k_search_e<true, E_KCAP_L, EH_L, 5> : k_search_e<false, E_KCAP_L, EH_L, 5>;
+  auto e_xl = peer ? k_search_e<true, E_KCAP_L, EH_XL, 6> : k_search_e<false, E_KCAP_L, EH_XL, 6>;
   if (a.dense == 2) {
     KCUDA(cudaFuncSetAttribute(e_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem_s));
     KCUDA(cudaFuncSetAttribute(e_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem_l));
+    KCUDA(cudaFuncSetAttribute(e_xl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem_xl));
   }
   // Class G: one CTA per query, histogram in a per-CTA global scratch.  At Swiss-Prot density it holds a
   // handful of very long queries and gets one CTA per SM (it runs underneath W and M and must leave them
@@ -745,8 +754,9 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   launch_g(side);
   profile_end(h, side);
   if (a.dense == 2) {
-    // the long queries of class D run on the side stream underneath the short ones
+    // the long queries of class D run on the side stream underneath the short ones: the (few) longest first
     int per_sm = 1;
+    e_xl<<<(unsigned)h->sm_count, E_THREADS, e_smem_xl, side>>>(a);
     KCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e_large, E_THREADS, e_smem_l));
     profile_begin(h, side, 1);
     e_large<<<(unsigned)h->sm_count * (unsigned)(per_sm < 1 ? 1 : per_sm), E_THREADS, e_smem_l, side>>>(a);
@@ -783,7 +793,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   a.ghash = ws.ghash.p + (size_t)g_ctas * 3 * a.ghash_slots;  // own scratch: the first G launch may still run
   launch_g(st);
   KCUDA(cudaStreamWaitEvent(st, h->chunk_ev[7], 0));
-  h->prof_all_launches += a.dense == 1 ? 4 : 5;
+  h->prof_all_launches += a.dense == 1 ? 4 : (a.dense == 2 ? 6 : 5);
   KCUDA(cudaGetLastError());
   return KAAMER_OK;
 }
@@ -1028,6 +1038,229 @@ int search_proteins_host(kaamer_gpu *h, const uint8_t *res, const uint64_t *off,
   *out_hits = hits;
 #undef HCHECK
 #undef HCUDA
+  return KAAMER_OK;
+}
+
+// ---- pipelined host-buffer path: submit / wait ------------------------------------------------
+// A blocking kaamer_gpu_search_proteins call costs, besides its kernels, two stream synchronisations, the
+// H2D of the offsets and the D2H of the hits — with 8 ranks on one host that tax grew to +60 % of a call
+// (SCALE_r01: e2e efficiency 0.64 at 8 GPUs).  The submit / wait pair keeps the device busy across calls:
+// submit enqueues EVERYTHING of a batch (offsets H2D, search kernels, CSR scan, and a gather kernel that
+// writes the hits straight into the caller-visible pinned result arrays over PCIe), wait is ONE event
+// synchronisation.  Two slots: batch k+1 is submitted before batch k is waited for, its kernels queue up
+// behind batch k's on the same stream (the scratch of the kernels is reused in stream order; only what the
+// host reads lives in the slot).  Result capacity is bounded before the launch: a query keeps at most
+// MaxResults hits (FilterResults, search.go:208-210).
+struct PendingSlot {
+  bool busy = false;
+  uint32_t nq = 0;
+  kaamer_opts opts{};
+  const uint8_t *res = nullptr;
+  const uint64_t *off = nullptr;
+  DevBuf<uint64_t> seq_off, hit_off, pool, counters;
+  DevBuf<uint32_t> n_hits, hit_base;
+  DevBuf<int32_t> size_in_kmer;
+  DevBuf<uint8_t> residues;  // pageable caller memory is staged here
+  kaamer_hits *hits = nullptr;
+  HitsOwner *owner = nullptr;
+  uint64_t *h_tail = nullptr;  // pinned: counters[CNT_N] + total hits
+  uint64_t cap_hits = 0, pool_cap = 0;
+  cudaEvent_t done = nullptr, copied = nullptr;
+  void drop_result() {
+    delete owner;
+    delete hits;
+    owner = nullptr;
+    hits = nullptr;
+  }
+};
+
+static PendingSlot *slots_of(kaamer_gpu *h) {
+  if (!h->pending) {
+    auto *sl = new PendingSlot[2];
+    for (int i = 0; i < 2; ++i) {
+      cudaEventCreateWithFlags(&sl[i].done, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&sl[i].copied, cudaEventDisableTiming);
+    }
+    h->pending = sl;
+  }
+  return static_cast<PendingSlot *>(h->pending);
+}
+
+void release_pending(kaamer_gpu *h) {
+  if (!h->pending) return;
+  auto *sl = static_cast<PendingSlot *>(h->pending);
+  for (int i = 0; i < 2; ++i) {
+    if (sl[i].busy) cudaEventSynchronize(sl[i].done);
+    sl[i].drop_result();
+    sl[i].seq_off.release(); sl[i].hit_off.release(); sl[i].pool.release(); sl[i].counters.release();
+    sl[i].n_hits.release(); sl[i].hit_base.release(); sl[i].size_in_kmer.release(); sl[i].residues.release();
+    if (sl[i].done) cudaEventDestroy(sl[i].done);
+    if (sl[i].copied) cudaEventDestroy(sl[i].copied);
+  }
+  delete[] sl;
+  h->pending = nullptr;
+}
+
+constexpr uint64_t SUBMIT_MAX_HITS = 32ull << 20;  // larger bounds (MaxResults in the thousands) take the blocking path
+
+// returns the slot (0 / 1), or -1: this batch cannot be pipelined (positions wanted, huge MaxResults)
+int search_proteins_submit(kaamer_gpu *h, const uint8_t *res, const uint64_t *off, uint32_t nq, const kaamer_opts *o,
+                           int *slot_out) {
+  *slot_out = -1;
+  const uint64_t per_q = o->max_results > 0 ? (uint64_t)o->max_results : 0;
+  if (o->want_positions || nq == 0 || (uint64_t)nq * per_q > SUBMIT_MAX_HITS) return KAAMER_OK;
+  if (off[0] != 0) {
+    set_error("seq_off[0] must be 0");
+    return KAAMER_ERR_ARG;
+  }
+  PendingSlot *sl = slots_of(h);
+  int s = -1;
+  for (int i = 0; i < 2; ++i)
+    if (!sl[i].busy) {
+      s = i;
+      break;
+    }
+  if (s < 0) {
+    set_error("two batches are already in flight on this handle: wait for one of them first");
+    return KAAMER_ERR_ARG;
+  }
+  PendingSlot &p = sl[s];
+  cudaStream_t st = h->stream;
+  const uint64_t n_res = off[nq];
+  p.nq = nq;
+  p.opts = *o;
+  p.res = res;
+  p.off = off;
+  p.cap_hits = (uint64_t)nq * per_q;
+  const uint64_t pq = per_q < 16 ? (per_q ? per_q : 1) : 16;
+  p.pool_cap = (uint64_t)nq * pq + 4096;
+  if (p.pool.n > p.pool_cap) p.pool_cap = p.pool.n;
+  KCHECK(p.seq_off.ensure((size_t)nq + 1));
+  KCHECK(p.hit_off.ensure((size_t)nq + 1));
+  KCHECK(p.n_hits.ensure((size_t)nq + 1));
+  KCHECK(p.hit_base.ensure(nq));
+  KCHECK(p.size_in_kmer.ensure(nq));
+  KCHECK(p.counters.ensure(CNT_N));
+  KCHECK(p.pool.ensure((size_t)p.pool_cap));
+  p.drop_result();
+  p.hits = new kaamer_hits();
+  memset(p.hits, 0, sizeof *p.hits);
+  p.owner = new HitsOwner();
+  p.hits->_owner = p.owner;
+  p.hits->n_rows = nq;
+  int rc = p.owner->alloc(&p.hits->hit_off, (size_t)nq + 1);
+  if (rc == KAAMER_OK) rc = p.owner->alloc(&p.hits->size_in_kmer, (size_t)nq);
+  if (rc == KAAMER_OK) rc = p.owner->alloc(&p.hits->subject_id, (size_t)p.cap_hits + 1);
+  if (rc == KAAMER_OK) rc = p.owner->alloc(&p.hits->kmatch, (size_t)p.cap_hits + 1);
+  if (rc == KAAMER_OK) rc = p.owner->alloc(&p.h_tail, (size_t)CNT_N + 2);
+  if (rc != KAAMER_OK) {
+    p.drop_result();
+    return rc;
+  }
+  auto fail = [&](const char *what, cudaError_t e) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    p.drop_result();
+    return KAAMER_ERR_CUDA;
+  };
+  // residues: read in place when the caller's buffer is page-locked, staged otherwise
+  const uint8_t *d_res = nullptr;
+  {
+    cudaPointerAttributes at;
+    if (n_res && cudaPointerGetAttributes(&at, res) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+      d_res = (const uint8_t *)at.devicePointer;
+    else
+      cudaGetLastError();
+  }
+  cudaError_t e = cudaMemcpyAsync(p.seq_off.p, off, ((size_t)nq + 1) * 8, cudaMemcpyHostToDevice, h->copy_stream);
+  if (e != cudaSuccess) return fail("offsets H2D", e);
+  if (!d_res) {
+    rc = p.residues.ensure((size_t)n_res + 16);
+    if (rc != KAAMER_OK) {
+      p.drop_result();
+      return rc;
+    }
+    if (n_res) {
+      e = cudaMemcpyAsync(p.residues.p, res, (size_t)n_res, cudaMemcpyHostToDevice, h->copy_stream);
+      if (e != cudaSuccess) return fail("residues H2D", e);
+    }
+    d_res = p.residues.p;
+  }
+  e = cudaEventRecord(p.copied, h->copy_stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(st, p.copied, 0);
+  if (e != cudaSuccess) return fail("copy event", e);
+  kaamer_dev_result dr{};
+  dr.n_hits = p.n_hits.p;
+  dr.hit_base = p.hit_base.p;
+  dr.size_in_kmer = p.size_in_kmer.p;
+  dr.pool = p.pool.p;
+  dr.pool_cap = p.pool_cap;
+  dr.counters = p.counters.p;
+  rc = search_proteins_device(h, d_res, p.seq_off.p, nq, o, &dr, st, 0, nullptr, nullptr);
+  if (rc != KAAMER_OK) {
+    p.drop_result();
+    return rc;
+  }
+  // CSR offsets, then the hits straight into the pinned result arrays (PCIe writes from the gather kernel)
+  size_t scan_tmp = 0;
+  cub::TransformInputIterator<uint64_t, WidenU32, const uint32_t *> in(p.n_hits.p, WidenU32());
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, in, p.hit_off.p, (int64_t)nq + 1, st);
+  rc = h->ws.f_tmp.ensure(scan_tmp + 16);
+  if (rc != KAAMER_OK) {
+    p.drop_result();
+    return rc;
+  }
+  e = cudaMemsetAsync(p.n_hits.p + nq, 0, 4, st);
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(h->ws.f_tmp.p, scan_tmp, in, p.hit_off.p, (int64_t)nq + 1, st);
+  if (e != cudaSuccess) return fail("scan", e);
+  uint32_t *out_subj = nullptr, *out_km = nullptr;
+  e = cudaHostGetDevicePointer((void **)&out_subj, p.hits->subject_id, 0);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&out_km, p.hits->kmatch, 0);
+  if (e != cudaSuccess) return fail("cudaHostGetDevicePointer(result arrays)", e);
+  if (p.cap_hits) {
+    const unsigned grid = (unsigned)(((uint64_t)nq * 32 + 255) / 256);
+    k_gather_hits<<<grid, 256, 0, st>>>(p.n_hits.p, p.hit_base.p, p.hit_off.p, p.pool.p, nq, out_subj, out_km);
+  }
+  h->prof_all_launches += 3;
+  e = cudaMemcpyAsync(p.h_tail, p.counters.p, CNT_N * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p.h_tail + CNT_N, p.hit_off.p + nq, 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p.hits->hit_off, p.hit_off.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p.hits->size_in_kmer, p.size_in_kmer.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaEventRecord(p.done, st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("result D2H", e);
+  p.busy = true;
+  *slot_out = s;
+  return KAAMER_OK;
+}
+
+int search_proteins_wait(kaamer_gpu *h, int slot, kaamer_hits **out_hits) {
+  PendingSlot *sl = slots_of(h);
+  if (slot < 0 || slot > 1 || !sl[slot].busy) {
+    set_error("no batch in flight in slot %d", slot);
+    return KAAMER_ERR_ARG;
+  }
+  PendingSlot &p = sl[slot];
+  cudaError_t e = cudaEventSynchronize(p.done);
+  p.busy = false;
+  if (e != cudaSuccess) {
+    set_error("search batch: %s", cudaGetErrorString(e));
+    p.drop_result();
+    return KAAMER_ERR_CUDA;
+  }
+  const uint64_t status = p.h_tail[CNT_STATUS];
+  if (status & (ST_POOL_OVERFLOW | ST_GHASH_OVERFLOW)) {
+    // rare: more candidates than the hit pool / the class-G histogram was sized for.  The blocking path has the
+    // retry loops; the caller's buffers are still valid (they are until wait returns)
+    if (status & ST_GHASH_OVERFLOW) KCHECK(grow_ghash(h, p.h_tail[CNT_GNEED]));
+    p.drop_result();
+    return search_proteins_host(h, p.res, p.off, p.nq, &p.opts, out_hits);
+  }
+  p.hits->n_hits = p.h_tail[CNT_N];
+  p.hits->n_lookups = p.h_tail[CNT_LOOKUPS];
+  p.hits->n_increments = p.h_tail[CNT_INCR];
+  *out_hits = p.hits;
+  p.hits = nullptr;  // handed over
+  p.owner = nullptr;
   return KAAMER_OK;
 }
 

@@ -18,7 +18,7 @@ constexpr int G_THREADS = 512;
 constexpr int FAST_C = 64;     // candidates ranked by counting below this, bitonic sort above
 constexpr int BIG_LIST = 32;   // posting lists at least this long are walked by the whole warp
 constexpr int MAX_PROBE = 96;  // linear-probe budget before a histogram is declared full
-constexpr int N_LISTS = 6;     // class lists: W, M, G, hand-offs to G, D (short queries), D (long queries)
+constexpr int N_LISTS = 7;     // class lists: W, M, G, hand-offs to G, D short / long / longest queries
 
 struct SearchArgs {
   const uint64_t *table;
@@ -58,8 +58,10 @@ struct SearchArgs {
   // when its threshold is too small for D's filter; d_mapb = bytes per byte map of class D
   int dense;             // 0: classes W / M / G; 1: class D first design (A/B only); 2: class D (search_dense2.cuh)
   uint32_t d_mapb;
-  int e_kcap;            // queries up to this many k-mers go to the short-query launch of class D
-  uint32_t e_mapw_small, e_mapw_large;  // words per bit map per warp (short / long launch)
+  int e_kcap, e_kcap_l;  // class D launches by query length: up to e_kcap k-mers, up to e_kcap_l, longer
+  uint32_t e_mapw_small, e_mapw_large, e_mapw_xl;  // words per bit map per warp of the three launches
+  int lists_sorted;      // every posting list is strictly descending (builders, checked views): class D may
+                         // verify its final candidates by binary search
 };
 
 // Copy src[0, len) into shared memory with aligned 16-byte loads (one request per 16 residues:

@@ -32,22 +32,24 @@
 namespace kaamer {
 
 constexpr int E_WARPS = 4, E_THREADS = E_WARPS * 32;
-constexpr int E_H = 512;       // slots of the exact hash of pushed subjects
+constexpr int E_NF = 16;       // final candidates verified by binary search (more: the lists are streamed again)
 constexpr int E_MAXK = 60000;  // 16-bit counts
 
-template <int KCAP>
+// KCAP: query k-mers staged at once; EH: slots of the exact hash of pushed subjects
+template <int KCAP, int EH>
 struct __align__(16) Dense2Smem {
   uint64_t ent[KCAP];
-  uint32_t hkeys[E_H];
-  uint32_t hcnt2[E_H / 2];
-  uint32_t fin[E_H / 32];
-  uint16_t cand[E_H];
+  uint32_t hkeys[EH];
+  uint32_t hcnt2[EH / 2];
+  uint32_t fin[EH / 32];
+  uint16_t cand[EH];
   uint16_t pp[KCAP + 8];
   uint8_t raw[KCAP + 64];
   uint8_t lut[256];
   SelectScratch ss;
   unsigned long long bloom;
   uint32_t nfinal, it;
+  uint32_t fid[E_NF], fslot[E_NF], fcnt[E_NF];  // final candidates: subject id, slot in H, exact count
 };
 
 __device__ __forceinline__ uint32_t e_hash1(uint32_t id, uint32_t nbits) { return __umulhi(id * 0x9E3779B1u, nbits); }
@@ -60,8 +62,8 @@ __device__ __forceinline__ uint32_t e_hash2(uint32_t id, uint32_t nbits) {
 
 // One chunk of the query: residues -> packed codes -> table entries in s.ent[0, kn).  Returns kn; every
 // thread returns in `tot` the posting total of the entries it probed.
-template <bool PEER, int KCAP>
-__device__ __forceinline__ int dense2_load_chunk(const SearchArgs &a, const PeerView *pv, Dense2Smem<KCAP> &s,
+template <bool PEER, int KCAP, int EH>
+__device__ __forceinline__ int dense2_load_chunk(const SearchArgs &a, const PeerView *pv, Dense2Smem<KCAP, EH> &s,
                                                  uint64_t b, int len, int K, int c, const uint8_t *res_end,
                                                  unsigned long long &tot) {
   const int tid = threadIdx.x;
@@ -113,8 +115,8 @@ __device__ __forceinline__ int dense2_load_chunk(const SearchArgs &a, const Peer
 //
 // M1 and M2 are interleaved, mm[word] = (M1 word, M2 word): an id names ONE word index and two bit positions
 // (from two multiplicative hashes), so the test is one 8-byte load and the verify another.
-template <int PASS, bool PEER, int R, int KCAP>
-__device__ __forceinline__ void dense2_stream(const SearchArgs &a, const PeerView *pv, Dense2Smem<KCAP> &s, uint2 *mm,
+template <int PASS, bool PEER, int R, int KCAP, int EH>
+__device__ __forceinline__ void dense2_stream(const SearchArgs &a, const PeerView *pv, Dense2Smem<KCAP, EH> &s, uint2 *mm,
                                               int lg, int kn, int wi, int nw, const SmemHashT<false> &hv,
                                               const CandList &cl, unsigned long long bloom) {
   const unsigned lane = threadIdx.x & 31;
@@ -222,13 +224,48 @@ __device__ __forceinline__ void dense2_stream(const SearchArgs &a, const PeerVie
   }
 }
 
-// CLS: class list (4: queries up to KCAP k-mers staged at once; 5: the long ones)
-template <bool PEER, int KCAP, int CLS>
-__global__ void __launch_bounds__(E_THREADS, CLS == 4 ? 6 : 4) k_search_e(SearchArgs a) {
+// Exact counts of the (few) final candidates without streaming the lists again: a posting list is sorted
+// (ids strictly descending, pkg/kvstore/kv_store.go:284-305), so "does list k hold subject X" is a binary
+// search — ~6 dependent loads against ~47 ids scanned.  One (list, candidate) pair per thread.
+template <bool PEER, int KCAP, int EH>
+__device__ __forceinline__ void dense2_verify(const SearchArgs &a, const PeerView *pv, Dense2Smem<KCAP, EH> &s, int kn,
+                                              int nf) {
+  const int total = kn * nf;
+  for (int p = threadIdx.x; p < total; p += E_THREADS) {
+    const int k = p / nf, f = p - k * nf;
+    const uint64_t e = s.ent[k];
+    const uint32_t cnt = (uint32_t)(e >> ENTRY_VALUE_BITS);
+    if (cnt == 0) continue;
+    const uint32_t x = s.fid[f];
+    bool hit = false;
+    if (cnt == 1) {
+      hit = (uint32_t)e == x;
+    } else {
+      const uint32_t *pl = post_ptr<PEER>(a, pv, e & ENTRY_VALUE_MASK);
+      uint32_t lo = 0, hi = cnt;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const uint32_t v = __ldg(pl + mid);
+        if (v == x) {
+          hit = true;
+          break;
+        }
+        if (v > x) lo = mid + 1;  // descending order
+        else hi = mid;
+      }
+    }
+    if (hit) atomicAdd(&s.fcnt[f], 1u);
+  }
+}
+
+// CLS: class list (4: queries up to KCAP k-mers staged at once; 5: longer ones; 6: the longest, chunked)
+template <bool PEER, int KCAP, int EH, int CLS>
+__global__ void __launch_bounds__(E_THREADS, CLS == 4 ? 6 : (CLS == 5 ? 4 : 1)) k_search_e(SearchArgs a) {
   extern __shared__ __align__(16) uint8_t dsm[];
-  using Smem = Dense2Smem<KCAP>;
+  using Smem = Dense2Smem<KCAP, EH>;
+  constexpr int E_H = EH;
   Smem &s = *reinterpret_cast<Smem *>(dsm);
-  const uint32_t mapw = CLS == 4 ? a.e_mapw_small : a.e_mapw_large;  // words per map per warp (a power of two)
+  const uint32_t mapw = CLS == 4 ? a.e_mapw_small : (CLS == 5 ? a.e_mapw_large : a.e_mapw_xl);  // words per map per warp (2^n)
   const int lg = 31 - __clz(mapw) + 5;                                  // log2 of the bits per map
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31;
@@ -283,11 +320,11 @@ __global__ void __launch_bounds__(E_THREADS, CLS == 4 ? 6 : 4) k_search_e(Search
     // ---- pass 1 ----
     for (int c = 0; c < nchunks; ++c) {
       unsigned long long tot = 0;
-      const int kn = dense2_load_chunk<PEER, KCAP>(a, pv, s, b, len, K, c, res_end, tot);
+      const int kn = dense2_load_chunk<PEER, KCAP, EH>(a, pv, s, b, len, K, c, res_end, tot);
       q_incr += tot;
       if (w < w_act) {
-        if (R == 2) dense2_stream<1, PEER, 2, KCAP>(a, pv, s, mm, lg, kn, w, w_act, hv, cl, 0ull);
-        else dense2_stream<1, PEER, 1, KCAP>(a, pv, s, mm, lg, kn, w, w_act, hv, cl, 0ull);
+        if (R == 2) dense2_stream<1, PEER, 2, KCAP, EH>(a, pv, s, mm, lg, kn, w, w_act, hv, cl, 0ull);
+        else dense2_stream<1, PEER, 1, KCAP, EH>(a, pv, s, mm, lg, kn, w, w_act, hv, cl, 0ull);
       }
     }
     __syncthreads();
@@ -308,8 +345,13 @@ __global__ void __launch_bounds__(E_THREADS, CLS == 4 ? 6 : 4) k_search_e(Search
       if (lane == 0) s.fin[slot >> 5] = bal;
       if (isfin) {
         atomicOr(&s.bloom, 1ull << ((key * 0x9E3779B1u) >> 26));
+        const uint32_t fi = atomicAdd(&s.nfinal, 1u);
+        if (fi < (uint32_t)E_NF) {
+          s.fid[fi] = key;
+          s.fslot[fi] = slot;
+          s.fcnt[fi] = 0;
+        }
       }
-      if (lane == 0 && bal) atomicAdd(&s.nfinal, (uint32_t)__popc(bal));
     }
     __syncthreads();
     {
@@ -323,15 +365,22 @@ __global__ void __launch_bounds__(E_THREADS, CLS == 4 ? 6 : 4) k_search_e(Search
     if (s.nfinal == 0) continue;  // nothing can reach kmin: no hits (n_hits[q] was zeroed by k_classify)
     // ---- pass 2: exact counts of the final candidates ----
     const unsigned long long bloom = s.bloom;
+    const int nf = (int)s.nfinal;
+    const bool by_search = nf <= E_NF && a.lists_sorted;
     for (int c = 0; c < nchunks; ++c) {
       int kn = K < KCAP ? K : KCAP;
       if (nchunks > 1) {
         unsigned long long tot = 0;
-        kn = dense2_load_chunk<PEER, KCAP>(a, pv, s, b, len, K, c, res_end, tot);
+        kn = dense2_load_chunk<PEER, KCAP, EH>(a, pv, s, b, len, K, c, res_end, tot);
       }
-      dense2_stream<2, PEER, 2, KCAP>(a, pv, s, mm, lg, kn, w, E_WARPS, hv, cl, bloom);
+      if (by_search) dense2_verify<PEER, KCAP, EH>(a, pv, s, kn, nf);
+      else dense2_stream<2, PEER, 2, KCAP, EH>(a, pv, s, mm, lg, kn, w, E_WARPS, hv, cl, bloom);
     }
     __syncthreads();
+    if (by_search) {
+      if (tid < nf) hv.add(s.fslot[tid], s.fcnt[tid]);  // (the counts of H were zeroed after the sweep)
+      __syncthreads();
+    }
     for (int base = 0; base < E_H; base += E_THREADS) {
       const uint32_t slot = base + tid;
       if (((s.fin[slot >> 5] >> (slot & 31u)) & 1u) && hv.count_at(slot) >= kmin)

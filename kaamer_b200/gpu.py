@@ -366,6 +366,20 @@ class GpuIndex:
                                                     C.byref(o), C.byref(hp)))
         return _collect_hits(hp)
 
+    def submit_proteins_ptr(self, res_ptr: int, off_ptr: int, nq: int, opts: SearchOptions) -> int:
+        """First half of the pipelined call (kaamer_gpu_search_proteins_submit): enqueue the batch, return a
+        ticket.  The buffers behind the pointers must stay alive and unchanged until `wait_proteins`."""
+        o = opts.c()
+        t = C.c_int32(-1)
+        check(_lib.lib().kaamer_gpu_search_proteins_submit(self._h, C.c_void_p(res_ptr), C.c_void_p(off_ptr), nq,
+                                                           C.byref(o), C.byref(t)))
+        return t.value
+
+    def wait_proteins(self, ticket: int) -> SearchResult:
+        hp = C.POINTER(_lib.Hits)()
+        check(_lib.lib().kaamer_gpu_search_proteins_wait(self._h, ticket, C.byref(hp)))
+        return _collect_hits(hp)
+
     def search_proteins_device(self, d_res: int, d_off: int, nq: int, opts: SearchOptions, n_hits: int,
                                hit_base: int, size_in_kmer: int, pool: int, pool_cap: int, counters: int,
                                stream: int = 0):

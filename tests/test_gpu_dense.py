@@ -216,3 +216,29 @@ def test_sampled_queries_against_the_restricted_oracle_index(monkeypatch):
             assert r.hits(j) == [(s, int(k)) for s, k in ora.hits(i)], (dense, j)
             assert int(r.size_in_kmer[j]) == int(ora.size_in_kmer[i])
     assert len(ora.subject) >= len(sample)
+
+
+@pytest.mark.parametrize("variant", ["streamed_again", "unsorted_view"])
+def test_class_d_second_pass_by_streaming(dense_setup, variant, monkeypatch):
+    """the final candidates are normally verified by binary search in the (descending) posting lists; an
+    index view whose lists are in another order, or the A/B hook, takes the streaming second pass instead"""
+    from kaamer_b200 import GpuIndex, SearchOptions
+    from oracle import oracle as o
+
+    monkeypatch.setenv("KAAMER_DENSE", "1")
+    q, qo = dense_setup["q"]
+    idx = dense_setup["idx"]
+    ora = o.search_proteins(idx, q, qo, o.opts(), 4)
+    if variant == "streamed_again":
+        monkeypatch.setenv("KAAMER_D_NO_BSEARCH", "1")
+        r = dense_setup["g"].search_proteins(q, qo, SearchOptions())
+    else:
+        post = idx.postings.copy()
+        rng = np.random.default_rng(2)
+        for k in range(len(idx.keys)):  # ascending instead of descending, or shuffled
+            b, e = int(idx.offsets[k]), int(idx.offsets[k + 1])
+            post[b:e] = post[b:e][::-1] if k % 2 else rng.permutation(post[b:e])
+        with GpuIndex.from_arrays(idx.keys, idx.offsets, post, idx.n_proteins, idx.n_aa, idx.n_kmers) as g:
+            r = g.search_proteins(q, qo, SearchOptions())
+    assert_same_hits(r, ora, variant)
+    assert r.n_increments == ora.n_increments

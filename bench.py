@@ -554,6 +554,37 @@ def main():
         d2h += r.hit_off.nbytes + r.subject.nbytes + r.kmatch.nbytes + r.size_in_kmer.nbytes
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # the same K steps through the submit / wait pair of the C ABI, two batches in flight: what a server that
+    # handles requests concurrently (the reference runs nbOfThreads queries at a time) gets per GPU
+    def submit(s):
+        hq, ho = h_batches[s % len(h_batches)]
+        return g.submit_proteins_ptr(hq.data_ptr(), ho.data_ptr(), nq, opts)
+
+    held = []
+    tk = submit(0)
+    for s in range(1, 8):  # warm the pinned-block cache with the steady-state population (three result sets alive)
+        nx = submit(s)
+        held.append(g.wait_proteins(tk))
+        held = held[-1:]
+        tk = nx
+    r = g.wait_proteins(tk)
+    barrier()
+    t0 = time.perf_counter()
+    pipe_res = pipe_hits = 0
+    t_submit = t_wait = 0.0
+    ticket = submit(0)
+    for s in range(1, a.steps + 1):
+        ta = time.perf_counter()
+        nxt = submit(s) if s < a.steps else None
+        tb = time.perf_counter()
+        r = g.wait_proteins(ticket)
+        t_submit += tb - ta
+        t_wait += time.perf_counter() - tb
+        pipe_res += int(batches[(s - 1) % len(batches)][1][-1])
+        pipe_hits += len(r.subject)
+        ticket = nxt
+    torch.cuda.synchronize()
+    pipe_s = time.perf_counter() - t0
     n_prof = min(a.steps, 4)
     g.profile_enable(True)
     g.profile_read(reset=True)
@@ -563,12 +594,13 @@ def main():
     prof_e2e = g.profile_read(reset=True)
     host_e2e = g.profile_host_read()
     g.profile_enable(False)
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    re_ = torch.tensor([float(e2e_res)], dtype=torch.float64, device=dev)
+    te = torch.tensor([e2e_s, pipe_s], dtype=torch.float64, device=dev)
+    re_ = torch.tensor([float(e2e_res), float(pipe_res)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dist.all_reduce(re_, op=dist.ReduceOp.SUM)
-    e2e_value = float(re_.item()) / float(te.item())
+    e2e_blocking = float(re_[0].item()) / float(te[0].item())
+    e2e_value = float(re_[1].item()) / float(te[1].item())
     h2d = int(np.mean([q.nbytes + (len(qo)) * 8 for q, qo in batches]))
 
     line = None
@@ -616,7 +648,12 @@ def main():
                                         f"{a.batches} rotating query batches ({a.batches * h2d / 1e6:.0f} MB)"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h / a.steps),
-                        "ms_per_step": 1e3 * float(te.item()) / a.steps,
+                        "ms_per_step": 1e3 * float(te[1].item()) / a.steps,
+                        "how": "kaamer_gpu_search_proteins_submit / _wait on pinned HOST buffers, two batches in flight per GPU "
+                               "(submit k+1, wait k): every step moves its inputs host->device and its hits device->host",
+                        "host_ms_per_step_rank0": {"in_submit": 1e3 * t_submit / a.steps, "in_wait": 1e3 * t_wait / a.steps},
+                        "blocking": {"value": e2e_blocking, "unit": UNIT, "ms_per_step": 1e3 * float(te[0].item()) / a.steps,
+                                     "how": "one kaamer_gpu_search_proteins call at a time (round 1's e2e definition)"},
                         "ms_per_call_rank0": {"min": 1e3 * min(step_s), "median": 1e3 * float(np.median(step_s)),
                                               "max": 1e3 * max(step_s), "argmax": int(np.argmax(step_s))},
                         "stage_ms_per_step": {"h2d_copy_stream": prof_e2e["kernel_ms"][4] / n_prof,

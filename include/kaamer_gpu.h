@@ -167,6 +167,13 @@ int kaamer_gpu_search_nucleotide(kaamer_gpu_t *h, const uint8_t *nt, const uint6
                                  uint32_t n_contigs, const kaamer_opts *opts, kaamer_hits **out);
 void kaamer_gpu_free_hits(kaamer_hits *);
 
+/* The genetic code of GetORFs.  The reference ALWAYS translates with table 11 (gcodeBacteria, dna.go:106: the
+ * geneticCode argument is ignored); that is the default here.  Honouring -g is a behaviour change and only
+ * happens through this explicit call: aas64 = the amino-acid letter ('*' = stop) of the 64
+ * codons in TCAG order (index 16*b0 + 4*b1 + b2, t=0 c=1 a=2 g=3), start_mask = bit i set when codon i is a
+ * start codon — the tables of pkg/search/gcode.go.  NULL restores table 11. */
+int kaamer_gpu_set_genetic_code(kaamer_gpu_t *h, const char *aas64, uint64_t start_mask);
+
 /* GetORFs alone (dna.go:65-181), for parity tests of the translation kernels. */
 typedef struct kaamer_orfs {
   uint64_t n_orfs;

@@ -199,6 +199,7 @@ SYMBOLS = [
     "kaamer_gpu_search_proteins_wait",
     "kaamer_gpu_search_nucleotide",
     "kaamer_gpu_free_hits",
+    "kaamer_gpu_set_genetic_code",
     "kaamer_gpu_get_orfs",
     "kaamer_gpu_free_orfs",
     "kaamer_gpu_align",
@@ -279,6 +280,7 @@ def lib() -> C.CDLL:
     L.kaamer_gpu_search_nucleotide.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(Opts), C.POINTER(C.POINTER(Hits))]
     L.kaamer_gpu_free_hits.argtypes = [C.POINTER(Hits)]
     L.kaamer_gpu_free_hits.restype = None
+    L.kaamer_gpu_set_genetic_code.argtypes = [vp, C.c_char_p, C.c_uint64]
     L.kaamer_gpu_get_orfs.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(C.POINTER(Orfs))]
     L.kaamer_gpu_free_orfs.argtypes = [C.POINTER(Orfs)]
     L.kaamer_gpu_free_orfs.restype = None

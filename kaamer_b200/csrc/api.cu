@@ -134,6 +134,7 @@ static int new_handle(int device, kaamer_gpu **out) {
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
   for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->chunk_ev[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->done_ev, cudaEventDisableTiming);
   if (e != cudaSuccess) {
@@ -168,6 +169,7 @@ static void destroy_handle(kaamer_gpu *h) {
   }
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   for (int i = 0; i < 8; ++i)
     if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
   if (h->done_ev) cudaEventDestroy(h->done_ev);
@@ -525,6 +527,7 @@ int kaamer_gpu_detach_shards(kaamer_gpu_t *h) {
   KCUDA(cudaSetDevice(h->device));
   KCUDA(cudaStreamSynchronize(h->stream));
   KCUDA(cudaStreamSynchronize(h->copy_stream));
+  KCUDA(cudaStreamSynchronize(h->side_stream));
   detach_shards_locked(h);
   return KAAMER_OK;
 }
@@ -580,6 +583,7 @@ static int kaamer_gpu_attach_shards_impl(kaamer_gpu_t *h, const kaamer_shard_han
   KCUDA(cudaSetDevice(h->device));
   KCUDA(cudaStreamSynchronize(h->stream));
   KCUDA(cudaStreamSynchronize(h->copy_stream));
+  KCUDA(cudaStreamSynchronize(h->side_stream));
   detach_shards_locked(h);
   // order by shard_lo and check that the ranges tile the dense code space
   std::vector<int> order(n_shards);

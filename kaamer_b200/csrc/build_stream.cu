@@ -9,7 +9,7 @@
 //   pass:  records -> (dense code << 32 | protein id) of the in-range windows (append)
 //          -> radix sort -> unique (a protein holding a k-mer twice counts once: set semantics)
 //          -> run-length encode by code -> postings appended (ids descending, kv_store.go:284-305)
-//          -> table[d] = count:28 | (count == 1 ? id : first posting index):36
+//          -> table[d] = count:27 | (count == 1 ? id : first posting index):37
 //
 // Peak memory = table + all postings + the pairs of ONE pass (x2 for the sort), so the whole C4 index
 // (14.5 GB table + ~59 GB postings) builds on one B200 in 16 passes, and a key-range shard of it in 2.

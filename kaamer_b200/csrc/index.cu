@@ -3,7 +3,7 @@
 // Replaces on the search path the two badger stores the reference probes per k-mer
 // (kmer_store -> kcomb_store, pkg/search/search.go:421-429):
 //   * table[d]   : direct-address array over the dense 7-mer code space (internal.cuh),
-//                  one 8-byte entry per possible k-mer = (count:28 | value:36);
+//                  one 8-byte entry per possible k-mer = (count:27 | value:37);
 //                  a singleton posting list is inlined in the entry, so the common
 //                  lookup is ONE 32-byte-sector HBM access;
 //   * postings[] : CSR protein-id lists (ids unique per k-mer, descending — the order

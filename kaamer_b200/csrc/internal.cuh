@@ -57,11 +57,12 @@ constexpr uint32_t PAIR_RADIX = 442;
 constexpr uint64_t DENSE_SPACE = (uint64_t)PAIR_RADIX * PAIR_RADIX * PAIR_RADIX * 21ull;
 constexpr uint32_t CODE_UNKNOWN = 0x80;
 
-// table entry: count:28 | value:36.  count==0 empty; count==1 value = protein id (posting
-// inlined); count>=2 value = first index of the posting list in postings[].
-constexpr int ENTRY_VALUE_BITS = 36;
+// table entry: count:27 | value:37.  count==0 empty; count==1 value = protein id (posting
+// inlined); count>=2 value = first index of the posting list in postings[] (mode P: shard:3 | index:34 —
+// 2^34 postings per shard hold the whole C4 database, 17 G postings, in ONE shard).
+constexpr int ENTRY_VALUE_BITS = 37;
 constexpr uint64_t ENTRY_VALUE_MASK = (1ull << ENTRY_VALUE_BITS) - 1;
-constexpr uint64_t ENTRY_MAX_COUNT = (1ull << 28) - 1;
+constexpr uint64_t ENTRY_MAX_COUNT = (1ull << 27) - 1;
 
 // L2-resident presence filter in front of the table: bit (d mod 2^29) is set when dense code d has
 // postings.  64 MB stay resident in the 126 MB L2, so a query k-mer that is absent from the database
@@ -243,9 +244,9 @@ struct Arena {
 // peer access enabled; other process: cudaIpcOpenMemHandle).  The search kernels resolve the
 // owner of a dense code with MAX_PEER_SHARDS-1 compares and read the 8-byte entry (and the
 // posting list) straight through NVLink.  A posting-list reference carries its shard in the top
-// bits of the 36-bit entry value, so per-shard posting indices are limited to 2^33.
+// bits of the 37-bit entry value, so per-shard posting indices are limited to 2^34.
 constexpr int MAX_PEER_SHARDS = 8;
-constexpr int PEER_SHARD_SHIFT = 33;
+constexpr int PEER_SHARD_SHIFT = 34;
 constexpr uint64_t PEER_LOCAL_MASK = (1ull << PEER_SHARD_SHIFT) - 1;
 struct PeerView {
   uint32_t fence[MAX_PEER_SHARDS + 1];  // fence[s] = first dense code of shard s; unused = 0xFFFFFFFF
@@ -401,12 +402,17 @@ struct kaamer_gpu {
   uint64_t prof_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // host-call pipeline: H2D of chunk c+1 on copy_stream overlaps the search of chunk c
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t side_stream = nullptr;  // class G / long-query kernels run underneath the main search stream
   cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t done_ev = nullptr;
   uint64_t prof_all_launches = 0;
   std::vector<kaamer::ProfSpan> prof_pending;
   double prof_host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // per-handle (= per-device context) one-time setup: constant tables and kernel attributes
+  // genetic code of the translated search (translate.cu); gcode_set false: table 11, the reference's
+  char gcode_aas[64] = {0};
+  uint64_t gcode_starts = 0;
+  bool gcode_set = false;
   void *pending = nullptr;          // PendingSlot[2] of the submit / wait pipeline (search.cu)
   kaamer_aln_model aln_model{};     // alignment DP model (align.cu); aln_model_set false: the reference default
   bool aln_model_set = false;

@@ -568,6 +568,22 @@ __global__ void k_gather_hits(const uint32_t *__restrict__ n_hits, const uint32_
   }
 }
 
+// compact device arrays -> the caller-visible pinned result arrays, coalesced 16-byte stores over PCIe
+// (the per-query fragments of k_gather_hits would cross the bus as 40-byte writes); n = hit_off[nq] is read
+// on the device, so the host needs no round trip to size the copy
+__global__ void __launch_bounds__(256) k_hits_to_host(const uint32_t *__restrict__ subj, const uint32_t *__restrict__ km,
+                                                      const uint64_t *__restrict__ total, uint64_t cap,
+                                                      uint32_t *h_subj, uint32_t *h_km) {
+  uint64_t n = *total;
+  if (n > cap) n = cap;
+  const uint64_t n4 = (n + 3) / 4;  // (the arrays are allocated in multiples of 16 bytes)
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    reinterpret_cast<uint4 *>(h_subj)[i] = reinterpret_cast<const uint4 *>(subj)[i];
+    reinterpret_cast<uint4 *>(h_km)[i] = reinterpret_cast<const uint4 *>(km)[i];
+  }
+}
+
 // ---- launch ---------------------------------------------------------------------------
 void profile_begin(kaamer_gpu *h, cudaStream_t st, int cls) {
   if (!h->profile) return;
@@ -746,7 +762,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   // Class G holds a handful of very long queries, one CTA each: its kernel is a long tail on a few
   // SMs.  It is launched first, on the side stream, so that it runs underneath W and M; a second
   // (normally empty) G launch after M takes the queries whose histograms outgrew class M.
-  cudaStream_t side = h->copy_stream;
+  cudaStream_t side = h->side_stream;
   KCUDA(cudaEventRecord(h->chunk_ev[6], st));
   KCUDA(cudaStreamWaitEvent(side, h->chunk_ev[6], 0));
   profile_begin(h, side, 2);
@@ -1061,6 +1077,7 @@ struct PendingSlot {
   DevBuf<uint32_t> n_hits, hit_base;
   DevBuf<int32_t> size_in_kmer;
   DevBuf<uint8_t> residues;  // pageable caller memory is staged here
+  DevBuf<uint32_t> d_subj, d_km;  // compact hits on the device
   kaamer_hits *hits = nullptr;
   HitsOwner *owner = nullptr;
   uint64_t *h_tail = nullptr;  // pinned: counters[CNT_N] + total hits
@@ -1093,7 +1110,7 @@ void release_pending(kaamer_gpu *h) {
     if (sl[i].busy) cudaEventSynchronize(sl[i].done);
     sl[i].drop_result();
     sl[i].seq_off.release(); sl[i].hit_off.release(); sl[i].pool.release(); sl[i].counters.release();
-    sl[i].n_hits.release(); sl[i].hit_base.release(); sl[i].size_in_kmer.release(); sl[i].residues.release();
+    sl[i].n_hits.release(); sl[i].hit_base.release(); sl[i].size_in_kmer.release(); sl[i].residues.release(); sl[i].d_subj.release(); sl[i].d_km.release();
     if (sl[i].done) cudaEventDestroy(sl[i].done);
     if (sl[i].copied) cudaEventDestroy(sl[i].copied);
   }
@@ -1150,8 +1167,11 @@ int search_proteins_submit(kaamer_gpu *h, const uint8_t *res, const uint64_t *of
   p.hits->n_rows = nq;
   int rc = p.owner->alloc(&p.hits->hit_off, (size_t)nq + 1);
   if (rc == KAAMER_OK) rc = p.owner->alloc(&p.hits->size_in_kmer, (size_t)nq);
-  if (rc == KAAMER_OK) rc = p.owner->alloc(&p.hits->subject_id, (size_t)p.cap_hits + 1);
-  if (rc == KAAMER_OK) rc = p.owner->alloc(&p.hits->kmatch, (size_t)p.cap_hits + 1);
+  const size_t cap4 = ((size_t)p.cap_hits + 3) & ~(size_t)3;  // whole 16-byte groups
+  if (rc == KAAMER_OK) rc = p.owner->alloc(&p.hits->subject_id, cap4 ? cap4 : 4);
+  if (rc == KAAMER_OK) rc = p.owner->alloc(&p.hits->kmatch, cap4 ? cap4 : 4);
+  if (rc == KAAMER_OK) rc = p.d_subj.ensure(cap4 + 4);
+  if (rc == KAAMER_OK) rc = p.d_km.ensure(cap4 + 4);
   if (rc == KAAMER_OK) rc = p.owner->alloc(&p.h_tail, (size_t)CNT_N + 2);
   if (rc != KAAMER_OK) {
     p.drop_result();
@@ -1218,9 +1238,10 @@ int search_proteins_submit(kaamer_gpu *h, const uint8_t *res, const uint64_t *of
   if (e != cudaSuccess) return fail("cudaHostGetDevicePointer(result arrays)", e);
   if (p.cap_hits) {
     const unsigned grid = (unsigned)(((uint64_t)nq * 32 + 255) / 256);
-    k_gather_hits<<<grid, 256, 0, st>>>(p.n_hits.p, p.hit_base.p, p.hit_off.p, p.pool.p, nq, out_subj, out_km);
+    k_gather_hits<<<grid, 256, 0, st>>>(p.n_hits.p, p.hit_base.p, p.hit_off.p, p.pool.p, nq, p.d_subj.p, p.d_km.p);
+    k_hits_to_host<<<h->sm_count * 2, 256, 0, st>>>(p.d_subj.p, p.d_km.p, p.hit_off.p + nq, p.cap_hits, out_subj, out_km);
   }
-  h->prof_all_launches += 3;
+  h->prof_all_launches += 4;
   e = cudaMemcpyAsync(p.h_tail, p.counters.p, CNT_N * 8, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(p.h_tail + CNT_N, p.hit_off.p + nq, 8, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(p.hits->hit_off, p.hit_off.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st);

@@ -427,10 +427,11 @@ template <int U, bool PEER = false, class Hash>
 __device__ __forceinline__ void warp_consume(const SearchArgs &a, const uint64_t (&ent)[U], const Hash &hv,
                                              uint32_t kmin, const CandList &cl, unsigned long long &q_incr,
                                              const PeerView *pv = nullptr) {
+  static_assert(U <= 4, "vhi packs one byte per entry");
   const unsigned lane = threadIdx.x & 31;
   uint32_t m[U];  // postings of this lane's short multi lists
   uint32_t vlo[U];
-  uint32_t vhi = 0;  // 4 high bits of each value, packed
+  uint32_t vhi = 0;  // the 5 high bits of each value, one byte each (U <= 4)
   uint32_t mt = 0;
   bool any_big = false;
 #pragma unroll
@@ -439,7 +440,7 @@ __device__ __forceinline__ void warp_consume(const SearchArgs &a, const uint64_t
     const uint64_t val = ent[u] & ENTRY_VALUE_MASK;
     q_incr += cnt;
     vlo[u] = (uint32_t)val;
-    vhi |= (uint32_t)(val >> 32) << (4 * u);
+    vhi |= (uint32_t)(val >> 32) << (8 * u);
     m[u] = (cnt >= 2 && cnt < BIG_LIST) ? cnt : 0u;
     mt += m[u];
     any_big |= cnt >= BIG_LIST;
@@ -476,7 +477,7 @@ __device__ __forceinline__ void warp_consume(const SearchArgs &a, const uint64_t
       if (!found) {
         if (r < mu) {
           sel_lo = lo;
-          sel_hi = (ohi >> (4 * u)) & 0xFu;
+          sel_hi = (ohi >> (8 * u)) & 0xFFu;
           found = true;
         } else {
           r -= mu;

@@ -30,11 +30,17 @@ namespace kaamer {
 
 constexpr int MIN_LEN_CDS = 21;  // dna.go:26
 
-// table 11, codon index = 16*b0 + 4*b1 + b2 with t=0 c=1 a=2 g=3
-__constant__ char c_aas[65] = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
-// start codons ttg ctg att atc ata atg gtg (gcode.go:40,56,69-72,88)
-constexpr uint64_t START_MASK = (1ull << 3) | (1ull << 19) | (1ull << 32) | (1ull << 33) | (1ull << 34) |
-                                (1ull << 35) | (1ull << 51);
+// table 11 (gcodeBacteria — the table GetORFs always uses, dna.go:106), codon index = 16*b0 + 4*b1 + b2
+// with t=0 c=1 a=2 g=3; start codons ttg ctg att atc ata atg gtg (gcode.go:40,56,69-72,88).  The table is a
+// per-handle parameter (kaamer_gpu_set_genetic_code, SURVEY §8f-4: the other tables of gcode.go behind an
+// explicit call); the default is table 11.
+static const char TABLE11_AAS[65] = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+constexpr uint64_t TABLE11_STARTS = (1ull << 3) | (1ull << 19) | (1ull << 32) | (1ull << 33) | (1ull << 34) |
+                                    (1ull << 35) | (1ull << 51);
+struct GCodeArg {
+  char aas[64];
+  uint64_t starts;
+};
 
 __device__ __forceinline__ int base_code(uint32_t c) {
   c |= 0x20u;  // strings.ToLower (dna.go:68) as far as a/c/g/t are concerned
@@ -53,6 +59,7 @@ __device__ __forceinline__ uint32_t find_contig(const uint64_t *__restrict__ cof
 }
 
 struct TranslateArgs {
+  GCodeArg gc;
   const uint8_t *nt;
   const uint64_t *coff;   // [nc+1] nucleotide offsets
   const uint64_t *cbase;  // [nc+1] codon-array offsets: contig c owns 6 frames of stride L/3+1
@@ -74,7 +81,7 @@ struct TranslateArgs {
 
 __global__ void __launch_bounds__(256) k_translate6(TranslateArgs a) {
   __shared__ char aas[64];
-  if (threadIdx.x < 64) aas[threadIdx.x] = c_aas[threadIdx.x];
+  if (threadIdx.x < 64) aas[threadIdx.x] = a.gc.aas[threadIdx.x];
   __syncthreads();
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool end_p = false, end_m = false;
@@ -97,7 +104,7 @@ __global__ void __launch_bounds__(256) k_translate6(TranslateArgs a) {
     uint8_t v = 0;
     if (ok) {
       const int idx = b0 * 16 + b1 * 4 + b2;
-      v = (uint8_t)aas[idx] | (uint8_t)(((START_MASK >> idx) & 1ull) << 7);
+      v = (uint8_t)aas[idx] | (uint8_t)(((a.gc.starts >> idx) & 1ull) << 7);
     }
     cod[(p % 3) * S + p / 3] = v;
     end_p = (v & 0x7F) == '*' || p / 3 == (L - p % 3) / 3 - 1;
@@ -109,7 +116,7 @@ __global__ void __launch_bounds__(256) k_translate6(TranslateArgs a) {
     uint8_t v = 0;
     if (ok) {
       const int idx = (b2 ^ 2) * 16 + (b1 ^ 2) * 4 + (b0 ^ 2);
-      v = (uint8_t)aas[idx] | (uint8_t)(((START_MASK >> idx) & 1ull) << 7);
+      v = (uint8_t)aas[idx] | (uint8_t)(((a.gc.starts >> idx) & 1ull) << 7);
     }
     cod[(3 + j % 3) * S + j / 3] = v;
     end_m = (v & 0x7F) == '*' || j / 3 == (L - j % 3) / 3 - 1;
@@ -457,6 +464,13 @@ int orfs_device(kaamer_gpu *h, const uint8_t *d_nt, const uint64_t *h_coff, uint
   TCUDA(cudaMemcpyAsync(d_cbase, cbase.data(), ((size_t)nc + 1) * 8, cudaMemcpyHostToDevice, st));
   TCUDA(cudaMemsetAsync(d_n, 0, 32, st));
   TranslateArgs ta{};
+  if (h->gcode_set) {
+    memcpy(ta.gc.aas, h->gcode_aas, 64);
+    ta.gc.starts = h->gcode_starts;
+  } else {
+    memcpy(ta.gc.aas, TABLE11_AAS, 64);
+    ta.gc.starts = TABLE11_STARTS;
+  }
   ta.nt = d_nt;
   ta.coff = d_coff;
   ta.cbase = d_cbase;
@@ -653,3 +667,26 @@ void kaamer_gpu_free_orfs(kaamer_orfs *o) {
 }
 
 }  // extern "C"
+
+extern "C" int kaamer_gpu_set_genetic_code(kaamer_gpu_t *h, const char *aas64, uint64_t start_mask) {
+  if (!h) {
+    kaamer::set_error("null handle");
+    return KAAMER_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!aas64) {
+    h->gcode_set = false;
+    return KAAMER_OK;
+  }
+  for (int i = 0; i < 64; ++i) {
+    const char c = aas64[i];
+    if (!((c >= 'A' && c <= 'Z') || c == '*')) {
+      kaamer::set_error("genetic code: amino-acid letter %d is not A-Z or '*'", i);
+      return KAAMER_ERR_ARG;
+    }
+  }
+  memcpy(h->gcode_aas, aas64, 64);
+  h->gcode_starts = start_mask;
+  h->gcode_set = true;
+  return KAAMER_OK;
+}

@@ -399,6 +399,12 @@ class GpuIndex:
                                                       C.byref(o), C.byref(hp)))
         return _collect_hits(hp)
 
+    def set_genetic_code(self, aas64: bytes | None = None, start_mask: int = 0) -> None:
+        """Genetic code of the translated search (explicit opt-in: the reference always uses table 11,
+        pkg/search/dna.go:106).  aas64: amino-acid letters of the 64 codons in TCAG order ('*' = stop),
+        start_mask: bit i = codon i starts an ORF.  None restores table 11."""
+        check(_lib.lib().kaamer_gpu_set_genetic_code(self._h, aas64, int(start_mask)))
+
     def get_orfs(self, nt, contig_off) -> "OrfTable":
         """GetORFs (pkg/search/dna.go:65-181) of every contig of the batch, on the device."""
         nt = np.ascontiguousarray(nt, dtype=np.uint8)

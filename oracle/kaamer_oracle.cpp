@@ -198,7 +198,7 @@ struct GCode {
     return t[x * 16 + y * 4 + z];
   }
 };
-const GCode g_gcode;
+GCode g_gcode;  // ko_set_genetic_code replaces the table (§8f-4); default = table 11
 
 struct Location {
   int64_t start = 0, end = 0;
@@ -974,6 +974,20 @@ int ko_align(const uint8_t *q_in, int32_t qlen, const uint8_t *s_in, int32_t sle
     aln_b[nn] = 0;
   }
   return 0;
+}
+
+// Replace the genetic code of ko_get_orfs / ko_search_nucleotide: aas64 in TCAG codon order ('*' = stop),
+// start_mask bit i = codon i is a start codon.  The reference always uses table 11 (dna.go:106).
+void ko_set_genetic_code(const char *aas64, uint64_t start_mask) {
+  if (!aas64) {
+    g_gcode = GCode();
+    return;
+  }
+  for (int i = 0; i < 64; ++i) {
+    g_gcode.t[i].aa = aas64[i];
+    g_gcode.t[i].stop = aas64[i] == '*';
+    g_gcode.t[i].start = ((start_mask >> i) & 1ull) != 0;
+  }
 }
 
 // AlnString (align.go:69-103): "aString\nalnMatch\nbString" from the two gapped strings of ko_align

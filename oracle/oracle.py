@@ -160,6 +160,8 @@ def lib():
     L.ko_aln_string.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32]
     L.ko_set_align_model.argtypes = [vp, C.c_int32]
     L.ko_set_align_model.restype = None
+    L.ko_set_genetic_code.argtypes = [C.c_char_p, C.c_uint64]
+    L.ko_set_genetic_code.restype = None
     L.ko_reset_align_model.argtypes = []
     L.ko_reset_align_model.restype = None
     L.kso_record.restype = C.c_uint32
@@ -404,6 +406,10 @@ def set_align_model(matrix26, gap_open: int) -> None:
         return
     m = np.ascontiguousarray(matrix26, dtype=np.int8).reshape(26, 26)
     lib().ko_set_align_model(_vp(m), int(gap_open))
+
+
+def set_genetic_code(aas64: bytes | None, start_mask: int = 0) -> None:
+    lib().ko_set_genetic_code(aas64, int(start_mask))
 
 
 def blosum62() -> np.ndarray:

@@ -21,6 +21,27 @@ def gcode11():
     return {c: {"aa": a, "start": s == "true", "stop": t == "true"} for c, a, s, t in rows}
 
 
+def gcodes():
+    """every table of pkg/search/gcode.go as (aas in TCAG order, start-codon mask)"""
+    src = open(os.path.join(REF, "pkg/search/gcode.go")).read()
+    parts = re.split(r"\nvar (gcode\w+) = map\[string\]AminoAcid\{", src)
+    out = {}
+    order = "tcag"
+    for name, body in zip(parts[1::2], parts[2::2]):
+        rows = re.findall(r'"([a-z]{3})":\s*AminoAcid\{AA:\s*"(.)",\s*Start:\s*(true|false),\s*Stop:\s*(true|false)\}', body)
+        assert len(rows) == 64, (name, len(rows))
+        aas = ["?"] * 64
+        mask = 0
+        for codon, aa, start, stop in rows:
+            i = order.index(codon[0]) * 16 + order.index(codon[1]) * 4 + order.index(codon[2])
+            assert (aa == "*") == (stop == "true"), (name, codon)
+            aas[i] = aa
+            if start == "true":
+                mask |= 1 << i
+        out[name] = {"aas": "".join(aas), "start_mask": mask}
+    return out
+
+
 def aa_alphabet():
     src = open(os.path.join(REF, "pkg/kvstore/k_store.go")).read()
     m = re.search(r"aa := \[\]rune\{([^}]*)\}", src)
@@ -65,6 +86,7 @@ def kat():
 
 if __name__ == "__main__":
     json.dump(gcode11(), open(os.path.join(OUT, "gcode11.json"), "w"), indent=0, sort_keys=True)
+    json.dump(gcodes(), open(os.path.join(OUT, "gcodes.json"), "w"), indent=0, sort_keys=True)
     json.dump({"alphabet": aa_alphabet()}, open(os.path.join(OUT, "aa_alphabet.json"), "w"))
     json.dump(matrix_scores(), open(os.path.join(OUT, "matrix_scores.json"), "w"), indent=0, sort_keys=True)
     json.dump(kat(), open(os.path.join(OUT, "kat.json"), "w"), indent=1)

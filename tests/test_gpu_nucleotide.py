@@ -213,3 +213,42 @@ def test_fastq_file_through_the_native_reader(small_db, gpu_small, tmp_path):
     r = gpu_small.search_nucleotide(b.residues, b.seq_off, SearchOptions())
     assert ora.n_rows > 50
     assert_same_rows(r, ora, "fastq file")
+
+
+def test_other_genetic_codes_behind_the_explicit_call(golden_dir):
+    """the reference always translates with table 11 (dna.go:106); the other tables of
+    pkg/search/gcode.go (extracted into tests/golden/gcodes.json) are a kaamer_gpu_set_genetic_code call away:
+    GetORFs under every table == the oracle under the same table, and the default is table 11 again after
+    a reset"""
+    import json
+    import os
+
+    from kaamer_b200 import GpuIndex
+    from oracle import oracle as o
+    from tests.helpers import assert_same_orfs
+
+    tables = json.load(open(os.path.join(golden_dir, "gcodes.json")))
+    assert tables["gcodeBacteria"] == tables["gcode_11"]
+    rng = np.random.default_rng(8)
+    contigs = [bytes(np.frombuffer(b"acgt", np.uint8)[rng.integers(0, 4, n)]) for n in (3000, 1501, 40, 7000)]
+    contigs.append(b"atg" + b"gct" * 30 + b"tga" + b"ata" + b"aaa" * 25 + b"aga" + b"ttgacgtnnacg")
+    nt, no = o.pack(contigs)
+    res, off = o.pack([b"MKTAYIAKQRQISFVKSHFSRQ"])
+    with GpuIndex.build(res, off, np.array([1], np.uint32), keep_proteins=False) as g:
+        base = g.get_orfs(nt, no)
+        seen = set()
+        try:
+            for name, t in sorted(tables.items()):
+                aas, mask = t["aas"].encode(), int(t["start_mask"])
+                o.set_genetic_code(aas, mask)
+                g.set_genetic_code(aas, mask)
+                got = g.get_orfs(nt, no)
+                assert_same_orfs(got, [o.get_orfs(c) for c in contigs])
+                seen.add((len(got), got.seq.tobytes()))
+            assert len(seen) > 3  # the tables really differ (stops / starts move the ORFs)
+        finally:
+            o.set_genetic_code(None)
+        g.set_genetic_code(None)
+        again = g.get_orfs(nt, no)
+        assert len(again) == len(base) and again.seq.tobytes() == base.seq.tobytes()
+        assert_same_orfs(again, [o.get_orfs(c) for c in contigs])

@@ -50,6 +50,11 @@ struct __align__(16) Dense2Smem {
   unsigned long long bloom;
   uint32_t nfinal, it;
   uint32_t fid[E_NF], fslot[E_NF], fcnt[E_NF];  // final candidates: subject id, slot in H, exact count
+  // window descriptors of the staged chunk: entry index | window number << 10 (one 64-id window of one list);
+  // lists of more than 64 windows, and what does not fit, go to the long-list queue lq (entry indices)
+  uint32_t nd, nlq;
+  uint16_t desc[(5 * KCAP) / 2];
+  uint16_t lq[KCAP];
 };
 
 __device__ __forceinline__ uint32_t e_hash1(uint32_t id, uint32_t nbits) { return __umulhi(id * 0x9E3779B1u, nbits); }
@@ -71,6 +76,10 @@ __device__ __forceinline__ int dense2_load_chunk(const SearchArgs &a, const Peer
   const int kn = K - kbeg < KCAP ? K - kbeg : KCAP;
   const int nres = len - kbeg < kn + 7 ? len - kbeg : kn + 7;
   __syncthreads();  // the previous users of raw / pp / ent are done
+  if (tid == 0) {
+    s.nd = 0;
+    s.nlq = 0;
+  }
   const int head = stage_bytes<E_THREADS>(s.raw, a.res + b + kbeg, nres, res_end, tid);
   __syncthreads();
   const uint8_t *r = s.raw + head;
@@ -97,13 +106,47 @@ __device__ __forceinline__ int dense2_load_chunk(const SearchArgs &a, const Peer
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int pos = base + u * E_THREADS + tid;
+      uint32_t nwin = 0;
       if (ok[u]) {
         s.ent[pos] = e[u];
-        tot += e[u] >> ENTRY_VALUE_BITS;
+        const uint32_t cnt = (uint32_t)(e[u] >> ENTRY_VALUE_BITS);
+        tot += cnt;
+        nwin = (cnt + 63u) >> 6;
+      }
+      // window descriptors, reserved with one shared-memory atomic per warp
+      const bool is_long = nwin > 64u;
+      const uint32_t want = is_long ? 0u : nwin;
+      uint32_t incl = want;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += t;
+      }
+      const uint32_t wtot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      uint32_t wbase = 0;
+      if ((threadIdx.x & 31) == 31 && wtot) wbase = atomicAdd(&s.nd, wtot);
+      wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
+      const uint32_t first = wbase + incl - want;
+      constexpr uint32_t DCAP = (5 * KCAP) / 2;
+      if (want && first + want <= DCAP) {
+        for (uint32_t wn = 0; wn < want; ++wn) s.desc[first + wn] = (uint16_t)((uint32_t)pos | (wn << 10));
+      } else if (is_long) {
+        s.lq[atomicAdd(&s.nlq, 1u)] = (uint16_t)pos;  // (rare: a list of more than 4096 ids)
       }
     }
   }
   __syncthreads();
+  if (s.nd > (uint32_t)((5 * KCAP) / 2)) {
+    // more windows than descriptors (a database ~3x denser than C4): every list of the chunk is walked
+    // through the long-list queue instead — slower per window, same result
+    __syncthreads();
+    if (tid == 0) s.nd = 0;
+    for (int pos = tid; pos < kn; pos += E_THREADS) {
+      const uint32_t cnt = (uint32_t)(s.ent[pos] >> ENTRY_VALUE_BITS);
+      if (cnt > 0 && ((cnt + 63u) >> 6) <= 64u) s.lq[atomicAdd(&s.nlq, 1u)] = (uint16_t)pos;
+    }
+    __syncthreads();
+  }
   return kn;
 }
 
@@ -115,43 +158,61 @@ __device__ __forceinline__ int dense2_load_chunk(const SearchArgs &a, const Peer
 //
 // M1 and M2 are interleaved, mm[word] = (M1 word, M2 word): an id names ONE word index and two bit positions
 // (from two multiplicative hashes), so the test is one 8-byte load and the verify another.
-template <int PASS, bool PEER, int R, int KCAP, int EH>
+// LONGQ = false: the windows are the descriptors desc[wi], desc[wi + nw], ... (one shared-memory read names the
+// entry and the window: no list-walking state).  LONGQ = true: the lists of the long-list queue, window by window.
+template <int PASS, bool PEER, int R, bool LONGQ, int KCAP, int EH>
 __device__ __forceinline__ void dense2_stream(const SearchArgs &a, const PeerView *pv, Dense2Smem<KCAP, EH> &s, uint2 *mm,
-                                              int lg, int kn, int wi, int nw, const SmemHashT<false> &hv,
-                                              const CandList &cl, unsigned long long bloom) {
+                                              int lg, int wi, int nw, const SmemHashT<false> &hv, const CandList &cl,
+                                              unsigned long long bloom) {
   const unsigned lane = threadIdx.x & 31;
-  int k = wi - nw;
-  uint32_t off = 0, cnt = 0, single = 0;
+  const int kn = LONGQ ? (int)s.nlq : (int)s.nd;
+  int k = LONGQ ? wi - nw : wi;
+  uint32_t off = 0, cnt = 0;
   const uint32_t *ptr = nullptr;
-  // warp-uniform iterator over (list, 64-id window); nv = 0 once exhausted
+  // warp-uniform iterator over 64-id windows; nv = 0 once exhausted
   auto fetch = [&](uint32_t &ia, uint32_t &ib, uint32_t &nv) {
     nv = 0;
     ia = ib = 0;
-    if (off >= cnt) {
-      do {
+    if constexpr (!LONGQ) {
+      if (k >= kn) return;
+      const uint32_t d = s.desc[k];
+      k += nw;
+      const uint64_t e = s.ent[d & 1023u];
+      const uint32_t c = (uint32_t)(e >> ENTRY_VALUE_BITS), o = (d >> 10) << 6;
+      nv = c - o < 64u ? c - o : 64u;
+      if (c == 1) {
+        ia = (uint32_t)e;  // the posting inlined in the entry (only lane 0 is valid: nv = 1)
+      } else {
+        const uint32_t *p = post_ptr<PEER>(a, pv, e & ENTRY_VALUE_MASK) + o + lane;
+        if (lane < nv) ia = __ldg(p);
+        if (lane + 32u < nv) ib = __ldg(p + 32);
+      }
+    } else {
+      if (off >= cnt) {
         k += nw;
         if (k >= kn) {
           k = kn;  // stay exhausted
           cnt = off = 0;
           return;
         }
-        const uint64_t e = s.ent[k];
-        cnt = (uint32_t)(e >> ENTRY_VALUE_BITS);
-        single = (uint32_t)e;
-        if (cnt >= 2) ptr = post_ptr<PEER>(a, pv, e & ENTRY_VALUE_MASK);
-      } while (cnt == 0);
-      off = 0;
-    }
-    const uint32_t rem = cnt - off;
-    nv = rem < 64u ? rem : 64u;
-    if (cnt == 1) {
-      ia = single;
-    } else {
+        const uint64_t e = s.ent[s.lq[k]];
+        cnt = (uint32_t)(e >> ENTRY_VALUE_BITS);  // >= 2: a long list, or one that did not fit the descriptors
+        off = 0;
+        ptr = post_ptr<PEER>(a, pv, e & ENTRY_VALUE_MASK);
+        if (cnt == 1) {  // (an inlined posting that did not fit the descriptor array)
+          ia = (uint32_t)e;
+          nv = 1;
+          off = 64;
+          return;
+        }
+      }
+      const uint32_t rem = cnt - off;
+      nv = rem < 64u ? rem : 64u;
       const uint32_t *p = ptr + off + lane;
       if (lane < nv) ia = __ldg(p);
       if (lane + 32u < nv) ib = __ldg(p + 32);
+      off += 64;
     }
-    off += 64;
   };
   constexpr int J = 2 * R;
   const int sh_w = 37 - lg, sh_b = 32 - lg;  // word index = x1 >> (32 - lg + 5), bit index = (x1 >> (32 - lg)) & 31
@@ -327,11 +388,12 @@ __global__ void __launch_bounds__(E_THREADS, CLS == 4 ? 6 : (CLS == 5 ? 4 : 1)) 
     // ---- pass 1 ----
     for (int c = 0; c < nchunks; ++c) {
       unsigned long long tot = 0;
-      const int kn = dense2_load_chunk<PEER, KCAP, EH>(a, pv, s, b, len, K, c, res_end, tot);
+      dense2_load_chunk<PEER, KCAP, EH>(a, pv, s, b, len, K, c, res_end, tot);
       q_incr += tot;
       if (w < w_act) {
-        if (R == 2) dense2_stream<1, PEER, 2, KCAP, EH>(a, pv, s, mm, lg, kn, w, w_act, hv, cl, 0ull);
-        else dense2_stream<1, PEER, 1, KCAP, EH>(a, pv, s, mm, lg, kn, w, w_act, hv, cl, 0ull);
+        if (R == 2) dense2_stream<1, PEER, 2, false, KCAP, EH>(a, pv, s, mm, lg, w, w_act, hv, cl, 0ull);
+        else dense2_stream<1, PEER, 1, false, KCAP, EH>(a, pv, s, mm, lg, w, w_act, hv, cl, 0ull);
+        if (s.nlq) dense2_stream<1, PEER, 1, true, KCAP, EH>(a, pv, s, mm, lg, w, w_act, hv, cl, 0ull);
       }
     }
     __syncthreads();
@@ -380,8 +442,12 @@ __global__ void __launch_bounds__(E_THREADS, CLS == 4 ? 6 : (CLS == 5 ? 4 : 1)) 
         unsigned long long tot = 0;
         kn = dense2_load_chunk<PEER, KCAP, EH>(a, pv, s, b, len, K, c, res_end, tot);
       }
-      if (by_search) dense2_verify<PEER, KCAP, EH>(a, pv, s, kn, nf);
-      else dense2_stream<2, PEER, 2, KCAP, EH>(a, pv, s, mm, lg, kn, w, E_WARPS, hv, cl, bloom);
+      if (by_search) {
+        dense2_verify<PEER, KCAP, EH>(a, pv, s, kn, nf);
+      } else {
+        dense2_stream<2, PEER, 1, false, KCAP, EH>(a, pv, s, mm, lg, w, E_WARPS, hv, cl, bloom);
+        if (s.nlq) dense2_stream<2, PEER, 1, true, KCAP, EH>(a, pv, s, mm, lg, w, E_WARPS, hv, cl, bloom);
+      }
     }
     __syncthreads();
     if (by_search) {

@@ -341,3 +341,44 @@ def test_fasta_file_to_hits_through_the_native_reader(small_db, gpu_small, tmp_p
     assert_same_hits(r, ora, "fasta file")
     np.testing.assert_array_equal(r.size_in_kmer, b.size_in_kmer)
     assert r.hits(50) == []  # lower-case residues are unknown letters: the last record finds nothing
+
+
+def test_submit_wait_pipeline_equals_the_blocking_call(small_db, gpu_small):
+    """kaamer_gpu_search_proteins_submit / _wait: two batches in flight, results identical to the blocking call
+    and to the oracle; a third submit is refused; pageable and pinned inputs; refused batch kinds"""
+    import torch
+
+    from kaamer_b200 import KaamerGpuError, SearchOptions, synth
+    from oracle import oracle as o
+
+    opts = SearchOptions()
+    batches = []
+    for b in range(5):
+        q, qo, _ = synth.protein_queries(small_db["res"], small_db["off"], 300 + 50 * b, config_index=1, stream=40 + b)
+        if b % 2:  # page-locked inputs on every second batch
+            q = torch.from_numpy(q).pin_memory().numpy()
+            qo = torch.from_numpy(qo.astype(np.int64)).pin_memory().numpy().view(np.uint64)
+        batches.append((q, np.ascontiguousarray(qo, dtype=np.uint64)))
+    expected = [o.search_proteins(small_db["idx"], q, qo, o.opts(), 4) for q, qo in batches]
+    t = gpu_small.submit_proteins_ptr(batches[0][0].ctypes.data, batches[0][1].ctypes.data, len(batches[0][1]) - 1, opts)
+    for b in range(1, 5):
+        t2 = gpu_small.submit_proteins_ptr(batches[b][0].ctypes.data, batches[b][1].ctypes.data, len(batches[b][1]) - 1, opts)
+        if b == 1:
+            with pytest.raises(KaamerGpuError):  # two in flight already
+                gpu_small.submit_proteins_ptr(batches[2][0].ctypes.data, batches[2][1].ctypes.data, 10, opts)
+        r = gpu_small.wait_proteins(t)
+        assert_same_hits(r, expected[b - 1], f"pipelined batch {b - 1}")
+        assert r.n_lookups == expected[b - 1].n_lookups and r.n_increments == expected[b - 1].n_increments
+        t = t2
+    assert_same_hits(gpu_small.wait_proteins(t), expected[4], "pipelined batch 4")
+    with pytest.raises(KaamerGpuError):
+        gpu_small.wait_proteins(t)  # nothing in flight in that slot any more
+    q, qo = batches[0]
+    with pytest.raises(KaamerGpuError):  # positions cannot be bounded beforehand: blocking call only
+        gpu_small.submit_proteins_ptr(q.ctypes.data, qo.ctypes.data, len(qo) - 1, SearchOptions(extract_positions=True))
+    # the blocking call (submit + wait inside) after the pipeline, and a MaxResults the pool must grow for
+    assert_same_hits(gpu_small.search_proteins(q, qo, opts), expected[0], "blocking after pipeline")
+    big = SearchOptions(min_kmatch=1, min_kratio=0.0, max_results=100)
+    ora = o.search_proteins(small_db["idx"], q, qo, o.opts(min_kmatch=1, min_kratio=0.0, max_results=100), 4)
+    tk = gpu_small.submit_proteins_ptr(q.ctypes.data, qo.ctypes.data, len(qo) - 1, big)
+    assert_same_hits(gpu_small.wait_proteins(tk), ora, "pool overflow inside a pipelined batch")

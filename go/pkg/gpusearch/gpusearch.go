@@ -210,3 +210,134 @@ func (ix *Index) Align(queries []string, pairQuery, pairSubject []uint32, lambda
 	}
 	return r, nil
 }
+
+// AlignText is Align plus AlignmentResult.AlnString (pkg/align/align.go:69-103) of every pair:
+// "<gapped query>\n<match line>\n<gapped subject>", what the JSON writer marshals (search.go:497-503).
+func (ix *Index) AlignText(queries []string, pairQuery, pairSubject []uint32, lambda, k float64,
+	gapOpen, gapExtend int, numberOfAA uint64) ([]Alignment, []string, error) {
+	if len(pairQuery) == 0 {
+		return nil, nil, nil
+	}
+	res, off := pack(queries)
+	ao := C.kaamer_aln_opts{lambda: C.double(lambda), K: C.double(k), gap_open: C.int32_t(gapOpen),
+		gap_extend: C.int32_t(gapExtend), number_of_aa: C.uint64_t(numberOfAA)}
+	out := make([]C.kaamer_aln, len(pairQuery))
+	var text *C.kaamer_aln_text
+	rc := C.kaamer_gpu_align_text(ix.h, (*C.uint8_t)(unsafe.Pointer(&res[0])), &off[0],
+		(*C.uint32_t)(unsafe.Pointer(&pairQuery[0])), (*C.uint32_t)(unsafe.Pointer(&pairSubject[0])),
+		C.uint32_t(len(pairQuery)), &ao, &out[0], &text)
+	if rc != C.KAAMER_OK {
+		return nil, nil, lastErr(rc)
+	}
+	defer C.kaamer_gpu_free_aln_text(text)
+	n := len(out)
+	offs := unsafe.Slice((*uint64)(unsafe.Pointer(text.off)), n+1)
+	blob := unsafe.Slice((*byte)(unsafe.Pointer(text.text)), int(offs[n]))
+	r := make([]Alignment, n)
+	s := make([]string, n)
+	for i, a := range out {
+		r[i] = Alignment{float32(a.identity), float32(a.similarity), int(a.length), int(a.mismatches),
+			int(a.gap_openings), int(a.raw), float64(a.bitscore), float64(a.evalue), int(a.query_start),
+			int(a.query_end), int(a.subject_start), int(a.subject_end), a.status != 0}
+		s[i] = string(blob[offs[i]:offs[i+1]])
+	}
+	return r, s, nil
+}
+
+// Ticket names a batch in flight (kaamer_gpu_search_proteins_submit).  The residues live in C memory
+// (kaamer_gpu_pinned_alloc) owned by the Ticket until Wait returns: cgo forbids C code to keep Go pointers.
+type Ticket struct {
+	id  C.int32_t
+	res unsafe.Pointer
+	off unsafe.Pointer
+	nq  int
+}
+
+// Submit enqueues a batch and returns at once; at most two batches may be in flight per Index.  A dispatcher
+// goroutine calls Submit for batch k+1 before Wait for batch k: the copies and the host work of one batch then
+// hide under the kernels of the other (the reference overlaps nbOfThreads queries, api/server.go:55-59).
+func (ix *Index) Submit(seqs []string, o Options) (*Ticket, error) {
+	res, off := pack(seqs)
+	var pres, poff unsafe.Pointer
+	if rc := C.kaamer_gpu_pinned_alloc(C.uint64_t(len(res)+16), &pres); rc != C.KAAMER_OK {
+		return nil, lastErr(rc)
+	}
+	if rc := C.kaamer_gpu_pinned_alloc(C.uint64_t(8*len(off)), &poff); rc != C.KAAMER_OK {
+		C.kaamer_gpu_pinned_free(pres)
+		return nil, lastErr(rc)
+	}
+	copy(unsafe.Slice((*byte)(pres), len(res)), res)
+	copy(unsafe.Slice((*C.uint64_t)(poff), len(off)), off)
+	t := &Ticket{res: pres, off: poff, nq: len(seqs)}
+	co := o.c()
+	if rc := C.kaamer_gpu_search_proteins_submit(ix.h, (*C.uint8_t)(pres), (*C.uint64_t)(poff),
+		C.uint32_t(len(seqs)), &co, &t.id); rc != C.KAAMER_OK {
+		C.kaamer_gpu_pinned_free(pres)
+		C.kaamer_gpu_pinned_free(poff)
+		return nil, lastErr(rc)
+	}
+	return t, nil
+}
+
+// Wait blocks until the hits of the batch are in host memory (one event synchronisation).
+func (ix *Index) Wait(t *Ticket) ([]Row, error) {
+	var hits *C.kaamer_hits
+	rc := C.kaamer_gpu_search_proteins_wait(ix.h, t.id, &hits)
+	C.kaamer_gpu_pinned_free(t.res)
+	C.kaamer_gpu_pinned_free(t.off)
+	if rc != C.KAAMER_OK {
+		return nil, lastErr(rc)
+	}
+	defer C.kaamer_gpu_free_hits(hits)
+	return rows(hits, false), nil
+}
+
+// SetAlignModel replaces the DP model of Align (explicit opt-in, SURVEY §8f-4): matrix in biogo
+// alphabet.Protein order "-ABCDEFGHIJKLMNPQRSTVWXYZ*" with row/column 0 = per-residue gap cost, e.g.
+// biogo's own matrix.BLOSUM62 flattened, and SWAffine.GapOpen.  nil restores the reference's model.
+func (ix *Index) SetAlignModel(matrix [][]int, gapOpen int) error {
+	if matrix == nil {
+		if rc := C.kaamer_gpu_set_align_model(ix.h, nil); rc != C.KAAMER_OK {
+			return lastErr(rc)
+		}
+		return nil
+	}
+	var m C.kaamer_aln_model
+	for i := 0; i < 26; i++ {
+		for j := 0; j < 26; j++ {
+			m.matrix[i*26+j] = C.int8_t(matrix[i][j])
+		}
+	}
+	m.gap_open = C.int32_t(gapOpen)
+	if rc := C.kaamer_gpu_set_align_model(ix.h, &m); rc != C.KAAMER_OK {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// FormatTSV writes the `-fmt tsv` rows of a whole batch (search.go:505-606) in one native call; the caller
+// does one w.Write.  names: Query.Name per query of the batch.
+func (ix *Index) FormatTSV(hits *C.kaamer_hits, aln []C.kaamer_aln, names []string, seqOff []C.uint64_t,
+	isProtein, withPositions, withAnnotations bool) ([]byte, error) {
+	nres, noff := pack(names)
+	var alnp *C.kaamer_aln
+	if len(aln) > 0 {
+		alnp = &aln[0]
+	}
+	var out *C.char
+	var n C.uint64_t
+	b2i := func(b bool) C.int {
+		if b {
+			return 1
+		}
+		return 0
+	}
+	nres = append(nres, 0)
+	rc := C.kaamer_host_format_tsv(ix.h, hits, alnp, (*C.char)(unsafe.Pointer(&nres[0])), &noff[0], &seqOff[0],
+		b2i(isProtein), b2i(withPositions), b2i(withAnnotations), &out, &n)
+	if rc != C.KAAMER_OK {
+		return nil, lastErr(rc)
+	}
+	defer C.kaamer_host_free_text(out)
+	return C.GoBytes(unsafe.Pointer(out), C.int(n)), nil
+}

@@ -216,29 +216,37 @@ __device__ __forceinline__ void dense2_stream(const SearchArgs &a, const PeerVie
   };
   constexpr int J = 2 * R;
   const int sh_w = 37 - lg, sh_b = 32 - lg;  // word index = x1 >> (32 - lg + 5), bit index = (x1 >> (32 - lg)) & 31
-  // two groups ahead: ncu showed 22 % of the stall samples on the first use of a window fetched only one
-  // group earlier (a posting list is a dependent HBM access behind its table entry)
-  uint32_t na[R], nb[R], nnv[R], fa[R], fb[R], fnv[R];
+  // AHEAD groups in flight beyond the one being processed.  Two on local HBM: ncu showed 22 % of the stall
+  // samples on the first use of a window fetched only one group earlier (a posting list is a dependent HBM
+  // access behind its table entry).  Six when the lists may live on another GPU (mode P): an NVLink round trip
+  // is several times an HBM one.
+  constexpr int AHEAD = PEER ? 6 : 2;
+  uint32_t qa[AHEAD][R], qb[AHEAD][R], qn[AHEAD][R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) fetch(na[r], nb[r], nnv[r]);
+  for (int d = 0; d < AHEAD; ++d)
 #pragma unroll
-  for (int r = 0; r < R; ++r) fetch(fa[r], fb[r], fnv[r]);
+    for (int r = 0; r < R; ++r) fetch(qa[d][r], qb[d][r], qn[d][r]);
 #pragma unroll 1
-  while (nnv[0] != 0) {
+  while (qn[0][0] != 0) {
     uint32_t id[J];
     bool v[J];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      id[2 * r] = na[r];
-      id[2 * r + 1] = nb[r];
-      v[2 * r] = lane < nnv[r];
-      v[2 * r + 1] = lane + 32u < nnv[r];
-      na[r] = fa[r];
-      nb[r] = fb[r];
-      nnv[r] = fnv[r];
+      id[2 * r] = qa[0][r];
+      id[2 * r + 1] = qb[0][r];
+      v[2 * r] = lane < qn[0][r];
+      v[2 * r + 1] = lane + 32u < qn[0][r];
     }
 #pragma unroll
-    for (int r = 0; r < R; ++r) fetch(fa[r], fb[r], fnv[r]);
+    for (int d = 0; d + 1 < AHEAD; ++d)
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        qa[d][r] = qa[d + 1][r];
+        qb[d][r] = qb[d + 1][r];
+        qn[d][r] = qn[d + 1][r];
+      }
+#pragma unroll
+    for (int r = 0; r < R; ++r) fetch(qa[AHEAD - 1][r], qb[AHEAD - 1][r], qn[AHEAD - 1][r]);
     if constexpr (PASS == 1) {
       uint32_t wd[J], b1[J], b2[J];
       uint2 w[J];
@@ -328,7 +336,7 @@ __device__ __forceinline__ void dense2_verify(const SearchArgs &a, const PeerVie
 
 // CLS: class list (4: queries up to KCAP k-mers staged at once; 5: longer ones; 6: the longest, chunked)
 template <bool PEER, int KCAP, int EH, int CLS>
-__global__ void __launch_bounds__(E_THREADS, CLS == 4 ? 6 : (CLS == 5 ? 4 : 1)) k_search_e(SearchArgs a) {
+__global__ void __launch_bounds__(E_THREADS, CLS == 4 ? (PEER ? 4 : 6) : (CLS == 5 ? (PEER ? 3 : 4) : 1)) k_search_e(SearchArgs a) {
   extern __shared__ __align__(16) uint8_t dsm[];
   using Smem = Dense2Smem<KCAP, EH>;
   constexpr int E_H = EH;

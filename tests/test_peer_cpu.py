@@ -119,7 +119,7 @@ class _FakeIndex:
         sh.table_fd, sh.postings_fd = fds
         return sh
 
-    def attach_shards(self, handles, presence_filter=True, replicate_table=False):
+    def attach_shards(self, handles, presence_filter=True, replicate_table=False, replicate_postings=False):
         seen = []
         for r, sh in enumerate(handles):
             assert (sh.shard_lo, sh.shard_hi) == (r * 100, (r + 1) * 100)

@@ -145,7 +145,7 @@ def kernel_source_hash() -> str:
     """sha256 (16 hex) of the search kernel sources: profiles/traffic.json carries the hash of the sources
     its ncu capture was taken from, a changed kernel makes the stored DRAM traffic stale (-> null)."""
     h = hashlib.sha256()
-    for f in ("search.cu", "search_common.cuh", "search_dense2.cuh", "internal.cuh"):
+    for f in ("search.cu", "search_common.cuh", "search_dense2.cuh", "search_dense3.cuh", "internal.cuh"):
         with open(os.path.join(ROOT, "kaamer_b200", "csrc", f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]

@@ -31,6 +31,7 @@
 #include "search_common.cuh"
 #include "search_dense.cuh"
 #include "search_dense2.cuh"
+#include "search_dense3.cuh"
 
 namespace kaamer {
 
@@ -61,7 +62,7 @@ __global__ void k_classify(SearchArgs a) {
     // per-warp state halves the resident warps and it ran at 10 G lookups/s against 24 G/s for
     // the CTA-per-query class M (profiles/r1_notes.md).
     if (go) {
-      if (a.dense) cls = (a.kmin[q] >= 3u && K <= D_MAXK) ? ((a.dense == 2 && K > a.e_kcap) ? (K > a.e_kcap_l ? 6 : 5) : 4) : 2;
+      if (a.dense) cls = (a.kmin[q] >= 3u && K <= D_MAXK) ? ((a.dense >= 2 && K > a.e_kcap) ? (K > a.e_kcap_l ? 6 : 5) : 4) : 2;
       else cls = K <= a.w_maxk ? 0 : (K <= a.m_maxk ? 1 : 2);
     }
   }
@@ -616,7 +617,8 @@ static void class_limits(const kaamer_gpu *h, int *w_maxk, int *m_maxk, int *den
   *dense = p >= 6.0 ? 2 : 0;
   if (const char *env = getenv("KAAMER_DENSE")) {
     const int v = atoi(env);
-    *dense = v == 1 ? 2 : (v == 11 ? 1 : 0);  // 1: class D; 11: its first design (A/B measurements); 0: off
+    // 1: class D; 12 / 11: its second / first design (A/B measurements); 0: off
+    *dense = v == 1 ? 2 : (v == 12 ? 3 : (v == 11 ? 1 : 0));
   }
   if (p < 0.5) p = 0.5;
   double w = 0.55 * W_H / p, m = 0.55 * M_H / p;
@@ -726,10 +728,41 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   auto e_small = peer ? k_search_e<true, E_KCAP_S, EH_S, 4> : k_search_e<false, E_KCAP_S, EH_S, 4>;
   auto e_large = peer ? k_search_e<true, E_KCAP_L, EH_L, 5> : k_search_e<false, E_KCAP_L, EH_L, 5>;
   auto e_xl = peer ? k_search_e<true, E_KCAP_L, EH_XL, 6> : k_search_e<false, E_KCAP_L, EH_XL, 6>;
-  if (a.dense == 2) {
+  if (a.dense == 3) {
     KCUDA(cudaFuncSetAttribute(e_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem_s));
     KCUDA(cudaFuncSetAttribute(e_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem_l));
     KCUDA(cudaFuncSetAttribute(e_xl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e_smem_xl));
+  }
+  // class D, third design (search_dense3.cuh): 4 / 8 / 16 warps per CTA for the three lengths; a warp's map is
+  // f_mapw 32-bit words (16 + 16 bits each)
+  constexpr int F_NW_S = 4, F_NW_L = 8, F_NW_XL = 16;
+  uint32_t f_mapw_s = 1024, f_mapw_l = 1024, f_mapw_xl = 2048;
+  if (const char *env = getenv("KAAMER_F_MAPW")) {  // tuning hook: "small,large,xl" words per warp map (powers of two)
+    unsigned ms = 0, ml = 0, mx = 0;
+    if (sscanf(env, "%u,%u,%u", &ms, &ml, &mx) == 3 && ms >= 64 && ms <= 8192 && ml >= 64 && ml <= 8192 && mx >= 64 &&
+        mx <= 2048 && (ms & (ms - 1)) == 0 && (ml & (ml - 1)) == 0 && (mx & (mx - 1)) == 0) {
+      f_mapw_s = ms;
+      f_mapw_l = ml;
+      f_mapw_xl = mx;
+    }
+  }
+  const int f_ph = peer ? F_PH_PEER : F_PH_LOCAL;
+  auto f_smem = [&](size_t s3, size_t s7, int nw, uint32_t mapw) {
+    return (((f_ph == F_PH_PEER ? s7 : s3) + 15) & ~(size_t)15) + (size_t)nw * mapw * 4;
+  };
+  const size_t f_smem_s = f_smem(sizeof(Dense3Smem<E_KCAP_S, EH_S, F_NW_S, F_PH_LOCAL>), sizeof(Dense3Smem<E_KCAP_S, EH_S, F_NW_S, F_PH_PEER>), F_NW_S, f_mapw_s);
+  const size_t f_smem_l = f_smem(sizeof(Dense3Smem<E_KCAP_L, EH_L, F_NW_L, F_PH_LOCAL>), sizeof(Dense3Smem<E_KCAP_L, EH_L, F_NW_L, F_PH_PEER>), F_NW_L, f_mapw_l);
+  const size_t f_smem_xl = f_smem(sizeof(Dense3Smem<E_KCAP_L, EH_XL, F_NW_XL, F_PH_LOCAL>), sizeof(Dense3Smem<E_KCAP_L, EH_XL, F_NW_XL, F_PH_PEER>), F_NW_XL, f_mapw_xl);
+  auto f_small = peer ? k_search_f<true, E_KCAP_S, EH_S, 4, F_NW_S, 4> : k_search_f<false, E_KCAP_S, EH_S, 4, F_NW_S, 6>;
+  auto f_large = peer ? k_search_f<true, E_KCAP_L, EH_L, 5, F_NW_L, 2> : k_search_f<false, E_KCAP_L, EH_L, 5, F_NW_L, 3>;
+  auto f_xl = peer ? k_search_f<true, E_KCAP_L, EH_XL, 6, F_NW_XL, 1> : k_search_f<false, E_KCAP_L, EH_XL, 6, F_NW_XL, 1>;
+  if (a.dense == 2) {
+    a.e_mapw_small = f_mapw_s;
+    a.e_mapw_large = f_mapw_l;
+    a.e_mapw_xl = f_mapw_xl;
+    KCUDA(cudaFuncSetAttribute(f_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f_smem_s));
+    KCUDA(cudaFuncSetAttribute(f_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f_smem_l));
+    KCUDA(cudaFuncSetAttribute(f_xl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f_smem_xl));
   }
   // Class G: one CTA per query, histogram in a per-CTA global scratch.  At Swiss-Prot density it holds a
   // handful of very long queries and gets one CTA per SM (it runs underneath W and M and must leave them
@@ -772,6 +805,13 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   if (a.dense == 2) {
     // the long queries of class D run on the side stream underneath the short ones: the (few) longest first
     int per_sm = 1;
+    f_xl<<<(unsigned)h->sm_count, F_NW_XL * 32, f_smem_xl, side>>>(a);
+    KCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f_large, F_NW_L * 32, f_smem_l));
+    profile_begin(h, side, 1);
+    f_large<<<(unsigned)h->sm_count * (unsigned)(per_sm < 1 ? 1 : per_sm), F_NW_L * 32, f_smem_l, side>>>(a);
+    profile_end(h, side);
+  } else if (a.dense == 3) {
+    int per_sm = 1;
     e_xl<<<(unsigned)h->sm_count, E_THREADS, e_smem_xl, side>>>(a);
     KCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e_large, E_THREADS, e_smem_l));
     profile_begin(h, side, 1);
@@ -780,6 +820,13 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   }
   KCUDA(cudaEventRecord(h->chunk_ev[7], side));
   if (a.dense == 2) {
+    int per_sm = 1;
+    KCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f_small, F_NW_S * 32, f_smem_s));
+    profile_begin(h, st, 6);
+    f_small<<<(unsigned)h->sm_count * (unsigned)(per_sm < 1 ? 1 : per_sm), F_NW_S * 32, f_smem_s, st>>>(a);
+    profile_end(h, st);
+    KCUDA(cudaStreamWaitEvent(st, h->chunk_ev[7], 0));  // the hand-offs of both launches are complete
+  } else if (a.dense == 3) {
     int per_sm = 1;
     KCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e_small, E_THREADS, e_smem_s));
     profile_begin(h, st, 6);

@@ -48,7 +48,7 @@ def dense_setup():
     g.close()
 
 
-@pytest.mark.parametrize("design", ["1", "11"])  # KAAMER_DENSE: class D, and its first design (kept for A/B)
+@pytest.mark.parametrize("design", ["1", "12", "11"])  # KAAMER_DENSE: class D, and its second / first designs (kept for A/B)
 @pytest.mark.parametrize("opts", [
     dict(),
     dict(min_kmatch=3, min_kratio=0.0, max_results=10),     # thr = 1, one streaming warp
@@ -76,8 +76,9 @@ def test_class_d_parity_on_a_dense_database(dense_setup, opts, design, monkeypat
 
 
 @pytest.mark.parametrize("design,var,val", [("11", "KAAMER_D_MAPKB", "1"), ("11", "KAAMER_D_MAPKB", "64"),
-                                            ("1", "KAAMER_E_MAPW", "64,64"), ("1", "KAAMER_E_MAPW", "128,512"),
-                                            ("1", "KAAMER_E_MAPW", "2048,4096")])
+                                            ("12", "KAAMER_E_MAPW", "64,64"), ("12", "KAAMER_E_MAPW", "128,512"),
+                                            ("12", "KAAMER_E_MAPW", "2048,4096"), ("1", "KAAMER_F_MAPW", "64,64,64"),
+                                            ("1", "KAAMER_F_MAPW", "128,512,256"), ("1", "KAAMER_F_MAPW", "4096,2048,2048")])
 def test_class_d_map_sizes(dense_setup, design, var, val, monkeypatch):
     """tiny maps (everything collides: pushes overflow H, class G takes the query) to large ones"""
     from kaamer_b200 import SearchOptions

@@ -43,16 +43,15 @@ constexpr int F_PH_LOCAL = KAAMER_F_PH, F_PH_PEER = 8;
 // KCAP: query k-mers staged at once; EH: slots of the exact hash; NW warps per CTA; PH windows in flight per warp.
 //
 // Windows of 32 ids.  The FIRST window of the list of k-mer `pos` is described by its table entry ent[pos]
-// itself (count | offset of the list); every further window gets a descriptor of the same layout in xd[]:
-// (ids in the window) << 37 | offset of its first id.  Both arrays end in NW * PH null descriptors so that the
-// pipelined fetch of a warp never checks a bound.  Lists of more than 64 windows, and windows that do not
-// fit xd, are walked through the long-list queue lq (entry indices) from their second window on.
+// itself (count | offset of the list); every further window gets a descriptor of the same layout behind the kn
+// entries of the chunk: (ids in the window) << 37 | offset of its first id.  The array ends in NW * PH null
+// descriptors so that the pipelined fetch of a warp never checks a bound.  Lists of more than 64 windows, and
+// windows that do not fit, are walked through the long-list queue lq (entry indices) from their second window on.
 template <int KCAP, int EH, int NW, int PH>
 struct __align__(16) Dense3Smem {
   static constexpr int PAD = NW * PH;
   static constexpr int XCAP = 2 * KCAP;
-  uint64_t ent[KCAP + PAD];
-  uint64_t xd[XCAP + PAD];
+  uint64_t ent[KCAP + XCAP + PAD];  // [0, kn): table entries = first windows; [kn, kn + nx): further windows; nulls
   uint32_t hkeys[EH];
   uint32_t hcnt2[EH / 2];
   uint32_t fin[EH / 32];
@@ -144,7 +143,7 @@ __device__ __forceinline__ int dense3_load_chunk(const SearchArgs &a, const Peer
         const uint64_t val = e[u] & ENTRY_VALUE_MASK;
         for (uint32_t wn = 1; wn <= want; ++wn) {
           const uint32_t o = wn << 5, rem = cnt - o;
-          s.xd[first + wn - 1u] = ((uint64_t)(rem < 32u ? rem : 32u) << ENTRY_VALUE_BITS) | (val + o);
+          s.ent[kn + first + wn - 1u] = ((uint64_t)(rem < 32u ? rem : 32u) << ENTRY_VALUE_BITS) | (val + o);
         }
       } else if (want || is_long) {
         if (want) atomicMin(&s.nx_end, first);      // (a database ~3x denser than C4: the descriptors are full)
@@ -155,10 +154,7 @@ __device__ __forceinline__ int dense3_load_chunk(const SearchArgs &a, const Peer
   __syncthreads();
   {
     const uint32_t nx = s.nd < s.nx_end ? s.nd : s.nx_end;
-    if (tid < Smem::PAD) {
-      s.ent[kn + tid] = 0ull;
-      s.xd[nx + tid] = 0ull;
-    }
+    if (tid < Smem::PAD) s.ent[kn + nx + tid] = 0ull;
   }
   __syncthreads();
   return kn;
@@ -170,18 +166,18 @@ struct HotState {
   uint32_t n0, n1;
 };
 
-// One window of pass 1: id = the lane's posting (valid when lane < nv).  mm: the warp's map, word = M1 bits
+// One window of pass 1: id = the lane's posting, or F_NONE.  mm: the warp's map, word = M1 bits
 // 0-15 | M2 bits 16-31; the word index is the top lgw bits of the multiplicative hash, the two bit numbers the
 // 4 + 4 bits below.
-__device__ __forceinline__ void dense3_window(uint32_t id, uint32_t nv, unsigned lane, uint32_t *mm, int sh_w, int sh_1,
-                                              int sh_2, const SmemHashT<true> &hv, uint32_t *flags, HotState &hot) {
+__device__ __forceinline__ void dense3_window(uint32_t id, unsigned lane, uint32_t *mm, int sh_w, int sh_1, int sh_2,
+                                              const SmemHashT<true> &hv, uint32_t *flags, HotState &hot) {
   const uint32_t x = id * 0x9E3779B1u;
   uint32_t *wp = mm + (x >> sh_w);
   uint32_t m1, m2;  // (opaque shifts: the compiler would turn `w & (1 << f)` into shift-and-mask sequences)
   asm("shl.b32 %0, 1, %1;" : "=r"(m1) : "r"((x >> sh_1) & 15u));
   asm("shl.b32 %0, 0x10000, %1;" : "=r"(m2) : "r"((x >> sh_2) & 15u));
   const uint32_t w = *wp;  // (the id of an invalid lane still names a valid word)
-  const bool v = lane < nv;
+  const bool v = id != F_NONE;
   const bool seen1 = (w & m1) != 0u, seen2 = (w & m2) != 0u;
   const bool push = v && seen1 && seen2;
   const bool need = v && !(seen1 && seen2);
@@ -225,59 +221,56 @@ __device__ __forceinline__ void dense3_window(uint32_t id, uint32_t nv, unsigned
   __syncwarp();
 }
 
-// Pass 1 of warp `wi` of `nw` over the windows arr[wi], arr[wi + nw], ... (n of them in all; arr = ent with
-// FIRST = true, xd otherwise).  The ids of PH - 1 windows are in flight while one is processed: each lane
-// copies its id of a window into the warp's ring with cp.async (LDGSTS) and the consumer waits with
-// cp.async.wait_group — loads into registers cannot be pipelined this deep: ptxas tracks all of them with one
-// of the six scoreboards of a warp, so waiting for the oldest waits for the youngest (profiles/r2t_*).  The
-// loop is unrolled by PH so that slot numbers are constants.
-template <bool PEER, bool FIRST, int PH>
-__device__ __forceinline__ void dense3_pass1(const SearchArgs &a, const PeerView *pv, const uint64_t *arr, int n,
+// Pass 1 of warp `wi` of `nw` over the windows win[wi], win[wi + nw], ... (n of them in all, the first kn being
+// table entries).  The ids of PH - 1 windows are in flight while one is processed: each lane copies its id of a
+// window into the warp's ring with cp.async (LDGSTS) — lanes without an id store F_NONE — and the consumer waits
+// with cp.async.wait_group.  Loads into registers cannot be pipelined this deep: ptxas tracks all of them with
+// one of the six scoreboards of a warp, so waiting for the oldest waits for the youngest (profiles/r2t_*).  One
+// copy of the loop body (slot numbers are run-time values): unrolled by PH it missed the instruction cache.
+template <bool PEER, int PH>
+__device__ __forceinline__ void dense3_pass1(const SearchArgs &a, const PeerView *pv, const uint64_t *win, int kn, int n,
                                              uint32_t *mm, int lgw, int wi, int nw, uint32_t *ring,
                                              const SmemHashT<true> &hv, uint32_t *flags, HotState &hot) {
   const unsigned lane = threadIdx.x & 31;
   const int sh_w = 32 - lgw, sh_1 = 28 - lgw, sh_2 = 24 - lgw;
   int left = wi < n ? (n - wi + nw - 1) / nw : 0;
-  const uint64_t *p = arr + wi;
+  const uint64_t *p = win + wi, *first_end = win + kn;
   const uint32_t *plane = PEER ? nullptr : a.postings + lane;
   asm volatile("" : "+l"(plane));  // (kept in registers: the compiler would rebuild it from the constant bank per window)
   const uint32_t rs = (uint32_t)__cvta_generic_to_shared(ring + lane);  // the lane's word of slot 0
-  auto fetch = [&](int slot, uint32_t &nv) {
+  constexpr uint32_t RING_BYTES = PH * 128u;
+  uint32_t wslot = 0;  // byte offset of the slot to fill; the slot behind it is the oldest one in flight
+  auto fetch = [&]() {
     const uint64_t e = *p;
+    const bool is_first = p < first_end;
     p += nw;
     const uint32_t c = (uint32_t)(e >> ENTRY_VALUE_BITS);
-    nv = c < 32u ? c : 32u;
-    uint32_t nl = nv;  // lanes that copy an id
-    if (FIRST && c == 1u) {  // the posting inlined in the entry (lane 0)
+    uint32_t nl = c < 32u ? c : 32u;  // lanes that copy an id
+    uint32_t other = F_NONE;          // what the other lanes store
+    if (is_first && c == 1u) {        // the posting inlined in the entry (lane 0)
       nl = 0;
-      if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(rs + slot * 128), "r"((uint32_t)e));
+      if (lane == 0) other = (uint32_t)e;
     }
     const uint32_t *ptr;
     if constexpr (PEER) ptr = post_ptr<PEER>(a, pv, e & ENTRY_VALUE_MASK) + lane;
     else ptr = plane + (e & ENTRY_VALUE_MASK);
     asm volatile(
-        "{\n .reg .pred p;\n setp.lt.u32 p, %2, %3;\n @p cp.async.ca.shared.global [%0], [%1], 4;\n}\n"
+        "{\n .reg .pred p;\n setp.lt.u32 p, %2, %3;\n @p cp.async.ca.shared.global [%0], [%1], 4;\n"
+        "@!p st.shared.u32 [%0], %4;\n}\n"
         "cp.async.commit_group;"
         :
-        : "r"(rs + slot * 128), "l"(__cvta_generic_to_global(ptr)), "r"(lane), "r"(nl));
+        : "r"(rs + wslot), "l"(__cvta_generic_to_global(ptr)), "r"(lane), "r"(nl), "r"(other));
+    wslot = wslot + 128u == RING_BYTES ? 0u : wslot + 128u;
   };
-  uint32_t qn[PH];
 #pragma unroll
-  for (int d = 0; d + 1 < PH; ++d) fetch(d, qn[d]);
-  while (left > 0) {
-#pragma unroll
-    for (int ph = 0; ph < PH; ++ph) {
-      if (left > 0) {
-        fetch((ph + PH - 1) % PH, qn[(ph + PH - 1) % PH]);
-        --left;
-        asm volatile("cp.async.wait_group %0;" ::"n"(PH - 1) : "memory");
-        if (qn[ph]) {
-          uint32_t id;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(id) : "r"(rs + ph * 128));
-          dense3_window(id, qn[ph], lane, mm, sh_w, sh_1, sh_2, hv, flags, hot);
-        }
-      }
-    }
+  for (int d = 0; d + 1 < PH; ++d) fetch();
+#pragma unroll 1
+  for (; left > 0; --left) {
+    fetch();
+    asm volatile("cp.async.wait_group %0;" ::"n"(PH - 1) : "memory");
+    uint32_t id;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(id) : "r"(rs + wslot));
+    if (__any_sync(0xFFFFFFFFu, id != F_NONE)) dense3_window(id, lane, mm, sh_w, sh_1, sh_2, hv, flags, hot);
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");  // (the null windows behind the last one: empty groups)
 }
@@ -298,9 +291,9 @@ __device__ __forceinline__ void dense3_pass1_long(const SearchArgs &a, const Pee
 #pragma unroll 1
     for (uint32_t off = 32; off < cnt; off += 32) {
       const uint32_t nv = cnt - off < 32u ? cnt - off : 32u;
-      uint32_t id = 0;
+      uint32_t id = F_NONE;
       if (lane < nv) id = __ldg(ptr + off + lane);
-      dense3_window(id, nv, lane, mm, sh_w, sh_1, sh_2, hv, flags, hot);
+      dense3_window(id, lane, mm, sh_w, sh_1, sh_2, hv, flags, hot);
     }
   }
 }
@@ -442,8 +435,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_search_f(SearchArgs a) {
       q_incr += tot;
       if (w < w_act) {
         const int nx = (int)(s.nd < s.nx_end ? s.nd : s.nx_end);
-        dense3_pass1<PEER, true, PH>(a, pv, s.ent, kn, mm, lgw, w, w_act, &s.u.ring[w][0][0], hv, &s.pflags, hot);
-        dense3_pass1<PEER, false, PH>(a, pv, s.xd, nx, mm, lgw, w, w_act, &s.u.ring[w][0][0], hv, &s.pflags, hot);
+        dense3_pass1<PEER, PH>(a, pv, s.ent, kn, kn + nx, mm, lgw, w, w_act, &s.u.ring[w][0][0], hv, &s.pflags, hot);
         if (s.nlq) dense3_pass1_long<PEER>(a, pv, s, mm, lgw, w, w_act, hv, &s.pflags, hot);
       }
     }

@@ -251,15 +251,23 @@ __device__ __forceinline__ void dense3_pass1(const SearchArgs &a, const PeerView
       nl = 0;
       if (lane == 0) other = (uint32_t)e;
     }
-    const uint32_t *ptr;
-    if constexpr (PEER) ptr = post_ptr<PEER>(a, pv, e & ENTRY_VALUE_MASK) + lane;
-    else ptr = plane + (e & ENTRY_VALUE_MASK);
+    uint64_t ptr;
+    if constexpr (PEER) {
+      ptr = (uint64_t)(post_ptr<PEER>(a, pv, e & ENTRY_VALUE_MASK) + lane);
+    } else {
+      // plane + 4 * value: one wide multiply-add for the low word, the 5 high bits of the value go to the high
+      // word (in PTX: the compiler expands the 64-bit form into six instructions)
+      asm("{\n .reg .b32 l, h, t;\n mad.wide.u32 %0, %1, 4, %3;\n and.b32 t, %2, 31;\n mov.b64 {l, h}, %0;\n"
+          " mad.lo.u32 h, t, 4, h;\n mov.b64 %0, {l, h};\n}"
+          : "=l"(ptr)
+          : "r"((uint32_t)e), "r"((uint32_t)(e >> 32)), "l"(plane));
+    }
     asm volatile(
         "{\n .reg .pred p;\n setp.lt.u32 p, %2, %3;\n @p cp.async.ca.shared.global [%0], [%1], 4;\n"
         "@!p st.shared.u32 [%0], %4;\n}\n"
         "cp.async.commit_group;"
         :
-        : "r"(rs + wslot), "l"(__cvta_generic_to_global(ptr)), "r"(lane), "r"(nl), "r"(other));
+        : "r"(rs + wslot), "l"(ptr), "r"(lane), "r"(nl), "r"(other));
     wslot = wslot + 128u == RING_BYTES ? 0u : wslot + 128u;
   };
 #pragma unroll
@@ -270,7 +278,7 @@ __device__ __forceinline__ void dense3_pass1(const SearchArgs &a, const PeerView
     asm volatile("cp.async.wait_group %0;" ::"n"(PH - 1) : "memory");
     uint32_t id;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(id) : "r"(rs + wslot));
-    if (__any_sync(0xFFFFFFFFu, id != F_NONE)) dense3_window(id, lane, mm, sh_w, sh_1, sh_2, hv, flags, hot);
+    dense3_window(id, lane, mm, sh_w, sh_1, sh_2, hv, flags, hot);  // (an empty window — a k-mer the database lacks — is harmless)
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");  // (the null windows behind the last one: empty groups)
 }

@@ -609,12 +609,13 @@ void profile_end(kaamer_gpu *h, cudaStream_t st) {
 // in class M).  Swiss-Prot scale (p = 0.53) keeps the full 512 / 2048.
 static void class_limits(const kaamer_gpu *h, int *w_maxk, int *m_maxk, int *dense) {
   double p = (double)h->idx.n_kmers * 2.7e-9;
-  // Dense database: above ~6 background postings per query k-mer (measured crossover: 8 M proteins, profiles/)
+  // Dense database: above ~3.5 background postings per query k-mer (measured: 4 M proteins, p = 3.7, 5.08 ms with
+  // class D against 5.77 ms; 2 M proteins, p = 1.9, 4.97 ms against 2.62 ms; profiles/r2_dense_probe.jsonl)
   // the shared-memory histograms of classes W
   // and M overflow for ordinary queries, and class D (search_dense.cuh), whose cost per posting is a byte
   // load and a byte store instead of an atomic, takes every query.  KAAMER_DENSE=0/1 forces the choice
   // (A/B measurements, parity tests).
-  *dense = p >= 6.0 ? 2 : 0;
+  *dense = p >= 3.5 ? 2 : 0;
   if (const char *env = getenv("KAAMER_DENSE")) {
     const int v = atoi(env);
     // 1: class D; 12 / 11: its second / first design (A/B measurements); 0: off
@@ -756,6 +757,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   auto f_small = peer ? k_search_f<true, E_KCAP_S, EH_S, 4, F_NW_S, 4> : k_search_f<false, E_KCAP_S, EH_S, 4, F_NW_S, 6>;
   auto f_large = peer ? k_search_f<true, E_KCAP_L, EH_L, 5, F_NW_L, 2> : k_search_f<false, E_KCAP_L, EH_L, 5, F_NW_L, 3>;
   auto f_xl = peer ? k_search_f<true, E_KCAP_L, EH_XL, 6, F_NW_XL, 1> : k_search_f<false, E_KCAP_L, EH_XL, 6, F_NW_XL, 1>;
+  auto f_xl2 = peer ? k_search_f<true, E_KCAP_L, EH_XL, 7, F_NW_XL, 1> : k_search_f<false, E_KCAP_L, EH_XL, 7, F_NW_XL, 1>;
   if (a.dense == 2) {
     a.e_mapw_small = f_mapw_s;
     a.e_mapw_large = f_mapw_l;
@@ -763,6 +765,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
     KCUDA(cudaFuncSetAttribute(f_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f_smem_s));
     KCUDA(cudaFuncSetAttribute(f_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f_smem_l));
     KCUDA(cudaFuncSetAttribute(f_xl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f_smem_xl));
+    KCUDA(cudaFuncSetAttribute(f_xl2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f_smem_xl));
   }
   // Class G: one CTA per query, histogram in a per-CTA global scratch.  At Swiss-Prot density it holds a
   // handful of very long queries and gets one CTA per SM (it runs underneath W and M and must leave them
@@ -826,6 +829,8 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
     f_small<<<(unsigned)h->sm_count * (unsigned)(per_sm < 1 ? 1 : per_sm), F_NW_S * 32, f_smem_s, st>>>(a);
     profile_end(h, st);
     KCUDA(cudaStreamWaitEvent(st, h->chunk_ev[7], 0));  // the hand-offs of both launches are complete
+    // queries whose repeated subjects overflowed H (large families): the 2048-slot launch takes them
+    f_xl2<<<(unsigned)h->sm_count, F_NW_XL * 32, f_smem_xl, st>>>(a);
   } else if (a.dense == 3) {
     int per_sm = 1;
     KCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e_small, E_THREADS, e_smem_s));
@@ -856,7 +861,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   a.ghash = ws.ghash.p + (size_t)g_ctas * 3 * a.ghash_slots;  // own scratch: the first G launch may still run
   launch_g(st);
   KCUDA(cudaStreamWaitEvent(st, h->chunk_ev[7], 0));
-  h->prof_all_launches += a.dense == 1 ? 4 : (a.dense == 2 ? 6 : 5);
+  h->prof_all_launches += a.dense == 1 ? 4 : (a.dense == 2 ? 7 : (a.dense == 3 ? 6 : 5));
   KCUDA(cudaGetLastError());
   return KAAMER_OK;
 }

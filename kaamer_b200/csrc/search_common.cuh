@@ -18,7 +18,7 @@ constexpr int G_THREADS = 512;
 constexpr int FAST_C = 64;     // candidates ranked by counting below this, bitonic sort above
 constexpr int BIG_LIST = 32;   // posting lists at least this long are walked by the whole warp
 constexpr int MAX_PROBE = 96;  // linear-probe budget before a histogram is declared full
-constexpr int N_LISTS = 7;     // class lists: W, M, G, hand-offs to G, D short / long / longest queries
+constexpr int N_LISTS = 8;     // class lists: W, M, G, hand-offs to G, D short / long / longest queries, D hand-offs
 
 struct SearchArgs {
   const uint64_t *table;

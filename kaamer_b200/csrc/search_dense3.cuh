@@ -377,7 +377,8 @@ __device__ __forceinline__ void dense3_verify(const SearchArgs &a, const PeerVie
   }
 }
 
-// CLS: class list (4: queries up to KCAP k-mers staged at once; 5: longer ones; 6: the longest, chunked);
+// CLS: class list (4: queries up to KCAP k-mers staged at once; 5: longer ones; 6: the longest, chunked; 7: the
+// queries whose repeated subjects overflowed H in launches 4 and 5);
 // NW warps per CTA, MINB CTAs per SM
 template <bool PEER, int KCAP, int EH, int CLS, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB) k_search_f(SearchArgs a) {
@@ -473,10 +474,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_search_f(SearchArgs a) {
     }
     __syncthreads();
     if (s.pflags) {
-      // more repeated subjects than H holds: class G counts this query exactly in global memory
+      // more repeated subjects than H holds (a query from a large family): the launch with the largest H takes
+      // it (list 7); if that one overflows too, class G counts the query exactly in global memory (list 3)
       if (tid == 0) {
-        const uint32_t slot = atomicAdd(&a.list_count[3], 1u);
-        a.lists[(size_t)3 * a.nq + slot] = q;
+        constexpr int TO = CLS <= 5 ? 7 : 3;
+        const uint32_t slot = atomicAdd(&a.list_count[TO], 1u);
+        a.lists[(size_t)TO * a.nq + slot] = q;
       }
       continue;
     }

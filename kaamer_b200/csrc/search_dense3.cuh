@@ -36,21 +36,24 @@ constexpr int F_NF = 16;       // final candidates verified by binary search (mo
 constexpr int F_MAXK = 60000;  // 16-bit counts
 constexpr uint32_t F_NONE = 0xFFFFFFFFu;
 #ifndef KAAMER_F_PH
-#define KAAMER_F_PH 7
+#define KAAMER_F_PH 6
 #endif
 constexpr int F_PH_LOCAL = KAAMER_F_PH, F_PH_PEER = 8;
 
 // KCAP: query k-mers staged at once; EH: slots of the exact hash; NW warps per CTA; PH windows in flight per warp.
 //
-// Windows of 32 ids.  The FIRST window of the list of k-mer `pos` is described by its table entry ent[pos]
+// Windows of 64 ids (two per lane: i = lane and lane + 32; the second half is skipped when the first is not full).
+// The FIRST window of the list of k-mer `pos` is described by its table entry ent[pos]
 // itself (count | offset of the list); every further window gets a descriptor of the same layout behind the kn
 // entries of the chunk: (ids in the window) << 37 | offset of its first id.  The array ends in NW * PH null
 // descriptors so that the pipelined fetch of a warp never checks a bound.  Lists of more than 64 windows, and
 // windows that do not fit, are walked through the long-list queue lq (entry indices) from their second window on.
+// (Lists have a median of 32 ids: half of them need no second half, a quarter one, and the per-window work —
+// descriptor, address, cp.async, loop — is paid once per 64 ids where it is needed most.)
 template <int KCAP, int EH, int NW, int PH>
 struct __align__(16) Dense3Smem {
   static constexpr int PAD = NW * PH;
-  static constexpr int XCAP = 2 * KCAP;
+  static constexpr int XCAP = KCAP;
   uint64_t ent[KCAP + XCAP + PAD];  // [0, kn): table entries = first windows; [kn, kn + nx): further windows; nulls
   uint32_t hkeys[EH];
   uint32_t hcnt2[EH / 2];
@@ -67,7 +70,7 @@ struct __align__(16) Dense3Smem {
   };
   union {
     Phases e;
-    uint32_t ring[NW][PH][32];  // ring[w][slot][lane]: the ids of window `slot` of warp w (cp.async destination)
+    uint32_t ring[NW][PH][64];  // ring[w][slot][i]: id i of window `slot` of warp w (cp.async destination)
   } u;
   unsigned long long bloom;
   uint32_t nfinal, it, pflags;                  // pflags: bit0 = H is full (pass 1)
@@ -125,7 +128,7 @@ __device__ __forceinline__ int dense3_load_chunk(const SearchArgs &a, const Peer
         tot += cnt;
       }
       // descriptors of windows 1, 2, ... of the list, reserved with one shared-memory atomic per warp
-      const uint32_t extra = cnt > 32u ? (cnt - 1u) >> 5 : 0u;
+      const uint32_t extra = cnt > 64u ? (cnt - 1u) >> 6 : 0u;
       const bool is_long = extra > 63u;
       const uint32_t want = is_long ? 0u : extra;
       uint32_t incl = want;
@@ -142,8 +145,8 @@ __device__ __forceinline__ int dense3_load_chunk(const SearchArgs &a, const Peer
       if (want && first + want <= XCAP) {
         const uint64_t val = e[u] & ENTRY_VALUE_MASK;
         for (uint32_t wn = 1; wn <= want; ++wn) {
-          const uint32_t o = wn << 5, rem = cnt - o;
-          s.ent[kn + first + wn - 1u] = ((uint64_t)(rem < 32u ? rem : 32u) << ENTRY_VALUE_BITS) | (val + o);
+          const uint32_t o = wn << 6, rem = cnt - o;
+          s.ent[kn + first + wn - 1u] = ((uint64_t)(rem < 64u ? rem : 64u) << ENTRY_VALUE_BITS) | (val + o);
         }
       } else if (want || is_long) {
         if (want) atomicMin(&s.nx_end, first);      // (a database ~3x denser than C4: the descriptors are full)
@@ -166,58 +169,76 @@ struct HotState {
   uint32_t n0, n1;
 };
 
-// One window of pass 1: id = the lane's posting, or F_NONE.  mm: the warp's map, word = M1 bits
-// 0-15 | M2 bits 16-31; the word index is the top lgw bits of the multiplicative hash, the two bit numbers the
-// 4 + 4 bits below.
-__device__ __forceinline__ void dense3_window(uint32_t id, unsigned lane, uint32_t *mm, int sh_w, int sh_1, int sh_2,
+// One step of pass 1: J ids per lane (of ONE list: distinct), F_NONE where there is none.  mm: the warp's map,
+// word = M1 bits 0-15 | M2 bits 16-31; the word index is the top lgw bits of the multiplicative hash, the two bit
+// numbers the 4 + 4 bits below.  All loads, then all stores, one __syncwarp, then the verify reads.
+template <int J>
+__device__ __forceinline__ void dense3_window(const uint32_t (&id)[J], uint32_t *mm, int sh_w, int sh_1, int sh_2,
                                               const SmemHashT<true> &hv, uint32_t *flags, HotState &hot) {
-  const uint32_t x = id * 0x9E3779B1u;
-  uint32_t *wp = mm + (x >> sh_w);
-  uint32_t m1, m2;  // (opaque shifts: the compiler would turn `w & (1 << f)` into shift-and-mask sequences)
-  asm("shl.b32 %0, 1, %1;" : "=r"(m1) : "r"((x >> sh_1) & 15u));
-  asm("shl.b32 %0, 0x10000, %1;" : "=r"(m2) : "r"((x >> sh_2) & 15u));
-  const uint32_t w = *wp;  // (the id of an invalid lane still names a valid word)
-  const bool v = id != F_NONE;
-  const bool seen1 = (w & m1) != 0u, seen2 = (w & m2) != 0u;
-  const bool push = v && seen1 && seen2;
-  const bool need = v && !(seen1 && seen2);
-  const uint32_t setbit = need ? (seen1 ? m2 : m1) : 0u;  // the bit this lane sets in this window, if any
-  if (need) *wp = w | setbit;
-  if (__any_sync(0xFFFFFFFFu, push)) {
-    // a hot subject is counted in a register (its bits are set: it always arrives here)
-    const bool h0 = push && id == hot.id0, h1 = push && id == hot.id1;
-    if (h0) ++hot.n0;
-    if (h1) ++hot.n1;
-    const bool cold = push && !h0 && !h1;
-    if (__any_sync(0xFFFFFFFFu, cold)) {
-      uint32_t after = 0;
-      if (cold) {
-        uint32_t slot = hv.home(id);
-        bool done = false;
+  uint32_t *wp[J];
+  uint32_t m1[J], m2[J], w[J], setbit[J];
+  bool push[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const uint32_t x = id[j] * 0x9E3779B1u;
+    wp[j] = mm + (x >> sh_w);
+    // (opaque shifts: the compiler would turn `w & (1 << f)` into shift-and-mask sequences)
+    asm("shl.b32 %0, 1, %1;" : "=r"(m1[j]) : "r"((x >> sh_1) & 15u));
+    asm("shl.b32 %0, 0x10000, %1;" : "=r"(m2[j]) : "r"((x >> sh_2) & 15u));
+    w[j] = *wp[j];  // (the id of an invalid lane still names a valid word)
+  }
+  bool any_push = false;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const bool v = id[j] != F_NONE;
+    const bool seen1 = (w[j] & m1[j]) != 0u, seen2 = (w[j] & m2[j]) != 0u;
+    push[j] = v && seen1 && seen2;
+    const bool need = v && !(seen1 && seen2);
+    setbit[j] = need ? (seen1 ? m2[j] : m1[j]) : 0u;  // the bit this lane sets for this id, if any
+    if (need) *wp[j] = w[j] | setbit[j];
+    any_push = any_push || push[j];
+  }
+  if (__any_sync(0xFFFFFFFFu, any_push)) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      // a hot subject is counted in a register (its bits are set: it always arrives here)
+      const bool h0 = push[j] && id[j] == hot.id0, h1 = push[j] && id[j] == hot.id1;
+      if (h0) ++hot.n0;
+      if (h1) ++hot.n1;
+      const bool cold = push[j] && !h0 && !h1;
+      if (__any_sync(0xFFFFFFFFu, cold)) {
+        uint32_t after = 0;
+        if (cold) {
+          uint32_t slot = hv.home(id[j]);
+          bool done = false;
 #pragma unroll 1
-        for (int probe = 0; probe < SmemHashT<true>::kMaxProbe; ++probe) {
-          const uint32_t cur = hv.cas(slot, id);
-          if (cur == EMPTY || cur == id) {
-            after = hv.inc(slot) + 1u;
-            done = true;
-            break;
+          for (int probe = 0; probe < SmemHashT<true>::kMaxProbe; ++probe) {
+            const uint32_t cur = hv.cas(slot, id[j]);
+            if (cur == EMPTY || cur == id[j]) {
+              after = hv.inc(slot) + 1u;
+              done = true;
+              break;
+            }
+            slot = (slot + 1) & hv.mask;
           }
-          slot = (slot + 1) & hv.mask;
+          if (!done) atomicOr(flags, 1u);  // more repeated subjects than H holds
         }
-        if (!done) atomicOr(flags, 1u);  // more repeated subjects than H holds
-      }
-      // a subject this warp has pushed three times becomes hot (a false positive of the maps rarely is)
-      const unsigned hm = __ballot_sync(0xFFFFFFFFu, after >= 3u);
-      if (hm && hot.id1 == F_NONE) {
-        const uint32_t cand = __shfl_sync(0xFFFFFFFFu, id, __ffs(hm) - 1);
-        if (hot.id0 == F_NONE) hot.id0 = cand;
-        else hot.id1 = cand;
+        // a subject this warp has pushed three times becomes hot (a false positive of the maps rarely is)
+        const unsigned hm = __ballot_sync(0xFFFFFFFFu, after >= 3u);
+        if (hm && hot.id1 == F_NONE) {
+          const uint32_t cand = __shfl_sync(0xFFFFFFFFu, id[j], __ffs(hm) - 1);
+          if (hot.id0 == F_NONE) hot.id0 = cand;
+          else hot.id1 = cand;
+        }
       }
     }
   }
   __syncwarp();
-  // verify: the store may have been overwritten by another lane's store to the same word
-  if (~(*wp) & setbit) atomicOr(wp, setbit);
+  // verify: a store may have been overwritten by another store to the same word (another lane's, or the lane's own
+  // second id)
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+    if (~(*wp[j]) & setbit[j]) atomicOr(wp[j], setbit[j]);
   __syncwarp();
 }
 
@@ -238,15 +259,15 @@ __device__ __forceinline__ void dense3_pass1(const SearchArgs &a, const PeerView
   const uint32_t *plane = PEER ? nullptr : a.postings + lane;
   asm volatile("" : "+l"(plane));  // (kept in registers: the compiler would rebuild it from the constant bank per window)
   const uint32_t rs = (uint32_t)__cvta_generic_to_shared(ring + lane);  // the lane's word of slot 0
-  constexpr uint32_t RING_BYTES = PH * 128u;
+  constexpr uint32_t RING_BYTES = PH * 256u;
   uint32_t wslot = 0;  // byte offset of the slot to fill; the slot behind it is the oldest one in flight
   auto fetch = [&]() {
     const uint64_t e = *p;
     const bool is_first = p < first_end;
     p += nw;
     const uint32_t c = (uint32_t)(e >> ENTRY_VALUE_BITS);
-    uint32_t nl = c < 32u ? c : 32u;  // lanes that copy an id
-    uint32_t other = F_NONE;          // what the other lanes store
+    uint32_t nl = c < 64u ? c : 64u;  // ids of the window
+    uint32_t other = F_NONE;          // what the lanes without an id store
     if (is_first && c == 1u) {        // the posting inlined in the entry (lane 0)
       nl = 0;
       if (lane == 0) other = (uint32_t)e;
@@ -264,11 +285,17 @@ __device__ __forceinline__ void dense3_pass1(const SearchArgs &a, const PeerView
     }
     asm volatile(
         "{\n .reg .pred p;\n setp.lt.u32 p, %2, %3;\n @p cp.async.ca.shared.global [%0], [%1], 4;\n"
-        "@!p st.shared.u32 [%0], %4;\n}\n"
-        "cp.async.commit_group;"
+        "@!p st.shared.u32 [%0], %4;\n}"
         :
         : "r"(rs + wslot), "l"(ptr), "r"(lane), "r"(nl), "r"(other));
-    wslot = wslot + 128u == RING_BYTES ? 0u : wslot + 128u;
+    if (nl >= 32u)  // (warp-uniform) the second half is read only behind a full first half
+      asm volatile(
+          "{\n .reg .pred p;\n setp.lt.u32 p, %2, %3;\n @p cp.async.ca.shared.global [%0+128], [%1+128], 4;\n"
+          "@!p st.shared.u32 [%0+128], %4;\n}"
+          :
+          : "r"(rs + wslot), "l"(ptr), "r"(lane + 32u), "r"(nl), "r"(F_NONE));
+    asm volatile("cp.async.commit_group;");
+    wslot = wslot + 256u == RING_BYTES ? 0u : wslot + 256u;
   };
 #pragma unroll
   for (int d = 0; d + 1 < PH; ++d) fetch();
@@ -276,9 +303,16 @@ __device__ __forceinline__ void dense3_pass1(const SearchArgs &a, const PeerView
   for (; left > 0; --left) {
     fetch();
     asm volatile("cp.async.wait_group %0;" ::"n"(PH - 1) : "memory");
-    uint32_t id;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(id) : "r"(rs + wslot));
-    dense3_window(id, lane, mm, sh_w, sh_1, sh_2, hv, flags, hot);  // (an empty window — a k-mer the database lacks — is harmless)
+    uint32_t ida, idb;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ida) : "r"(rs + wslot));
+    asm volatile("ld.shared.u32 %0, [%1+128];" : "=r"(idb) : "r"(rs + wslot));  // (stale unless the first half is full)
+    if (__all_sync(0xFFFFFFFFu, ida != F_NONE)) {
+      const uint32_t id[2] = {ida, idb};
+      dense3_window<2>(id, mm, sh_w, sh_1, sh_2, hv, flags, hot);
+    } else {
+      const uint32_t id[1] = {ida};  // (an empty window — a k-mer the database lacks — is harmless)
+      dense3_window<1>(id, mm, sh_w, sh_1, sh_2, hv, flags, hot);
+    }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");  // (the null windows behind the last one: empty groups)
 }
@@ -297,11 +331,11 @@ __device__ __forceinline__ void dense3_pass1_long(const SearchArgs &a, const Pee
     const uint32_t cnt = (uint32_t)(e >> ENTRY_VALUE_BITS);
     const uint32_t *ptr = post_ptr<PEER>(a, pv, e & ENTRY_VALUE_MASK);
 #pragma unroll 1
-    for (uint32_t off = 32; off < cnt; off += 32) {
+    for (uint32_t off = 64; off < cnt; off += 32) {
       const uint32_t nv = cnt - off < 32u ? cnt - off : 32u;
-      uint32_t id = F_NONE;
-      if (lane < nv) id = __ldg(ptr + off + lane);
-      dense3_window(id, lane, mm, sh_w, sh_1, sh_2, hv, flags, hot);
+      uint32_t id[1] = {F_NONE};
+      if (lane < nv) id[0] = __ldg(ptr + off + lane);
+      dense3_window<1>(id, mm, sh_w, sh_1, sh_2, hv, flags, hot);
     }
   }
 }

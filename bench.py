@@ -287,9 +287,10 @@ def c4_roofline(ms, c, prof, peak):
     k_large = prof["kernel_ms"][1] / max(1, prof["kernel_launches"][1])
     achieved = lookups * abytes / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "kernel": "k_search_e (class D: short-query launch + long-query launch, concurrent)",
+            "kernel": "k_search_f (class D, search_dense3.cuh: launches by query length — 4 / 8 / 16 warps per CTA — on "
+                      "two streams, plus the hand-off launch)",
             "kernel_ms_per_launch": {"short_queries": k_small, "long_queries_side_stream": k_large},
-            "note": "the two launches overlap (two streams): `achieved` is over the whole step, not a single launch",
+            "note": "the launches overlap (two streams): `achieved` is over the whole step, not a single launch",
             "postings_per_lookup": pbar, "algorithmic_bytes_per_lookup": abytes,
             "lookups_per_s": lookups / (ms * 1e-3), "traffic": None}
 
@@ -594,6 +595,31 @@ def main():
     prof_e2e = g.profile_read(reset=True)
     host_e2e = g.profile_host_read()
     g.profile_enable(False)
+    # What the host link gives each GPU while ALL ranks copy at once: the e2e step moves h2d bytes per batch, so
+    # h2d / this bandwidth is its floor.  (GPUs of one box share PCIe switch uplinks and host memory.)
+    link = {}
+    try:
+        big = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+        dbig = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        dbig.copy_(big, non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            dbig.copy_(big, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        gbs = torch.tensor([4 * big.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9], dtype=torch.float64, device=dev)
+        gmin, gsum = gbs.clone(), gbs.clone()
+        if world > 1:
+            dist.all_reduce(gmin, op=dist.ReduceOp.MIN)
+            dist.all_reduce(gsum, op=dist.ReduceOp.SUM)
+        link = {"h2d_gbs_per_gpu_min_over_ranks": float(gmin.item()), "h2d_gbs_all_ranks": float(gsum.item()),
+                "how": f"4 x 256 MiB pinned host -> device copies on every rank at the same time ({world} ranks)"}
+        del big, dbig
+    except Exception as e:  # noqa: BLE001
+        link = {"error": str(e)}
     te = torch.tensor([e2e_s, pipe_s], dtype=torch.float64, device=dev)
     re_ = torch.tensor([float(e2e_res), float(pipe_res)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -656,6 +682,8 @@ def main():
                                      "how": "one kaamer_gpu_search_proteins call at a time (round 1's e2e definition)"},
                         "ms_per_call_rank0": {"min": 1e3 * min(step_s), "median": 1e3 * float(np.median(step_s)),
                                               "max": 1e3 * max(step_s), "argmax": int(np.argmax(step_s))},
+                        "host_link": dict(link, **({"floor_ms_per_step": h2d / (link["h2d_gbs_per_gpu_min_over_ranks"] * 1e9) * 1e3}
+                                                   if "h2d_gbs_per_gpu_min_over_ranks" in link else {})),
                         "stage_ms_per_step": {"h2d_copy_stream": prof_e2e["kernel_ms"][4] / n_prof,
                                               "search_kernels": sum(prof_e2e["kernel_ms"][:3]) / n_prof,
                                               "compaction_d2h": prof_e2e["kernel_ms"][5] / n_prof,

@@ -754,8 +754,8 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   const size_t f_smem_s = f_smem(sizeof(Dense3Smem<E_KCAP_S, EH_S, F_NW_S, F_PH_LOCAL>), sizeof(Dense3Smem<E_KCAP_S, EH_S, F_NW_S, F_PH_PEER>), F_NW_S, f_mapw_s);
   const size_t f_smem_l = f_smem(sizeof(Dense3Smem<E_KCAP_L, EH_L, F_NW_L, F_PH_LOCAL>), sizeof(Dense3Smem<E_KCAP_L, EH_L, F_NW_L, F_PH_PEER>), F_NW_L, f_mapw_l);
   const size_t f_smem_xl = f_smem(sizeof(Dense3Smem<E_KCAP_L, EH_XL, F_NW_XL, F_PH_LOCAL>), sizeof(Dense3Smem<E_KCAP_L, EH_XL, F_NW_XL, F_PH_PEER>), F_NW_XL, f_mapw_xl);
-  auto f_small = peer ? k_search_f<true, E_KCAP_S, EH_S, 4, F_NW_S, 4> : k_search_f<false, E_KCAP_S, EH_S, 4, F_NW_S, 6>;
-  auto f_large = peer ? k_search_f<true, E_KCAP_L, EH_L, 5, F_NW_L, 2> : k_search_f<false, E_KCAP_L, EH_L, 5, F_NW_L, 3>;
+  auto f_small = peer ? k_search_f<true, E_KCAP_S, EH_S, 4, F_NW_S, 5> : k_search_f<false, E_KCAP_S, EH_S, 4, F_NW_S, 6>;
+  auto f_large = peer ? k_search_f<true, E_KCAP_L, EH_L, 5, F_NW_L, 3> : k_search_f<false, E_KCAP_L, EH_L, 5, F_NW_L, 3>;
   auto f_xl = peer ? k_search_f<true, E_KCAP_L, EH_XL, 6, F_NW_XL, 1> : k_search_f<false, E_KCAP_L, EH_XL, 6, F_NW_XL, 1>;
   auto f_xl2 = peer ? k_search_f<true, E_KCAP_L, EH_XL, 7, F_NW_XL, 1> : k_search_f<false, E_KCAP_L, EH_XL, 7, F_NW_XL, 1>;
   if (a.dense == 2) {
@@ -805,11 +805,16 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   a.g_list = 2;
   launch_g(side);
   profile_end(h, side);
+  // Posting lists read through NVLink (mode P without replicated postings): fewer CTAs per SM — more outstanding
+  // small remote reads make the peer path slower, not faster (measured at 2 GPUs: 20.1 ms per step with four CTAs
+  // per SM, 24.2 ms with six; profiles/r2_classD_notes.md)
+  const bool lists_remote = peer && h->idx.repl_postings == nullptr;
   if (a.dense == 2) {
     // the long queries of class D run on the side stream underneath the short ones: the (few) longest first
     int per_sm = 1;
     f_xl<<<(unsigned)h->sm_count, F_NW_XL * 32, f_smem_xl, side>>>(a);
     KCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f_large, F_NW_L * 32, f_smem_l));
+    if (lists_remote && per_sm > 2) per_sm = 2;
     profile_begin(h, side, 1);
     f_large<<<(unsigned)h->sm_count * (unsigned)(per_sm < 1 ? 1 : per_sm), F_NW_L * 32, f_smem_l, side>>>(a);
     profile_end(h, side);
@@ -825,6 +830,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   if (a.dense == 2) {
     int per_sm = 1;
     KCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f_small, F_NW_S * 32, f_smem_s));
+    if (lists_remote && per_sm > 4) per_sm = 4;
     profile_begin(h, st, 6);
     f_small<<<(unsigned)h->sm_count * (unsigned)(per_sm < 1 ? 1 : per_sm), F_NW_S * 32, f_smem_s, st>>>(a);
     profile_end(h, st);

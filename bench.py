@@ -292,7 +292,20 @@ def c4_roofline(ms, c, prof, peak):
             "kernel_ms_per_launch": {"short_queries": k_small, "long_queries_side_stream": k_large},
             "note": "the launches overlap (two streams): `achieved` is over the whole step, not a single launch",
             "postings_per_lookup": pbar, "algorithmic_bytes_per_lookup": abytes,
-            "lookups_per_s": lookups / (ms * 1e-3), "traffic": None}
+            "lookups_per_s": lookups / (ms * 1e-3), **c4_traffic()}
+
+
+def c4_traffic():
+    """DRAM bytes per batch of the class D launches (all query-length launches of one step), from the ncu capture
+    recorded in profiles/traffic.json; null when the kernel sources changed since."""
+    tot, notes = 0.0, []
+    for cls in (4, 5, 6, 7):
+        t, note = traffic_from_profiles(f"k_search_f<CLS{cls}>")
+        if t is None:
+            return {"traffic": None, "traffic_note": note}
+        tot += t
+        notes.append(note)
+    return {"traffic": tot, "traffic_note": "sum over the launches by query length; " + notes[0]}
 
 
 def c4_block(a, local_rank, dev, peak, threads):

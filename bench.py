@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--ref-queries", type=int, default=16384, help="queries per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--c4-proteins", type=int, default=50_000_000, help="C4 database size (0: skip c4 / sharded)")
-    ap.add_argument("--c4-sample", type=int, default=8, help="C4 queries checked against the restricted oracle index")
+    ap.add_argument("--c4-sample", type=int, default=64, help="C4 queries checked against the restricted oracle index")
     ap.add_argument("--no-stages", action="store_true", help="skip the C2 / C5 stage lines")
     ap.add_argument("--sustain-s", type=float, default=1.5, help="length of the sustained loop (clock sampling)")
     return ap.parse_args()

@@ -754,7 +754,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   const size_t f_smem_s = f_smem(sizeof(Dense3Smem<E_KCAP_S, EH_S, F_NW_S, F_PH_LOCAL>), sizeof(Dense3Smem<E_KCAP_S, EH_S, F_NW_S, F_PH_PEER>), F_NW_S, f_mapw_s);
   const size_t f_smem_l = f_smem(sizeof(Dense3Smem<E_KCAP_L, EH_L, F_NW_L, F_PH_LOCAL>), sizeof(Dense3Smem<E_KCAP_L, EH_L, F_NW_L, F_PH_PEER>), F_NW_L, f_mapw_l);
   const size_t f_smem_xl = f_smem(sizeof(Dense3Smem<E_KCAP_L, EH_XL, F_NW_XL, F_PH_LOCAL>), sizeof(Dense3Smem<E_KCAP_L, EH_XL, F_NW_XL, F_PH_PEER>), F_NW_XL, f_mapw_xl);
-  auto f_small = peer ? k_search_f<true, E_KCAP_S, EH_S, 4, F_NW_S, 5> : k_search_f<false, E_KCAP_S, EH_S, 4, F_NW_S, 6>;
+  auto f_small = peer ? k_search_f<true, E_KCAP_S, EH_S, 4, F_NW_S, 5> : k_search_f<false, E_KCAP_S, EH_S, 4, F_NW_S, 7>;
   auto f_large = peer ? k_search_f<true, E_KCAP_L, EH_L, 5, F_NW_L, 3> : k_search_f<false, E_KCAP_L, EH_L, 5, F_NW_L, 3>;
   auto f_xl = peer ? k_search_f<true, E_KCAP_L, EH_XL, 6, F_NW_XL, 1> : k_search_f<false, E_KCAP_L, EH_XL, 6, F_NW_XL, 1>;
   auto f_xl2 = peer ? k_search_f<true, E_KCAP_L, EH_XL, 7, F_NW_XL, 1> : k_search_f<false, E_KCAP_L, EH_XL, 7, F_NW_XL, 1>;

@@ -36,7 +36,7 @@ constexpr int F_NF = 16;       // final candidates verified by binary search (mo
 constexpr int F_MAXK = 60000;  // 16-bit counts
 constexpr uint32_t F_NONE = 0xFFFFFFFFu;
 #ifndef KAAMER_F_PH
-#define KAAMER_F_PH 6
+#define KAAMER_F_PH 4
 #endif
 constexpr int F_PH_LOCAL = KAAMER_F_PH, F_PH_PEER = 8;
 
@@ -53,7 +53,7 @@ constexpr int F_PH_LOCAL = KAAMER_F_PH, F_PH_PEER = 8;
 template <int KCAP, int EH, int NW, int PH>
 struct __align__(16) Dense3Smem {
   static constexpr int PAD = NW * PH;
-  static constexpr int XCAP = KCAP;
+  static constexpr int XCAP = KCAP / 2;
   uint64_t ent[KCAP + XCAP + PAD];  // [0, kn): table entries = first windows; [kn, kn + nx): further windows; nulls
   uint32_t hkeys[EH];
   uint32_t hcnt2[EH / 2];

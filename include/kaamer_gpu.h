@@ -147,7 +147,17 @@ typedef struct kaamer_hits {
  * KmerSearch (search.go:414-440), sortMapByValue (:132-152) and FilterResults (:189-220).
  * residues: query sequences as read by GetQueriesFasta (already upper-cased by the host
  * reader, search.go:295); seq_off[nq+1].  Queries with SizeInKmer < 7 yield no hits
- * (search_protein.go:74-76 kills the worker instead; documented deviation). */
+ * (search_protein.go:74-76 kills the worker instead; documented deviation).
+ *
+ * Limits (every one answered with an error code, never with a partial result):
+ *  - a posting list holds at most 2^27 - 1 proteins, a shard at most 2^34 postings, protein ids < 2^32 - 1
+ *    (KAAMER_ERR_LIMIT / _FORMAT when the index is built or opened);
+ *  - the kernel is chosen from the density of the database: shared-memory histograms (classes W / M) up to ~3.5
+ *    background postings per query k-mer, the filter kernel of search_dense3.cuh (class D) above; a query whose
+ *    repeated subjects overflow a class is searched again by the next one, last by class G (global-memory
+ *    histogram), which GROWS its table and repeats the batch when a query touches more subjects than it holds —
+ *    the reference returns results for such queries, so does this call (KAAMER_ERR_LIMIT only beyond 2^30 slots);
+ *  - queries of more than 60000 k-mers on a dense database go to class G directly. */
 int kaamer_gpu_search_proteins(kaamer_gpu_t *h, const uint8_t *residues, const uint64_t *seq_off,
                                uint32_t nq, const kaamer_opts *opts, kaamer_hits **out);
 

@@ -330,6 +330,43 @@ def c4_block(a, local_rank, dev, peak, threads):
            "status_flags": int(c[3]), "hits_per_batch": int(result0[2].sum()),
            "lookups_by_class_W_M_G_D": [int(x) for x in c[4:8]],
            "roofline": c4_roofline(ms, c, prof, peak)}
+    # the same batches through the C ABI with pinned HOST buffers, two batches in flight (what `e2e` is for C3)
+    try:
+        from kaamer_b200 import SearchOptions
+
+        hb = []
+        for bi in range(2):
+            dq, dqo = db.queries(bi, a.queries)
+            hb.append((dq.cpu().pin_memory(), dqo.to(torch.int64).cpu().pin_memory()))
+        opts = SearchOptions()
+
+        def submit(i):
+            hq, ho = hb[i % 2]
+            return g.submit_proteins_ptr(hq.data_ptr(), ho.data_ptr(), a.queries, opts)
+
+        tk = submit(0)
+        for i in range(1, 4):  # warm the pinned result blocks
+            nx = submit(i)
+            g.wait_proteins(tk)
+            tk = nx
+        g.wait_proteins(tk)
+        n_e2e = max(3, min(a.steps, 8))
+        t1 = time.perf_counter()
+        tk = submit(0)
+        res_e2e = hits_e2e = 0
+        for i in range(1, n_e2e + 1):
+            nx = submit(i) if i < n_e2e else None
+            r = g.wait_proteins(tk)
+            res_e2e += int(hb[(i - 1) % 2][1][-1])
+            hits_e2e += len(r.subject)
+            tk = nx
+        e2e_s = time.perf_counter() - t1
+        out["e2e"] = {"value": res_e2e / e2e_s, "unit": UNIT, "ms_per_step": e2e_s / n_e2e * 1e3, "steps": n_e2e,
+                      "h2d_bytes_per_step": int(hb[0][0].numel() + hb[0][1].numel() * 8), "hits_per_batch": hits_e2e // n_e2e,
+                      "how": "kaamer_gpu_search_proteins_submit / _wait on pinned HOST buffers, two batches in flight"}
+        del hb
+    except Exception as e:  # noqa: BLE001
+        out["e2e"] = {"error": str(e)}
     if a.c4_sample > 0:
         out["parity_sample"] = c4_parity_sample(SEED_C4, a.c4_proteins, result0, a.c4_sample, threads)
         st = g.dbstats()

@@ -60,3 +60,20 @@ def test_bench_line_gpu():
     st = d["stages"]
     assert "error" not in st["c5"] and st["c5"]["parity_spot_check"]["dp_score_and_raw_equal_oracle"] is True
     assert "error" not in st["c2"] and st["c2"]["value"] > 0
+
+
+def test_traffic_json_was_captured_from_the_current_kernel_sources():
+    """bench.py reports roofline.traffic only while profiles/traffic.json carries the hash of the kernel sources its
+    ncu captures were taken from; a kernel edit without a new capture must show up here, not as a silent null"""
+    import json
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    assert {"k_search_wt<W>", "k_search_m", "k_search_f<CLS4>", "k_search_f<CLS5>", "k_search_f<CLS6>"} <= set(t["kernels"])
+    for name, e in t["kernels"].items():
+        assert e["source_sha16"] == bench.kernel_source_hash(), name
+        assert e["dram_bytes_per_launch"] > 0
+    assert bench.traffic_from_profiles("k_search_wt<W>")[0] > 1e9
+    assert bench.c4_traffic()["traffic"] > 5e9

@@ -398,6 +398,7 @@ def sharded_block(a, rank, local_rank, world, dev, peak, threads):
     out = {"workload": f"C4: {a.c4_proteins} synthetic proteins, index built as {world} key-range shards (one per GPU, "
                        f"fences of equal expected k-mer mass), {a.queries} queries per rank and step",
            "db_residues": n_aa, "db_kmers": n_kmers, "shard_build_s": build_s, "modes": {}}
+    first_result = None
     for mode, kw in (("P_postings_sharded_table_replicated", dict(replicate_table=True)),
                      ("R_built_sharded_searched_replicated", dict(replicate_table=True, replicate_postings=True))):
         t1 = time.time()
@@ -428,6 +429,20 @@ def sharded_block(a, rank, local_rank, world, dev, peak, threads):
              "collectives_on_the_data_path": 0}
         if rank == 0 and a.c4_sample > 0 and mode.startswith("P_"):
             m["parity_sample"] = c4_parity_sample(SEED_C4, a.c4_proteins, result0, a.c4_sample, threads)
+            first_result = result0
+        elif rank == 0 and mode.startswith("R_") and first_result is not None:
+            # the same batch as in mode P (whose sample is checked against the oracle): every query of the batch must
+            # come back with the same hits, Kmatch and rank
+            _, _, nh0, hb0, pool0 = first_result
+            _, _, nh1, hb1, pool1 = result0
+            same = bool(np.array_equal(nh0, nh1))
+            bad = 0
+            if same:
+                for j in np.flatnonzero(nh0):
+                    if not np.array_equal(pool0[int(hb0[j]):int(hb0[j]) + int(nh0[j])], pool1[int(hb1[j]):int(hb1[j]) + int(nh1[j])]):
+                        bad += 1
+            m["parity_whole_batch_vs_mode_P"] = {"queries": int(len(nh0)), "hits": int(nh1.sum()), "n_hits_equal": same,
+                                                 "queries_with_different_hits": bad}
         dist.barrier()
         out["modes"][mode] = m
         g.detach_shards()

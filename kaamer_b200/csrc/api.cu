@@ -515,6 +515,7 @@ static void detach_shards_locked(kaamer_gpu *h) {
   h->idx.full_table = nullptr;
   if (h->idx.repl_postings) cudaFree(h->idx.repl_postings);
   h->idx.repl_postings = nullptr;
+  h->idx.flat_view = false;
   h->idx.peer = PeerView{};
 }
 
@@ -678,6 +679,17 @@ static int kaamer_gpu_attach_shards_impl(kaamer_gpu_t *h, const kaamer_shard_han
         return KAAMER_ERR_CUDA;
       }
       for (int i = 0; i < n_shards; ++i) pv.postings[i] = h->idx.repl_postings + base[i];
+      if (total <= PEER_LOCAL_MASK) {
+        // offsets instead of (shard, local) pairs: the PEER kernels decode them as shard 0 + offset, and the
+        // protein search runs its non-PEER kernels on the replica (search.cu flat view)
+        int rcf = flatten_table(h, h->idx.full_table, base.data(), n_shards, h->stream);
+        if (rcf != KAAMER_OK) {
+          detach_shards_locked(h);
+          return rcf;
+        }
+        for (int i = 0; i < n_shards; ++i) pv.postings[i] = h->idx.repl_postings;
+        h->idx.flat_view = true;
+      }
     }
   } else if (n_shards > 1 && !(flags & KAAMER_ATTACH_NO_PRESENCE_FILTER)) {
     // local replica of "which k-mers exist": 1 bit per dense code, built by streaming every shard once

@@ -314,6 +314,9 @@ struct DevIndex {
   uint32_t *presence = nullptr;    // presence filter over the whole key space (mode P, api.cu)
   uint64_t *full_table = nullptr;  // replicated table over the whole key space (mode P, api.cu)
   uint32_t *repl_postings = nullptr;  // local copy of every shard's postings (KAAMER_ATTACH_REPLICATE_POSTINGS)
+  // table AND postings replicated and the entries rewritten to offsets into repl_postings: the handle is a plain
+  // whole index again (full_table / repl_postings) and the protein search runs its non-PEER kernels on it
+  bool flat_view = false;
   // key-range shards keep table and postings in shareable memory (vmm.cu); a full index uses cudaMalloc
   VmmAlloc vm_table, vm_postings;
 };
@@ -466,6 +469,7 @@ __device__ __forceinline__ uint32_t filter_kmin(long long min_kmatch, double rat
 int build_presence(kaamer_gpu *h, const PeerView &pv, uint32_t *d_bits, cudaStream_t st);
 // search.cu: local copy of every shard's table range, multi-posting entries tagged with their shard
 int replicate_table(kaamer_gpu *h, const PeerView &pv, uint64_t *d_full, cudaStream_t st);
+int flatten_table(kaamer_gpu *h, uint64_t *d_full, const uint64_t *base, int n_shards, cudaStream_t st);
 // align.cu
 int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, const uint32_t *pair_q,
                 const uint32_t *pair_s, uint32_t n_pairs, const kaamer_aln_opts *o, kaamer_aln *out,

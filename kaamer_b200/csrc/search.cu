@@ -542,6 +542,33 @@ int replicate_table(kaamer_gpu *h, const PeerView &pv, uint64_t *d_full, cudaStr
   return KAAMER_OK;
 }
 
+// Built sharded, searched replicated: every shard's postings were copied into one local array (shard s at
+// base[s]), so the shard tag of a multi-posting entry becomes a plain offset: value = base[shard] + local.  The
+// PEER kernels still decode such an entry (shard 0, whose pointer is the start of the array), and the protein
+// search can use its non-PEER kernels on (full table, replicated postings).
+struct FlatBases {
+  uint64_t base[MAX_PEER_SHARDS];
+};
+__global__ void __launch_bounds__(256) k_flatten_table(uint64_t *__restrict__ full, FlatBases fb) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; d < DENSE_SPACE; d += stride) {
+    const uint64_t e = full[d];
+    if ((e >> ENTRY_VALUE_BITS) >= 2ull) {
+      const uint64_t val = e & ENTRY_VALUE_MASK;
+      const uint64_t flat = fb.base[val >> PEER_SHARD_SHIFT] + (val & PEER_LOCAL_MASK);
+      full[d] = (e & ~ENTRY_VALUE_MASK) | flat;
+    }
+  }
+}
+int flatten_table(kaamer_gpu *h, uint64_t *d_full, const uint64_t *base, int n_shards, cudaStream_t st) {
+  FlatBases fb{};
+  for (int i = 0; i < n_shards && i < MAX_PEER_SHARDS; ++i) fb.base[i] = base[i];
+  k_flatten_table<<<h->sm_count * 16, 256, 0, st>>>(d_full, fb);
+  KCUDA(cudaGetLastError());
+  KCUDA(cudaStreamSynchronize(st));
+  return KAAMER_OK;
+}
+
 int build_presence(kaamer_gpu *h, const PeerView &pv, uint32_t *d_bits, cudaStream_t st) {
   const uint64_t n_words = (DENSE_SPACE + 31) / 32;
   k_presence<<<h->sm_count * 16, 256, 0, st>>>(pv, d_bits, n_words);
@@ -653,8 +680,9 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
     set_error("no index resident");
     return KAAMER_ERR_ARG;
   }
-  const bool peer = h->idx.peer.n > 0;
-  if (!peer && (h->idx.d_lo != 0 || h->idx.d_hi != DENSE_SPACE)) {
+  const bool flat = h->idx.flat_view;  // built sharded, everything replicated: a plain whole index
+  const bool peer = h->idx.peer.n > 0 && !flat;
+  if (!peer && !flat && (h->idx.d_lo != 0 || h->idx.d_hi != DENSE_SPACE)) {
     set_error("this handle holds the key-range shard [%llu, %llu) only: attach the other shards "
               "(kaamer_gpu_attach_shards) or use the kaamer_gpu_shard_* steps",
               (unsigned long long)h->idx.d_lo, (unsigned long long)h->idx.d_hi);
@@ -666,10 +694,10 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   KCHECK(ws.kmin.ensure(nq));
   uint32_t *list_count = ws.lists.p + (size_t)N_LISTS * nq;
   SearchArgs a{};
-  a.table = h->idx.table;
-  a.d_lo = h->idx.d_lo;
-  a.d_hi = h->idx.d_hi;
-  a.postings = h->idx.postings;
+  a.table = flat ? h->idx.full_table : h->idx.table;
+  a.d_lo = flat ? 0 : h->idx.d_lo;
+  a.d_hi = flat ? DENSE_SPACE : h->idx.d_hi;
+  a.postings = flat ? h->idx.repl_postings : h->idx.postings;
   a.res = d_res;
   a.off = d_off;
   a.nq = nq;
@@ -689,7 +717,7 @@ int search_proteins_device(kaamer_gpu *h, const uint8_t *d_res, const uint64_t *
   a.nt_mode = nt_mode;
   a.any0 = d_any0;
   a.peer = h->idx.d_peer;
-  a.filter = h->idx.filter;
+  a.filter = flat ? nullptr : h->idx.filter;  // (the presence bits cover the handle's own key range only)
   class_limits(h, &a.w_maxk, &a.m_maxk, &a.dense);
   a.d_mapb = dense_mapb();
   const size_t d_smem = ((sizeof(DenseSmem) + 15) & ~(size_t)15) + 2 * (size_t)a.d_mapb;

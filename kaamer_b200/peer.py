@@ -43,13 +43,14 @@ def _close_fds(sh) -> None:
             setattr(sh, name, -1)
 
 
-def attach_all(indices: "list[GpuIndex]", presence_filter: bool = True, replicate_table: bool = False) -> None:
+def attach_all(indices: "list[GpuIndex]", presence_filter: bool = True, replicate_table: bool = False,
+               replicate_postings: bool = False) -> None:
     """Single process driving several shards (one Go server process with several GPUs, or the
     single-GPU tests): every handle attaches the exports of all of them (by pointer)."""
     handles = [g.export_shard() for g in indices]
     try:
         for g in indices:
-            g.attach_shards(handles, presence_filter, replicate_table)
+            g.attach_shards(handles, presence_filter, replicate_table, replicate_postings)
     finally:
         for sh in handles:
             _close_fds(sh)

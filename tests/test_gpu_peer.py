@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _peer_handles(small_db, G, dev=0, presence_filter=True, replicate_table=False):
+def _peer_handles(small_db, G, dev=0, presence_filter=True, replicate_table=False, replicate_postings=False):
     from kaamer_b200 import GpuIndex
     from kaamer_b200.peer import attach_all
     from kaamer_b200.sharded import make_fences
@@ -24,12 +24,12 @@ def _peer_handles(small_db, G, dev=0, presence_filter=True, replicate_table=Fals
     fences = make_fences(idx.keys, idx.offsets, G)
     hs = [GpuIndex.build(small_db["res"], small_db["off"], small_db["ids"], keep_proteins=False, device=dev,
                          shard=(int(fences[r]), int(fences[r + 1]))) for r in range(G)]
-    attach_all(hs, presence_filter, replicate_table)
+    attach_all(hs, presence_filter, replicate_table, replicate_postings)
     return hs
 
 
 @pytest.mark.parametrize("G,presence", [(1, True), (2, True), (2, False), (3, True), (8, True), (8, False),
-                                        (2, "replicate"), (3, "replicate")])
+                                        (2, "replicate"), (3, "replicate"), (2, "replicate_all"), (8, "replicate_all")])
 def test_peer_protein_search_parity(small_db, G, presence):
     """every shard handle answers the whole batch exactly like the single index (all size classes:
     short, 700-residue, 3000-residue and 12000-residue queries)"""
@@ -42,7 +42,10 @@ def test_peer_protein_search_parity(small_db, G, presence):
     seqs += [b"", b"MKT", small_db["res"][:12].tobytes(), b"A" * 700, small_db["res"][:3000].tobytes(),
              small_db["res"][5000:17000].tobytes()]
     q, qo = o.pack(seqs)
-    hs = _peer_handles(small_db, G, presence_filter=presence is True, replicate_table=presence == "replicate")
+    # "replicate_all": built sharded, searched replicated — table and postings of every shard copied at attach, the
+    # entries rewritten to offsets into the copy (flat view: the non-PEER search kernels run on the replica)
+    hs = _peer_handles(small_db, G, presence_filter=presence is True, replicate_table=presence == "replicate",
+                       replicate_postings=presence == "replicate_all")
     try:
         for opts in (SearchOptions(), SearchOptions(min_kmatch=1, min_kratio=0.0, max_results=100),
                      SearchOptions(min_kmatch=4, min_kratio=0.3, max_results=2)):
@@ -58,14 +61,14 @@ def test_peer_protein_search_parity(small_db, G, presence):
             g.close()
 
 
-@pytest.mark.parametrize("replicate", [False, True])
+@pytest.mark.parametrize("replicate", [False, True, "all"])
 def test_peer_positions_and_nucleotide_parity(small_db, replicate):
     """PositionHits, translated search and SetBestStartCodon read the table too (finish.cu)"""
     from kaamer_b200 import SearchOptions, synth
     from oracle import oracle as o
 
     idx = small_db["idx"]
-    hs = _peer_handles(small_db, 3, replicate_table=replicate)
+    hs = _peer_handles(small_db, 3, replicate_table=replicate is True, replicate_postings=replicate == "all")
     try:
         q, qo, _ = synth.protein_queries(small_db["res"], small_db["off"], 200, config_index=1, stream=9)
         ora = o.search_proteins(idx, q, qo, o.opts(want_positions=True), 4)

@@ -351,17 +351,21 @@ def c4_block(a, local_rank, dev, peak, threads):
             tk = nx
         g.wait_proteins(tk)
         n_e2e = max(3, min(a.steps, 8))
-        t1 = time.perf_counter()
-        tk = submit(0)
-        res_e2e = hits_e2e = 0
-        for i in range(1, n_e2e + 1):
-            nx = submit(i) if i < n_e2e else None
-            r = g.wait_proteins(tk)
-            res_e2e += int(hb[(i - 1) % 2][1][-1])
-            hits_e2e += len(r.subject)
-            tk = nx
-        e2e_s = time.perf_counter() - t1
+        passes = []
+        for _ in range(3):  # three timed passes of n_e2e steps; the line reports the median pass and lists all
+            t1 = time.perf_counter()
+            tk = submit(0)
+            res_e2e = hits_e2e = 0
+            for i in range(1, n_e2e + 1):
+                nx = submit(i) if i < n_e2e else None
+                r = g.wait_proteins(tk)
+                res_e2e += int(hb[(i - 1) % 2][1][-1])
+                hits_e2e += len(r.subject)
+                tk = nx
+            passes.append(time.perf_counter() - t1)
+        e2e_s = sorted(passes)[1]
         out["e2e"] = {"value": res_e2e / e2e_s, "unit": UNIT, "ms_per_step": e2e_s / n_e2e * 1e3, "steps": n_e2e,
+                      "ms_per_step_of_each_pass": [x / n_e2e * 1e3 for x in passes],
                       "h2d_bytes_per_step": int(hb[0][0].numel() + hb[0][1].numel() * 8), "hits_per_batch": hits_e2e // n_e2e,
                       "how": "kaamer_gpu_search_proteins_submit / _wait on pinned HOST buffers, two batches in flight"}
         del hb

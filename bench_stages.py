@@ -194,6 +194,7 @@ def c5_on(g, res, off, ids, q, qo, steps, warmup, cpu_pairs):
             out = g.align(q, qo, pq, ps, number_of_aa=n_aa)
         dt = (time.perf_counter() - t0) / a.steps
         prof = g.profile_read(reset=True)
+        plan = g.align_last_plan()
     k_ms = prof["kernel_ms"][3] / a.steps
     # CPU restatement on a bounded sample of the same pairs
     rng = np.random.default_rng(1)
@@ -220,6 +221,8 @@ def c5_on(g, res, off, ids, q, qo, steps, warmup, cpu_pairs):
         "workload": f"C5 re-alignment: all {len(pq)} (query, hit) pairs of one C3 batch ({a.queries} queries, {a.db_proteins}-protein DB), BLOSUM62 11/1",
         "metric": "cell updates/sec", "unit": "GCUPS", "value": cells / (k_ms * 1e-3) / 1e9 if k_ms else None,
         "pairs": int(len(pq)), "cells": cells, "kernel_ms": k_ms,
+        "plan": {"long_pairs_one_cta_each": plan[0], "single_pairs_one_warp_each": plan[1],
+                 "packed_jobs_two_pairs_per_warp_int16x2_dpx": plan[2]},
         "e2e": {"value": cells / dt / 1e9, "unit": "GCUPS", "ms_per_step": 1e3 * dt,
                 "note": "kaamer_gpu_align on host buffers: H2D queries + pair list, chunked kernels, D2H of 64 B per pair"},
         "roofline": {"bound": "integer ALU / shared memory (no dense contraction, no HBM roofline; SURVEY §8d)",

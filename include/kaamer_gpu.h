@@ -245,6 +245,12 @@ typedef struct kaamer_aln_model {
 } kaamer_aln_model;
 int kaamer_gpu_default_align_model(kaamer_aln_model *out);
 int kaamer_gpu_set_align_model(kaamer_gpu_t *h, const kaamer_aln_model *model);
+/* How the calling thread's last kaamer_gpu_align[_text] call was scheduled (measurement / test aid, no
+ * reference counterpart): out[0] = long pairs (one CTA each), out[1] = pairs run one warp each (32-bit lanes),
+ * out[2] = packed jobs (two pairs per warp in int16x2 lanes with the DPX instructions: taken for the default
+ * zero-gap-row model when both sequences are shorter than 16384 and largest matrix entry x min(n, m) <= 16000,
+ * i.e. min(n, m) <= 1454 with BLOSUM62; results are identical either way). */
+void kaamer_gpu_align_last_plan(uint32_t out[3]);
 
 /* ---- device-resident entry points (inputs already in HBM; used by bench.py `value`, by the
  * multi-GPU drivers and by callers that keep query batches on the device).  All pointers are

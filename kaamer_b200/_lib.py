@@ -207,6 +207,7 @@ SYMBOLS = [
     "kaamer_gpu_free_aln_text",
     "kaamer_gpu_default_align_model",
     "kaamer_gpu_set_align_model",
+    "kaamer_gpu_align_last_plan",
     "kaamer_gpu_search_proteins_device",
     "kaamer_gpu_dense_space",
     "kaamer_gpu_shard_route",
@@ -291,6 +292,8 @@ def lib() -> C.CDLL:
     L.kaamer_gpu_free_aln_text.restype = None
     L.kaamer_gpu_default_align_model.argtypes = [C.POINTER(AlnModel)]
     L.kaamer_gpu_set_align_model.argtypes = [vp, C.POINTER(AlnModel)]
+    L.kaamer_gpu_align_last_plan.argtypes = [C.POINTER(C.c_uint32)]
+    L.kaamer_gpu_align_last_plan.restype = None
     L.kaamer_gpu_search_proteins_device.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(Opts), C.POINTER(DevResult), vp]
     L.kaamer_gpu_dense_space.restype = C.c_uint64
     L.kaamer_gpu_dense_space.argtypes = []

@@ -30,6 +30,7 @@
 #include <type_traits>
 
 #include "internal.cuh"
+#include "align_packed.cuh"
 
 namespace kaamer {
 
@@ -382,7 +383,7 @@ __device__ __forceinline__ void build_profile(int8_t *prof, const int8_t *b62, c
 // (diagonal, up or left) with ONE memory round trip; the path is then followed through
 // shuffles and a new window is fetched only when the layer changes or the window is used up.
 __device__ __forceinline__ void traceback_and_emit(const AlnArgs &a, const AlnPair &pr, const uint8_t *scratch,
-                                                   const uint8_t *q, int n, const uint8_t *s, int cw, int best_s,
+                                                   int nrows, const uint8_t *q, int n, const uint8_t *s, int cw, int best_s,
                                                    uint32_t best_pos, bool bad, const int8_t *s_b62,
                                                    const int8_t *s_lidx, const int8_t *s_apos) {
   const unsigned lane = threadIdx.x & 31;
@@ -419,7 +420,7 @@ __device__ __forceinline__ void traceback_and_emit(const AlnArgs &a, const AlnPa
       const int wi = i - di * (int)lane, wj = j - dj * (int)lane;
       uint32_t F = 0, QA = 0, SB = 0;
       if (wi > 0 && wj > 0) {
-        F = dir_at(scratch, n, cw, wi, wj);
+        F = dir_at(scratch, nrows, cw, wi, wj);
         QA = fix_u(q[wi - 1]);
         SB = fix_u(s[wj - 1]);
       }
@@ -452,7 +453,10 @@ __device__ __forceinline__ void traceback_and_emit(const AlnArgs &a, const AlnPa
             done = true;
             break;
           }
+          // layer of the predecessor: 0 / 1 / 2 in the bytes of the 32-bit kernels; the packed kernel stores the two
+          // raw comparisons (bit 0: U beats M, bit 1: L beats both), so 3 also means L
           layer = (int)(__shfl_sync(0xFFFFFFFFu, F, k + 1) & 3u);
+          layer = layer > 2 ? 2 : layer;
         } else if (layer == 1) {
           open_seg(1);
           if (rev && lane == 0) rev[aln_len] = (uint16_t)(ca | ('-' << 8));
@@ -585,7 +589,90 @@ __global__ void __launch_bounds__(ALN_WARPS * 32) k_sw_affine(AlnArgs a) {
     }
   }
   __syncwarp();
-  traceback_and_emit(a, pr, scratch, q, n, s, cw, best_s, best_pos, bad, s_b62, s_lidx, s_apos);
+  traceback_and_emit(a, pr, scratch, n, q, n, s, cw, best_s, best_pos, bad, s_b62, s_lidx, s_apos);
+}
+
+// ---- one warp per TWO pairs: int16x2 lanes, DPX (align_packed.cuh) ------------------------------
+// a.pairs holds 2 * a.n_pairs entries: job k = pairs (2k, 2k+1), same cw, traceback regions of the job's
+// geometry (rows = max n, columns = max m), the block-boundary column behind the second region.
+// MAXCW bounds the instantiated column widths (and so the registers: 4 CTAs per SM up to 8 columns per lane).
+template <int MAXCW>
+__global__ void __launch_bounds__(ALN_WARPS * 32, MAXCW <= 8 ? 4 : 2) k_sw_affine_pk(AlnArgs a, int pcols) {
+  extern __shared__ __align__(16) int8_t pk_prof[];  // [ALN_WARPS][2][PK_PROF_ROWS * pcols]
+  __shared__ int8_t s_b62[26 * 32];
+  __shared__ int8_t s_lidx[256];
+  __shared__ int8_t s_apos[256];
+  load_tables(a.tables, s_b62, s_lidx, s_apos);
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t ji = blockIdx.x * ALN_WARPS + w;
+  if (ji >= a.n_pairs) return;
+  const AlnPair pa = a.pairs[2 * ji], pb = a.pairs[2 * ji + 1];
+  const uint8_t *qA = a.q_res + a.q_off[pa.q], *qB = a.q_res + a.q_off[pb.q];
+  const int nA = (int)(a.q_off[pa.q + 1] - a.q_off[pa.q]), nB = (int)(a.q_off[pb.q + 1] - a.q_off[pb.q]);
+  const uint8_t *sA = a.p_res + a.p_off[pa.s], *sB = a.p_res + a.p_off[pb.s];
+  const int mA = (int)(a.p_off[pa.s + 1] - a.p_off[pa.s]), mB = (int)(a.p_off[pb.s + 1] - a.p_off[pb.s]);
+  // illegal letters: biogo returns an error that kaamer ignores (align.go:67) -> empty alignment
+  bool badA = false, badB = false;
+  for (int i = lane; i < nA; i += 32) badA |= s_lidx[fix_u(qA[i])] < 0;
+  for (int j = lane; j < mA; j += 32) badA |= s_lidx[fix_u(sA[j])] < 0;
+  for (int i = lane; i < nB; i += 32) badB |= s_lidx[fix_u(qB[i])] < 0;
+  for (int j = lane; j < mB; j += 32) badB |= s_lidx[fix_u(sB[j])] < 0;
+  badA = __any_sync(0xFFFFFFFFu, badA);
+  badB = __any_sync(0xFFFFFFFFu, badB);
+  const int N = nA > nB ? nA : nB, Mx = mA > mB ? mA : mB;  // the geometry the host sized the regions for
+  const int cw = (int)pa.cw, bw = 32 * cw;
+  uint8_t *scrA = a.scratch + pa.scratch, *scrB = a.scratch + pb.scratch;
+  int bsA = 0, bsB = 0;
+  uint32_t bpA = 0, bpB = 0;
+  if (N > 0 && Mx > 0 && !(badA && badB)) {
+    const int nblk = (Mx + bw - 1) / bw;
+    uint32_t *bnd = reinterpret_cast<uint32_t *>(scrB + pk_flags_bytes((uint64_t)N, (uint64_t)Mx, cw));  // in place: 3 x u32[N]
+    int8_t *profA = pk_prof + (size_t)w * 2 * PK_PROF_ROWS * pcols, *profB = profA + (size_t)PK_PROF_ROWS * pcols;
+    PkBlockArgs g;
+    g.profA = profA;
+    g.profB = profB;
+    g.pcols = pcols;
+    g.lidx = s_lidx;
+    g.qA = qA;
+    g.qB = qB;
+    g.nA = badA ? 0 : nA;  // a pair with illegal letters: pad rows and pad columns only, nothing positive
+    g.nB = badB ? 0 : nB;
+    g.N = N;
+    g.open2 = ((uint32_t)(uint16_t)(int16_t)a.open) * 0x00010001u;
+    g.zero2 = a.zero_gap ? 0u : 0x00010001u;  // always 0 here (the packed path is the zero-gap-row model)
+    for (int blk = 0; blk < nblk; ++blk) {
+      __syncwarp();
+      pk_build_profile(profA, pcols, s_b62, s_lidx, sA, badA ? 0 : mA, blk, bw, (int)lane);
+      pk_build_profile(profB, pcols, s_b62, s_lidx, sB, badB ? 0 : mB, blk, bw, (int)lane);
+      __syncwarp();
+      g.dirsA = scrA + (size_t)blk * block_stride(N, cw);
+      g.dirsB = scrB + (size_t)blk * block_stride(N, cw);
+      g.bnd_in = blk > 0 ? bnd : nullptr;
+      g.bnd_out = blk + 1 < nblk ? bnd : nullptr;
+      if constexpr (MAXCW >= 16) {
+        if (cw == 16) dp_block_packed<16>(g, blk, bsA, bpA, bsB, bpB);
+        else if (cw == 12) dp_block_packed<12>(g, blk, bsA, bpA, bsB, bpB);
+      }
+      if (cw == 8) dp_block_packed<8>(g, blk, bsA, bpA, bsB, bpB);
+      else if (cw == 4) dp_block_packed<4>(g, blk, bsA, bpA, bsB, bpB);
+    }
+    // end cells: maximum score, then last in row-major order (larger i, then larger j)
+    for (int o = 16; o > 0; o >>= 1) {
+      const int osA = __shfl_xor_sync(0xFFFFFFFFu, bsA, o), osB = __shfl_xor_sync(0xFFFFFFFFu, bsB, o);
+      const uint32_t opA = __shfl_xor_sync(0xFFFFFFFFu, bpA, o), opB = __shfl_xor_sync(0xFFFFFFFFu, bpB, o);
+      if (osA > bsA || (osA == bsA && opA > bpA)) {
+        bsA = osA;
+        bpA = opA;
+      }
+      if (osB > bsB || (osB == bsB && opB > bpB)) {
+        bsB = osB;
+        bpB = opB;
+      }
+    }
+  }
+  __syncwarp();
+  traceback_and_emit(a, pa, scrA, N, qA, nA, sA, cw, badA ? 0 : bsA, bpA, badA, s_b62, s_lidx, s_apos);
+  traceback_and_emit(a, pb, scrB, N, qB, nB, sB, cw, badB ? 0 : bsB, bpB, badB, s_b62, s_lidx, s_apos);
 }
 
 // ---- one CTA per pair (long pairs): the column blocks are pipelined over the warps --------------
@@ -669,7 +756,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 4) k_sw_affine_cta(AlnArgs a) 
       best_pos = op;
     }
   }
-  traceback_and_emit(a, pr, scratch, q, n, s, cw, best_s, best_pos, bad, s_b62, s_lidx, s_apos);
+  traceback_and_emit(a, pr, scratch, n, q, n, s, cw, best_s, best_pos, bad, s_b62, s_lidx, s_apos);
 }
 
 // ---- AlnString (align.go:69-103): one warp per pair turns the reversed columns into the three lines ----
@@ -724,6 +811,138 @@ static uint64_t pair_scratch_bytes(uint64_t n, uint64_t m, int cw, bool big) {
   uint64_t b = nblk * (n + 31) * 32 * cw + (big ? nblk : 1) * 3 * 4 * n;
   return (b + 255) & ~255ull;
 }
+
+// estimated warp instructions of one pair in the one-warp-per-pair kernel: instructions per wavefront step counted
+// in the SASS of dp_block<CW> (158 / 245 / 341 / 435 for 4 / 8 / 12 / 16 columns per lane)
+static double single_work(uint64_t n, uint64_t m, int cw) {
+  const uint64_t bw = 32ull * cw, nblk = (m + bw - 1) / bw;
+  return (double)nblk * (double)(n + 31) * (66.0 + 23.0 * cw);
+}
+
+// ---- packed jobs: two pairs per warp (k_sw_affine_pk) ---------------------------------------------
+// Instructions per wavefront step of dp_block_packed<CW>, counted in the SASS: 187 / 305 / 458 / 595 for
+// 4 / 8 / 12 / 16 columns per lane, i.e. ~50 + 34 per column for BOTH pairs (two single pairs: 2 x (66 + 23)).
+constexpr double PK_OVH = 50.0, PK_CELL = 34.0;
+constexpr double PK_ACCEPT = 0.9;  // a job must cost less than this share of its two pairs run one by one
+
+struct PackedConfig {
+  bool on;
+  int maxcw;          // 4, 8, 12 or 16 columns per lane
+  uint64_t max_cells; // pairs below this many cells may be packed
+  uint32_t max_min_dim;  // min(n, m) bound that keeps every DP value below PK_MAX_SCORE
+};
+
+struct PkJob {
+  uint32_t a, b;  // pair indices
+  int cw;
+  uint32_t N, Mx;  // rows / columns of the job
+  double work;
+};
+
+// Test / measurement hooks: KAAMER_ALIGN_PACKED=0 keeps every pair on the 32-bit kernels,
+// KAAMER_ALIGN_PK_MAXCW=4|8|12|16 bounds the columns per lane, KAAMER_ALIGN_PK_CELLS=<cells> lets pairs of up
+// to that many cells be packed (default: below the one-CTA-per-pair threshold).
+static PackedConfig packed_config(const kaamer_aln_model &model, bool zero_gap) {
+  PackedConfig c{zero_gap, 16, BIG_CELLS, 0};
+  if (const char *e = getenv("KAAMER_ALIGN_PACKED")) c.on = c.on && atoi(e) != 0;
+  if (const char *e = getenv("KAAMER_ALIGN_PK_MAXCW")) {
+    const int v = atoi(e);
+    if (v == 4 || v == 8 || v == 12 || v == 16) c.maxcw = v;
+  }
+  if (const char *e = getenv("KAAMER_ALIGN_PK_CELLS")) {
+    const long long v = atoll(e);
+    if (v > 0) c.max_cells = (uint64_t)v;
+  }
+  int max_entry = 1;
+  for (int i = 1; i < 26; ++i)
+    for (int j = 1; j < 26; ++j) max_entry = model.matrix[i * 26 + j] > max_entry ? model.matrix[i * 26 + j] : max_entry;
+  c.max_min_dim = (uint32_t)(PK_MAX_SCORE / max_entry);
+  return c;
+}
+
+static int choose_cw_pk(uint64_t m, int maxcw) {
+  int best = 4;
+  double best_cost = 1e300;
+  for (int cw = 4; cw <= maxcw; cw += 4) {
+    const uint64_t bw = 32ull * cw, nblk = (m + bw - 1) / bw;
+    const double cost = (double)nblk * (PK_OVH + PK_CELL * cw);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = cw;
+    }
+  }
+  return best;
+}
+
+static double packed_work(uint64_t N, uint64_t Mx, int cw) {
+  const uint64_t bw = 32ull * cw, nblk = (Mx + bw - 1) / bw;
+  return (double)nblk * (double)(N + 31) * (PK_OVH + PK_CELL * cw);
+}
+
+// Pairs of similar geometry become jobs: the eligible pairs are sorted by (padded columns, rows) descending
+// (two counting-sort passes) and neighbours are joined when the job is cheaper than the two pairs run singly.
+// The jobs come out ordered by estimated work, largest first.
+static void plan_packed_jobs(const PackedConfig &pk, const std::vector<uint32_t> &dim_n, const std::vector<uint32_t> &dim_m,
+                             const std::vector<uint64_t> &cost, std::vector<PkJob> &jobs, std::vector<uint8_t> &in_job) {
+  const uint32_t n_pairs = (uint32_t)dim_n.size();
+  std::vector<uint32_t> el, key;
+  el.reserve(n_pairs);
+  key.reserve(n_pairs);
+  for (uint32_t i = 0; i < n_pairs; ++i) {
+    const uint32_t n = dim_n[i], m = dim_m[i];
+    if (n < 1 || m < 1 || n > (uint32_t)PK_MAX_DIM || m > (uint32_t)PK_MAX_DIM) continue;
+    if ((n < m ? n : m) > pk.max_min_dim || cost[i] >= pk.max_cells) continue;
+    const int cw = choose_cw_pk(m, pk.maxcw);
+    const uint32_t bw = 32u * (uint32_t)cw, padded = (m + bw - 1) / bw * bw;  // <= 16384 + 511
+    const uint32_t k = ((padded / 128u) << 14) | n;                          // 8 + 14 bits
+    el.push_back(i);
+    key.push_back(0x3FFFFFu - k);  // ascending sort of the complement = descending (padded, n)
+  }
+  const uint32_t ne = (uint32_t)el.size();
+  if (ne < 2) return;
+  std::vector<uint32_t> el2(ne), key2(ne);
+  for (int pass = 0; pass < 2; ++pass) {
+    const int shift = pass * 11;
+    uint32_t cnt[2049] = {0};
+    for (uint32_t x = 0; x < ne; ++x) cnt[((key[x] >> shift) & 2047u) + 1]++;
+    for (int b = 0; b < 2048; ++b) cnt[b + 1] += cnt[b];
+    for (uint32_t x = 0; x < ne; ++x) {
+      const uint32_t at = cnt[(key[x] >> shift) & 2047u]++;
+      el2[at] = el[x];
+      key2[at] = key[x];
+    }
+    el.swap(el2);
+    key.swap(key2);
+  }
+  std::vector<PkJob> raw;
+  raw.reserve(ne / 2);
+  double max_work = 1.0;
+  for (uint32_t x = 0; x + 1 < ne;) {
+    const uint32_t A = el[x], B = el[x + 1];
+    const uint32_t N = dim_n[A] > dim_n[B] ? dim_n[A] : dim_n[B], Mx = dim_m[A] > dim_m[B] ? dim_m[A] : dim_m[B];
+    const int cw = choose_cw_pk(Mx, pk.maxcw);
+    const double w = packed_work(N, Mx, cw);
+    const double singly = single_work(dim_n[A], dim_m[A], choose_cw(dim_m[A])) + single_work(dim_n[B], dim_m[B], choose_cw(dim_m[B]));
+    if (w <= PK_ACCEPT * singly) {
+      raw.push_back(PkJob{A, B, cw, N, Mx, w});
+      in_job[A] = in_job[B] = 1;
+      max_work = w > max_work ? w : max_work;
+      x += 2;
+    } else {
+      x += 1;
+    }
+  }
+  // largest first (1024 buckets, as for the single pairs)
+  constexpr int NB = 1024;
+  std::vector<uint32_t> start(NB + 1, 0);
+  auto bucket_of = [&](double w) { return (uint32_t)(NB - 1 - (int)(w * (NB - 1) / max_work)); };
+  for (const PkJob &j : raw) start[bucket_of(j.work) + 1]++;
+  for (int b = 0; b < NB; ++b) start[b + 1] += start[b];
+  jobs.resize(raw.size());
+  for (const PkJob &j : raw) jobs[start[bucket_of(j.work)]++] = j;
+}
+
+static thread_local uint32_t t_last_plan[3] = {0, 0, 0};  // long pairs, single pairs, packed jobs of the last call
 
 int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, const uint32_t *pair_q,
                 const uint32_t *pair_s, uint32_t n_pairs, const kaamer_aln_opts *o, kaamer_aln *out,
@@ -785,6 +1004,8 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `t` is a stack object
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_affine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WARP_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_affine_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_affine_pk<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ALN_WARPS * 2 * PK_PROF_ROWS * 256);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_affine_pk<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ALN_WARPS * 2 * PK_PROF_ROWS * 512);
     if (e != cudaSuccess) {
       set_error("alignment tables: %s", cudaGetErrorString(e));
       drop_text();
@@ -795,9 +1016,8 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
   uint32_t nq = 0;
   for (uint32_t i = 0; i < n_pairs; ++i) nq = pair_q[i] + 1 > nq ? pair_q[i] + 1 : nq;
   const uint64_t n_qres = q_off[nq];
-  // cost-ordered pair list (long pairs first: short tail, similar pairs share a CTA)
   std::vector<uint64_t> cost(n_pairs);
-  uint64_t max_cost = 1;
+  std::vector<uint32_t> dim_n(n_pairs), dim_m(n_pairs);
   for (uint32_t i = 0; i < n_pairs; ++i) {
     if (pair_s[i] > ix.max_protein_id) {
       set_error("pair %u: subject id %u not in the protein table (max %u)", i, pair_s[i], ix.max_protein_id);
@@ -813,20 +1033,37 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
       return KAAMER_ERR_LIMIT;
     }
     cost[i] = n * m;
-    max_cost = cost[i] > max_cost ? cost[i] : max_cost;
+    dim_n[i] = (uint32_t)n;
+    dim_m[i] = (uint32_t)m;
   }
-  constexpr int NB = 1024;
-  std::vector<uint32_t> bucket_start(NB + 1, 0), order(n_pairs);
-  auto bucket_of = [&](uint64_t c) { return (uint32_t)(NB - 1 - (c * (NB - 1)) / max_cost); };  // descending cost
-  for (uint32_t i = 0; i < n_pairs; ++i) bucket_start[bucket_of(cost[i]) + 1]++;
-  for (int b = 0; b < NB; ++b) bucket_start[b + 1] += bucket_start[b];
+  // Three kinds of work: long pairs (one CTA each), packed jobs (two pairs per warp, int16x2) and single
+  // pairs (one warp each); each list cost-ordered, longest first (short tail, similar pairs share a CTA).
+  const PackedConfig pk = packed_config(model, zero_gap);
+  std::vector<PkJob> jobs;
+  std::vector<uint8_t> in_job(n_pairs, 0);
+  if (pk.on && n_pairs >= 2) plan_packed_jobs(pk, dim_n, dim_m, cost, jobs, in_job);
+  std::vector<uint32_t> order;  // the pairs outside the jobs
   {
+    uint64_t max_cost = 1;
+    uint32_t n_rest = 0;
+    for (uint32_t i = 0; i < n_pairs; ++i)
+      if (!in_job[i]) {
+        max_cost = cost[i] > max_cost ? cost[i] : max_cost;
+        ++n_rest;
+      }
+    constexpr int NB = 1024;
+    std::vector<uint32_t> bucket_start(NB + 1, 0);
+    order.resize(n_rest);
+    auto bucket_of = [&](uint64_t c) { return (uint32_t)(NB - 1 - (c * (NB - 1)) / max_cost); };  // descending cost
+    for (uint32_t i = 0; i < n_pairs; ++i)
+      if (!in_job[i]) bucket_start[bucket_of(cost[i]) + 1]++;
+    for (int b = 0; b < NB; ++b) bucket_start[b + 1] += bucket_start[b];
     std::vector<uint32_t> cur(bucket_start.begin(), bucket_start.end() - 1);
-    for (uint32_t i = 0; i < n_pairs; ++i) order[cur[bucket_of(cost[i])]++] = i;
+    for (uint32_t i = 0; i < n_pairs; ++i)
+      if (!in_job[i]) order[cur[bucket_of(cost[i])]++] = i;
+    // the long pairs (one CTA each) first, exactly
+    std::stable_partition(order.begin(), order.end(), [&](uint32_t i) { return cost[i] >= BIG_CELLS; });
   }
-  // the long pairs (one CTA each) first, exactly
-  std::stable_partition(order.begin(), order.end(), [&](uint32_t i) { return cost[i] >= BIG_CELLS; });
-  // device buffers
   // device buffers live in the handle's workspace (allocating tens of GB per call costs more than
   // the kernels)
   SearchWorkspace &ws = h->ws;
@@ -856,41 +1093,83 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
   d_out = reinterpret_cast<kaamer_aln *>(ws.a_out.p);
   ACUDA(cudaMemcpyAsync(d_q, q_res, (size_t)n_qres, cudaMemcpyHostToDevice, st));
   ACUDA(cudaMemcpyAsync(d_qoff, q_off, ((size_t)nq + 1) * 8, cudaMemcpyHostToDevice, st));
-  // chunks under the traceback-memory budget
+  // chunks under the traceback-memory budget: the items are walked longest first (long pairs, then jobs and
+  // single pairs merged by their estimated work), a chunk ends where the next item does not fit
   size_t free_b = 0, total_b = 0;
   ACUDA(cudaMemGetInfo(&free_b, &total_b));
   uint64_t budget = (free_b + ws.a_scratch.n) / 2;
   if (budget > (16ull << 30)) budget = 16ull << 30;
-  std::vector<AlnPair> pairs(n_pairs);
-  std::vector<uint32_t> chunk_end;
+  struct Chunk {
+    uint32_t big_end, job_end, small_end;
+  };
+  std::vector<Chunk> chunks;
+  std::vector<AlnPair> big_pairs, small_pairs, job_pairs;  // device order: [long | single | jobs (two entries each)]
+  job_pairs.reserve(jobs.size() * 2);
   uint64_t used = 0, max_used = 0;
-  uint32_t n_big = 0;
-  for (uint32_t k = 0; k < n_pairs; ++k) {
-    const uint32_t i = order[k];
-    const uint64_t n = q_off[pair_q[i] + 1] - q_off[pair_q[i]];
-    const uint64_t m = ix.h_prot_off[pair_s[i] + 1] - ix.h_prot_off[pair_s[i]];
-    const bool big = n * m >= BIG_CELLS;
-    const int cw = (big || !zero_gap) ? 8 : choose_cw(m);
-    const uint64_t b = pair_scratch_bytes(n, m, cw, big);
+  int pk_maxcw_used = 0;
+  bool too_large = false;
+  auto place = [&](uint64_t b, uint32_t i) -> uint64_t {
     if (b > budget) {
-      set_error("pair %u (%llu x %llu) needs %llu bytes of traceback state, more than the device has free", i,
-                (unsigned long long)n, (unsigned long long)m, (unsigned long long)b);
+      set_error("pair %u (%u x %u) needs %llu bytes of traceback state, more than the device has free", i, dim_n[i],
+                dim_m[i], (unsigned long long)b);
+      too_large = true;
+      return 0;
+    }
+    if (used + b > budget) {
+      chunks.push_back(Chunk{(uint32_t)big_pairs.size(), (uint32_t)(job_pairs.size() / 2), (uint32_t)small_pairs.size()});
+      used = 0;
+    }
+    const uint64_t at = used;
+    used += b;
+    max_used = used > max_used ? used : max_used;
+    return at;
+  };
+  {
+    size_t k = 0;
+    for (; k < order.size() && cost[order[k]] >= BIG_CELLS; ++k) {
+      const uint32_t i = order[k];
+      const uint64_t at = place(pair_scratch_bytes(dim_n[i], dim_m[i], 8, true), i);
+      big_pairs.push_back(AlnPair{i, pair_q[i], pair_s[i], 8u, at});
+    }
+    size_t j = 0;
+    while (!too_large && (k < order.size() || j < jobs.size())) {
+      bool take_job = j < jobs.size();
+      if (take_job && k < order.size()) {
+        const uint32_t i = order[k];
+        take_job = jobs[j].work >= single_work(dim_n[i], dim_m[i], zero_gap ? choose_cw(dim_m[i]) : 8);
+      }
+      if (take_job) {
+        const PkJob &jb = jobs[j++];
+        const uint64_t fb = pk_flags_bytes(jb.N, jb.Mx, jb.cw);
+        const uint64_t at = place(2 * fb + ((3ull * 4 * jb.N + 255) & ~255ull), jb.a);
+        job_pairs.push_back(AlnPair{jb.a, pair_q[jb.a], pair_s[jb.a], (uint32_t)jb.cw, at});
+        job_pairs.push_back(AlnPair{jb.b, pair_q[jb.b], pair_s[jb.b], (uint32_t)jb.cw, at + fb});
+        pk_maxcw_used = jb.cw > pk_maxcw_used ? jb.cw : pk_maxcw_used;
+      } else {
+        const uint32_t i = order[k++];
+        const int cw = zero_gap ? choose_cw(dim_m[i]) : 8;
+        const uint64_t at = place(pair_scratch_bytes(dim_n[i], dim_m[i], cw, false), i);
+        small_pairs.push_back(AlnPair{i, pair_q[i], pair_s[i], (uint32_t)cw, at});
+      }
+    }
+    if (too_large) {
       cleanup();
       return KAAMER_ERR_NOMEM;
     }
-    if (used + b > budget) {
-      chunk_end.push_back(k);
-      used = 0;
-    }
-    if (big) n_big = k + 1;  // cost-ordered: the long pairs are a prefix
-    pairs[k] = AlnPair{i, pair_q[i], pair_s[i], (uint32_t)cw, used};
-    used += b;
-    max_used = used > max_used ? used : max_used;
   }
-  chunk_end.push_back(n_pairs);
+  chunks.push_back(Chunk{(uint32_t)big_pairs.size(), (uint32_t)(job_pairs.size() / 2), (uint32_t)small_pairs.size()});
   KCHECK(ws.a_scratch.ensure((size_t)max_used + 256));
   d_scratch = ws.a_scratch.p;
-  ACUDA(cudaMemcpyAsync(d_pairs, pairs.data(), (size_t)n_pairs * sizeof(AlnPair), cudaMemcpyHostToDevice, st));
+  AlnPair *d_big = d_pairs, *d_small = d_pairs + big_pairs.size(), *d_jobs = d_small + small_pairs.size();
+  if (!big_pairs.empty())
+    ACUDA(cudaMemcpyAsync(d_big, big_pairs.data(), big_pairs.size() * sizeof(AlnPair), cudaMemcpyHostToDevice, st));
+  if (!small_pairs.empty())
+    ACUDA(cudaMemcpyAsync(d_small, small_pairs.data(), small_pairs.size() * sizeof(AlnPair), cudaMemcpyHostToDevice, st));
+  if (!job_pairs.empty())
+    ACUDA(cudaMemcpyAsync(d_jobs, job_pairs.data(), job_pairs.size() * sizeof(AlnPair), cudaMemcpyHostToDevice, st));
+  t_last_plan[0] = (uint32_t)big_pairs.size();
+  t_last_plan[1] = (uint32_t)small_pairs.size();
+  t_last_plan[2] = (uint32_t)(job_pairs.size() / 2);
   AlnArgs a{};
   a.q_res = d_q;
   a.q_off = d_qoff;
@@ -913,9 +1192,7 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
     // room for the reversed columns of every pair: an alignment has at most n + m columns
     rev_off.resize((size_t)n_pairs + 1);
     rev_off[0] = 0;
-    for (uint32_t i = 0; i < n_pairs; ++i)
-      rev_off[i + 1] = rev_off[i] + (q_off[pair_q[i] + 1] - q_off[pair_q[i]]) +
-                       (ix.h_prot_off[pair_s[i] + 1] - ix.h_prot_off[pair_s[i]]);
+    for (uint32_t i = 0; i < n_pairs; ++i) rev_off[i + 1] = rev_off[i] + dim_n[i] + dim_m[i];
     if (ws.a_rev.ensure((size_t)rev_off[n_pairs] * 2 + 16) != KAAMER_OK ||
         ws.a_revoff.ensure((size_t)2 * n_pairs + 2) != KAAMER_OK) {
       cleanup();
@@ -925,25 +1202,34 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
     a.rev = reinterpret_cast<uint16_t *>(ws.a_rev.p);
     a.rev_off = ws.a_revoff.p;
   }
-  // Per chunk: the long pairs (one CTA each) on `st`, the rest (one warp each) on the second
-  // stream so that both kernels share the GPU; the chunk's scratch is reused only after both end.
+  // Per chunk: the long pairs (one CTA each) on `st`, the jobs and the single pairs (one warp each) on the
+  // second stream so that the kernels share the GPU; the chunk's scratch is reused only after all ended.
   cudaStream_t st2 = h->copy_stream;
-  uint32_t begin = 0;
+  const int pk_pcols = 32 * (pk_maxcw_used ? pk_maxcw_used : 4);
+  const size_t pk_smem = (size_t)ALN_WARPS * 2 * PK_PROF_ROWS * pk_pcols;
+  Chunk prev{0, 0, 0};
   profile_begin(h, st, 3);
-  for (uint32_t end : chunk_end) {
-    if (end > begin) {
-      const uint32_t big_end = n_big > begin ? (n_big < end ? n_big : end) : begin;
+  for (const Chunk &ch : chunks) {
+    if (ch.big_end > prev.big_end || ch.job_end > prev.job_end || ch.small_end > prev.small_end) {
       ACUDA(cudaEventRecord(h->chunk_ev[0], st));
       ACUDA(cudaStreamWaitEvent(st2, h->chunk_ev[0], 0));
-      if (big_end > begin) {
-        a.pairs = d_pairs + begin;
-        a.n_pairs = big_end - begin;
+      if (ch.big_end > prev.big_end) {
+        a.pairs = d_big + prev.big_end;
+        a.n_pairs = ch.big_end - prev.big_end;
         k_sw_affine_cta<<<a.n_pairs, BIG_WARPS * 32, BIG_SMEM, st>>>(a);
         h->prof_all_launches += 1;
       }
-      if (end > big_end) {
-        a.pairs = d_pairs + big_end;
-        a.n_pairs = end - big_end;
+      if (ch.job_end > prev.job_end) {
+        a.pairs = d_jobs + 2 * (size_t)prev.job_end;
+        a.n_pairs = ch.job_end - prev.job_end;  // jobs
+        const unsigned grid = (a.n_pairs + ALN_WARPS - 1) / ALN_WARPS;
+        if (pk_maxcw_used <= 8) k_sw_affine_pk<8><<<grid, ALN_WARPS * 32, pk_smem, st2>>>(a, pk_pcols);
+        else k_sw_affine_pk<16><<<grid, ALN_WARPS * 32, pk_smem, st2>>>(a, pk_pcols);
+        h->prof_all_launches += 1;
+      }
+      if (ch.small_end > prev.small_end) {
+        a.pairs = d_small + prev.small_end;
+        a.n_pairs = ch.small_end - prev.small_end;
         k_sw_affine<<<(a.n_pairs + ALN_WARPS - 1) / ALN_WARPS, ALN_WARPS * 32, WARP_SMEM, st2>>>(a);
         h->prof_all_launches += 1;
       }
@@ -951,7 +1237,7 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
       ACUDA(cudaEventRecord(h->chunk_ev[1], st2));
       ACUDA(cudaStreamWaitEvent(st, h->chunk_ev[1], 0));
     }
-    begin = end;
+    prev = ch;
   }
   profile_end(h, st);
   ACUDA(cudaMemcpyAsync(out, d_out, (size_t)n_pairs * sizeof(kaamer_aln), cudaMemcpyDeviceToHost, st));
@@ -1017,6 +1303,11 @@ void kaamer_gpu_free_aln_text(kaamer_aln_text *t) {
   if (!t) return;
   delete (HitsOwner *)t->_owner;
   delete t;
+}
+
+void kaamer_gpu_align_last_plan(uint32_t out[3]) {
+  if (!out) return;
+  for (int i = 0; i < 3; ++i) out[i] = t_last_plan[i];
 }
 
 int kaamer_gpu_default_align_model(kaamer_aln_model *out) {

@@ -431,6 +431,13 @@ class GpuIndex:
         check(_lib.lib().kaamer_gpu_default_align_model(C.byref(m)))
         return np.array(list(m.matrix), dtype=np.int8).reshape(26, 26), int(m.gap_open)
 
+    @staticmethod
+    def align_last_plan():
+        """(long pairs, single pairs, packed int16x2 jobs) of this thread's last `align` call"""
+        out = (C.c_uint32 * 3)()
+        _lib.lib().kaamer_gpu_align_last_plan(out)
+        return int(out[0]), int(out[1]), int(out[2])
+
     def set_align_model(self, matrix26=None, gap_open: int = -11) -> None:
         """Replace the DP model of `align` (explicit opt-in: the reference hard-wires BLOSUM62 / -11).
         matrix26[26, 26] in biogo order, row / column 0 = per-residue gap cost; None restores the default."""

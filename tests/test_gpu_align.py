@@ -227,3 +227,88 @@ def test_alignment_model_is_a_runtime_parameter(model):
                 assert (out["gap_openings"] == 0).all() and (out["length"] > 0).any()
     finally:
         o.set_align_model(None, 0)
+
+
+def _with_env(**kv):
+    import contextlib
+    import os
+
+    @contextlib.contextmanager
+    def cm():
+        old = {k: os.environ.get(k) for k in kv}
+        try:
+            for k, v in kv.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = str(v)
+            yield
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+
+    return cm()
+
+
+def test_packed_int16x2_jobs_equal_the_32bit_kernels_and_the_oracle(small_db):
+    """k_sw_affine_pk (two pairs per warp, int16x2 lanes, DPX) is the default for pairs it can hold; every column
+    width and the 32-bit kernels must give the same AlignmentResult and AlnString for every pair, and those
+    equal the oracle's"""
+    from kaamer_b200 import GpuIndex, SearchOptions, synth
+    from oracle import oracle as o
+
+    res, off, ids = small_db["res"], small_db["off"], small_db["ids"]
+    subjects = _subjects_by_id(res, off, ids)
+    q, qo, _ = synth.protein_queries(res, off, 300, config_index=1, stream=33)
+    queries = [q[int(qo[i]):int(qo[i + 1])].tobytes() for i in range(len(qo) - 1)]
+    with GpuIndex.build(res, off, ids, keep_proteins=True) as g:
+        r = g.search_proteins(q, qo, SearchOptions(min_kmatch=1, min_kratio=0.0, max_results=6))
+        pairs = [(i, int(s)) for i in range(r.n_rows) for s in r.subject[int(r.hit_off[i]):int(r.hit_off[i + 1])]]
+        assert len(pairs) > 400
+        pq, ps = [p[0] for p in pairs], [p[1] for p in pairs]
+        n_aa = g.dbstats()["NumberOfAA"]
+        with _with_env(KAAMER_ALIGN_PACKED=0):
+            ref, ref_text = g.align(q, qo, pq, ps, number_of_aa=n_aa, want_text=True)
+            assert g.align_last_plan()[2] == 0
+        _check(ref[:250], pairs[:250], queries, subjects, o.aln_params(n_aa), "32-bit kernels")
+        assert (ref["gap_openings"] > 0).sum() > 5 and (ref["length"] > 50).sum() > 100
+        for maxcw in (None, 4, 8, 12, 16):
+            with _with_env(KAAMER_ALIGN_PACKED=None, KAAMER_ALIGN_PK_MAXCW=maxcw):
+                out, text = g.align(q, qo, pq, ps, number_of_aa=n_aa, want_text=True)
+                big, single, jobs = g.align_last_plan()
+            assert jobs > len(pairs) // 4, (maxcw, big, single, jobs)
+            assert big + single + 2 * jobs == len(pairs)
+            for f in ref.dtype.names:
+                same = (out[f] == ref[f]) | ((out[f] != out[f]) & (ref[f] != ref[f]))  # NaN == NaN
+                assert same.all(), (maxcw, f, int(np.flatnonzero(~same)[0]), out[f][~same][:3], ref[f][~same][:3])
+            assert text == ref_text, maxcw
+        # an odd number of pairs, two pairs, one pair (never packed)
+        for n in (7, 2, 1):
+            out = g.align(q, qo, pq[:n], ps[:n], number_of_aa=n_aa)
+            assert out.tobytes() == ref[:n].tobytes() or all((out[f] == ref[f][:n]).all() for f in INT_FIELDS)
+        assert g.align_last_plan()[2] == 0
+
+
+def test_packed_jobs_on_the_edge_cases():
+    """the edge pair set (illegal letters, U / - / *, lower case, multi-block and long subjects, saturating W runs)
+    with the packed kernel taking pairs of up to 8 M cells: equal to the 32-bit kernels pair by pair"""
+    from kaamer_b200 import GpuIndex
+
+    res, off, ids, subjects, queries, q, qo, pairs = _edge_inputs()
+    pq, ps = [p[0] for p in pairs], [p[1] for p in pairs]
+    with GpuIndex.build(res, off, ids, keep_proteins=True) as g:
+        with _with_env(KAAMER_ALIGN_PACKED=0):
+            ref, ref_text = g.align(q, qo, pq, ps, number_of_aa=3_500_000, want_text=True)
+        for cells in (None, 8 << 20):
+            for maxcw in (8, 16):
+                with _with_env(KAAMER_ALIGN_PK_CELLS=cells, KAAMER_ALIGN_PK_MAXCW=maxcw):
+                    out, text = g.align(q, qo, pq, ps, number_of_aa=3_500_000, want_text=True)
+                    plan = g.align_last_plan()
+                assert plan[2] > 20, plan
+                for f in ref.dtype.names:
+                    same = (out[f] == ref[f]) | ((out[f] != out[f]) & (ref[f] != ref[f]))
+                    assert same.all(), (cells, maxcw, f, int(np.flatnonzero(~same)[0]))
+                assert text == ref_text

@@ -355,13 +355,22 @@ __device__ __forceinline__ void dp_block(const int8_t *prof, const int8_t *lidx,
   }
 }
 
-__device__ __forceinline__ uint32_t dir_at(const uint8_t *scratch, int n, int cw, int i, int j) {
+// tail_from: first column (0-based) of a last block of 4 columns per lane (packed jobs, align_packed.cuh
+// pk_geo), 0x7FFFFFFF when every block has cw columns per lane
+__device__ __forceinline__ uint32_t dir_at(const uint8_t *scratch, int n, int cw, int tail_from, int i, int j) {
   // cell (i, j), 1-based
-  const int col = j - 1, r = i - 1;
+  int col = j - 1;
+  const int r = i - 1;
+  size_t base = 0;
+  if (col >= tail_from) {
+    base = (size_t)(tail_from / (32 * cw)) * block_stride(n, cw);
+    col -= tail_from;
+    cw = 4;
+  }
   const int bw = 32 * cw;
   const int blk = col / bw, in = col - blk * bw;
   const int lane = in / cw, c = in - lane * cw;
-  return scratch[(size_t)blk * block_stride(n, cw) + ((size_t)(r + lane) * 32 + lane) * cw + c];
+  return scratch[base + (size_t)blk * block_stride(n, cw) + ((size_t)(r + lane) * 32 + lane) * cw + c];
 }
 
 // block profile: prof[a][col] = B62[a][s_col]; columns past the subject end score -100 so that
@@ -383,7 +392,8 @@ __device__ __forceinline__ void build_profile(int8_t *prof, const int8_t *b62, c
 // (diagonal, up or left) with ONE memory round trip; the path is then followed through
 // shuffles and a new window is fetched only when the layer changes or the window is used up.
 __device__ __forceinline__ void traceback_and_emit(const AlnArgs &a, const AlnPair &pr, const uint8_t *scratch,
-                                                   int nrows, const uint8_t *q, int n, const uint8_t *s, int cw, int best_s,
+                                                   int nrows, int tail_from, const uint8_t *q, int n, const uint8_t *s, int cw,
+                                                   int best_s,
                                                    uint32_t best_pos, bool bad, const int8_t *s_b62,
                                                    const int8_t *s_lidx, const int8_t *s_apos) {
   const unsigned lane = threadIdx.x & 31;
@@ -420,7 +430,7 @@ __device__ __forceinline__ void traceback_and_emit(const AlnArgs &a, const AlnPa
       const int wi = i - di * (int)lane, wj = j - dj * (int)lane;
       uint32_t F = 0, QA = 0, SB = 0;
       if (wi > 0 && wj > 0) {
-        F = dir_at(scratch, nrows, cw, wi, wj);
+        F = dir_at(scratch, nrows, cw, tail_from, wi, wj);
         QA = fix_u(q[wi - 1]);
         SB = fix_u(s[wj - 1]);
       }
@@ -589,15 +599,13 @@ __global__ void __launch_bounds__(ALN_WARPS * 32) k_sw_affine(AlnArgs a) {
     }
   }
   __syncwarp();
-  traceback_and_emit(a, pr, scratch, n, q, n, s, cw, best_s, best_pos, bad, s_b62, s_lidx, s_apos);
+  traceback_and_emit(a, pr, scratch, n, 0x7FFFFFFF, q, n, s, cw, best_s, best_pos, bad, s_b62, s_lidx, s_apos);
 }
 
 // ---- one warp per TWO pairs: int16x2 lanes, DPX (align_packed.cuh) ------------------------------
-// a.pairs holds 2 * a.n_pairs entries: job k = pairs (2k, 2k+1), same cw, traceback regions of the job's
-// geometry (rows = max n, columns = max m), the block-boundary column behind the second region.
-// MAXCW bounds the instantiated column widths (and so the registers: 4 CTAs per SM up to 8 columns per lane).
-template <int MAXCW>
-__global__ void __launch_bounds__(ALN_WARPS * 32, MAXCW <= 8 ? 4 : 2) k_sw_affine_pk(AlnArgs a, int pcols) {
+// a.pairs holds 2 * a.n_pairs entries: job k = pairs (2k, 2k+1), same cw (4 or 8), traceback regions of the
+// job's geometry (rows = max n, columns = max m, pk_geo), the block-boundary column behind the second region.
+__global__ void __launch_bounds__(ALN_WARPS * 32, 4) k_sw_affine_pk(AlnArgs a, int pcols) {
   extern __shared__ __align__(16) int8_t pk_prof[];  // [ALN_WARPS][2][PK_PROF_ROWS * pcols]
   __shared__ int8_t s_b62[26 * 32];
   __shared__ int8_t s_lidx[256];
@@ -620,41 +628,38 @@ __global__ void __launch_bounds__(ALN_WARPS * 32, MAXCW <= 8 ? 4 : 2) k_sw_affin
   badA = __any_sync(0xFFFFFFFFu, badA);
   badB = __any_sync(0xFFFFFFFFu, badB);
   const int N = nA > nB ? nA : nB, Mx = mA > mB ? mA : mB;  // the geometry the host sized the regions for
-  const int cw = (int)pa.cw, bw = 32 * cw;
+  const int cw = (int)pa.cw;
+  const PkGeo geo = pk_geo(Mx, cw);
+  const int tail_from = pk_tail_from(Mx, cw);
   uint8_t *scrA = a.scratch + pa.scratch, *scrB = a.scratch + pb.scratch;
   int bsA = 0, bsB = 0;
   uint32_t bpA = 0, bpB = 0;
   if (N > 0 && Mx > 0 && !(badA && badB)) {
-    const int nblk = (Mx + bw - 1) / bw;
+    const int nblk = geo.blocks();
     uint32_t *bnd = reinterpret_cast<uint32_t *>(scrB + pk_flags_bytes((uint64_t)N, (uint64_t)Mx, cw));  // in place: 3 x u32[N]
     int8_t *profA = pk_prof + (size_t)w * 2 * PK_PROF_ROWS * pcols, *profB = profA + (size_t)PK_PROF_ROWS * pcols;
+    // a pair with illegal letters: pad rows and pad columns only, nothing positive
+    const int nAd = badA ? 0 : nA, nBd = badB ? 0 : nB, mAd = badA ? 0 : mA, mBd = badB ? 0 : mB;
     PkBlockArgs g;
     g.profA = profA;
     g.profB = profB;
     g.pcols = pcols;
-    g.lidx = s_lidx;
-    g.qA = qA;
-    g.qB = qB;
-    g.nA = badA ? 0 : nA;  // a pair with illegal letters: pad rows and pad columns only, nothing positive
-    g.nB = badB ? 0 : nB;
     g.N = N;
     g.open2 = ((uint32_t)(uint16_t)(int16_t)a.open) * 0x00010001u;
     g.zero2 = a.zero_gap ? 0u : 0x00010001u;  // always 0 here (the packed path is the zero-gap-row model)
     for (int blk = 0; blk < nblk; ++blk) {
+      const int bcw = blk < geo.nfull ? cw : geo.tail_cw, bw = 32 * bcw;
+      const int col0 = blk * 32 * cw;  // every block before this one has cw columns per lane
       __syncwarp();
-      pk_build_profile(profA, pcols, s_b62, s_lidx, sA, badA ? 0 : mA, blk, bw, (int)lane);
-      pk_build_profile(profB, pcols, s_b62, s_lidx, sB, badB ? 0 : mB, blk, bw, (int)lane);
+      pk_build_profile(profA, pcols, s_b62, s_lidx, sA, mAd, col0, bw, (int)lane);
+      pk_build_profile(profB, pcols, s_b62, s_lidx, sB, mBd, col0, bw, (int)lane);
       __syncwarp();
       g.dirsA = scrA + (size_t)blk * block_stride(N, cw);
       g.dirsB = scrB + (size_t)blk * block_stride(N, cw);
       g.bnd_in = blk > 0 ? bnd : nullptr;
       g.bnd_out = blk + 1 < nblk ? bnd : nullptr;
-      if constexpr (MAXCW >= 16) {
-        if (cw == 16) dp_block_packed<16>(g, blk, bsA, bpA, bsB, bpB);
-        else if (cw == 12) dp_block_packed<12>(g, blk, bsA, bpA, bsB, bpB);
-      }
-      if (cw == 8) dp_block_packed<8>(g, blk, bsA, bpA, bsB, bpB);
-      else if (cw == 4) dp_block_packed<4>(g, blk, bsA, bpA, bsB, bpB);
+      if (bcw == 8) dp_block_packed<8>(g, s_lidx, qA, nAd, qB, nBd, col0, bsA, bpA, bsB, bpB);
+      else dp_block_packed<4>(g, s_lidx, qA, nAd, qB, nBd, col0, bsA, bpA, bsB, bpB);
     }
     // end cells: maximum score, then last in row-major order (larger i, then larger j)
     for (int o = 16; o > 0; o >>= 1) {
@@ -671,8 +676,8 @@ __global__ void __launch_bounds__(ALN_WARPS * 32, MAXCW <= 8 ? 4 : 2) k_sw_affin
     }
   }
   __syncwarp();
-  traceback_and_emit(a, pa, scrA, N, qA, nA, sA, cw, badA ? 0 : bsA, bpA, badA, s_b62, s_lidx, s_apos);
-  traceback_and_emit(a, pb, scrB, N, qB, nB, sB, cw, badB ? 0 : bsB, bpB, badB, s_b62, s_lidx, s_apos);
+  traceback_and_emit(a, pa, scrA, N, tail_from, qA, nA, sA, cw, badA ? 0 : bsA, bpA, badA, s_b62, s_lidx, s_apos);
+  traceback_and_emit(a, pb, scrB, N, tail_from, qB, nB, sB, cw, badB ? 0 : bsB, bpB, badB, s_b62, s_lidx, s_apos);
 }
 
 // ---- one CTA per pair (long pairs): the column blocks are pipelined over the warps --------------
@@ -756,7 +761,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 4) k_sw_affine_cta(AlnArgs a) 
       best_pos = op;
     }
   }
-  traceback_and_emit(a, pr, scratch, n, q, n, s, cw, best_s, best_pos, bad, s_b62, s_lidx, s_apos);
+  traceback_and_emit(a, pr, scratch, n, 0x7FFFFFFF, q, n, s, cw, best_s, best_pos, bad, s_b62, s_lidx, s_apos);
 }
 
 // ---- AlnString (align.go:69-103): one warp per pair turns the reversed columns into the three lines ----
@@ -820,14 +825,15 @@ static double single_work(uint64_t n, uint64_t m, int cw) {
 }
 
 // ---- packed jobs: two pairs per warp (k_sw_affine_pk) ---------------------------------------------
-// Instructions per wavefront step of dp_block_packed<CW>, counted in the SASS: 187 / 305 / 458 / 595 for
-// 4 / 8 / 12 / 16 columns per lane, i.e. ~50 + 34 per column for BOTH pairs (two single pairs: 2 x (66 + 23)).
-constexpr double PK_OVH = 50.0, PK_CELL = 34.0;
+// Instructions per wavefront step of dp_block_packed<CW>, counted in the SASS: ~187 / ~305 for 4 / 8 columns per
+// lane, i.e. ~50 + 32 per column for BOTH pairs (two single pairs: 2 x (66 + 23 per column)).  12 and 16 columns
+// per lane were built and measured: 187 registers, two CTAs per SM, 50 ms against 36 ms for the C5 batch.
+constexpr double PK_OVH = 50.0, PK_CELL = 32.0;
 constexpr double PK_ACCEPT = 0.9;  // a job must cost less than this share of its two pairs run one by one
 
 struct PackedConfig {
   bool on;
-  int maxcw;          // 4, 8, 12 or 16 columns per lane
+  int maxcw;          // 4 or 8 columns per lane
   uint64_t max_cells; // pairs below this many cells may be packed
   uint32_t max_min_dim;  // min(n, m) bound that keeps every DP value below PK_MAX_SCORE
 };
@@ -840,14 +846,14 @@ struct PkJob {
 };
 
 // Test / measurement hooks: KAAMER_ALIGN_PACKED=0 keeps every pair on the 32-bit kernels,
-// KAAMER_ALIGN_PK_MAXCW=4|8|12|16 bounds the columns per lane, KAAMER_ALIGN_PK_CELLS=<cells> lets pairs of up
+// KAAMER_ALIGN_PK_MAXCW=4|8 bounds the columns per lane, KAAMER_ALIGN_PK_CELLS=<cells> lets pairs of up
 // to that many cells be packed (default: below the one-CTA-per-pair threshold).
 static PackedConfig packed_config(const kaamer_aln_model &model, bool zero_gap) {
-  PackedConfig c{zero_gap, 16, BIG_CELLS, 0};
+  PackedConfig c{zero_gap, 8, BIG_CELLS, 0};
   if (const char *e = getenv("KAAMER_ALIGN_PACKED")) c.on = c.on && atoi(e) != 0;
   if (const char *e = getenv("KAAMER_ALIGN_PK_MAXCW")) {
     const int v = atoi(e);
-    if (v == 4 || v == 8 || v == 12 || v == 16) c.maxcw = v;
+    if (v == 4 || v == 8) c.maxcw = v;
   }
   if (const char *e = getenv("KAAMER_ALIGN_PK_CELLS")) {
     const long long v = atoll(e);
@@ -860,23 +866,20 @@ static PackedConfig packed_config(const kaamer_aln_model &model, bool zero_gap) 
   return c;
 }
 
-static int choose_cw_pk(uint64_t m, int maxcw) {
-  int best = 4;
-  double best_cost = 1e300;
-  for (int cw = 4; cw <= maxcw; cw += 4) {
-    const uint64_t bw = 32ull * cw, nblk = (m + bw - 1) / bw;
-    const double cost = (double)nblk * (PK_OVH + PK_CELL * cw);
-    if (cost < best_cost) {
-      best_cost = cost;
-      best = cw;
-    }
-  }
-  return best;
+// instructions per row of a job of `cols` columns: its blocks (pk_geo) x (overhead + per-column work)
+static double packed_row_work(uint64_t cols, int cw) {
+  const PkGeo g = pk_geo((int)cols, cw);
+  return (double)g.nfull * (PK_OVH + PK_CELL * cw) + (g.tail_cw ? PK_OVH + PK_CELL * 4 : 0.0);
 }
 
+static int choose_cw_pk(uint64_t m, int maxcw) {
+  if (maxcw < 8) return 4;
+  return packed_row_work(m, 8) <= packed_row_work(m, 4) ? 8 : 4;
+}
+
+// every block of a job sweeps all rows (+ 31 steps to fill and drain the wavefront)
 static double packed_work(uint64_t N, uint64_t Mx, int cw) {
-  const uint64_t bw = 32ull * cw, nblk = (Mx + bw - 1) / bw;
-  return (double)nblk * (double)(N + 31) * (PK_OVH + PK_CELL * cw);
+  return (double)(N + 31) * packed_row_work(Mx, cw);
 }
 
 // Pairs of similar geometry become jobs: the eligible pairs are sorted by (padded columns, rows) descending
@@ -893,7 +896,7 @@ static void plan_packed_jobs(const PackedConfig &pk, const std::vector<uint32_t>
     if (n < 1 || m < 1 || n > (uint32_t)PK_MAX_DIM || m > (uint32_t)PK_MAX_DIM) continue;
     if ((n < m ? n : m) > pk.max_min_dim || cost[i] >= pk.max_cells) continue;
     const int cw = choose_cw_pk(m, pk.maxcw);
-    const uint32_t bw = 32u * (uint32_t)cw, padded = (m + bw - 1) / bw * bw;  // <= 16384 + 511
+    const uint32_t padded = (uint32_t)pk_padded_cols(m, cw);  // <= 16384 + 255
     const uint32_t k = ((padded / 128u) << 14) | n;                          // 8 + 14 bits
     el.push_back(i);
     key.push_back(0x3FFFFFu - k);  // ascending sort of the complement = descending (padded, n)
@@ -1004,8 +1007,7 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `t` is a stack object
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_affine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WARP_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_affine_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_affine_pk<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ALN_WARPS * 2 * PK_PROF_ROWS * 256);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_affine_pk<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ALN_WARPS * 2 * PK_PROF_ROWS * 512);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_affine_pk, cudaFuncAttributeMaxDynamicSharedMemorySize, ALN_WARPS * 2 * PK_PROF_ROWS * 256);
     if (e != cudaSuccess) {
       set_error("alignment tables: %s", cudaGetErrorString(e));
       drop_text();
@@ -1223,8 +1225,7 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
         a.pairs = d_jobs + 2 * (size_t)prev.job_end;
         a.n_pairs = ch.job_end - prev.job_end;  // jobs
         const unsigned grid = (a.n_pairs + ALN_WARPS - 1) / ALN_WARPS;
-        if (pk_maxcw_used <= 8) k_sw_affine_pk<8><<<grid, ALN_WARPS * 32, pk_smem, st2>>>(a, pk_pcols);
-        else k_sw_affine_pk<16><<<grid, ALN_WARPS * 32, pk_smem, st2>>>(a, pk_pcols);
+        k_sw_affine_pk<<<grid, ALN_WARPS * 32, pk_smem, st2>>>(a, pk_pcols);
         h->prof_all_launches += 1;
       }
       if (ch.small_end > prev.small_end) {

@@ -5,8 +5,8 @@
 // pair A in the low 16 bits, pair B in the high 16 bits, updated by the sm_90+/sm_100 DPX instructions
 //     VIADDMNMX.S16x2[.RELU]   max(a + b, c[, 0]) per half            (__viaddmax_s16x2[_relu])
 //     VIMNMX.S16x2 R, P0, P1   max(a, b) per half + "a >= b" per half  (__vibmax_s16x2)
-// so a cell of BOTH pairs costs 9 score instructions + 10 flag instructions + 3 for the end cell instead of
-// 22 per pair.  Valid while every DP value fits 15 bits: the host takes this path only for the zero-gap-row
+// so a cell of BOTH pairs costs 10 score instructions + 10 flag instructions + 2 for the end cell instead of
+// 22 per pair.  Valid while every DP value fits a signed 16-bit half: the host takes this path only for the zero-gap-row
 // model and pairs with (largest matrix entry) x min(n, m) <= PK_MAX_SCORE; everything else keeps the 32-bit
 // kernels.  Rows / columns past the end of the shorter pair score PK_PAD_SCORE: they never influence a real
 // cell (dependencies run right / down) and never hold the maximum (they are <= maximum - 100).
@@ -29,7 +29,7 @@ constexpr int PK_PROF_ROWS = 27;  // 26 letters + the row of a query position pa
 constexpr int PK_PAD_ROW = 26;
 constexpr int PK_PAD_SCORE = -100;
 constexpr int PK_MAX_DIM = 16383;    // rows / columns per pair: row indices are packed 16-bit values, 0xFFFF = none
-constexpr int PK_MAX_SCORE = 16000;  // bound on any DP value of a packed pair
+constexpr int PK_MAX_SCORE = 32000;  // bound on any DP value of a packed pair
 
 PK_HD uint8_t pk_fix_u(uint8_t c) { return (c == 'u' || c == 'U') ? (uint8_t)'*' : c; }  // align.go:54-55
 
@@ -69,10 +69,38 @@ PK_HD uint32_t pk_ld_l2(const uint32_t *p) {
 #endif
 }
 
-// bytes of one pair's traceback region of a packed job: [nblk][rows + 31 steps][32 lanes][cw bytes]
+// Column blocks of a packed job.  cw = 4: blocks of 128 columns.  cw = 8: blocks of 256 columns, and a last
+// block of 128 columns (4 per lane) when at most 128 columns are left over -- a 350-column subject costs
+// 256 + 128 columns instead of 512.
+struct PkGeo {
+  int nfull;     // blocks of 32 * cw columns
+  int tail_cw;   // 0: no further block; 4: one more block of 128 columns
+  PK_HD int blocks() const { return nfull + (tail_cw ? 1 : 0); }
+};
+PK_HD PkGeo pk_geo(int cols, int cw) {
+  PkGeo g;
+  const int bw = 32 * cw;
+  g.nfull = cols / bw;
+  const int rem = cols - g.nfull * bw;
+  g.tail_cw = 0;
+  if (rem > 0) {
+    if (cw == 8 && rem <= 128) g.tail_cw = 4;
+    else g.nfull += 1;
+  }
+  return g;
+}
+PK_HD uint64_t pk_padded_cols(uint64_t cols, int cw) {
+  const PkGeo g = pk_geo((int)cols, cw);
+  return (uint64_t)g.nfull * 32ull * (uint64_t)cw + (g.tail_cw ? 128ull : 0ull);
+}
+// first column (0-based) of the 4-wide tail block, or "never"
+PK_HD int pk_tail_from(int cols, int cw) {
+  const PkGeo g = pk_geo(cols, cw);
+  return g.tail_cw ? g.nfull * 32 * cw : 0x7FFFFFFF;
+}
+// bytes of one pair's traceback region of a packed job: per block [rows + 31 steps][32 lanes][block cw bytes]
 PK_HD uint64_t pk_flags_bytes(uint64_t rows, uint64_t cols, int cw) {
-  const uint64_t bw = 32ull * (uint64_t)cw, nblk = (cols + bw - 1) / bw;
-  return (nblk * (rows + 31) * 32 * (uint64_t)cw + 255) & ~255ull;
+  return (pk_padded_cols(cols, cw) * (rows + 31) + 255) & ~255ull;
 }
 
 template <int V>
@@ -182,9 +210,6 @@ struct PkLane {
 struct PkBlockArgs {
   const int8_t *profA, *profB;  // block profiles [PK_PROF_ROWS][pcols] of the two subjects
   int pcols;
-  const int8_t *lidx;           // alphabet.Protein.LetterIndex()
-  const uint8_t *qA, *qB;       // query residues
-  int nA, nB;                   // rows each pair really has in the DP (0: pair with illegal letters)
   int N;                        // rows of the job = max over the two pairs (geometry of both traceback regions)
   uint32_t open2;               // SWAffine.GapOpen in both halves
   uint32_t zero2;               // 0, from a run-time value: kept in a register (a literal 0 is re-materialised per cell)
@@ -193,10 +218,20 @@ struct PkBlockArgs {
   uint32_t *bnd_out;
 };
 
+// profile rows of query position `row` of both pairs: row of pair A | row of pair B << 8 (PK_PAD_ROW past the
+// end of a pair; nA / nB = 0 for a pair with illegal letters)
+PK_HD uint32_t pk_query_rows(const int8_t *lidx, const uint8_t *qA, int nA, const uint8_t *qB, int nB, int row) {
+  const uint32_t a = row < nA ? (uint32_t)lidx[pk_fix_u(qA[row])] : (uint32_t)PK_PAD_ROW;
+  const uint32_t b = row < nB ? (uint32_t)lidx[pk_fix_u(qB[row])] : (uint32_t)PK_PAD_ROW;
+  return a | (b << 8);
+}
+
 // One wavefront step of one lane: row r = t - lane of this lane's CW columns, both pairs.
-// inM / inL / inB: pubM / pubL / pubB of lane - 1 after the previous step (warp shuffle on the device).
+// inM / inL / inB: pubM / pubL / pubB of lane - 1 after the previous step (warp shuffle on the device);
+// qi2 = pk_query_rows of row r (on the device the lanes load 32 rows at a time and pass them round by shuffle).
 template <int CW>
-PK_HD void pk_step(PkLane<CW> &s, const PkBlockArgs &g, int lane, int t, uint32_t inM, uint32_t inL, uint32_t inB) {
+PK_HD void pk_step(PkLane<CW> &s, const PkBlockArgs &g, int lane, int t, uint32_t inM, uint32_t inL, uint32_t inB,
+                   uint32_t qi2) {
   const int r = t - lane;
   const bool active = r >= 0 && r < g.N;
   if (lane == 0) {
@@ -210,17 +245,12 @@ PK_HD void pk_step(PkLane<CW> &s, const PkBlockArgs &g, int lane, int t, uint32_
   uint32_t diag = s.prevB;
   s.prevB = inB;
   if (!active) return;
-  const int qiA = r < g.nA ? (int)g.lidx[pk_fix_u(g.qA[r])] : PK_PAD_ROW;
-  const int qiB = r < g.nB ? (int)g.lidx[pk_fix_u(g.qB[r])] : PK_PAD_ROW;
+  const int qiA = (int)(qi2 & 0xFFu), qiB = (int)(qi2 >> 8);
   uint32_t pwA[CW / 4], pwB[CW / 4];
   {
     const int8_t *pa = g.profA + qiA * g.pcols + lane * CW;
     const int8_t *pb = g.profB + qiB * g.pcols + lane * CW;
-    if constexpr (CW == 16) {
-      const uint4 a = *reinterpret_cast<const uint4 *>(pa), b = *reinterpret_cast<const uint4 *>(pb);
-      pwA[0] = a.x, pwA[1] = a.y, pwA[2] = a.z, pwA[3] = a.w;
-      pwB[0] = b.x, pwB[1] = b.y, pwB[2] = b.z, pwB[3] = b.w;
-    } else if constexpr (CW == 8) {
+    if constexpr (CW == 8) {
       const uint2 a = *reinterpret_cast<const uint2 *>(pa), b = *reinterpret_cast<const uint2 *>(pb);
       pwA[0] = a.x, pwA[1] = a.y;
       pwB[0] = b.x, pwB[1] = b.y;
@@ -281,10 +311,7 @@ PK_HD void pk_step(PkLane<CW> &s, const PkBlockArgs &g, int lane, int t, uint32_
   {
     const uint32_t at = ((uint32_t)t * 32u + (uint32_t)lane) * (uint32_t)CW;
     uint32_t *da = reinterpret_cast<uint32_t *>(g.dirsA + at), *db = reinterpret_cast<uint32_t *>(g.dirsB + at);
-    if constexpr (CW == 16) {
-      *reinterpret_cast<uint4 *>(da) = make_uint4(fwA[0], fwA[1], fwA[2], fwA[3]);
-      *reinterpret_cast<uint4 *>(db) = make_uint4(fwB[0], fwB[1], fwB[2], fwB[3]);
-    } else if constexpr (CW == 8) {
+    if constexpr (CW == 8) {
       *reinterpret_cast<uint2 *>(da) = make_uint2(fwA[0], fwA[1]);
       *reinterpret_cast<uint2 *>(db) = make_uint2(fwB[0], fwB[1]);
     } else {
@@ -330,9 +357,9 @@ PK_HD void pk_block_end(const PkLane<CW> &s, int j0, int &sA, uint32_t &posA, in
 // block profile of one subject: prof[a][col] = matrix[a][s_col]; columns past the subject end and the row of
 // a query position past the end of its pair score PK_PAD_SCORE.  `lane` of 32 fills its columns.
 PK_HD void pk_build_profile(int8_t *prof, int pcols, const int8_t *b62, const int8_t *lidx, const uint8_t *s, int m,
-                            int blk, int bw, int lane) {
+                            int col0, int bw, int lane) {
   for (int col = lane; col < bw; col += 32) {
-    const int j = blk * bw + col;
+    const int j = col0 + col;
     const int sj = j < m ? (int)lidx[pk_fix_u(s[j])] : -1;
 #pragma unroll 1
     for (int aa = 0; aa < 26; ++aa) prof[aa * pcols + col] = sj >= 0 ? b62[aa * 32 + sj] : (int8_t)PK_PAD_SCORE;
@@ -341,21 +368,35 @@ PK_HD void pk_build_profile(int8_t *prof, int pcols, const int8_t *b62, const in
 }
 
 #if defined(__CUDACC__)
-// One column block (32 * CW subject columns) of both pairs swept over all rows by one warp.
+// One column block (32 * CW subject columns from column col0) of both pairs swept over all rows by one warp.
+// Query rows: every 32 steps each lane translates ONE query position of both pairs (residue -> profile row);
+// lane l needs row t - l at step t, which is held by lane (t - l) & 31 of the current or the previous group.
 template <int CW>
-__device__ __forceinline__ void dp_block_packed(const PkBlockArgs &g, int blk, int &sA, uint32_t &posA, int &sB,
+__device__ __forceinline__ void dp_block_packed(const PkBlockArgs &g, const int8_t *lidx, const uint8_t *qA, int nA,
+                                                const uint8_t *qB, int nB, int col0, int &sA, uint32_t &posA, int &sB,
                                                 uint32_t &posB) {
   const int lane = (int)(threadIdx.x & 31u);
   PkLane<CW> s;
   s.init();
+  const uint32_t pad2 = (uint32_t)PK_PAD_ROW | ((uint32_t)PK_PAD_ROW << 8);
+  uint32_t q_prev = pad2, q_cur = pk_query_rows(lidx, qA, nA, qB, nB, lane),
+           q_next = pk_query_rows(lidx, qA, nA, qB, nB, 32 + lane);
   const int steps = g.N + 31;
   for (int t = 0; t < steps; ++t) {
+    if ((t & 31) == 0 && t > 0) {
+      q_prev = q_cur;
+      q_cur = q_next;
+      q_next = pk_query_rows(lidx, qA, nA, qB, nB, (t & ~31) + 32 + lane);
+    }
+    const int r = t - lane;
+    const uint32_t from_cur = __shfl_sync(0xFFFFFFFFu, q_cur, r & 31), from_prev = __shfl_sync(0xFFFFFFFFu, q_prev, r & 31);
+    const uint32_t qi2 = (r >> 5) == (t >> 5) ? from_cur : from_prev;
     const uint32_t inM = __shfl_up_sync(0xFFFFFFFFu, s.pubM, 1);
     const uint32_t inL = __shfl_up_sync(0xFFFFFFFFu, s.pubL, 1);
     const uint32_t inB = __shfl_up_sync(0xFFFFFFFFu, s.pubB, 1);
-    pk_step<CW>(s, g, lane, t, inM, inL, inB);
+    pk_step<CW>(s, g, lane, t, inM, inL, inB, qi2);
   }
-  pk_block_end<CW>(s, blk * 32 * CW + lane * CW, sA, posA, sB, posB);
+  pk_block_end<CW>(s, col0 + lane * CW, sA, posA, sB, posB);
 }
 #endif
 

@@ -59,8 +59,13 @@ static Ref scalar_dp(const std::vector<uint8_t> &q, const std::vector<uint8_t> &
   return R;
 }
 
+struct Rows {
+  const uint8_t *qA, *qB;
+  int nA, nB;
+};
+
 template <int CW>
-static void emulate_block(const PkBlockArgs &g, int blk, int &sA, uint32_t &pA, int &sB, uint32_t &pB) {
+static void emulate_block(const PkBlockArgs &g, const Rows &q, int col0, int &sA, uint32_t &pA, int &sB, uint32_t &pB) {
   static PkLane<CW> st[32];
   for (int l = 0; l < 32; ++l) st[l].init();
   const int steps = g.N + 31;
@@ -69,55 +74,70 @@ static void emulate_block(const PkBlockArgs &g, int blk, int &sA, uint32_t &pA, 
     for (int l = 0; l < 32; ++l) pm[l] = st[l].pubM, pl[l] = st[l].pubL, pb[l] = st[l].pubB;
     for (int l = 0; l < 32; ++l) {
       const int src = l ? l - 1 : 0;  // __shfl_up_sync: lane 0 reads itself
-      pk_step<CW>(st[l], g, l, t, pm[src], pl[src], pb[src]);
+      const int r = t - l;  // (the kernel passes the rows round by shuffle; a row outside [0, N) is never used)
+      const uint32_t qi2 = r >= 0 ? pk_query_rows(LIDX, q.qA, q.nA, q.qB, q.nB, r) : 0x1A1Au;
+      pk_step<CW>(st[l], g, l, t, pm[src], pl[src], pb[src], qi2);
     }
   }
   // the kernel's butterfly reduction: higher score, then larger position
   for (int l = 0; l < 32; ++l) {
     int a = 0, b = 0;
     uint32_t ap = 0, bp = 0;
-    pk_block_end<CW>(st[l], blk * 32 * CW + l * CW, a, ap, b, bp);
+    pk_block_end<CW>(st[l], col0 + l * CW, a, ap, b, bp);
     if (a > sA || (a == sA && ap > pA)) sA = a, pA = ap;
     if (b > sB || (b == sB && bp > pB)) sB = b, pB = bp;
   }
 }
 
-static uint8_t dir_at(const uint8_t *scratch, int nrows, int cw, int i, int j) {  // align.cu dir_at
-  const int col = j - 1, r = i - 1, bw = 32 * cw;
-  const int blk = col / bw, in = col - blk * bw, lane = in / cw, c = in - lane * cw;
-  return scratch[(size_t)blk * ((size_t)(nrows + 31) * 32 * cw) + ((size_t)(r + lane) * 32 + lane) * cw + c];
+static uint8_t dir_at(const uint8_t *scratch, int nrows, int cw, int tail_from, int i, int j) {  // align.cu dir_at
+  int col = j - 1;
+  const int r = i - 1;
+  size_t base = 0;
+  if (col >= tail_from) {
+    base = (size_t)(tail_from / (32 * cw)) * ((size_t)(nrows + 31) * 32 * cw);
+    col -= tail_from;
+    cw = 4;
+  }
+  const int bw = 32 * cw, blk = col / bw, in = col - blk * bw, lane = in / cw, c = in - lane * cw;
+  return scratch[base + (size_t)blk * ((size_t)(nrows + 31) * 32 * cw) + ((size_t)(r + lane) * 32 + lane) * cw + c];
 }
 
 static long run_job(const std::vector<uint8_t> &qA, const std::vector<uint8_t> &sA, const std::vector<uint8_t> &qB,
                     const std::vector<uint8_t> &sB, bool badB, int cw, int open) {
   const int nA = (int)qA.size(), mA = (int)sA.size(), nB = (int)qB.size(), mB = (int)sB.size();
-  const int N = std::max(nA, nB), Mx = std::max(mA, mB), bw = 32 * cw, nblk = (Mx + bw - 1) / bw, pcols = 512;
+  const int N = std::max(nA, nB), Mx = std::max(mA, mB), pcols = 256;
+  const PkGeo geo = pk_geo(Mx, cw);
+  const int nblk = geo.blocks(), tail_from = pk_tail_from(Mx, cw);
   const size_t fb = (size_t)pk_flags_bytes(N, Mx, cw);
   std::vector<uint8_t> regA(fb + 64, 0xEE), regB(fb + 64, 0xEE);
   std::vector<uint32_t> bnd((size_t)3 * N + 8, 0xDEADBEEFu);
-  alignas(16) static int8_t profA[PK_PROF_ROWS * 512], profB[PK_PROF_ROWS * 512];
+  alignas(16) static int8_t profA[PK_PROF_ROWS * 256], profB[PK_PROF_ROWS * 256];
   int bsA = 0, bsB = 0;
   uint32_t bpA = 0, bpB = 0;
   const int mBd = badB ? 0 : mB, nBd = badB ? 0 : nB;
+  const Rows rows{qA.data(), qB.data(), nA, nBd};
   for (int blk = 0; blk < nblk; ++blk) {
+    const int bcw = blk < geo.nfull ? cw : geo.tail_cw, bw = 32 * bcw, col0 = blk * 32 * cw;
     memset(profA, 0x55, sizeof profA);
     memset(profB, 0x55, sizeof profB);
     for (int l = 0; l < 32; ++l) {
-      pk_build_profile(profA, pcols, B62, LIDX, sA.data(), mA, blk, bw, l);
-      pk_build_profile(profB, pcols, B62, LIDX, sB.data(), mBd, blk, bw, l);
+      pk_build_profile(profA, pcols, B62, LIDX, sA.data(), mA, col0, bw, l);
+      pk_build_profile(profB, pcols, B62, LIDX, sB.data(), mBd, col0, bw, l);
     }
     PkBlockArgs g{};
-    g.profA = profA, g.profB = profB, g.pcols = pcols, g.lidx = LIDX;
-    g.qA = qA.data(), g.qB = qB.data(), g.nA = nA, g.nB = nBd, g.N = N;
+    g.profA = profA, g.profB = profB, g.pcols = pcols, g.N = N;
     g.open2 = ((uint32_t)(uint16_t)(int16_t)open) * 0x00010001u;
+    g.zero2 = 0u;
     g.dirsA = regA.data() + (size_t)blk * ((size_t)(N + 31) * 32 * cw);
     g.dirsB = regB.data() + (size_t)blk * ((size_t)(N + 31) * 32 * cw);
     g.bnd_in = blk > 0 ? bnd.data() : nullptr;
     g.bnd_out = blk + 1 < nblk ? bnd.data() : nullptr;
-    if (cw == 16) emulate_block<16>(g, blk, bsA, bpA, bsB, bpB);
-    else if (cw == 12) emulate_block<12>(g, blk, bsA, bpA, bsB, bpB);
-    else if (cw == 8) emulate_block<8>(g, blk, bsA, bpA, bsB, bpB);
-    else emulate_block<4>(g, blk, bsA, bpA, bsB, bpB);
+    if (bcw == 8) emulate_block<8>(g, rows, col0, bsA, bpA, bsB, bpB);
+    else emulate_block<4>(g, rows, col0, bsA, bpA, bsB, bpB);
+  }
+  if (regA[fb] != 0xEE || regB[fb] != 0xEE) {
+    printf("traceback region overrun (cw %d, %d x %d)\n", cw, N, Mx);
+    return 1;
   }
   long bad = 0;
   auto check = [&](const char *name, const std::vector<uint8_t> &q, const std::vector<uint8_t> &s,
@@ -135,10 +155,10 @@ static long run_job(const std::vector<uint8_t> &qA, const std::vector<uint8_t> &
     long cells_bad = 0;
     for (int i = 1; i <= n; ++i)
       for (int j = 1; j <= m; ++j)
-        if (dir_at(reg.data(), N, cw, i, j) != R.f[(size_t)(i - 1) * m + (j - 1)]) {
+        if (dir_at(reg.data(), N, cw, tail_from, i, j) != R.f[(size_t)(i - 1) * m + (j - 1)]) {
           if (cells_bad++ < 3)
             printf("%s (%d x %d, cw %d): cell (%d, %d) flags %02x, expected %02x\n", name, n, m, cw, i, j,
-                   dir_at(reg.data(), N, cw, i, j), R.f[(size_t)(i - 1) * m + (j - 1)]);
+                   dir_at(reg.data(), N, cw, tail_from, i, j), R.f[(size_t)(i - 1) * m + (j - 1)]);
         }
     bad += cells_bad;
   };
@@ -181,9 +201,8 @@ int main(int argc, char **argv) {
     return o;
   };
   long bad = 0, cells = 0;
-  const int cws[4] = {4, 8, 12, 16};
   for (int k = 0; k < jobs; ++k) {
-    const int cw = cws[k % 4];
+    const int cw = k % 3 == 1 ? 4 : 8;  // 8: blocks of 256 columns + a 128-column tail block when that is enough
     const int lenA = 1 + (int)(rng() % (k % 7 == 0 ? 1300 : 420)), lenB = 1 + (int)(rng() % (k % 5 == 0 ? 900 : 420));
     auto baseA = rnd(lenA), baseB = rnd(lenB);
     auto qA = k % 3 ? mutate(baseA, 0.25, 0.03) : rnd(1 + (int)(rng() % 300));

@@ -275,7 +275,7 @@ def test_packed_int16x2_jobs_equal_the_32bit_kernels_and_the_oracle(small_db):
             assert g.align_last_plan()[2] == 0
         _check(ref[:250], pairs[:250], queries, subjects, o.aln_params(n_aa), "32-bit kernels")
         assert (ref["gap_openings"] > 0).sum() > 5 and (ref["length"] > 50).sum() > 100
-        for maxcw in (None, 4, 8, 12, 16):
+        for maxcw in (None, 4, 8):
             with _with_env(KAAMER_ALIGN_PACKED=None, KAAMER_ALIGN_PK_MAXCW=maxcw):
                 out, text = g.align(q, qo, pq, ps, number_of_aa=n_aa, want_text=True)
                 big, single, jobs = g.align_last_plan()
@@ -303,7 +303,7 @@ def test_packed_jobs_on_the_edge_cases():
         with _with_env(KAAMER_ALIGN_PACKED=0):
             ref, ref_text = g.align(q, qo, pq, ps, number_of_aa=3_500_000, want_text=True)
         for cells in (None, 8 << 20):
-            for maxcw in (8, 16):
+            for maxcw in (4, 8):
                 with _with_env(KAAMER_ALIGN_PK_CELLS=cells, KAAMER_ALIGN_PK_MAXCW=maxcw):
                     out, text = g.align(q, qo, pq, ps, number_of_aa=3_500_000, want_text=True)
                     plan = g.align_last_plan()

@@ -17,10 +17,8 @@ from kaamer_b200.makedb import fasta_protein_ids  # noqa: E402
 SETTINGS = [
     {"KAAMER_ALIGN_PACKED": "0"},
     {},
-    {"KAAMER_ALIGN_PK_MAXCW": "8"},
-    {"KAAMER_ALIGN_PK_MAXCW": "12"},
-    {"KAAMER_ALIGN_PK_CELLS": str(8 << 20)},
-    {"KAAMER_ALIGN_PK_CELLS": str(8 << 20), "KAAMER_ALIGN_PK_MAXCW": "8"},
+    {"KAAMER_ALIGN_PK_MAXCW": "4"},
+    {"KAAMER_ALIGN_PK_CELLS": str(4 << 20)},
 ]
 
 
@@ -30,12 +28,15 @@ def main():
     ids = fasta_protein_ids(len(off) - 1)
     q, qo, _ = synth.protein_queries(res, off, nq, config_index=3, stream=100)
     keys = sorted({k for s in SETTINGS for k in s})
+    only = os.environ.get("C5_SETTINGS")  # e.g. "0,2": indices into SETTINGS
+    todo = [SETTINGS[int(i)] for i in only.split(",")] if only else SETTINGS
+    steps = int(os.environ.get("C5_STEPS", 3))
     with GpuIndex.build(res, off, ids, keep_proteins=True) as g:
-        for s in SETTINGS:
+        for s in todo:
             for k in keys:
                 os.environ.pop(k, None)
             os.environ.update(s)
-            line = bench_stages.c5_on(g, res, off, ids, q, qo, steps=3, warmup=1, cpu_pairs=400)
+            line = bench_stages.c5_on(g, res, off, ids, q, qo, steps=steps, warmup=1, cpu_pairs=400)
             line["env"] = s
             print(json.dumps(line), flush=True)
 

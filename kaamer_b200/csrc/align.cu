@@ -389,8 +389,9 @@ __device__ __forceinline__ void build_profile(int8_t *prof, const int8_t *b62, c
 
 // Traceback + the post-processing of align.go:72-157, executed by one whole warp: the 32 lanes
 // fetch a window of 32 traceback bytes (and residues) ahead of the path in its current direction
-// (diagonal, up or left) with ONE memory round trip; the path is then followed through
-// shuffles and a new window is fetched only when the layer changes or the window is used up.
+// (diagonal, up or left) with ONE memory round trip.  A diagonal run is consumed whole -- votes find its end,
+// the statistics are population counts and one warp sum --, gap runs are followed cell by cell through shuffles;
+// a new window is fetched when the layer changes or the window is used up.
 __device__ __forceinline__ void traceback_and_emit(const AlnArgs &a, const AlnPair &pr, const uint8_t *scratch,
                                                    int nrows, int tail_from, const uint8_t *q, int n, const uint8_t *s, int cw,
                                                    int best_s,
@@ -429,45 +430,57 @@ __device__ __forceinline__ void traceback_and_emit(const AlnArgs &a, const AlnPa
       const int di = layer == 2 ? 0 : 1, dj = layer == 1 ? 0 : 1;
       const int wi = i - di * (int)lane, wj = j - dj * (int)lane;
       uint32_t F = 0, QA = 0, SB = 0;
-      if (wi > 0 && wj > 0) {
+      const bool inb = wi > 0 && wj > 0;
+      if (inb) {
         F = dir_at(scratch, nrows, cw, tail_from, wi, wj);
         QA = fix_u(q[wi - 1]);
         SB = fix_u(s[wj - 1]);
+      }
+      if (layer == 0) {
+        // The diagonal run inside this window, all its cells at once.  Cell k (lane k) is consumed when the cells
+        // before it are and it lies inside the table, its M is not 0 and -- for k > 0 -- the path enters it in
+        // layer M: lay = layer of the predecessor stored in the byte (0 / 1 / 2 from the 32-bit kernels; the
+        // packed kernel stores the two raw comparisons, so 3 also means L).  Cell 31 is left to the next window.
+        uint32_t lay = F & 3u;
+        lay = lay > 2u ? 2u : lay;
+        const bool stop = (F & 4u) != 0;
+        const bool ok = inb && !stop && (lane == 0 || lay == 0u) && lane < 31;
+        const uint32_t okm = __ballot_sync(0xFFFFFFFFu, ok), inbm = __ballot_sync(0xFFFFFFFFu, inb);
+        const int kf = __ffs((int)~okm) - 1;  // first cell that is not consumed: 0 .. 31
+        if (kf > 0) {
+          open_seg(0);
+          const bool mine = (int)lane < kf;
+          const bool eq = QA == SB;
+          int v = 0;
+          bool sim = false;
+          if (mine) {
+            v = s_b62[s_lidx[QA] * 32 + s_lidx[SB]];
+            sim = eq || s_b62[s_apos[SB] * 32 + s_apos[QA]] > 0;  // GetAlnScoreAA (align.go:91)
+            if (rev) rev[aln_len + (int)lane] = (uint16_t)(QA | (SB << 8));
+          }
+          cur_score += __reduce_add_sync(0xFFFFFFFFu, v);
+          identity += (float)__popc(__ballot_sync(0xFFFFFFFFu, mine && eq));  // align.go:82-86 (counts: exact in float32)
+          similarity += (float)__popc(__ballot_sync(0xFFFFFFFFu, sim));
+          mismatches += __popc(__ballot_sync(0xFFFFFFFFu, mine && !eq && SB != '-' && QA != '-'));  // align.go:88-90
+          nb_pos += (float)kf;
+          cur_lq += kf;
+          cur_ls += kf;
+          aln_len += kf;
+          i -= kf;
+          j -= kf;
+        }
+        // why the run ended at cell kf: outside the table, the path turns into U / L there, or its M is 0
+        const uint32_t lay_f = __shfl_sync(0xFFFFFFFFu, lay, kf);
+        if (kf > 0 && !((inbm >> kf) & 1u)) done = true;
+        else if (kf > 0 && lay_f != 0u) layer = (int)lay_f;
+        else if (kf < 31) done = true;
+        continue;
       }
       const int layer0 = layer;
       for (int k = 0; k < 31; ++k) {  // window cell k == current cell (i, j); k+1 stays inside the window
         const uint32_t f = __shfl_sync(0xFFFFFFFFu, F, k);
         const uint32_t ca = __shfl_sync(0xFFFFFFFFu, QA, k), cb = __shfl_sync(0xFFFFFFFFu, SB, k);
-        if (layer == 0) {
-          if (f & 4u) {
-            done = true;
-            break;
-          }
-          open_seg(0);
-          if (rev && lane == 0) rev[aln_len] = (uint16_t)(ca | (cb << 8));
-          cur_score += s_b62[s_lidx[ca] * 32 + s_lidx[cb]];
-          cur_lq++;
-          cur_ls++;
-          if (cb == ca) {  // align.go:82-86
-            identity += 1.f;
-            similarity += 1.f;
-          } else {
-            if (cb != '-' && ca != '-') mismatches += 1;                      // align.go:88-90
-            if (s_b62[s_apos[cb] * 32 + s_apos[ca]] > 0) similarity += 1.f;  // GetAlnScoreAA (:91)
-          }
-          nb_pos += 1.f;
-          aln_len++;
-          --i;
-          --j;
-          if (i == 0 || j == 0) {
-            done = true;
-            break;
-          }
-          // layer of the predecessor: 0 / 1 / 2 in the bytes of the 32-bit kernels; the packed kernel stores the two
-          // raw comparisons (bit 0: U beats M, bit 1: L beats both), so 3 also means L
-          layer = (int)(__shfl_sync(0xFFFFFFFFu, F, k + 1) & 3u);
-          layer = layer > 2 ? 2 : layer;
-        } else if (layer == 1) {
+        if (layer == 1) {
           open_seg(1);
           if (rev && lane == 0) rev[aln_len] = (uint16_t)(ca | ('-' << 8));
           cur_score += s_b62[s_lidx[ca] * 32];  // the model's gap cost of this query residue (0 by default)
@@ -508,7 +521,7 @@ __device__ __forceinline__ void traceback_and_emit(const AlnArgs &a, const AlnPa
             break;
           }
         }
-        if (layer != layer0) break;  // the path turned: fetch a window in the new direction
+        if (layer != layer0) break;  // the gap closed: fetch a window along the diagonal
       }
     }
     flush();

@@ -31,6 +31,7 @@
 
 #include "internal.cuh"
 #include "align_packed.cuh"
+#include "align_plan.hpp"
 
 namespace kaamer {
 
@@ -104,14 +105,6 @@ static void make_tables(AlnTables *t, const kaamer_aln_model *model) {
     t->aa_pos[c] = (int8_t)i;
   }
 }
-
-struct AlnPair {
-  uint32_t out_index;  // position in the caller's pair list
-  uint32_t q;          // query index
-  uint32_t s;          // subject protein id
-  uint32_t cw;         // columns per lane (4 or 8)
-  uint64_t scratch;    // byte offset of the pair's traceback region
-};
 
 struct AlnArgs {
   const uint8_t *q_res;
@@ -803,161 +796,6 @@ __global__ void __launch_bounds__(128) k_aln_text(const AlnTables *t, const kaam
   }
 }
 
-// ---------------------------------------------------------------------------------------
-constexpr uint64_t BIG_CELLS = 2ull << 20;  // pairs at least this large get a whole CTA
-
-// columns per lane of the warp-per-pair kernel: the cost of a pair is
-// blocks x (rows + 31) x (per-step overhead + CW x per-cell work), ~40 and ~22.5 instructions
-static int choose_cw(uint64_t m) {
-  int best = 4;
-  double best_cost = 1e300;
-  for (int cw = 4; cw <= 16; cw += 4) {
-    const uint64_t bw = 32ull * cw, nblk = (m + bw - 1) / bw;
-    const double cost = (double)nblk * (40.0 + 22.5 * cw);
-    if (cost < best_cost) {
-      best_cost = cost;
-      best = cw;
-    }
-  }
-  return best;
-}
-
-static uint64_t pair_scratch_bytes(uint64_t n, uint64_t m, int cw, bool big) {
-  const uint64_t bw = 32ull * cw;
-  const uint64_t nblk = (m + bw - 1) / bw;
-  // traceback bytes + boundary columns (one per block in the pipelined kernel, one in place otherwise)
-  uint64_t b = nblk * (n + 31) * 32 * cw + (big ? nblk : 1) * 3 * 4 * n;
-  return (b + 255) & ~255ull;
-}
-
-// estimated warp instructions of one pair in the one-warp-per-pair kernel: instructions per wavefront step counted
-// in the SASS of dp_block<CW> (158 / 245 / 341 / 435 for 4 / 8 / 12 / 16 columns per lane)
-static double single_work(uint64_t n, uint64_t m, int cw) {
-  const uint64_t bw = 32ull * cw, nblk = (m + bw - 1) / bw;
-  return (double)nblk * (double)(n + 31) * (66.0 + 23.0 * cw);
-}
-
-// ---- packed jobs: two pairs per warp (k_sw_affine_pk) ---------------------------------------------
-// Instructions per wavefront step of dp_block_packed<CW>, counted in the SASS: ~187 / ~305 for 4 / 8 columns per
-// lane, i.e. ~50 + 32 per column for BOTH pairs (two single pairs: 2 x (66 + 23 per column)).  12 and 16 columns
-// per lane were built and measured: 187 registers, two CTAs per SM, 50 ms against 36 ms for the C5 batch.
-constexpr double PK_OVH = 50.0, PK_CELL = 32.0;
-constexpr double PK_ACCEPT = 0.9;  // a job must cost less than this share of its two pairs run one by one
-
-struct PackedConfig {
-  bool on;
-  int maxcw;          // 4 or 8 columns per lane
-  uint64_t max_cells; // pairs below this many cells may be packed
-  uint32_t max_min_dim;  // min(n, m) bound that keeps every DP value below PK_MAX_SCORE
-};
-
-struct PkJob {
-  uint32_t a, b;  // pair indices
-  int cw;
-  uint32_t N, Mx;  // rows / columns of the job
-  double work;
-};
-
-// Test / measurement hooks: KAAMER_ALIGN_PACKED=0 keeps every pair on the 32-bit kernels,
-// KAAMER_ALIGN_PK_MAXCW=4|8 bounds the columns per lane, KAAMER_ALIGN_PK_CELLS=<cells> lets pairs of up
-// to that many cells be packed (default: below the one-CTA-per-pair threshold).
-static PackedConfig packed_config(const kaamer_aln_model &model, bool zero_gap) {
-  PackedConfig c{zero_gap, 8, BIG_CELLS, 0};
-  if (const char *e = getenv("KAAMER_ALIGN_PACKED")) c.on = c.on && atoi(e) != 0;
-  if (const char *e = getenv("KAAMER_ALIGN_PK_MAXCW")) {
-    const int v = atoi(e);
-    if (v == 4 || v == 8) c.maxcw = v;
-  }
-  if (const char *e = getenv("KAAMER_ALIGN_PK_CELLS")) {
-    const long long v = atoll(e);
-    if (v > 0) c.max_cells = (uint64_t)v;
-  }
-  int max_entry = 1;
-  for (int i = 1; i < 26; ++i)
-    for (int j = 1; j < 26; ++j) max_entry = model.matrix[i * 26 + j] > max_entry ? model.matrix[i * 26 + j] : max_entry;
-  c.max_min_dim = (uint32_t)(PK_MAX_SCORE / max_entry);
-  return c;
-}
-
-// instructions per row of a job of `cols` columns: its blocks (pk_geo) x (overhead + per-column work)
-static double packed_row_work(uint64_t cols, int cw) {
-  const PkGeo g = pk_geo((int)cols, cw);
-  return (double)g.nfull * (PK_OVH + PK_CELL * cw) + (g.tail_cw ? PK_OVH + PK_CELL * 4 : 0.0);
-}
-
-static int choose_cw_pk(uint64_t m, int maxcw) {
-  if (maxcw < 8) return 4;
-  return packed_row_work(m, 8) <= packed_row_work(m, 4) ? 8 : 4;
-}
-
-// every block of a job sweeps all rows (+ 31 steps to fill and drain the wavefront)
-static double packed_work(uint64_t N, uint64_t Mx, int cw) {
-  return (double)(N + 31) * packed_row_work(Mx, cw);
-}
-
-// Pairs of similar geometry become jobs: the eligible pairs are sorted by (padded columns, rows) descending
-// (two counting-sort passes) and neighbours are joined when the job is cheaper than the two pairs run singly.
-// The jobs come out ordered by estimated work, largest first.
-static void plan_packed_jobs(const PackedConfig &pk, const std::vector<uint32_t> &dim_n, const std::vector<uint32_t> &dim_m,
-                             const std::vector<uint64_t> &cost, std::vector<PkJob> &jobs, std::vector<uint8_t> &in_job) {
-  const uint32_t n_pairs = (uint32_t)dim_n.size();
-  std::vector<uint32_t> el, key;
-  el.reserve(n_pairs);
-  key.reserve(n_pairs);
-  for (uint32_t i = 0; i < n_pairs; ++i) {
-    const uint32_t n = dim_n[i], m = dim_m[i];
-    if (n < 1 || m < 1 || n > (uint32_t)PK_MAX_DIM || m > (uint32_t)PK_MAX_DIM) continue;
-    if ((n < m ? n : m) > pk.max_min_dim || cost[i] >= pk.max_cells) continue;
-    const int cw = choose_cw_pk(m, pk.maxcw);
-    const uint32_t padded = (uint32_t)pk_padded_cols(m, cw);  // <= 16384 + 255
-    const uint32_t k = ((padded / 128u) << 14) | n;                          // 8 + 14 bits
-    el.push_back(i);
-    key.push_back(0x3FFFFFu - k);  // ascending sort of the complement = descending (padded, n)
-  }
-  const uint32_t ne = (uint32_t)el.size();
-  if (ne < 2) return;
-  std::vector<uint32_t> el2(ne), key2(ne);
-  for (int pass = 0; pass < 2; ++pass) {
-    const int shift = pass * 11;
-    uint32_t cnt[2049] = {0};
-    for (uint32_t x = 0; x < ne; ++x) cnt[((key[x] >> shift) & 2047u) + 1]++;
-    for (int b = 0; b < 2048; ++b) cnt[b + 1] += cnt[b];
-    for (uint32_t x = 0; x < ne; ++x) {
-      const uint32_t at = cnt[(key[x] >> shift) & 2047u]++;
-      el2[at] = el[x];
-      key2[at] = key[x];
-    }
-    el.swap(el2);
-    key.swap(key2);
-  }
-  std::vector<PkJob> raw;
-  raw.reserve(ne / 2);
-  double max_work = 1.0;
-  for (uint32_t x = 0; x + 1 < ne;) {
-    const uint32_t A = el[x], B = el[x + 1];
-    const uint32_t N = dim_n[A] > dim_n[B] ? dim_n[A] : dim_n[B], Mx = dim_m[A] > dim_m[B] ? dim_m[A] : dim_m[B];
-    const int cw = choose_cw_pk(Mx, pk.maxcw);
-    const double w = packed_work(N, Mx, cw);
-    const double singly = single_work(dim_n[A], dim_m[A], choose_cw(dim_m[A])) + single_work(dim_n[B], dim_m[B], choose_cw(dim_m[B]));
-    if (w <= PK_ACCEPT * singly) {
-      raw.push_back(PkJob{A, B, cw, N, Mx, w});
-      in_job[A] = in_job[B] = 1;
-      max_work = w > max_work ? w : max_work;
-      x += 2;
-    } else {
-      x += 1;
-    }
-  }
-  // largest first (1024 buckets, as for the single pairs)
-  constexpr int NB = 1024;
-  std::vector<uint32_t> start(NB + 1, 0);
-  auto bucket_of = [&](double w) { return (uint32_t)(NB - 1 - (int)(w * (NB - 1) / max_work)); };
-  for (const PkJob &j : raw) start[bucket_of(j.work) + 1]++;
-  for (int b = 0; b < NB; ++b) start[b + 1] += start[b];
-  jobs.resize(raw.size());
-  for (const PkJob &j : raw) jobs[start[bucket_of(j.work)]++] = j;
-}
-
 static thread_local uint32_t t_last_plan[3] = {0, 0, 0};  // long pairs, single pairs, packed jobs of the last call
 
 int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, const uint32_t *pair_q,
@@ -1051,34 +889,6 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
     dim_n[i] = (uint32_t)n;
     dim_m[i] = (uint32_t)m;
   }
-  // Three kinds of work: long pairs (one CTA each), packed jobs (two pairs per warp, int16x2) and single
-  // pairs (one warp each); each list cost-ordered, longest first (short tail, similar pairs share a CTA).
-  const PackedConfig pk = packed_config(model, zero_gap);
-  std::vector<PkJob> jobs;
-  std::vector<uint8_t> in_job(n_pairs, 0);
-  if (pk.on && n_pairs >= 2) plan_packed_jobs(pk, dim_n, dim_m, cost, jobs, in_job);
-  std::vector<uint32_t> order;  // the pairs outside the jobs
-  {
-    uint64_t max_cost = 1;
-    uint32_t n_rest = 0;
-    for (uint32_t i = 0; i < n_pairs; ++i)
-      if (!in_job[i]) {
-        max_cost = cost[i] > max_cost ? cost[i] : max_cost;
-        ++n_rest;
-      }
-    constexpr int NB = 1024;
-    std::vector<uint32_t> bucket_start(NB + 1, 0);
-    order.resize(n_rest);
-    auto bucket_of = [&](uint64_t c) { return (uint32_t)(NB - 1 - (c * (NB - 1)) / max_cost); };  // descending cost
-    for (uint32_t i = 0; i < n_pairs; ++i)
-      if (!in_job[i]) bucket_start[bucket_of(cost[i]) + 1]++;
-    for (int b = 0; b < NB; ++b) bucket_start[b + 1] += bucket_start[b];
-    std::vector<uint32_t> cur(bucket_start.begin(), bucket_start.end() - 1);
-    for (uint32_t i = 0; i < n_pairs; ++i)
-      if (!in_job[i]) order[cur[bucket_of(cost[i])]++] = i;
-    // the long pairs (one CTA each) first, exactly
-    std::stable_partition(order.begin(), order.end(), [&](uint32_t i) { return cost[i] >= BIG_CELLS; });
-  }
   // device buffers live in the handle's workspace (allocating tens of GB per call costs more than
   // the kernels)
   SearchWorkspace &ws = h->ws;
@@ -1108,71 +918,24 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
   d_out = reinterpret_cast<kaamer_aln *>(ws.a_out.p);
   ACUDA(cudaMemcpyAsync(d_q, q_res, (size_t)n_qres, cudaMemcpyHostToDevice, st));
   ACUDA(cudaMemcpyAsync(d_qoff, q_off, ((size_t)nq + 1) * 8, cudaMemcpyHostToDevice, st));
-  // chunks under the traceback-memory budget: the items are walked longest first (long pairs, then jobs and
-  // single pairs merged by their estimated work), a chunk ends where the next item does not fit
+  // Three kinds of work: long pairs (one CTA each), packed jobs (two pairs per warp, int16x2) and single pairs
+  // (one warp each), in chunks under the traceback-memory budget (align_plan.hpp)
   size_t free_b = 0, total_b = 0;
   ACUDA(cudaMemGetInfo(&free_b, &total_b));
   uint64_t budget = (free_b + ws.a_scratch.n) / 2;
   if (budget > (16ull << 30)) budget = 16ull << 30;
-  struct Chunk {
-    uint32_t big_end, job_end, small_end;
-  };
-  std::vector<Chunk> chunks;
-  std::vector<AlnPair> big_pairs, small_pairs, job_pairs;  // device order: [long | single | jobs (two entries each)]
-  job_pairs.reserve(jobs.size() * 2);
-  uint64_t used = 0, max_used = 0;
-  int pk_maxcw_used = 0;
-  bool too_large = false;
-  auto place = [&](uint64_t b, uint32_t i) -> uint64_t {
-    if (b > budget) {
-      set_error("pair %u (%u x %u) needs %llu bytes of traceback state, more than the device has free", i, dim_n[i],
-                dim_m[i], (unsigned long long)b);
-      too_large = true;
-      return 0;
-    }
-    if (used + b > budget) {
-      chunks.push_back(Chunk{(uint32_t)big_pairs.size(), (uint32_t)(job_pairs.size() / 2), (uint32_t)small_pairs.size()});
-      used = 0;
-    }
-    const uint64_t at = used;
-    used += b;
-    max_used = used > max_used ? used : max_used;
-    return at;
-  };
-  {
-    size_t k = 0;
-    for (; k < order.size() && cost[order[k]] >= BIG_CELLS; ++k) {
-      const uint32_t i = order[k];
-      const uint64_t at = place(pair_scratch_bytes(dim_n[i], dim_m[i], 8, true), i);
-      big_pairs.push_back(AlnPair{i, pair_q[i], pair_s[i], 8u, at});
-    }
-    size_t j = 0;
-    while (!too_large && (k < order.size() || j < jobs.size())) {
-      bool take_job = j < jobs.size();
-      if (take_job && k < order.size()) {
-        const uint32_t i = order[k];
-        take_job = jobs[j].work >= single_work(dim_n[i], dim_m[i], zero_gap ? choose_cw(dim_m[i]) : 8);
-      }
-      if (take_job) {
-        const PkJob &jb = jobs[j++];
-        const uint64_t fb = pk_flags_bytes(jb.N, jb.Mx, jb.cw);
-        const uint64_t at = place(2 * fb + ((3ull * 4 * jb.N + 255) & ~255ull), jb.a);
-        job_pairs.push_back(AlnPair{jb.a, pair_q[jb.a], pair_s[jb.a], (uint32_t)jb.cw, at});
-        job_pairs.push_back(AlnPair{jb.b, pair_q[jb.b], pair_s[jb.b], (uint32_t)jb.cw, at + fb});
-        pk_maxcw_used = jb.cw > pk_maxcw_used ? jb.cw : pk_maxcw_used;
-      } else {
-        const uint32_t i = order[k++];
-        const int cw = zero_gap ? choose_cw(dim_m[i]) : 8;
-        const uint64_t at = place(pair_scratch_bytes(dim_n[i], dim_m[i], cw, false), i);
-        small_pairs.push_back(AlnPair{i, pair_q[i], pair_s[i], (uint32_t)cw, at});
-      }
-    }
-    if (too_large) {
-      cleanup();
-      return KAAMER_ERR_NOMEM;
-    }
+  AlnPlan plan;
+  if (!build_align_plan(n_pairs, pair_q, pair_s, dim_n, dim_m, cost, zero_gap, packed_config(model, zero_gap), budget, plan)) {
+    const uint32_t i = (uint32_t)plan.too_large_pair;
+    set_error("pair %u (%u x %u) needs %llu bytes of traceback state, more than the device has free", i, dim_n[i],
+              dim_m[i], (unsigned long long)plan.too_large_bytes);
+    cleanup();
+    return KAAMER_ERR_NOMEM;
   }
-  chunks.push_back(Chunk{(uint32_t)big_pairs.size(), (uint32_t)(job_pairs.size() / 2), (uint32_t)small_pairs.size()});
+  const std::vector<AlnPair> &big_pairs = plan.big_pairs, &small_pairs = plan.small_pairs, &job_pairs = plan.job_pairs;
+  const std::vector<AlnChunk> &chunks = plan.chunks;
+  const uint64_t max_used = plan.max_used;
+  const int pk_maxcw_used = plan.pk_maxcw_used;
   KCHECK(ws.a_scratch.ensure((size_t)max_used + 256));
   d_scratch = ws.a_scratch.p;
   AlnPair *d_big = d_pairs, *d_small = d_pairs + big_pairs.size(), *d_jobs = d_small + small_pairs.size();
@@ -1222,9 +985,9 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
   cudaStream_t st2 = h->copy_stream;
   const int pk_pcols = 32 * (pk_maxcw_used ? pk_maxcw_used : 4);
   const size_t pk_smem = (size_t)ALN_WARPS * 2 * PK_PROF_ROWS * pk_pcols;
-  Chunk prev{0, 0, 0};
+  AlnChunk prev{0, 0, 0};
   profile_begin(h, st, 3);
-  for (const Chunk &ch : chunks) {
+  for (const AlnChunk &ch : chunks) {
     if (ch.big_end > prev.big_end || ch.job_end > prev.job_end || ch.small_end > prev.small_end) {
       ACUDA(cudaEventRecord(h->chunk_ev[0], st));
       ACUDA(cudaStreamWaitEvent(st2, h->chunk_ev[0], 0));

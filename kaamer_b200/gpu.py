@@ -453,17 +453,20 @@ class GpuIndex:
         check(_lib.lib().kaamer_gpu_set_align_model(self._h, C.byref(m)))
 
     def align(self, q_residues, q_off, pair_query, pair_subject, lambda_: float = 0.267, K: float = 0.041,
-              gap_open: int = 11, gap_extend: int = 1, number_of_aa: int = 0, want_text: bool = False):
+              gap_open: int = 11, gap_extend: int = 1, number_of_aa: int = 0, want_text: bool = False, out=None):
         """align.Align (pkg/align/align.go:46-161) for (query index, subject protein id) pairs;
         defaults = blosum62_11_1 (pkg/align/matrixScores.go:59).  Returns a structured array
-        with the fields of AlignmentResult (align.go:25-40)."""
+        with the fields of AlignmentResult (align.go:25-40).  `out`: optional caller-owned result array (ALN_DTYPE,
+        one row per pair; page-locked memory makes the device-to-host copy a DMA)."""
         q_residues = np.ascontiguousarray(q_residues, dtype=np.uint8)
         q_off = np.ascontiguousarray(q_off, dtype=np.uint64)
         pq = np.ascontiguousarray(pair_query, dtype=np.uint32)
         ps = np.ascontiguousarray(pair_subject, dtype=np.uint32)
         assert len(pq) == len(ps)
         o = _lib.AlnOpts(lambda_, K, gap_open, gap_extend, number_of_aa)
-        out = np.zeros(len(pq), dtype=ALN_DTYPE)
+        if out is None:
+            out = np.zeros(len(pq), dtype=ALN_DTYPE)
+        assert out.dtype == ALN_DTYPE and len(out) == len(pq) and out.flags["C_CONTIGUOUS"]
         if not want_text:
             check(_lib.lib().kaamer_gpu_align(self._h, _vp(q_residues), _vp(q_off), _vp(pq), _vp(ps), len(pq),
                                               C.byref(o), _vp(out)))

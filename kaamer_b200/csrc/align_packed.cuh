@@ -382,6 +382,7 @@ __device__ __forceinline__ void dp_block_packed(const PkBlockArgs &g, const int8
   uint32_t q_prev = pad2, q_cur = pk_query_rows(lidx, qA, nA, qB, nB, lane),
            q_next = pk_query_rows(lidx, qA, nA, qB, nB, 32 + lane);
   const int steps = g.N + 31;
+#pragma unroll 2  // (the loop-carried registers rotate through moves otherwise: ~14 of ~290 instructions per step)
   for (int t = 0; t < steps; ++t) {
     if ((t & 31) == 0 && t > 0) {
       q_prev = q_cur;

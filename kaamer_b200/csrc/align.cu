@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(ALN_WARPS * 32) k_sw_affine(AlnArgs a) {
 
 // ---- one warp per TWO pairs: int16x2 lanes, DPX (align_packed.cuh) ------------------------------
 // a.pairs holds 2 * a.n_pairs entries: job k = pairs (2k, 2k+1), same cw (4 or 8), traceback regions of the
-// job's geometry (rows = max n, columns = max m, pk_geo), the block-boundary column behind the second region.
+// job's geometry (rows = max n, columns = max m, pk_geo), the block-boundary column (16 bytes per row) behind the second region.
 __global__ void __launch_bounds__(ALN_WARPS * 32, 4) k_sw_affine_pk(AlnArgs a, int pcols) {
   extern __shared__ __align__(16) int8_t pk_prof[];  // [ALN_WARPS][2][PK_PROF_ROWS * pcols]
   __shared__ int8_t s_b62[26 * 32];
@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(ALN_WARPS * 32, 4) k_sw_affine_pk(AlnArgs a, i
   uint32_t bpA = 0, bpB = 0;
   if (N > 0 && Mx > 0 && !(badA && badB)) {
     const int nblk = geo.blocks();
-    uint32_t *bnd = reinterpret_cast<uint32_t *>(scrB + pk_flags_bytes((uint64_t)N, (uint64_t)Mx, cw));  // in place: 3 x u32[N]
+    uint4 *bnd = reinterpret_cast<uint4 *>(scrB + pk_flags_bytes((uint64_t)N, (uint64_t)Mx, cw));  // in place: one uint4 per row
     int8_t *profA = pk_prof + (size_t)w * 2 * PK_PROF_ROWS * pcols, *profB = profA + (size_t)PK_PROF_ROWS * pcols;
     // a pair with illegal letters: pad rows and pad columns only, nothing positive
     const int nAd = badA ? 0 : nA, nBd = badB ? 0 : nB, mAd = badA ? 0 : mA, mBd = badB ? 0 : mB;
@@ -922,8 +922,14 @@ int align_pairs(kaamer_gpu *h, const uint8_t *q_res, const uint64_t *q_off, cons
   // (one warp each), in chunks under the traceback-memory budget (align_plan.hpp)
   size_t free_b = 0, total_b = 0;
   ACUDA(cudaMemGetInfo(&free_b, &total_b));
-  uint64_t budget = (free_b + ws.a_scratch.n) / 2;
-  if (budget > (16ull << 30)) budget = 16ull << 30;
+  // traceback state of a chunk: at most half of what is free, and at most 32 GB (the C5 batch needs 27 GB: one
+  // chunk, so the long-pair kernel runs underneath all the jobs); KAAMER_ALIGN_SCRATCH_GB: measurement hook
+  uint64_t budget = (free_b + ws.a_scratch.n) / 2, cap = 32ull << 30;
+  if (const char *e = getenv("KAAMER_ALIGN_SCRATCH_GB")) {
+    const long long v = atoll(e);
+    if (v >= 1 && v <= 128) cap = (uint64_t)v << 30;
+  }
+  if (budget > cap) budget = cap;
   AlnPlan plan;
   if (!build_align_plan(n_pairs, pair_q, pair_s, dim_n, dim_m, cost, zero_gap, packed_config(model, zero_gap), budget, plan)) {
     const uint32_t i = (uint32_t)plan.too_large_pair;

@@ -61,7 +61,7 @@ PK_HD uint32_t pk_add2(uint32_t a, uint32_t b) {
 #endif
 }
 
-PK_HD uint32_t pk_ld_l2(const uint32_t *p) {
+PK_HD uint4 pk_ld_l2(const uint4 *p) {
 #ifdef __CUDA_ARCH__
   return __ldcg(p);  // the boundary column is written by this warp's lane 31: read it from L2
 #else
@@ -98,6 +98,8 @@ PK_HD int pk_tail_from(int cols, int cw) {
   const PkGeo g = pk_geo(cols, cw);
   return g.tail_cw ? g.nfull * 32 * cw : 0x7FFFFFFF;
 }
+// bytes of the block-boundary column of a packed job (16 per row: one 128-bit store / load per step)
+PK_HD uint64_t pk_bnd_bytes(uint64_t rows) { return (16ull * rows + 255) & ~255ull; }
 // bytes of one pair's traceback region of a packed job: per block [rows + 31 steps][32 lanes][block cw bytes]
 PK_HD uint64_t pk_flags_bytes(uint64_t rows, uint64_t cols, int cw) {
   return (pk_padded_cols(cols, cw) * (rows + 31) + 255) & ~255ull;
@@ -214,8 +216,8 @@ struct PkBlockArgs {
   uint32_t open2;               // SWAffine.GapOpen in both halves
   uint32_t zero2;               // 0, from a run-time value: kept in a register (a literal 0 is re-materialised per cell)
   uint8_t *dirsA, *dirsB;       // this block's traceback lines: [N + 31][32][CW]
-  const uint32_t *bnd_in;       // block-boundary column (M, L, max) of the previous block: [3][N] packed words
-  uint32_t *bnd_out;
+  const uint4 *bnd_in;          // block-boundary column of the previous block: one (M, L, max, -) per row
+  uint4 *bnd_out;
 };
 
 // profile rows of query position `row` of both pairs: row of pair A | row of pair B << 8 (PK_PAD_ROW past the
@@ -237,9 +239,10 @@ PK_HD void pk_step(PkLane<CW> &s, const PkBlockArgs &g, int lane, int t, uint32_
   if (lane == 0) {
     inM = inL = inB = 0u;
     if (g.bnd_in && active) {
-      inM = pk_ld_l2(g.bnd_in + (uint32_t)r);
-      inL = pk_ld_l2(g.bnd_in + (uint32_t)(g.N + r));
-      inB = pk_ld_l2(g.bnd_in + (uint32_t)(2 * g.N + r));
+      const uint4 v = pk_ld_l2(g.bnd_in + (uint32_t)r);
+      inM = v.x;
+      inL = v.y;
+      inB = v.z;
     }
   }
   uint32_t diag = s.prevB;
@@ -322,11 +325,7 @@ PK_HD void pk_step(PkLane<CW> &s, const PkBlockArgs &g, int lane, int t, uint32_
       }
     }
   }
-  if (lane == 31 && g.bnd_out) {
-    g.bnd_out[(uint32_t)r] = s.pubM;
-    g.bnd_out[(uint32_t)(g.N + r)] = s.pubL;
-    g.bnd_out[(uint32_t)(2 * g.N + r)] = s.pubB;
-  }
+  if (lane == 31 && g.bnd_out) g.bnd_out[(uint32_t)r] = make_uint4(s.pubM, s.pubL, s.pubB, 0u);
 }
 
 // this lane's end-cell candidates merged into the running (score, position) of each pair:

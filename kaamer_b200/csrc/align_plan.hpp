@@ -321,7 +321,7 @@ inline bool build_align_plan(uint32_t n_pairs, const uint32_t *pair_q, const uin
     if (take_job) {
       const PkJob &jb = jobs[j++];
       const uint64_t fb = ((uint64_t)(jb.cw == 8 ? T.padded_pk8[jb.Mx] : T.padded_pk4[jb.Mx]) * (jb.N + 31ull) + 255) & ~255ull;  // pk_flags_bytes
-      const uint64_t at = place(2 * fb + ((3ull * 4 * jb.N + 255) & ~255ull), jb.a);
+      const uint64_t at = place(2 * fb + pk_bnd_bytes(jb.N), jb.a);
       job_pairs.push_back(AlnPair{jb.a, pair_q[jb.a], pair_s[jb.a], (uint32_t)jb.cw, at});
       job_pairs.push_back(AlnPair{jb.b, pair_q[jb.b], pair_s[jb.b], (uint32_t)jb.cw, at + fb});
       plan.pk_maxcw_used = jb.cw > plan.pk_maxcw_used ? jb.cw : plan.pk_maxcw_used;

@@ -110,7 +110,7 @@ static long run_job(const std::vector<uint8_t> &qA, const std::vector<uint8_t> &
   const int nblk = geo.blocks(), tail_from = pk_tail_from(Mx, cw);
   const size_t fb = (size_t)pk_flags_bytes(N, Mx, cw);
   std::vector<uint8_t> regA(fb + 64, 0xEE), regB(fb + 64, 0xEE);
-  std::vector<uint32_t> bnd((size_t)3 * N + 8, 0xDEADBEEFu);
+  std::vector<uint4> bnd((size_t)N + 2, make_uint4(0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0u));
   alignas(16) static int8_t profA[PK_PROF_ROWS * 256], profB[PK_PROF_ROWS * 256];
   int bsA = 0, bsB = 0;
   uint32_t bpA = 0, bpB = 0;

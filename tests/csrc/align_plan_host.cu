@@ -83,7 +83,7 @@ static void check_plan(const char *name, uint32_t n_pairs, const std::vector<uin
     for (uint32_t k = prev.job_end; k < c.job_end; ++k) {
       const AlnPair &a = plan.job_pairs[2 * k], &b = plan.job_pairs[2 * k + 1];
       const uint32_t N = std::max(dn[a.out_index], dn[b.out_index]), Mx = std::max(dm[a.out_index], dm[b.out_index]);
-      iv.push_back({a.scratch, a.scratch + 2 * pk_flags_bytes(N, Mx, (int)a.cw) + ((3ull * 4 * N + 255) & ~255ull)});
+      iv.push_back({a.scratch, a.scratch + 2 * pk_flags_bytes(N, Mx, (int)a.cw) + pk_bnd_bytes(N)});
     }
     std::sort(iv.begin(), iv.end(), [](const Interval &x, const Interval &y) { return x.b < y.b; });
     for (size_t k = 0; k < iv.size(); ++k) {

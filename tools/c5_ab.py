@@ -17,6 +17,7 @@ from kaamer_b200.makedb import fasta_protein_ids  # noqa: E402
 SETTINGS = [
     {"KAAMER_ALIGN_PACKED": "0"},
     {},
+    {"KAAMER_ALIGN_SCRATCH_GB": "16"},
     {"KAAMER_ALIGN_PK_MAXCW": "4"},
     {"KAAMER_ALIGN_PK_CELLS": str(4 << 20)},
 ]

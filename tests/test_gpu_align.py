@@ -178,7 +178,7 @@ def test_aln_string_equals_the_reference_layout():
     assert n_gapped > 10 and any(t == b"\n\n" for t in texts)
 
 
-@pytest.mark.parametrize("model", ["gap_row_minus4", "gap_row_ragged", "pam_like", "default_again"])
+@pytest.mark.parametrize("model", ["gap_row_minus4", "gap_row_ragged", "pam_like", "zero_gap_other_matrix", "default_again"])
 def test_alignment_model_is_a_runtime_parameter(model):
     """whichever gap row biogo's BLOSUM62 carries, and §8f-4's other matrices, are a kaamer_gpu_set_align_model
     call away: the general cell update against the oracle under the same model, bit-exact"""
@@ -209,6 +209,16 @@ def test_alignment_model_is_a_runtime_parameter(model):
         m[:, 0] = -1
         m[0, 0] = 0
         gap_open = -9
+    elif model == "zero_gap_other_matrix":
+        # another matrix and gap open WITH a zero gap row: the packed int16x2 kernel takes it (its score bound
+        # follows the largest entry)
+        rng = np.random.default_rng(6)
+        sym = rng.integers(-6, 7, (26, 26))
+        m = np.triu(sym) + np.triu(sym, 1).T
+        m[np.arange(1, 26), np.arange(1, 26)] = rng.integers(5, 18, 25)
+        m[0, :] = 0
+        m[:, 0] = 0
+        gap_open = -7
     try:
         o.set_align_model(m if model != "default_again" else None, gap_open)
         with GpuIndex.build(res, off, ids, keep_proteins=True) as g:
@@ -218,6 +228,8 @@ def test_alignment_model_is_a_runtime_parameter(model):
             else:
                 g.set_align_model(m, gap_open)
             out, texts = g.align(q, qo, [p[0] for p in pairs], [p[1] for p in pairs], number_of_aa=3_500_000, want_text=True)
+            # packed jobs exactly when the model has a zero gap row
+            assert (g.align_last_plan()[2] > 0) == (model in ("zero_gap_other_matrix", "default_again")), g.align_last_plan()
             _check(out, pairs, queries, subjects, prm, model)
             for k, (qi, sid) in enumerate(pairs):
                 assert texts[k] == o.aln_string(queries[qi], subjects[sid], prm), (model, k)

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <random>
 #include <vector>
@@ -140,6 +141,18 @@ int main() {
       check_plan(name, n_pairs, pq, ps, dn, dm, cost, true, cw4, 16ull << 30);
       snprintf(name, sizeof name, "n=%u kind=%d 32-bit only", n_pairs, kind);
       check_plan(name, n_pairs, pq, ps, dn, dm, cost, false, off, 1ull << 30);
+    }
+  }
+  {  // the per-length tables state the cost model functions
+    const PlanTables &T = plan_tables();
+    for (int k = 0; k < 20000; ++k) {
+      const uint32_t n = 1 + rng() % 16000, m = 1 + rng() % PK_MAX_DIM, big_m = 1 + rng() % 65534;
+      const int cw8 = choose_cw_pk(m, 8);
+      CHECK(T.cw_pk8[m] == cw8 && T.padded_pk8[m] == pk_padded_cols(m, cw8) && T.padded_pk4[m] == pk_padded_cols(m, 4), "packed tables at m = %u", m);
+      const double w8 = packed_work(n, m, cw8), w4 = packed_work(n, m, 4), ws = single_work(n, big_m, choose_cw(big_m));
+      CHECK(std::abs((double)(n + 31) * T.row_pk8[m] - w8) <= 1e-6 * w8 && std::abs((double)(n + 31) * T.row_pk4[m] - w4) <= 1e-6 * w4, "packed work at %u x %u", n, m);
+      CHECK(T.cw_single[big_m] == choose_cw(big_m) && std::abs((double)(n + 31) * T.row_single[big_m] - ws) <= 1e-6 * ws, "single work at %u x %u", n, big_m);
+      CHECK(pk_flags_bytes(n, m, cw8) == (((uint64_t)T.padded_pk8[m] * (n + 31ull) + 255) & ~255ull), "region bytes at %u x %u", n, m);
     }
   }
   {  // a pair that cannot fit

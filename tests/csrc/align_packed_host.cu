@@ -214,6 +214,23 @@ int main(int argc, char **argv) {
     cells += (long)qA.size() * baseA.size() + (badB ? 0 : (long)qB.size() * baseB.size());
     if (bad > 20) break;
   }
+  // geometry corners: single cells, the longest query the packed path takes, subjects at the block / tail boundaries
+  {
+    const int ms[] = {1, 127, 128, 129, 255, 256, 257, 383, 384, 385, 511, 512, 513, 640, 641};
+    for (int m : ms)
+      for (int cw : {4, 8}) {
+        auto sA = rnd(m), sB = rnd(std::max(1, m - 1 - (int)(rng() % 5)));
+        auto qA = mutate(sA, 0.2, 0.02), qB = mutate(sB, 0.3, 0.05);
+        bad += run_job(qA, sA, qB, sB, false, cw, -11);
+        cells += (long)qA.size() * sA.size() + (long)qB.size() * sB.size();
+      }
+    auto one = rnd(1);
+    bad += run_job(one, one, one, rnd(3), false, 8, -11);
+    auto longq = rnd(PK_MAX_DIM), narrow = rnd(5), shortq = rnd(9), wide = rnd(300);
+    bad += run_job(longq, narrow, shortq, wide, false, 8, -11);  // N = 16383 rows, the other pair 9 x 300
+    bad += run_job(shortq, wide, longq, narrow, true, 4, -11);
+    cells += 2 * ((long)PK_MAX_DIM * 5 + 9 * 300);
+  }
   printf("%d jobs, %ld cells, %ld mismatches\n", jobs, cells, bad);
   return bad ? 1 : 0;
 }
